@@ -1,0 +1,101 @@
+// Internal interfaces of the tile-classifier forward (K2): fp32 CUDA-core path and
+// bf16 tcgen05 path share the model object defined in model.cu.
+#pragma once
+#include <cuda.h>  // CUtensorMap (types only; the encoder is fetched at run time)
+
+#include "common.cuh"
+
+namespace cs {
+
+// ---------------------------------------------------------------------------
+// fp32 path (fwd_fp32.cu)
+// ---------------------------------------------------------------------------
+struct ConvF32Args {
+  const float* in;  // element (n, ci, y, x) at n*in_sn + ci*in_sc + y*in_sy + x*in_sx
+  int64_t in_sn, in_sc, in_sy, in_sx;
+  int Hi, Wi, Cin, Ho, Wo, Cout, k, stride, pad;
+  const float* w;         // [k*k*Cin][Cout], row index (dy*k+dx)*Cin + ci
+  const float* bias;      // [Cout] (folded BN shift)
+  const float* residual;  // nullable, NHWC like out
+  float* out;             // [M][Cout], M = n*Ho*Wo  (NHWC)
+  int64_t M;
+  int relu;
+};
+int launch_conv_fp32(const ConvF32Args& a, cudaStream_t st);
+int launch_maxpool_fp32(const float* in, float* out, int64_t n, int Hi, int Wi, int C,
+                        cudaStream_t st);
+int launch_head_fp32(const float* x4, int64_t n, int P, int C, const float* fc_w,
+                     const float* fc_b, float* prob_out, float* logits_out, float* feat_out,
+                     cudaStream_t st);
+
+// ---------------------------------------------------------------------------
+// bf16 tcgen05 path (fwd_tc.cu)
+// ---------------------------------------------------------------------------
+constexpr int kGemmBM = 128;       // UMMA M (rows per CTA tile)
+constexpr int kGemmBK = 64;        // bf16 elements per K step = one 128-byte swizzle row
+constexpr int kMaxSteps = 20;      // K steps per (layer, n-variant)
+constexpr int kMaxVariants = 4;
+
+// One K step of 64 channels: which A box to fetch and which B columns it meets.
+struct KStep {
+  int16_t a_c0;  // A coordinate 0 (channel, or K column in 2-D mode), elements
+  int16_t b_k;   // B coordinate 0 (K column), elements
+  int8_t dx, dy; // 4-D mode: A coordinates 1 and 2 (pixel shift; may be -1)
+  uint8_t map;   // A tensor map index
+  uint8_t pad_;
+};
+
+struct GemmParams {
+  CUtensorMap a_map[4];
+  CUtensorMap b_map;
+  KStep steps[kMaxVariants][kMaxSteps];
+  int n_steps[kMaxVariants];
+  int n_variants;     // 1: every n-tile walks steps[0]; else steps[n_tile]
+  int a_mode;         // 0: 2-D {k, row}; 1: 4-D {c, x, y, tile}
+  int units_per_mtile;  // 4-D mode: tiles (instances) per 128-row M tile
+  int num_m_tiles, num_n_tiles;
+  int n_total;        // output row pitch, elements
+  int64_t m_valid;    // rows that exist
+  const float* bias;  // [n_total]
+  const __nv_bfloat16* res_hi;  // nullable
+  const __nv_bfloat16* res_lo;  // nullable
+  __nv_bfloat16* out_hi;
+  __nv_bfloat16* out_lo;  // nullable
+  float* out_f32;         // nullable: raw fp32 result (diagnostics)
+  int relu;
+};
+
+// BN (the CTA's N tile) must be 64, 128 or 256.
+int launch_conv_gemm(const GemmParams& p, int BN, cudaStream_t st);
+
+// Host: 4-D activation map {C, W, H, T} with a {64, bw, bh, bt} box, 128-byte swizzle.
+int make_act_map_4d(CUtensorMap* map, const void* base, int C, int W, int H, int64_t T,
+                    int64_t stride_x_elems, int64_t stride_y_elems, int64_t stride_t_elems,
+                    int box_w, int box_h, int box_t);
+// Host: 2-D K-major matrix map {K, rows} with a {64, box_rows} box, 128-byte swizzle.
+int make_mat_map_2d(CUtensorMap* map, const void* base, int64_t K, int64_t rows,
+                    int64_t row_pitch_elems, int box_rows);
+
+struct StemArgs {
+  // source A: u8 images + uniform grid
+  const uint8_t* img;
+  int H, W, tile, interval, grid_w;
+  int64_t tiles_per_bag;
+  int64_t inst_begin;
+  // source B: materialised fp32 NCHW tiles (nullable)
+  const float* x;
+  int64_t count;          // instances in this batch
+  const float* w;         // [147][64] fp32 (folded)
+  const float* bias;      // [64]
+  __nv_bfloat16* out_hi;  // [count][Hp*Wp][64]
+  __nv_bfloat16* out_lo;
+};
+int launch_stem_bf16(const StemArgs& a, cudaStream_t st);
+
+int launch_head_bf16(const __nv_bfloat16* x_hi, const __nv_bfloat16* x_lo, int64_t n, int P,
+                     int C, const float* fc_w, const float* fc_b, float* prob_out,
+                     float* logits_out, float* feat_out, cudaStream_t st);
+
+int get_norm_lut_host(float* dst768);
+
+}  // namespace cs

@@ -1,0 +1,713 @@
+// Model object for the tile classifier: weight packing, per-layer GEMM planning and the
+// forward drivers behind cs_model_forward_tiles / cs_model_forward_tensor.
+//
+// Reference network: MILResNet with BasicBlock (model/resnet.py:15-43, 81-127, 179-193,
+// 234-269); ctor layer counts from MILresnet18/34 (:336-352).  The caller has folded
+// eval-mode BN into every conv (fp32).  Activation layout on the device is
+// [instance][pixel (row-major y,x)][channel]; bf16 mode keeps a `hi` tensor (MMA
+// operand) and, for block outputs, a `lo` tensor (value - hi) for the residual stream.
+#include <math.h>
+#include <string.h>
+
+#include <memory>
+#include <vector>
+
+#include "fwd.cuh"
+
+namespace cs {
+namespace {
+
+uint16_t f32_to_bf16_rn(float f) {
+  uint32_t u;
+  memcpy(&u, &f, 4);
+  if ((u & 0x7fffffffu) > 0x7f800000u) return (uint16_t)((u >> 16) | 0x40);  // NaN
+  uint32_t lsb = (u >> 16) & 1u;
+  u += 0x7fffu + lsb;
+  return (uint16_t)(u >> 16);
+}
+
+struct ConvW {
+  int cin = 0, cout = 0, k = 0, stride = 1, pad = 0;
+  std::vector<float> w;  // OIHW, BN folded
+  std::vector<float> b;  // [cout]
+  float* d_w32 = nullptr;  // [k*k*cin][cout]
+  float* d_b = nullptr;
+};
+
+struct BlockDesc {
+  int conv1, conv2, ds;  // indices into convs; ds = -1 when the block has no downsample
+  int cin, cout, stride;
+};
+
+struct ConvGeom {
+  int Hi, Wi, Cin, Ho, Wo, Cout, k, stride, pad;
+};
+
+struct PlannedConv {
+  GemmParams p;
+  int BN = 0;
+  bool dense = false;
+  int Po = 0;  // output pixels per instance
+  __nv_bfloat16* d_B = nullptr;
+  float* d_bias = nullptr;
+};
+
+void free_planned(PlannedConv& pc) {
+  if (pc.d_B) cudaFree(pc.d_B);
+  if (pc.d_bias) cudaFree(pc.d_bias);
+  pc.d_B = nullptr;
+  pc.d_bias = nullptr;
+}
+
+// Builds the GEMM description of one convolution (optionally with the block's 1x1
+// stride-2 downsample fused as extra K steps reading `ds_in_hi`).
+//   in_hi     : conv input  [b_pad][Hi*Wi][Cin] bf16
+//   ds_in_hi  : block input [b_pad][Hx*Wx][Cx]  bf16 (only when gds != nullptr)
+int plan_conv(const ConvGeom& g, const float* w_oihw, const float* bias, const ConvGeom* gds,
+              const float* wds_oihw, const float* bds, const __nv_bfloat16* in_hi,
+              const __nv_bfloat16* ds_in_hi, int64_t b_pad, PlannedConv* out) {
+  PlannedConv pc;
+  memset(&pc.p, 0, sizeof(pc.p));
+  const int Po = g.Ho * g.Wo, Pi = g.Hi * g.Wi;
+  pc.Po = Po;
+  if (g.Cin % 64 != 0 || g.Cout % 64 != 0) {
+    set_error("plan_conv: channels %d -> %d must be multiples of 64", g.Cin, g.Cout);
+    return CS_ERR_UNSUPPORTED;
+  }
+  if (gds && (gds->k != 1 || gds->Ho != g.Ho || gds->Wo != g.Wo || gds->Cout != g.Cout ||
+              gds->Cin % 64 != 0)) {
+    set_error("plan_conv: unsupported downsample geometry");
+    return CS_ERR_UNSUPPORTED;
+  }
+  std::vector<float> bias_full;
+  std::vector<uint16_t> B;
+  int64_t K_cat = 0;
+  int rc;
+
+  if (Po >= 16) {
+    // ---- shifted-box form: rows = (instance, oy, ox)
+    if (kGemmBM % Po != 0 || g.Cout > 256 || g.k != 3 || g.pad != 1 ||
+        (g.stride != 1 && g.stride != 2) || (g.stride == 2 && (g.Hi != 2 * g.Ho || g.Wi != 2 * g.Wo))) {
+      set_error("plan_conv: unsupported shifted-box geometry Ho=%d Wo=%d Cout=%d k=%d s=%d", g.Ho,
+                g.Wo, g.Cout, g.k, g.stride);
+      return CS_ERR_UNSUPPORTED;
+    }
+    pc.dense = false;
+    pc.BN = g.Cout;
+    pc.p.a_mode = 1;
+    pc.p.units_per_mtile = kGemmBM / Po;
+    pc.p.num_n_tiles = 1;
+    pc.p.n_variants = 1;
+    pc.p.n_total = g.Cout;
+    const int K_main = 9 * g.Cin;
+    K_cat = K_main + (gds ? gds->Cin : 0);
+    int ns = 0;
+    int n_maps = 0;
+    if (g.stride == 1) {
+      rc = make_act_map_4d(&pc.p.a_map[0], in_hi, g.Cin, g.Wi, g.Hi, b_pad, g.Cin,
+                           (int64_t)g.Wi * g.Cin, (int64_t)Pi * g.Cin, g.Wo, g.Ho, kGemmBM / Po);
+      if (rc != CS_OK) return rc;
+      n_maps = 1;
+    } else {
+      for (int a = 0; a < 2; ++a)
+        for (int b = 0; b < 2; ++b) {
+          rc = make_act_map_4d(&pc.p.a_map[a * 2 + b], in_hi + ((int64_t)a * g.Wi + b) * g.Cin,
+                               g.Cin, g.Wo, g.Ho, b_pad, 2 * g.Cin, (int64_t)2 * g.Wi * g.Cin,
+                               (int64_t)Pi * g.Cin, g.Wo, g.Ho, kGemmBM / Po);
+          if (rc != CS_OK) return rc;
+        }
+      n_maps = 4;
+    }
+    for (int dy = 0; dy < 3; ++dy)
+      for (int dx = 0; dx < 3; ++dx)
+        for (int c0 = 0; c0 < g.Cin; c0 += 64) {
+          if (ns >= kMaxSteps) { set_error("plan_conv: too many K steps"); return CS_ERR_UNSUPPORTED; }
+          KStep& st = pc.p.steps[0][ns++];
+          st.a_c0 = (int16_t)c0;
+          st.b_k = (int16_t)((dy * 3 + dx) * g.Cin + c0);
+          if (g.stride == 1) {
+            st.map = 0; st.dx = (int8_t)(dx - 1); st.dy = (int8_t)(dy - 1);
+          } else {
+            // iy = 2*oy + dy - 1: dy=0 -> phase 1 shift -1; dy=1 -> phase 0; dy=2 -> phase 1
+            int pa = (dy == 1) ? 0 : 1, pb = (dx == 1) ? 0 : 1;
+            st.map = (uint8_t)(pa * 2 + pb);
+            st.dy = (int8_t)(dy == 0 ? -1 : 0);
+            st.dx = (int8_t)(dx == 0 ? -1 : 0);
+          }
+        }
+    if (gds) {
+      if (n_maps >= 4) { set_error("plan_conv: no free A map for the downsample"); return CS_ERR_UNSUPPORTED; }
+      // 1x1 stride-2 conv on the block input: parity phase (0,0), no shift.
+      rc = make_act_map_4d(&pc.p.a_map[n_maps], ds_in_hi, gds->Cin, g.Wo, g.Ho, b_pad, 2 * gds->Cin,
+                           (int64_t)2 * gds->Wi * gds->Cin, (int64_t)gds->Hi * gds->Wi * gds->Cin,
+                           g.Wo, g.Ho, kGemmBM / Po);
+      if (rc != CS_OK) return rc;
+      for (int c0 = 0; c0 < gds->Cin; c0 += 64) {
+        if (ns >= kMaxSteps) { set_error("plan_conv: too many K steps"); return CS_ERR_UNSUPPORTED; }
+        KStep& st = pc.p.steps[0][ns++];
+        st.a_c0 = (int16_t)c0; st.b_k = (int16_t)(K_main + c0);
+        st.map = (uint8_t)n_maps; st.dx = 0; st.dy = 0;
+      }
+    }
+    pc.p.n_steps[0] = ns;
+    // B[co][(dy*3+dx)*Cin + ci] (+ [K_main + ci] for the downsample)
+    B.assign((size_t)g.Cout * K_cat, 0);
+    for (int co = 0; co < g.Cout; ++co) {
+      for (int ci = 0; ci < g.Cin; ++ci)
+        for (int t = 0; t < 9; ++t)
+          B[(size_t)co * K_cat + t * g.Cin + ci] = f32_to_bf16_rn(w_oihw[((size_t)co * g.Cin + ci) * 9 + t]);
+      if (gds)
+        for (int ci = 0; ci < gds->Cin; ++ci)
+          B[(size_t)co * K_cat + K_main + ci] = f32_to_bf16_rn(wds_oihw[(size_t)co * gds->Cin + ci]);
+    }
+    bias_full.resize(g.Cout);
+    for (int co = 0; co < g.Cout; ++co) bias_full[co] = bias[co] + (gds ? bds[co] : 0.f);
+  } else {
+    // ---- dense form: rows = instances, N = (out pixel, co), K = (in pixel, ci)
+    pc.dense = true;
+    const int N_total = Po * g.Cout;
+    pc.BN = (N_total % 256 == 0) ? 256 : (N_total % 128 == 0 ? 128 : 64);
+    pc.p.a_mode = 0;
+    pc.p.units_per_mtile = kGemmBM;
+    pc.p.num_n_tiles = N_total / pc.BN;
+    pc.p.n_total = N_total;
+    if (pc.p.num_n_tiles > kMaxVariants) {
+      set_error("plan_conv: %d N tiles exceed %d variants", pc.p.num_n_tiles, kMaxVariants);
+      return CS_ERR_UNSUPPORTED;
+    }
+    pc.p.n_variants = pc.p.num_n_tiles;
+    const int64_t K_main = (int64_t)Pi * g.Cin;
+    const int64_t K_ds = gds ? (int64_t)gds->Hi * gds->Wi * gds->Cin : 0;
+    K_cat = K_main + K_ds;
+    if (K_cat > 32767) { set_error("plan_conv: dense K %lld too large", (long long)K_cat); return CS_ERR_UNSUPPORTED; }
+    rc = make_mat_map_2d(&pc.p.a_map[0], in_hi, K_main, b_pad, K_main, kGemmBM);
+    if (rc != CS_OK) return rc;
+    if (gds) {
+      rc = make_mat_map_2d(&pc.p.a_map[1], ds_in_hi, K_ds, b_pad, K_ds, kGemmBM);
+      if (rc != CS_OK) return rc;
+    }
+    B.assign((size_t)N_total * K_cat, 0);
+    for (int oy = 0; oy < g.Ho; ++oy)
+      for (int ox = 0; ox < g.Wo; ++ox) {
+        const int po = oy * g.Wo + ox;
+        for (int dy = 0; dy < g.k; ++dy)
+          for (int dx = 0; dx < g.k; ++dx) {
+            int iy = oy * g.stride - g.pad + dy, ix = ox * g.stride - g.pad + dx;
+            if (iy < 0 || iy >= g.Hi || ix < 0 || ix >= g.Wi) continue;
+            const int pi = iy * g.Wi + ix;
+            for (int co = 0; co < g.Cout; ++co) {
+              uint16_t* dst = &B[((size_t)po * g.Cout + co) * K_cat + (size_t)pi * g.Cin];
+              const float* src = &w_oihw[(size_t)co * g.Cin * g.k * g.k + dy * g.k + dx];
+              for (int ci = 0; ci < g.Cin; ++ci) dst[ci] = f32_to_bf16_rn(src[(size_t)ci * g.k * g.k]);
+            }
+          }
+        if (gds) {
+          const int pi = (oy * gds->stride) * gds->Wi + ox * gds->stride;
+          for (int co = 0; co < g.Cout; ++co) {
+            uint16_t* dst = &B[((size_t)po * g.Cout + co) * K_cat + K_main + (size_t)pi * gds->Cin];
+            for (int ci = 0; ci < gds->Cin; ++ci) dst[ci] = f32_to_bf16_rn(wds_oihw[(size_t)co * gds->Cin + ci]);
+          }
+        }
+      }
+    // K steps per N tile: only 64-wide K blocks with a non-zero weight in that tile
+    for (int nt = 0; nt < pc.p.num_n_tiles; ++nt) {
+      int ns = 0;
+      for (int64_t kb = 0; kb < K_cat; kb += 64) {
+        bool any = false;
+        for (int n = nt * pc.BN; n < (nt + 1) * pc.BN && !any; ++n)
+          for (int kk = 0; kk < 64; ++kk)
+            if ((B[(size_t)n * K_cat + kb + kk] & 0x7fff) != 0) { any = true; break; }
+        if (!any) continue;
+        if (ns >= kMaxSteps) { set_error("plan_conv: too many dense K steps"); return CS_ERR_UNSUPPORTED; }
+        KStep& st = pc.p.steps[nt][ns++];
+        st.b_k = (int16_t)kb;
+        if (kb < K_main) { st.map = 0; st.a_c0 = (int16_t)kb; }
+        else { st.map = 1; st.a_c0 = (int16_t)(kb - K_main); }
+        st.dx = st.dy = 0;
+      }
+      if (ns == 0) {  // all-zero weights: keep one step so the accumulator is defined
+        KStep& st = pc.p.steps[nt][ns++];
+        st.b_k = 0; st.map = 0; st.a_c0 = 0; st.dx = st.dy = 0;
+      }
+      pc.p.n_steps[nt] = ns;
+    }
+    bias_full.resize(N_total);
+    for (int po = 0; po < Po; ++po)
+      for (int co = 0; co < g.Cout; ++co) bias_full[(size_t)po * g.Cout + co] = bias[co] + (gds ? bds[co] : 0.f);
+  }
+
+  CS_CUDA(cudaMalloc(&pc.d_B, B.size() * sizeof(uint16_t)));
+  CS_CUDA(cudaMemcpy(pc.d_B, B.data(), B.size() * sizeof(uint16_t), cudaMemcpyHostToDevice));
+  CS_CUDA(cudaMalloc(&pc.d_bias, bias_full.size() * sizeof(float)));
+  CS_CUDA(cudaMemcpy(pc.d_bias, bias_full.data(), bias_full.size() * sizeof(float), cudaMemcpyHostToDevice));
+  rc = make_mat_map_2d(&pc.p.b_map, pc.d_B, K_cat, pc.p.n_total, K_cat, pc.BN);
+  if (rc != CS_OK) { free_planned(pc); return rc; }
+  pc.p.bias = pc.d_bias;
+  *out = pc;
+  return CS_OK;
+}
+
+struct TcPlan {
+  int tile = 0;
+  int64_t max_batch = 0, b_pad = 0;
+  void* ws = nullptr;
+  std::vector<PlannedConv> layers;  // conv1, conv2 of every block in order
+  __nv_bfloat16* buf_hi[3] = {nullptr, nullptr, nullptr};
+  __nv_bfloat16* buf_lo[2] = {nullptr, nullptr};
+  const __nv_bfloat16* x4_hi = nullptr;
+  const __nv_bfloat16* x4_lo = nullptr;
+  int P4 = 1, C4 = 512;
+  ~TcPlan() { for (auto& l : layers) free_planned(l); }
+};
+
+int64_t round_up(int64_t v, int64_t a) { return (v + a - 1) / a * a; }
+
+int64_t act_elems(int tile) { return (int64_t)(tile / 4) * (tile / 4) * 64; }
+
+constexpr int64_t kFp32Chunk = 4096;
+
+int64_t fp32_floats_per_inst(int tile) {
+  return (int64_t)3 * tile * tile + (int64_t)(tile / 2) * (tile / 2) * 64 + 4 * act_elems(tile);
+}
+
+}  // namespace
+}  // namespace cs
+
+using namespace cs;
+
+struct cs_model {
+  int arch = 0;
+  std::vector<ConvW> convs;
+  std::vector<BlockDesc> blocks;
+  int feat_dim = 512;
+  float* d_fc_w = nullptr;
+  float* d_fc_b = nullptr;
+  std::unique_ptr<TcPlan> plan;
+  int64_t last_launches = 0;
+};
+
+namespace cs {
+namespace {
+
+int build_tc_plan(cs_model* m, int tile, int64_t max_batch, void* ws, int64_t ws_bytes) {
+  auto plan = std::make_unique<TcPlan>();
+  plan->tile = tile;
+  plan->max_batch = max_batch;
+  plan->b_pad = round_up(max_batch, kGemmBM);
+  plan->ws = ws;
+  const int64_t E = act_elems(tile);
+  const int64_t buf_bytes = round_up(plan->b_pad * E * 2, 1024);
+  if (ws_bytes < 5 * buf_bytes + 1024) {
+    set_error("bf16 workspace too small: %lld < %lld", (long long)ws_bytes,
+              (long long)(5 * buf_bytes + 1024));
+    return CS_ERR_WORKSPACE;
+  }
+  uintptr_t base = round_up((int64_t)(uintptr_t)ws, 1024);
+  for (int i = 0; i < 3; ++i) plan->buf_hi[i] = reinterpret_cast<__nv_bfloat16*>(base + i * buf_bytes);
+  for (int i = 0; i < 2; ++i) plan->buf_lo[i] = reinterpret_cast<__nv_bfloat16*>(base + (3 + i) * buf_bytes);
+
+  // x lives in (hi[xi], lo[xi]); mid in hi[2]; y in (hi[1-xi], lo[1-xi])
+  int xi = 0;
+  int H = tile / 4, W = tile / 4, C = 64;
+  for (const BlockDesc& b : m->blocks) {
+    const ConvW& c1 = m->convs[b.conv1];
+    const ConvW& c2 = m->convs[b.conv2];
+    const int Ho = (H + 2 - 3) / b.stride + 1, Wo = (W + 2 - 3) / b.stride + 1;
+    ConvGeom g1{H, W, C, Ho, Wo, b.cout, 3, b.stride, 1};
+    ConvGeom g2{Ho, Wo, b.cout, Ho, Wo, b.cout, 3, 1, 1};
+    PlannedConv p1, p2;
+    int rc = plan_conv(g1, c1.w.data(), c1.b.data(), nullptr, nullptr, nullptr, plan->buf_hi[xi],
+                       nullptr, plan->b_pad, &p1);
+    if (rc != CS_OK) return rc;
+    p1.p.out_hi = plan->buf_hi[2];
+    p1.p.out_lo = nullptr;
+    p1.p.res_hi = p1.p.res_lo = nullptr;
+    p1.p.relu = 1;
+    plan->layers.push_back(p1);
+    if (b.ds >= 0) {
+      const ConvW& cd = m->convs[b.ds];
+      ConvGeom gd{H, W, C, Ho, Wo, b.cout, 1, b.stride, 0};
+      rc = plan_conv(g2, c2.w.data(), c2.b.data(), &gd, cd.w.data(), cd.b.data(), plan->buf_hi[2],
+                     plan->buf_hi[xi], plan->b_pad, &p2);
+      if (rc != CS_OK) return rc;
+      p2.p.res_hi = p2.p.res_lo = nullptr;
+    } else {
+      rc = plan_conv(g2, c2.w.data(), c2.b.data(), nullptr, nullptr, nullptr, plan->buf_hi[2],
+                     nullptr, plan->b_pad, &p2);
+      if (rc != CS_OK) return rc;
+      p2.p.res_hi = plan->buf_hi[xi];
+      p2.p.res_lo = plan->buf_lo[xi];
+    }
+    p2.p.out_hi = plan->buf_hi[1 - xi];
+    p2.p.out_lo = plan->buf_lo[1 - xi];
+    p2.p.relu = 1;
+    plan->layers.push_back(p2);
+    xi = 1 - xi;
+    H = Ho; W = Wo; C = b.cout;
+  }
+  plan->x4_hi = plan->buf_hi[xi];
+  plan->x4_lo = plan->buf_lo[xi];
+  plan->P4 = H * W;
+  plan->C4 = C;
+  m->plan = std::move(plan);
+  return CS_OK;
+}
+
+int run_tc_batch(cs_model* m, const StemArgs& stem_in, int64_t count, float* prob_out,
+                 float* logits_out, float* feat_out, cudaStream_t st) {
+  TcPlan& pl = *m->plan;
+  StemArgs sa = stem_in;
+  sa.count = count;
+  sa.w = m->convs[0].d_w32;
+  sa.bias = m->convs[0].d_b;
+  sa.out_hi = pl.buf_hi[0];
+  sa.out_lo = pl.buf_lo[0];
+  int rc = launch_stem_bf16(sa, st);
+  if (rc != CS_OK) return rc;
+  m->last_launches++;
+  for (PlannedConv& pc : pl.layers) {
+    GemmParams p = pc.p;
+    int64_t rows = pc.dense ? count : count * pc.Po;
+    p.m_valid = rows;
+    p.num_m_tiles = (int)ceil_div<int64_t>(rows, kGemmBM);
+    rc = launch_conv_gemm(p, pc.BN, st);
+    if (rc != CS_OK) return rc;
+    m->last_launches++;
+  }
+  rc = launch_head_bf16(pl.x4_hi, pl.x4_lo, count, pl.P4, pl.C4, m->d_fc_w, m->d_fc_b, prob_out,
+                        logits_out, feat_out, st);
+  if (rc != CS_OK) return rc;
+  m->last_launches++;
+  return CS_OK;
+}
+
+// fp32 path for `count` instances whose normalised NCHW tiles are at x_in.
+int run_fp32_batch(cs_model* m, const float* x_in, int tile, int64_t count, float* ws_f,
+                   float* prob_out, float* logits_out, float* feat_out, cudaStream_t st) {
+  const int S = tile;
+  const int Hc = S / 2, Hp = S / 4;
+  float* c1 = ws_f;
+  float* bufs[4];
+  float* q = c1 + count * (int64_t)Hc * Hc * 64;
+  for (int i = 0; i < 4; ++i) { bufs[i] = q; q += count * act_elems(tile); }
+  const ConvW& stem = m->convs[0];
+  ConvF32Args a{};
+  a.in = x_in; a.in_sn = (int64_t)3 * S * S; a.in_sc = (int64_t)S * S; a.in_sy = S; a.in_sx = 1;
+  a.Hi = S; a.Wi = S; a.Cin = 3; a.Ho = Hc; a.Wo = Hc; a.Cout = 64; a.k = 7; a.stride = 2; a.pad = 3;
+  a.w = stem.d_w32; a.bias = stem.d_b; a.residual = nullptr; a.out = c1;
+  a.M = count * Hc * Hc; a.relu = 1;
+  int rc = launch_conv_fp32(a, st);
+  if (rc != CS_OK) return rc;
+  rc = launch_maxpool_fp32(c1, bufs[0], count, Hc, Hc, 64, st);
+  if (rc != CS_OK) return rc;
+  m->last_launches += 2;
+  int xi = 0, H = Hp, W = Hp, C = 64;
+  for (const BlockDesc& b : m->blocks) {
+    const ConvW& w1 = m->convs[b.conv1];
+    const ConvW& w2 = m->convs[b.conv2];
+    const int Ho = (H + 2 - 3) / b.stride + 1, Wo = (W + 2 - 3) / b.stride + 1;
+    float* x = bufs[xi];
+    float* mid = bufs[2];
+    float* dsb = bufs[3];
+    float* y = bufs[1 - xi];
+    ConvF32Args c{};
+    c.in = x; c.in_sn = (int64_t)H * W * C; c.in_sc = 1; c.in_sy = (int64_t)W * C; c.in_sx = C;
+    c.Hi = H; c.Wi = W; c.Cin = C; c.Ho = Ho; c.Wo = Wo; c.Cout = b.cout; c.k = 3; c.stride = b.stride; c.pad = 1;
+    c.w = w1.d_w32; c.bias = w1.d_b; c.residual = nullptr; c.out = mid; c.M = count * Ho * Wo; c.relu = 1;
+    rc = launch_conv_fp32(c, st);
+    if (rc != CS_OK) return rc;
+    m->last_launches++;
+    const float* res = x;
+    if (b.ds >= 0) {
+      const ConvW& wd = m->convs[b.ds];
+      ConvF32Args d = c;
+      d.k = 1; d.pad = 0; d.w = wd.d_w32; d.bias = wd.d_b; d.out = dsb; d.relu = 0;
+      rc = launch_conv_fp32(d, st);
+      if (rc != CS_OK) return rc;
+      m->last_launches++;
+      res = dsb;
+    }
+    ConvF32Args e{};
+    e.in = mid; e.in_sn = (int64_t)Ho * Wo * b.cout; e.in_sc = 1; e.in_sy = (int64_t)Wo * b.cout; e.in_sx = b.cout;
+    e.Hi = Ho; e.Wi = Wo; e.Cin = b.cout; e.Ho = Ho; e.Wo = Wo; e.Cout = b.cout; e.k = 3; e.stride = 1; e.pad = 1;
+    e.w = w2.d_w32; e.bias = w2.d_b; e.residual = res; e.out = y; e.M = count * Ho * Wo; e.relu = 1;
+    rc = launch_conv_fp32(e, st);
+    if (rc != CS_OK) return rc;
+    m->last_launches++;
+    xi = 1 - xi; H = Ho; W = Wo; C = b.cout;
+  }
+  rc = launch_head_fp32(bufs[xi], count, H * W, C, m->d_fc_w, m->d_fc_b, prob_out, logits_out,
+                        feat_out, st);
+  if (rc != CS_OK) return rc;
+  m->last_launches++;
+  return CS_OK;
+}
+
+int check_forward_args(const char* fn, const cs_model* m, int tile, int precision, void* ws,
+                       int64_t ws_bytes, int64_t max_batch) {
+  CS_REQUIRE(m != nullptr, "%s: model is NULL", fn);
+  CS_REQUIRE(tile == 16 || tile == 32, "%s: tile %d unsupported (16 or 32)", fn, tile);
+  CS_REQUIRE(precision == CS_PREC_FP32 || precision == CS_PREC_BF16, "%s: bad precision %d", fn, precision);
+  CS_REQUIRE(ws != nullptr && max_batch > 0, "%s: workspace is NULL or max_batch <= 0", fn);
+  int64_t need = cs_model_workspace_bytes(m, tile, max_batch, precision);
+  if (ws_bytes < need) {
+    set_error("%s: workspace %lld B < required %lld B", fn, (long long)ws_bytes, (long long)need);
+    return CS_ERR_WORKSPACE;
+  }
+  return CS_OK;
+}
+
+int ensure_plan(cs_model* m, int tile, int64_t max_batch, void* ws, int64_t ws_bytes) {
+  if (m->plan && m->plan->tile == tile && m->plan->max_batch == max_batch && m->plan->ws == ws)
+    return CS_OK;
+  m->plan.reset();
+  return build_tc_plan(m, tile, max_batch, ws, ws_bytes);
+}
+
+}  // namespace
+}  // namespace cs
+
+extern "C" {
+
+int cs_model_create(int arch, int n_convs, const float* const* conv_w_host,
+                    const float* const* conv_b_host, const float* fc_w_host,
+                    const float* fc_b_host, cs_model** out) {
+  CS_REQUIRE(out != nullptr, "cs_model_create: out is NULL");
+  *out = nullptr;
+  CS_REQUIRE(conv_w_host && conv_b_host && fc_w_host && fc_b_host, "cs_model_create: NULL weights");
+  std::vector<int> layers;
+  if (arch == CS_ARCH_RESNET18) layers = {2, 2, 2, 2};
+  else if (arch == CS_ARCH_RESNET34) layers = {3, 4, 6, 3};
+  else { set_error("cs_model_create: unknown arch %d", arch); return CS_ERR_UNSUPPORTED; }
+  int rc = cs_check_device();
+  if (rc != CS_OK) return rc;
+
+  auto m = std::make_unique<cs_model>();
+  m->arch = arch;
+  auto add_conv = [&](int cin, int cout, int k, int stride, int pad) {
+    ConvW c; c.cin = cin; c.cout = cout; c.k = k; c.stride = stride; c.pad = pad;
+    m->convs.push_back(std::move(c));
+    return (int)m->convs.size() - 1;
+  };
+  add_conv(3, 64, 7, 2, 3);
+  int inplanes = 64;
+  const int planes[4] = {64, 128, 256, 512};
+  for (int L = 0; L < 4; ++L)
+    for (int bi = 0; bi < layers[L]; ++bi) {
+      int stride = (bi == 0 && L > 0) ? 2 : 1;
+      BlockDesc b;
+      b.cin = inplanes; b.cout = planes[L]; b.stride = stride;
+      b.conv1 = add_conv(inplanes, planes[L], 3, stride, 1);
+      b.conv2 = add_conv(planes[L], planes[L], 3, 1, 1);
+      b.ds = (stride != 1 || inplanes != planes[L]) ? add_conv(inplanes, planes[L], 1, stride, 0) : -1;
+      inplanes = planes[L];
+      m->blocks.push_back(b);
+    }
+  CS_REQUIRE((int)m->convs.size() == n_convs, "cs_model_create: arch %d has %d convs, got %d", arch,
+             (int)m->convs.size(), n_convs);
+  for (int i = 0; i < n_convs; ++i) {
+    ConvW& c = m->convs[i];
+    CS_REQUIRE(conv_w_host[i] && conv_b_host[i], "cs_model_create: conv %d weights NULL", i);
+    size_t nw = (size_t)c.cout * c.cin * c.k * c.k;
+    c.w.assign(conv_w_host[i], conv_w_host[i] + nw);
+    c.b.assign(conv_b_host[i], conv_b_host[i] + c.cout);
+    // fp32 device layout [(dy*k+dx)*cin + ci][cout]
+    std::vector<float> t(nw);
+    const int kk = c.k * c.k;
+    for (int co = 0; co < c.cout; ++co)
+      for (int ci = 0; ci < c.cin; ++ci)
+        for (int tp = 0; tp < kk; ++tp)
+          t[((size_t)tp * c.cin + ci) * c.cout + co] = c.w[((size_t)co * c.cin + ci) * kk + tp];
+    CS_CUDA(cudaMalloc(&c.d_w32, nw * sizeof(float)));
+    CS_CUDA(cudaMemcpy(c.d_w32, t.data(), nw * sizeof(float), cudaMemcpyHostToDevice));
+    CS_CUDA(cudaMalloc(&c.d_b, c.cout * sizeof(float)));
+    CS_CUDA(cudaMemcpy(c.d_b, c.b.data(), c.cout * sizeof(float), cudaMemcpyHostToDevice));
+  }
+  m->feat_dim = 512;
+  CS_CUDA(cudaMalloc(&m->d_fc_w, 2 * 512 * sizeof(float)));
+  CS_CUDA(cudaMemcpy(m->d_fc_w, fc_w_host, 2 * 512 * sizeof(float), cudaMemcpyHostToDevice));
+  CS_CUDA(cudaMalloc(&m->d_fc_b, 2 * sizeof(float)));
+  CS_CUDA(cudaMemcpy(m->d_fc_b, fc_b_host, 2 * sizeof(float), cudaMemcpyHostToDevice));
+  *out = m.release();
+  return CS_OK;
+}
+
+int cs_model_destroy(cs_model* m) {
+  if (!m) return CS_OK;
+  m->plan.reset();
+  for (ConvW& c : m->convs) {
+    if (c.d_w32) cudaFree(c.d_w32);
+    if (c.d_b) cudaFree(c.d_b);
+  }
+  if (m->d_fc_w) cudaFree(m->d_fc_w);
+  if (m->d_fc_b) cudaFree(m->d_fc_b);
+  delete m;
+  return CS_OK;
+}
+
+int64_t cs_model_workspace_bytes(const cs_model* m, int tile, int64_t max_batch, int precision) {
+  (void)m;
+  if (max_batch <= 0 || (tile != 16 && tile != 32)) return 0;
+  // fp32 chunk buffers are needed in both modes only when the fp32 path runs
+  if (precision == CS_PREC_FP32) {
+    int64_t chunk = max_batch < kFp32Chunk ? max_batch : kFp32Chunk;
+    return chunk * fp32_floats_per_inst(tile) * 4 + 4096;
+  }
+  int64_t b_pad = round_up(max_batch, kGemmBM);
+  return 5 * round_up(b_pad * act_elems(tile) * 2, 1024) + 4096;
+}
+
+int cs_model_forward_tiles(cs_model* m, const uint8_t* img, int n_bags, int H, int W, int tile,
+                           int interval, int64_t inst_begin, int64_t inst_count, int precision,
+                           float* prob_out, float* feat_out, void* workspace,
+                           int64_t workspace_bytes, int64_t max_batch, void* stream) {
+  int rc = check_forward_args("cs_model_forward_tiles", m, tile, precision, workspace,
+                              workspace_bytes, max_batch);
+  if (rc != CS_OK) return rc;
+  CS_REQUIRE(img && prob_out, "cs_model_forward_tiles: NULL pointer");
+  int gh = grid_count(H, tile, interval), gw = grid_count(W, tile, interval);
+  CS_REQUIRE(gh > 0 && gw > 0, "cs_model_forward_tiles: bad geometry H=%d W=%d tile=%d interval=%d",
+             H, W, tile, interval);
+  const int64_t T = (int64_t)gh * gw;
+  CS_REQUIRE(inst_begin >= 0 && inst_count >= 0 && inst_begin + inst_count <= (int64_t)n_bags * T,
+             "cs_model_forward_tiles: instance range [%lld,+%lld) outside %d bags x %lld tiles",
+             (long long)inst_begin, (long long)inst_count, n_bags, (long long)T);
+  cudaStream_t st = as_stream(stream);
+  m->last_launches = 0;
+  if (precision == CS_PREC_BF16) {
+    rc = ensure_plan(m, tile, max_batch, workspace, workspace_bytes);
+    if (rc != CS_OK) return rc;
+    StemArgs sa{};
+    sa.img = img; sa.H = H; sa.W = W; sa.tile = tile; sa.interval = interval; sa.grid_w = gw;
+    sa.tiles_per_bag = T; sa.x = nullptr;
+    for (int64_t done = 0; done < inst_count; done += max_batch) {
+      int64_t cnt = inst_count - done < max_batch ? inst_count - done : max_batch;
+      sa.inst_begin = inst_begin + done;
+      rc = run_tc_batch(m, sa, cnt, prob_out + done, nullptr,
+                        feat_out ? feat_out + done * m->feat_dim : nullptr, st);
+      if (rc != CS_OK) return rc;
+    }
+  } else {
+    int64_t chunk = max_batch < kFp32Chunk ? max_batch : kFp32Chunk;
+    float* x_in = reinterpret_cast<float*>(round_up((int64_t)(uintptr_t)workspace, 256));
+    float* rest = x_in + chunk * 3 * tile * tile;
+    for (int64_t done = 0; done < inst_count; done += chunk) {
+      int64_t cnt = inst_count - done < chunk ? inst_count - done : chunk;
+      rc = cs_unfold_normalize(img, n_bags, H, W, tile, interval, inst_begin + done, cnt, x_in, stream);
+      if (rc != CS_OK) return rc;
+      m->last_launches++;
+      rc = run_fp32_batch(m, x_in, tile, cnt, rest, prob_out + done, nullptr,
+                          feat_out ? feat_out + done * m->feat_dim : nullptr, st);
+      if (rc != CS_OK) return rc;
+    }
+  }
+  return CS_OK;
+}
+
+int cs_model_forward_tensor(cs_model* m, const float* x, int64_t n, int tile, int precision,
+                            float* logits_out, float* feat_out, void* workspace,
+                            int64_t workspace_bytes, int64_t max_batch, void* stream) {
+  int rc = check_forward_args("cs_model_forward_tensor", m, tile, precision, workspace,
+                              workspace_bytes, max_batch);
+  if (rc != CS_OK) return rc;
+  CS_REQUIRE(x && n >= 0, "cs_model_forward_tensor: NULL input or n < 0");
+  CS_REQUIRE(logits_out || feat_out, "cs_model_forward_tensor: no output requested");
+  cudaStream_t st = as_stream(stream);
+  m->last_launches = 0;
+  const int64_t per = (int64_t)3 * tile * tile;
+  if (precision == CS_PREC_BF16) {
+    rc = ensure_plan(m, tile, max_batch, workspace, workspace_bytes);
+    if (rc != CS_OK) return rc;
+    StemArgs sa{};
+    sa.tile = tile;
+    for (int64_t done = 0; done < n; done += max_batch) {
+      int64_t cnt = n - done < max_batch ? n - done : max_batch;
+      sa.x = x + done * per;
+      rc = run_tc_batch(m, sa, cnt, nullptr, logits_out ? logits_out + done * 2 : nullptr,
+                        feat_out ? feat_out + done * m->feat_dim : nullptr, st);
+      if (rc != CS_OK) return rc;
+    }
+  } else {
+    int64_t chunk = max_batch < kFp32Chunk ? max_batch : kFp32Chunk;
+    float* x_unused = reinterpret_cast<float*>(round_up((int64_t)(uintptr_t)workspace, 256));
+    float* rest = x_unused + chunk * 3 * tile * tile;
+    for (int64_t done = 0; done < n; done += chunk) {
+      int64_t cnt = n - done < chunk ? n - done : chunk;
+      rc = run_fp32_batch(m, x + done * per, tile, cnt, rest, nullptr,
+                          logits_out ? logits_out + done * 2 : nullptr,
+                          feat_out ? feat_out + done * m->feat_dim : nullptr, st);
+      if (rc != CS_OK) return rc;
+    }
+  }
+  return CS_OK;
+}
+
+int64_t cs_model_last_launch_count(const cs_model* m) { return m ? m->last_launches : 0; }
+
+// ---------------------------------------------------------------------------
+// Diagnostics (used by tests/): run the production planner + tcgen05 kernel on one
+// convolution or one plain GEMM and return the raw fp32 result.
+// ---------------------------------------------------------------------------
+
+// out_f32[M][N] = A[M][K] . B[N][K]^T + bias[N];  A, B bf16 (device), K multiple of 64 and
+// <= 1280, N multiple of bn, bn in {64,128,256}.
+int cs_debug_gemm_bf16(const void* a_bf16, const void* b_bf16, int64_t M, int N, int K,
+                       const float* bias, int bn, float* out_f32, void* stream) {
+  CS_REQUIRE(a_bf16 && b_bf16 && bias && out_f32, "cs_debug_gemm_bf16: NULL pointer");
+  CS_REQUIRE(K % 64 == 0 && K / 64 <= kMaxSteps && N % bn == 0 && M > 0,
+             "cs_debug_gemm_bf16: bad shape M=%lld N=%d K=%d bn=%d", (long long)M, N, K, bn);
+  int rc = cs_check_device();
+  if (rc != CS_OK) return rc;
+  GemmParams p;
+  memset(&p, 0, sizeof(p));
+  rc = make_mat_map_2d(&p.a_map[0], a_bf16, K, M, K, kGemmBM);
+  if (rc != CS_OK) return rc;
+  rc = make_mat_map_2d(&p.b_map, b_bf16, K, N, K, bn);
+  if (rc != CS_OK) return rc;
+  p.n_variants = 1;
+  p.n_steps[0] = K / 64;
+  for (int s = 0; s < K / 64; ++s) {
+    p.steps[0][s].a_c0 = (int16_t)(s * 64);
+    p.steps[0][s].b_k = (int16_t)(s * 64);
+  }
+  p.a_mode = 0;
+  p.units_per_mtile = kGemmBM;
+  p.num_m_tiles = (int)ceil_div<int64_t>(M, kGemmBM);
+  p.num_n_tiles = N / bn;
+  p.n_total = N;
+  p.m_valid = M;
+  p.bias = bias;
+  p.out_f32 = out_f32;
+  return launch_conv_gemm(p, bn, as_stream(stream));
+}
+
+// One 3x3 conv (pad 1, stride 1|2) through plan_conv: in_hi bf16 [n][Hi*Wi][Cin] (device),
+// w_host fp32 OIHW, bias_host fp32 -> out_f32 [n][Ho*Wo][Cout] (device), no ReLU.
+// n must be a multiple of 128.
+int cs_debug_conv3x3_bf16(const void* in_hi, int64_t n, int Hi, int Wi, int Cin, int Cout,
+                          int stride, const float* w_host, const float* bias_host,
+                          float* out_f32, void* stream) {
+  CS_REQUIRE(in_hi && w_host && bias_host && out_f32, "cs_debug_conv3x3_bf16: NULL pointer");
+  CS_REQUIRE(n > 0 && n % kGemmBM == 0, "cs_debug_conv3x3_bf16: n must be a positive multiple of 128");
+  int rc = cs_check_device();
+  if (rc != CS_OK) return rc;
+  ConvGeom g{Hi, Wi, Cin, (Hi + 2 - 3) / stride + 1, (Wi + 2 - 3) / stride + 1, Cout, 3, stride, 1};
+  PlannedConv pc;
+  rc = plan_conv(g, w_host, bias_host, nullptr, nullptr, nullptr,
+                 reinterpret_cast<const __nv_bfloat16*>(in_hi), nullptr, n, &pc);
+  if (rc != CS_OK) return rc;
+  GemmParams p = pc.p;
+  int64_t rows = pc.dense ? n : n * pc.Po;
+  p.m_valid = rows;
+  p.num_m_tiles = (int)ceil_div<int64_t>(rows, kGemmBM);
+  p.out_f32 = out_f32;
+  p.relu = 0;
+  rc = launch_conv_gemm(p, pc.BN, as_stream(stream));
+  cudaError_t e = cudaStreamSynchronize(as_stream(stream));
+  free_planned(pc);
+  if (rc != CS_OK) return rc;
+  CS_CUDA(e);
+  return CS_OK;
+}
+
+}  // extern "C"

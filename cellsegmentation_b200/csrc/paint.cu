@@ -1,0 +1,140 @@
+// K4a: painting kept tiles into per-bag maps.
+//
+// Reference:
+//   generate_masks  utils/image_processing.py:91-98   mask[g][x:x+S, y:y+S] = 1
+//   heatmap         utils/image_processing.py:153-158 map[g][x:x+S, y:y+S] = prob,
+//                   visited in ascending (bag, prob) order, so the last write is the
+//                   largest kept covering probability: per-pixel max.
+//   heatmap         :165   255 - np.uint8(255 * map)   (float64 product, truncation)
+//
+// One warp paints one tile row-by-row; masks are idempotent byte stores, heatmaps
+// use atomicMax on the int view of non-negative floats.
+#include "common.cuh"
+
+namespace {
+
+struct Grid {
+  int H, W, tile, interval, grid_w;
+  int64_t tiles_per_bag;
+  int bag_base, n_bags;
+};
+
+__device__ __forceinline__ bool tile_origin(const Grid& g, int32_t inst, int64_t* bag, int* row0,
+                                            int* col0) {
+  int64_t b = inst / g.tiles_per_bag;
+  int t = (int)(inst - b * g.tiles_per_bag);
+  int gy = t / g.grid_w, gx = t - gy * g.grid_w;
+  *bag = g.bag_base + b;
+  *row0 = cs::grid_coord(gy, g.H, g.tile, g.interval);
+  *col0 = cs::grid_coord(gx, g.W, g.tile, g.interval);
+  return inst >= 0 && *bag < g.n_bags;
+}
+
+__global__ void __launch_bounds__(256)
+paint_mask_kernel(Grid g, const int32_t* __restrict__ sel, int64_t n_sel, uint8_t* __restrict__ out) {
+  int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  int lane = threadIdx.x & 31;
+  int64_t n_warps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+  int S = g.tile;
+  for (int64_t j = warp; j < n_sel; j += n_warps) {
+    int64_t bag; int r0, c0;
+    if (!tile_origin(g, sel[j], &bag, &r0, &c0)) continue;
+    uint8_t* base = out + (bag * g.H + r0) * (int64_t)g.W + c0;
+    for (int e = lane; e < S * S; e += 32) {
+      int y = e / S, x = e - y * S;
+      base[(int64_t)y * g.W + x] = 1;
+    }
+  }
+}
+
+__global__ void __launch_bounds__(256)
+paint_heat_kernel(Grid g, const int32_t* __restrict__ sel, const float* __restrict__ prob,
+                  int64_t n_sel, float* __restrict__ out) {
+  int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  int lane = threadIdx.x & 31;
+  int64_t n_warps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+  int S = g.tile;
+  for (int64_t j = warp; j < n_sel; j += n_warps) {
+    int64_t bag; int r0, c0;
+    if (!tile_origin(g, sel[j], &bag, &r0, &c0)) continue;
+    float p = prob[j];
+    if (!(p >= 0.0f)) continue;  // negative or NaN never passes `prob > thr >= 0`
+    int pi = __float_as_int(p);
+    int* base = reinterpret_cast<int*>(out) + (bag * g.H + r0) * (int64_t)g.W + c0;
+    for (int e = lane; e < S * S; e += 32) {
+      int y = e / S, x = e - y * S;
+      atomicMax(base + (int64_t)y * g.W + x, pi);
+    }
+  }
+}
+
+__global__ void __launch_bounds__(256)
+heat_to_gray_kernel(const float* __restrict__ heat, int64_t n, uint8_t* __restrict__ gray) {
+  int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+    double v = 255.0 * (double)heat[i];       // numpy: float64 array times python int
+    gray[i] = (uint8_t)(255 - (int)(uint8_t)(int)v);  // np.uint8() truncates toward zero
+  }
+}
+
+int make_grid(const char* fn, int H, int W, int tile, int interval, int bag_base, int n_bags,
+              Grid* g) {
+  int gh = cs::grid_count(H, tile, interval), gw = cs::grid_count(W, tile, interval);
+  CS_REQUIRE(gh > 0 && gw > 0, "%s: bad geometry H=%d W=%d tile=%d interval=%d", fn, H, W, tile,
+             interval);
+  CS_REQUIRE(bag_base >= 0 && n_bags > 0, "%s: bad bag_base/n_bags", fn);
+  *g = Grid{H, W, tile, interval, gw, (int64_t)gh * gw, bag_base, n_bags};
+  return CS_OK;
+}
+
+int warp_grid(int64_t n_items) {
+  int64_t want = cs::ceil_div<int64_t>(n_items * 32, 256);
+  int64_t cap = (int64_t)cs::kNumSMs * 8 * 4;
+  return (int)(want < cap ? (want > 0 ? want : 1) : cap);
+}
+
+}  // namespace
+
+extern "C" {
+
+int cs_paint_mask(const int32_t* sel_idx, int64_t n_sel, int H, int W, int tile, int interval,
+                  int bag_base, int n_bags, uint8_t* mask_out, void* stream) {
+  CS_REQUIRE(mask_out != nullptr && (sel_idx != nullptr || n_sel == 0), "cs_paint_mask: NULL pointer");
+  CS_REQUIRE(n_sel >= 0, "cs_paint_mask: n_sel < 0");
+  Grid g;
+  int rc = make_grid("cs_paint_mask", H, W, tile, interval, bag_base, n_bags, &g);
+  if (rc != CS_OK) return rc;
+  if (n_sel == 0) return CS_OK;
+  paint_mask_kernel<<<warp_grid(n_sel), 256, 0, cs::as_stream(stream)>>>(g, sel_idx, n_sel, mask_out);
+  CS_LAUNCH_CHECK();
+  return CS_OK;
+}
+
+int cs_paint_heatmap(const int32_t* sel_idx, const float* sel_prob, int64_t n_sel, int H, int W,
+                     int tile, int interval, int bag_base, int n_bags, float* heat_out,
+                     void* stream) {
+  CS_REQUIRE(heat_out != nullptr && ((sel_idx != nullptr && sel_prob != nullptr) || n_sel == 0),
+             "cs_paint_heatmap: NULL pointer");
+  CS_REQUIRE(n_sel >= 0, "cs_paint_heatmap: n_sel < 0");
+  Grid g;
+  int rc = make_grid("cs_paint_heatmap", H, W, tile, interval, bag_base, n_bags, &g);
+  if (rc != CS_OK) return rc;
+  if (n_sel == 0) return CS_OK;
+  paint_heat_kernel<<<warp_grid(n_sel), 256, 0, cs::as_stream(stream)>>>(g, sel_idx, sel_prob,
+                                                                        n_sel, heat_out);
+  CS_LAUNCH_CHECK();
+  return CS_OK;
+}
+
+int cs_heatmap_to_gray(const float* heat, int64_t n, uint8_t* gray_out, void* stream) {
+  CS_REQUIRE(heat && gray_out, "cs_heatmap_to_gray: NULL pointer");
+  CS_REQUIRE(n >= 0, "cs_heatmap_to_gray: n < 0");
+  if (n == 0) return CS_OK;
+  int64_t want = cs::ceil_div<int64_t>(n, 256);
+  int grid = (int)(want < 148 * 32 ? want : 148 * 32);
+  heat_to_gray_kernel<<<grid, 256, 0, cs::as_stream(stream)>>>(heat, n, gray_out);
+  CS_LAUNCH_CHECK();
+  return CS_OK;
+}
+
+}  // extern "C"

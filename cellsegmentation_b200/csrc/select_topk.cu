@@ -1,0 +1,349 @@
+// K3: segmented (per-bag) ordering, adaptive top-k selection, threshold ranking.
+//
+// Reference:
+//   sample()            inference.py:31-42   order = np.lexsort((probs, groups));
+//                                            index[i] = groups[i] != groups[(i+k_i) % N]
+//   make_train_data()   dataset/dataset.py:168-169   pseudo-label = labels[bag] != 0
+//   rank()              test_tile.py:63-79   keep prob > threshold in lexsort order
+//
+// groups (tileIDX) is non-decreasing, so lexsort((probs, groups)) is an
+// independent stable sort of every bag's probabilities: ascending prob, ties by
+// ascending instance index, NaN last.  One CTA owns one bag: the bag's keys are
+// loaded once from HBM (coalesced), ordered in shared memory by a bitonic network
+// on (sortable-u32 key, u16 local index) pairs, and only the kept entries are
+// written back.  No host round trip: per-bag counts -> device scan -> emit.
+//
+// Literal predicate.  With s = segment start, T = segment size, k' = k mod N and
+// local sorted rank j, u = s + j + k':
+//   u <  N : kept iff j >= T - k'
+//   u >= N : kept iff j <  N - k'          (wrap-around into an earlier bag)
+// i.e. ranks [max(0,T-k'), min(T,J0)) U [max(0,J0), min(T,N-k')) with J0 = N-k'-s.
+// Normal case: the last min(k,T) ranks.  k' = 0 keeps nothing (also k = N).
+//
+// Algorithmic bytes: 4 B/instance read + 5 B per kept instance + 4 B/bag label.
+#include "common.cuh"
+
+namespace {
+
+constexpr int kThreads = 512;
+constexpr int kMaxSegPow2 = 32768;  // 6 B * 32768 = 192 KB of shared memory
+
+struct Segs {
+  const int64_t* offsets;  // nullptr -> uniform
+  int64_t uniform_T;
+  int n_bags;
+  __device__ __forceinline__ int64_t start(int b) const {
+    return offsets ? offsets[b] : (int64_t)b * uniform_T;
+  }
+  __device__ __forceinline__ int64_t total() const {
+    return offsets ? offsets[n_bags] : (int64_t)n_bags * uniform_T;
+  }
+};
+
+__device__ __forceinline__ int pow2_ceil(int v) {
+  int p = 1;
+  while (p < v) p <<= 1;
+  return p;
+}
+
+// Kept ranks of one bag under the literal predicate: [a1,b1) U [a2,b2).
+struct Kept {
+  int a1, b1, a2, b2;
+  __device__ __forceinline__ int count() const { return (b1 - a1) + (b2 - a2); }
+};
+
+__device__ __forceinline__ Kept kept_ranges(int64_t s, int64_t T, int64_t N, int64_t k) {
+  Kept r{0, 0, 0, 0};
+  if (T <= 0 || N <= 0) return r;
+  int64_t kp = k % N;
+  int64_t J0 = N - kp - s;
+  int64_t a1 = T - kp > 0 ? T - kp : 0;
+  int64_t b1 = T < J0 ? T : J0;
+  int64_t a2 = J0 > 0 ? J0 : 0;
+  int64_t b2 = T < N - kp ? T : N - kp;
+  if (b1 < a1) b1 = a1;
+  if (b2 < a2) b2 = a2;
+  r.a1 = (int)a1; r.b1 = (int)b1; r.a2 = (int)a2; r.b2 = (int)b2;
+  return r;
+}
+
+__device__ __forceinline__ int64_t bag_k(const int32_t* labels, int b, int32_t tiles_per_pos,
+                                         int32_t topk_neg) {
+  int32_t c = labels[b];
+  return c == 0 ? (int64_t)topk_neg : (int64_t)c * (int64_t)tiles_per_pos;
+}
+
+// ---- per-bag kept counts ----------------------------------------------------
+__global__ void select_count_kernel(Segs segs, const int32_t* __restrict__ labels,
+                                    int32_t tiles_per_pos, int32_t topk_neg,
+                                    int64_t* __restrict__ counts) {
+  int b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= segs.n_bags) return;
+  int64_t s = segs.start(b), e = segs.start(b + 1), N = segs.total();
+  counts[b] = kept_ranges(s, e - s, N, bag_k(labels, b, tiles_per_pos, topk_neg)).count();
+}
+
+__global__ void __launch_bounds__(256)
+rank_count_kernel(Segs segs, const float* __restrict__ prob, float thr,
+                  int64_t* __restrict__ counts) {
+  int b = blockIdx.x;
+  int64_t s = segs.start(b), e = segs.start(b + 1);
+  int c = 0;
+  for (int64_t i = s + threadIdx.x; i < e; i += blockDim.x) c += (prob[i] > thr) ? 1 : 0;
+  __shared__ int wsum[8];
+  for (int o = 16; o > 0; o >>= 1) c += __shfl_xor_sync(0xffffffffu, c, o);
+  if ((threadIdx.x & 31) == 0) wsum[threadIdx.x >> 5] = c;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    int t = 0;
+    for (int w = 0; w < (int)(blockDim.x >> 5); ++w) t += wsum[w];
+    counts[b] = t;
+  }
+}
+
+// In-place exclusive scan of counts[0..n) into offsets[0..n]; offsets[n] = total.
+// One CTA; n_bags is at most ~1e5, so a serial-over-chunks block scan is enough.
+__global__ void __launch_bounds__(1024)
+exclusive_scan_kernel(int64_t* __restrict__ data, int n) {
+  __shared__ int64_t warp_tot[32];
+  __shared__ int64_t carry;
+  if (threadIdx.x == 0) carry = 0;
+  __syncthreads();
+  for (int base = 0; base < n; base += 1024) {
+    int i = base + threadIdx.x;
+    int64_t v = i < n ? data[i] : 0;
+    int64_t x = v;
+    for (int o = 1; o < 32; o <<= 1) {
+      int64_t y = __shfl_up_sync(0xffffffffu, x, o);
+      if ((threadIdx.x & 31) >= o) x += y;
+    }
+    if ((threadIdx.x & 31) == 31) warp_tot[threadIdx.x >> 5] = x;
+    __syncthreads();
+    if (threadIdx.x < 32) {
+      int64_t w = warp_tot[threadIdx.x];
+      int64_t xs = w;
+      for (int o = 1; o < 32; o <<= 1) {
+        int64_t y = __shfl_up_sync(0xffffffffu, xs, o);
+        if (threadIdx.x >= o) xs += y;
+      }
+      warp_tot[threadIdx.x] = xs - w;  // exclusive warp prefix
+    }
+    __syncthreads();
+    int64_t excl = carry + warp_tot[threadIdx.x >> 5] + (x - v);
+    if (i < n) data[i] = excl;
+    __syncthreads();
+    if (threadIdx.x == 1023) carry = excl + v;
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) data[n] = carry;
+}
+
+// ---- per-bag sort + emit ----------------------------------------------------
+enum Mode { kLexsort = 0, kSelect = 1, kRank = 2 };
+
+struct EmitArgs {
+  const int32_t* labels;
+  int32_t tiles_per_pos, topk_neg;
+  float thr;
+  int32_t* idx_out;
+  uint8_t* label_out;
+  float* prob_out;
+  const int64_t* out_offsets;  // [n_bags+1]
+  int64_t capacity;
+};
+
+template <int kMode>
+__global__ void __launch_bounds__(kThreads)
+seg_sort_kernel(Segs segs, const float* __restrict__ prob, EmitArgs ea) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  const int b = blockIdx.x;
+  const int64_t s = segs.start(b);
+  const int T = (int)(segs.start(b + 1) - s);
+  if (T <= 0) return;
+  const int P = pow2_ceil(T);
+  uint32_t* key = reinterpret_cast<uint32_t*>(smem_raw);
+  uint16_t* idx = reinterpret_cast<uint16_t*>(smem_raw + (size_t)P * 4);
+
+  for (int i = threadIdx.x; i < P; i += kThreads) {
+    key[i] = i < T ? cs::float_sort_key(prob[s + i]) : 0xffffffffu;
+    idx[i] = (uint16_t)(i < T ? i : 0xffff);
+  }
+  __syncthreads();
+
+  // Bitonic network on (key, idx); padding (0xffffffff, 0xffff) sorts after every
+  // real entry, including NaNs (their idx is < 0xffff because T <= 32768).
+  for (int k = 2; k <= P; k <<= 1) {
+    for (int j = k >> 1; j > 0; j >>= 1) {
+      for (int t = threadIdx.x; t < (P >> 1); t += kThreads) {
+        int lo = ((t & ~(j - 1)) << 1) | (t & (j - 1));
+        int hi = lo | j;
+        uint32_t ka = key[lo], kb = key[hi];
+        uint16_t ia = idx[lo], ib = idx[hi];
+        bool a_gt_b = (ka > kb) || (ka == kb && ia > ib);
+        bool asc = (lo & k) == 0;
+        if (a_gt_b == asc) {
+          key[lo] = kb; key[hi] = ka;
+          idx[lo] = ib; idx[hi] = ia;
+        }
+      }
+      __syncthreads();
+    }
+  }
+
+  if (kMode == kLexsort) {
+    for (int r = threadIdx.x; r < T; r += kThreads) ea.idx_out[s + r] = (int32_t)(s + idx[r]);
+  } else if (kMode == kSelect) {
+    const int64_t N = segs.total();
+    const Kept kr = kept_ranges(s, T, N, bag_k(ea.labels, b, ea.tiles_per_pos, ea.topk_neg));
+    const int64_t o0 = ea.out_offsets[b];
+    const uint8_t pl = ea.labels[b] == 0 ? 0 : 1;
+    const int n1 = kr.b1 - kr.a1, n = kr.count();
+    for (int q = threadIdx.x; q < n; q += kThreads) {
+      int r = q < n1 ? kr.a1 + q : kr.a2 + (q - n1);
+      int64_t pos = o0 + q;
+      if (pos < ea.capacity) {
+        ea.idx_out[pos] = (int32_t)(s + idx[r]);
+        ea.label_out[pos] = pl;
+      }
+    }
+  } else {  // kRank: prob > thr is a suffix of the ascending order, NaN excluded
+    const int64_t o0 = ea.out_offsets[b];
+    const int n = (int)(ea.out_offsets[b + 1] - o0);
+    // first rank whose prob > thr: kept entries are contiguous up to the first NaN
+    const uint32_t kthr = cs::float_sort_key(ea.thr);
+    // binary search for first key > kthr (thr NaN -> nothing is kept, n == 0)
+    int lo = 0, hi = T;
+    while (lo < hi) {
+      int mid = (lo + hi) >> 1;
+      if (key[mid] > kthr) hi = mid; else lo = mid + 1;
+    }
+    for (int q = threadIdx.x; q < n; q += kThreads) {
+      int r = lo + q;
+      int64_t pos = o0 + q;
+      if (pos < ea.capacity) {
+        int64_t gi = s + idx[r];
+        ea.idx_out[pos] = (int32_t)gi;
+        if (ea.prob_out) ea.prob_out[pos] = prob[gi];
+      }
+    }
+  }
+}
+
+int64_t* g_scan_dummy = nullptr;
+
+struct SegHostInfo {
+  int max_pow2;
+};
+
+// Largest segment decides the shared-memory footprint.  Uniform segments are known
+// on the host; ragged ones are bounded by the caller through `uniform_T` (used as
+// the maximum segment size when offsets are given).
+int seg_smem_bytes(int64_t max_T, size_t* bytes) {
+  CS_REQUIRE(max_T > 0 && max_T <= kMaxSegPow2,
+             "segment size %lld outside (0, %d]: unsupported by the per-bag sort",
+             (long long)max_T, kMaxSegPow2);
+  int p = 1;
+  while (p < max_T) p <<= 1;
+  *bytes = (size_t)p * 6;
+  return CS_OK;
+}
+
+template <int kMode>
+int launch_sort(const Segs& segs, const float* prob, const EmitArgs& ea, int64_t max_T,
+                cudaStream_t st) {
+  size_t smem = 0;
+  int rc = seg_smem_bytes(max_T, &smem);
+  if (rc != CS_OK) return rc;
+  static bool attr_set[64][3] = {{false}};
+  int dev = 0;
+  CS_CUDA(cudaGetDevice(&dev));
+  if (dev >= 64 || !attr_set[dev][kMode]) {
+    CS_CUDA(cudaFuncSetAttribute(seg_sort_kernel<kMode>,
+                                 cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSegPow2 * 6));
+    if (dev < 64) attr_set[dev][kMode] = true;
+  }
+  seg_sort_kernel<kMode><<<segs.n_bags, kThreads, smem, st>>>(segs, prob, ea);
+  CS_LAUNCH_CHECK();
+  return CS_OK;
+}
+
+int check_segs(const char* fn, const float* prob, const int64_t* seg_offsets, int64_t uniform_T,
+               int n_bags) {
+  CS_REQUIRE(prob != nullptr, "%s: prob is NULL", fn);
+  CS_REQUIRE(n_bags > 0, "%s: n_bags = %d", fn, n_bags);
+  CS_REQUIRE(uniform_T > 0,
+             "%s: uniform_T must be > 0 (the segment size, or the maximum segment size when "
+             "seg_offsets is given)", fn);
+  if (!seg_offsets)
+    CS_REQUIRE((int64_t)n_bags * uniform_T < (int64_t)INT32_MAX,
+               "%s: %lld instances do not fit int32 indices", fn,
+               (long long)n_bags * (long long)uniform_T);
+  return CS_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+int cs_lexsort_segments(const float* prob, const int64_t* seg_offsets, int64_t uniform_T,
+                        int n_bags, int32_t* order_out, void* stream) {
+  int rc = check_segs("cs_lexsort_segments", prob, seg_offsets, uniform_T, n_bags);
+  if (rc != CS_OK) return rc;
+  CS_REQUIRE(order_out != nullptr, "cs_lexsort_segments: order_out is NULL");
+  Segs segs{seg_offsets, uniform_T, n_bags};
+  EmitArgs ea{};
+  ea.idx_out = order_out;
+  return launch_sort<kLexsort>(segs, prob, ea, uniform_T, cs::as_stream(stream));
+}
+
+int cs_select_topk(const float* prob, const int64_t* seg_offsets, int64_t uniform_T, int n_bags,
+                   const int32_t* labels, int32_t tiles_per_pos, int32_t topk_neg,
+                   int32_t* sel_idx_out, uint8_t* sel_label_out, int64_t* sel_offsets_out,
+                   int64_t capacity, void* stream) {
+  int rc = check_segs("cs_select_topk", prob, seg_offsets, uniform_T, n_bags);
+  if (rc != CS_OK) return rc;
+  CS_REQUIRE(labels && sel_idx_out && sel_label_out && sel_offsets_out,
+             "cs_select_topk: NULL pointer");
+  CS_REQUIRE(tiles_per_pos >= 0 && topk_neg >= 0 && capacity >= 0,
+             "cs_select_topk: tiles_per_pos, topk_neg and capacity must be >= 0");
+  cudaStream_t st = cs::as_stream(stream);
+  Segs segs{seg_offsets, uniform_T, n_bags};
+  select_count_kernel<<<cs::ceil_div(n_bags, 256), 256, 0, st>>>(segs, labels, tiles_per_pos,
+                                                                 topk_neg, sel_offsets_out);
+  CS_LAUNCH_CHECK();
+  exclusive_scan_kernel<<<1, 1024, 0, st>>>(sel_offsets_out, n_bags);
+  CS_LAUNCH_CHECK();
+  EmitArgs ea{};
+  ea.labels = labels;
+  ea.tiles_per_pos = tiles_per_pos;
+  ea.topk_neg = topk_neg;
+  ea.idx_out = sel_idx_out;
+  ea.label_out = sel_label_out;
+  ea.out_offsets = sel_offsets_out;
+  ea.capacity = capacity;
+  return launch_sort<kSelect>(segs, prob, ea, uniform_T, st);
+}
+
+int cs_rank_threshold(const float* prob, const int64_t* seg_offsets, int64_t uniform_T, int n_bags,
+                      float threshold, int32_t* sel_idx_out, float* sel_prob_out,
+                      int64_t* sel_offsets_out, int64_t capacity, void* stream) {
+  int rc = check_segs("cs_rank_threshold", prob, seg_offsets, uniform_T, n_bags);
+  if (rc != CS_OK) return rc;
+  CS_REQUIRE(sel_idx_out && sel_offsets_out, "cs_rank_threshold: NULL pointer");
+  CS_REQUIRE(capacity >= 0, "cs_rank_threshold: capacity < 0");
+  cudaStream_t st = cs::as_stream(stream);
+  Segs segs{seg_offsets, uniform_T, n_bags};
+  rank_count_kernel<<<n_bags, 256, 0, st>>>(segs, prob, threshold, sel_offsets_out);
+  CS_LAUNCH_CHECK();
+  exclusive_scan_kernel<<<1, 1024, 0, st>>>(sel_offsets_out, n_bags);
+  CS_LAUNCH_CHECK();
+  EmitArgs ea{};
+  ea.thr = threshold;
+  ea.idx_out = sel_idx_out;
+  ea.prob_out = sel_prob_out;
+  ea.out_offsets = sel_offsets_out;
+  ea.capacity = capacity;
+  return launch_sort<kRank>(segs, prob, ea, uniform_T, st);
+}
+
+}  // extern "C"

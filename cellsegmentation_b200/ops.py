@@ -1,0 +1,287 @@
+"""Torch-tensor front end of the C ABI: one function per kernel family.
+
+PyTorch is used for device memory and streams only; every computation below is a call
+into libcellseg_b200.so on the current CUDA stream.
+"""
+import ctypes
+
+import numpy as np
+import torch
+
+from . import _capi
+from ._capi import CS_PREC_BF16, CS_PREC_FP32, check, cur_stream, lib, ptr
+
+PRECISIONS = {"fp32": CS_PREC_FP32, "bf16": CS_PREC_BF16}
+
+
+def _req_cuda(t, name, dtype=None):
+    if not (isinstance(t, torch.Tensor) and t.is_cuda):
+        raise _capi.CellSegError("%s must be a CUDA tensor (no CPU fallback exists)" % name)
+    if dtype is not None and t.dtype != dtype:
+        raise TypeError("%s must be %s, got %s" % (name, dtype, t.dtype))
+    if not t.is_contiguous():
+        raise ValueError("%s must be contiguous" % name)
+    return t
+
+
+def grid_count(dim, tile, interval):
+    """Grid positions along one axis (dataset/dataset.py:728-740)."""
+    return lib().cs_grid_count(int(dim), int(tile), int(interval))
+
+
+def grid_coords(H, W, tile, interval):
+    """int32 [T,2] (row, col) upper-left corners in get_tiles order (dataset/dataset.py:718-742)."""
+    T = grid_count(H, tile, interval) * grid_count(W, tile, interval)
+    if T <= 0:
+        raise ValueError("bad tile geometry H=%d W=%d tile=%d interval=%d" % (H, W, tile, interval))
+    out = np.empty((T, 2), np.int32)
+    check(lib().cs_grid_coords_host(H, W, tile, interval,
+                                    out.ctypes.data_as(ctypes.POINTER(ctypes.c_int32)), T),
+          "cs_grid_coords_host")
+    return out
+
+
+def unfold_normalize(img, tile, interval, inst_begin=0, inst_count=None):
+    """img u8 [Nb,H,W,3] (cuda) -> f32 [n,3,tile,tile]: crop + ToTensor + Normalize."""
+    _req_cuda(img, "img", torch.uint8)
+    Nb, H, W, _ = img.shape
+    T = grid_count(H, tile, interval) * grid_count(W, tile, interval)
+    if inst_count is None:
+        inst_count = Nb * T - inst_begin
+    out = torch.empty((inst_count, 3, tile, tile), dtype=torch.float32, device=img.device)
+    check(lib().cs_unfold_normalize(ptr(img), Nb, H, W, tile, interval, inst_begin, inst_count,
+                                    ptr(out), cur_stream()), "cs_unfold_normalize")
+    return out
+
+
+def gather_normalize(img, tile, bag, x, y):
+    """Tiles img[bag[j], x[j]:x[j]+S, y[j]:y[j]+S] -> f32 [n,3,S,S] (LystoDataset mode 3)."""
+    _req_cuda(img, "img", torch.uint8)
+    for t, nm in ((bag, "bag"), (x, "x"), (y, "y")):
+        _req_cuda(t, nm, torch.int32)
+    Nb, H, W, _ = img.shape
+    n = bag.numel()
+    out = torch.empty((n, 3, tile, tile), dtype=torch.float32, device=img.device)
+    check(lib().cs_gather_normalize(ptr(img), Nb, H, W, tile, ptr(bag), ptr(x), ptr(y), n, ptr(out),
+                                    cur_stream()), "cs_gather_normalize")
+    return out
+
+
+def _segs(seg_offsets, uniform_T, n_bags):
+    if seg_offsets is not None:
+        _req_cuda(seg_offsets, "seg_offsets", torch.int64)
+        if seg_offsets.numel() != n_bags + 1:
+            raise ValueError("seg_offsets must have n_bags+1 entries")
+    return ptr(seg_offsets), int(uniform_T)
+
+
+def lexsort_segments(prob, n_bags, uniform_T, seg_offsets=None):
+    """np.lexsort((probs, groups)) for non-decreasing groups; int32 [N]."""
+    _req_cuda(prob, "prob", torch.float32)
+    so, T = _segs(seg_offsets, uniform_T, n_bags)
+    order = torch.empty(prob.numel(), dtype=torch.int32, device=prob.device)
+    check(lib().cs_lexsort_segments(ptr(prob), so, T, n_bags, ptr(order), cur_stream()),
+          "cs_lexsort_segments")
+    return order
+
+
+def select_topk(prob, labels, n_bags, uniform_T, tiles_per_pos, topk_neg, seg_offsets=None,
+                capacity=None):
+    """Adaptive top-k (inference.py:31-42). Returns (idx i32 [M], pseudo-label u8 [M], offsets i64)."""
+    _req_cuda(prob, "prob", torch.float32)
+    _req_cuda(labels, "labels", torch.int32)
+    so, T = _segs(seg_offsets, uniform_T, n_bags)
+    if capacity is None:
+        capacity = prob.numel()
+    idx = torch.empty(capacity, dtype=torch.int32, device=prob.device)
+    lab = torch.empty(capacity, dtype=torch.uint8, device=prob.device)
+    off = torch.empty(n_bags + 1, dtype=torch.int64, device=prob.device)
+    check(lib().cs_select_topk(ptr(prob), so, T, n_bags, ptr(labels), int(tiles_per_pos),
+                               int(topk_neg), ptr(idx), ptr(lab), ptr(off), capacity, cur_stream()),
+          "cs_select_topk")
+    M = int(off[-1].item())
+    if M > capacity:
+        raise _capi.CellSegError("select_topk: %d kept instances exceed capacity %d" % (M, capacity))
+    return idx[:M], lab[:M], off
+
+
+def rank_threshold(prob, n_bags, uniform_T, threshold, seg_offsets=None, capacity=None):
+    """rank() (test_tile.py:63-79): kept idx i32 [M], prob f32 [M], offsets i64 [n_bags+1]."""
+    _req_cuda(prob, "prob", torch.float32)
+    so, T = _segs(seg_offsets, uniform_T, n_bags)
+    if capacity is None:
+        capacity = prob.numel()
+    idx = torch.empty(capacity, dtype=torch.int32, device=prob.device)
+    sp = torch.empty(capacity, dtype=torch.float32, device=prob.device)
+    off = torch.empty(n_bags + 1, dtype=torch.int64, device=prob.device)
+    check(lib().cs_rank_threshold(ptr(prob), so, T, n_bags, float(threshold), ptr(idx), ptr(sp),
+                                  ptr(off), capacity, cur_stream()), "cs_rank_threshold")
+    M = int(off[-1].item())
+    if M > capacity:
+        raise _capi.CellSegError("rank_threshold: %d kept instances exceed capacity %d" % (M, capacity))
+    return idx[:M], sp[:M], off
+
+
+def paint_mask(sel_idx, n_bags, H, W, tile, interval, bag_base=0, out=None):
+    """generate_masks painting loop: u8 [n_bags,H,W] with 1 inside every kept tile."""
+    _req_cuda(sel_idx, "sel_idx", torch.int32)
+    if out is None:
+        out = torch.zeros((n_bags, H, W), dtype=torch.uint8, device=sel_idx.device)
+    check(lib().cs_paint_mask(ptr(sel_idx), sel_idx.numel(), H, W, tile, interval, bag_base, n_bags,
+                              ptr(out), cur_stream()), "cs_paint_mask")
+    return out
+
+
+def paint_heatmap(sel_idx, sel_prob, n_bags, H, W, tile, interval, bag_base=0, out=None):
+    """heatmap painting loop: f32 [n_bags,H,W], per-pixel max of kept covering probs."""
+    _req_cuda(sel_idx, "sel_idx", torch.int32)
+    _req_cuda(sel_prob, "sel_prob", torch.float32)
+    if out is None:
+        out = torch.zeros((n_bags, H, W), dtype=torch.float32, device=sel_idx.device)
+    check(lib().cs_paint_heatmap(ptr(sel_idx), ptr(sel_prob), sel_idx.numel(), H, W, tile, interval,
+                                 bag_base, n_bags, ptr(out), cur_stream()), "cs_paint_heatmap")
+    return out
+
+
+def heatmap_to_gray(heat):
+    """255 - np.uint8(255 * heat) with the float64 product numpy performs."""
+    _req_cuda(heat, "heat", torch.float32)
+    out = torch.empty(heat.shape, dtype=torch.uint8, device=heat.device)
+    check(lib().cs_heatmap_to_gray(ptr(heat), heat.numel(), ptr(out), cur_stream()),
+          "cs_heatmap_to_gray")
+    return out
+
+
+def hsv_refine(img, mask, v_thresh=170, out=None):
+    """preprocess_masks lines 117-120: (mask != 0) & (max(R,G,B) <= v_thresh) as u8 0/1."""
+    _req_cuda(img, "img", torch.uint8)
+    _req_cuda(mask, "mask", torch.uint8)
+    n_px = mask.numel()
+    if img.numel() != 3 * n_px:
+        raise ValueError("img must hold 3 bytes per mask pixel")
+    if out is None:
+        out = torch.empty_like(mask)
+    check(lib().cs_hsv_refine(ptr(img), ptr(mask), n_px, int(v_thresh), ptr(out), cur_stream()),
+          "cs_hsv_refine")
+    return out
+
+
+def bgr2hsv(img):
+    """cv2.cvtColor(img, cv2.COLOR_BGR2HSV) for u8 [...,3], bit-exact."""
+    _req_cuda(img, "img", torch.uint8)
+    out = torch.empty_like(img)
+    check(lib().cs_bgr2hsv_u8(ptr(img), img.numel() // 3, ptr(out), cur_stream()), "cs_bgr2hsv_u8")
+    return out
+
+
+class TileClassifier:
+    """Device-side tile classifier built from BN-folded fp32 conv weights.
+
+    convs: list of (weight [Cout,Cin,k,k], bias [Cout]) CPU float32 tensors in network order
+    (stem; per BasicBlock conv1, conv2, [downsample]); fc_w [2,512], fc_b [2].
+    """
+
+    def __init__(self, arch, convs, fc_w, fc_b, device=None):
+        if arch not in _capi.CS_ARCH:
+            raise _capi.CellSegError("arch %r has no sm_100a kernels (resnet18 / resnet34)" % arch)
+        self.arch = arch
+        self.device = torch.device("cuda", torch.cuda.current_device()) if device is None else device
+        ws = [np.ascontiguousarray(w.detach().cpu().numpy(), dtype=np.float32) for w, _ in convs]
+        bs = [np.ascontiguousarray(b.detach().cpu().numpy(), dtype=np.float32) for _, b in convs]
+        fw = np.ascontiguousarray(fc_w.detach().cpu().numpy(), dtype=np.float32)
+        fb = np.ascontiguousarray(fc_b.detach().cpu().numpy(), dtype=np.float32)
+        n = len(ws)
+        wp = (ctypes.c_void_p * n)(*[w.ctypes.data for w in ws])
+        bp = (ctypes.c_void_p * n)(*[b.ctypes.data for b in bs])
+        handle = ctypes.c_void_p()
+        with torch.cuda.device(self.device):
+            check(lib().cs_model_create(_capi.CS_ARCH[arch], n, wp, bp, fw.ctypes.data, fb.ctypes.data,
+                                        ctypes.byref(handle)), "cs_model_create")
+        self._h = handle
+        self._ws = None
+        self._ws_key = None
+
+    def close(self):
+        if getattr(self, "_h", None):
+            lib().cs_model_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _workspace(self, tile, max_batch, precision):
+        key = (tile, max_batch, precision)
+        if self._ws_key != key:
+            nbytes = lib().cs_model_workspace_bytes(self._h, tile, max_batch, precision)
+            if nbytes <= 0:
+                raise _capi.CellSegError("unsupported tile size %d" % tile)
+            self._ws = torch.empty(nbytes, dtype=torch.uint8, device=self.device)
+            self._ws_key = key
+        return self._ws
+
+    def forward_tiles(self, img, tile, interval, inst_begin=0, inst_count=None, precision="bf16",
+                      max_batch=18944, want_features=False, prob_out=None):
+        """Fused unfold -> CNN -> softmax[:,1] over instances of the resident u8 bag array."""
+        _req_cuda(img, "img", torch.uint8)
+        Nb, H, W, _ = img.shape
+        T = grid_count(H, tile, interval) * grid_count(W, tile, interval)
+        if inst_count is None:
+            inst_count = Nb * T - inst_begin
+        prec = PRECISIONS[precision]
+        ws = self._workspace(tile, max_batch, prec)
+        if prob_out is None:
+            prob_out = torch.empty(inst_count, dtype=torch.float32, device=img.device)
+        feat = torch.empty((inst_count, 512), dtype=torch.float32, device=img.device) if want_features else None
+        check(lib().cs_model_forward_tiles(self._h, ptr(img), Nb, H, W, tile, interval, inst_begin,
+                                           inst_count, prec, ptr(prob_out), ptr(feat), ptr(ws),
+                                           ws.numel(), max_batch, cur_stream()),
+              "cs_model_forward_tiles")
+        return (prob_out, feat) if want_features else prob_out
+
+    def forward_tensor(self, x, precision="bf16", max_batch=18944, want_features=False):
+        """Drop-in for model(x): x f32 [n,3,S,S] normalised tiles -> logits f32 [n,2]."""
+        _req_cuda(x, "x", torch.float32)
+        n, _, S, _ = x.shape
+        prec = PRECISIONS[precision]
+        ws = self._workspace(S, max_batch, prec)
+        logits = torch.empty((n, 2), dtype=torch.float32, device=x.device)
+        feat = torch.empty((n, 512), dtype=torch.float32, device=x.device) if want_features else None
+        check(lib().cs_model_forward_tensor(self._h, ptr(x), n, S, prec, ptr(logits), ptr(feat),
+                                            ptr(ws), ws.numel(), max_batch, cur_stream()),
+              "cs_model_forward_tensor")
+        return (logits, feat) if want_features else logits
+
+    @property
+    def last_launch_count(self):
+        return int(lib().cs_model_last_launch_count(self._h))
+
+
+def debug_gemm_bf16(a, b, bias, bn):
+    """A [M,K] bf16, B [N,K] bf16, bias f32 [N] -> f32 [M,N] through the tcgen05 kernel."""
+    _req_cuda(a, "a", torch.bfloat16)
+    _req_cuda(b, "b", torch.bfloat16)
+    _req_cuda(bias, "bias", torch.float32)
+    M, K = a.shape
+    N = b.shape[0]
+    out = torch.zeros((M, N), dtype=torch.float32, device=a.device)
+    check(lib().cs_debug_gemm_bf16(ptr(a), ptr(b), M, N, K, ptr(bias), bn, ptr(out), cur_stream()),
+          "cs_debug_gemm_bf16")
+    return out
+
+
+def debug_conv3x3_bf16(x_hi, w, bias, stride):
+    """x_hi bf16 [n,H,W,Cin] (cuda), w f32 [Cout,Cin,3,3] (cpu), bias f32 [Cout] (cpu) -> f32 [n,Ho,Wo,Cout]."""
+    _req_cuda(x_hi, "x_hi", torch.bfloat16)
+    n, H, W, Cin = x_hi.shape
+    Cout = w.shape[0]
+    Ho, Wo = (H + 2 - 3) // stride + 1, (W + 2 - 3) // stride + 1
+    wn = np.ascontiguousarray(w.detach().cpu().numpy(), dtype=np.float32)
+    bn_ = np.ascontiguousarray(bias.detach().cpu().numpy(), dtype=np.float32)
+    out = torch.zeros((n, Ho, Wo, Cout), dtype=torch.float32, device=x_hi.device)
+    check(lib().cs_debug_conv3x3_bf16(ptr(x_hi), n, H, W, Cin, Cout, stride, wn.ctypes.data,
+                                      bn_.ctypes.data, ptr(out), cur_stream()),
+          "cs_debug_conv3x3_bf16")
+    return out

@@ -1,0 +1,243 @@
+/*
+ * cellseg_b200.h — C ABI of libcellseg_b200.so
+ *
+ * B200-native (sm_100a) kernels for the Stage-2 multiple-instance hot path of
+ * Newiz430/CellSegmentation and the Stage-3 HSV mask refinement.  The reference
+ * is pure Python and has no FFI of its own, so every entry point below names the
+ * reference *function* it replaces (path:line under the reference tree); the
+ * ctypes stubs that bind them live in cellsegmentation_b200/_capi.py and are
+ * reproduced in INTEGRATION.md.
+ *
+ * Conventions (all entry points)
+ *   - plain pointers and sizes only; every pointer is a DEVICE pointer unless the
+ *     parameter name ends in `_host`
+ *   - `stream` is a cudaStream_t passed as void*; work is asynchronous on it
+ *   - no allocation inside the hot entry points: the caller owns all buffers;
+ *     workspace sizes are queried first (cs_*_workspace_bytes)
+ *   - return 0 (CS_OK) or a negative cs_status; cs_last_error() gives the text of
+ *     the last failure on the calling thread
+ *   - bags = images, instances = tiles; instance order is the reference's dataset
+ *     order: bag-major, then get_tiles() row-major order inside a bag
+ */
+#ifndef CELLSEG_B200_H_
+#define CELLSEG_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef enum cs_status {
+  CS_OK = 0,
+  CS_ERR_INVALID_ARG = -1,
+  CS_ERR_CUDA = -2,
+  CS_ERR_WORKSPACE = -3,
+  CS_ERR_UNSUPPORTED = -4,
+  CS_ERR_DEVICE = -5
+} cs_status;
+
+/* Numeric mode of the tile-classifier forward. */
+typedef enum cs_precision {
+  CS_PREC_FP32 = 0, /* CUDA-core FFMA, fp32 everywhere: parity mode (<=1e-4 abs on probs) */
+  CS_PREC_BF16 = 1  /* tcgen05 bf16 operands, fp32 accumulate in TMEM, hi/lo residual stream */
+} cs_precision;
+
+typedef enum cs_arch {
+  CS_ARCH_RESNET18 = 0, /* model/resnet.py:336-343  BasicBlock [2,2,2,2] */
+  CS_ARCH_RESNET34 = 1  /* model/resnet.py:346-352  BasicBlock [3,4,6,3] */
+} cs_arch;
+
+/* Library version: major*10000 + minor*100 + patch. */
+int cs_version(void);
+/* Text of the last error raised on this thread ("" if none). Never NULL. */
+const char* cs_last_error(void);
+/* 0 if a compute-capability-10.x device is current, CS_ERR_DEVICE otherwise. */
+int cs_check_device(void);
+
+/* ---------------------------------------------------------------------------
+ * Tile grid.  Replaces get_tiles(image, interval, size)
+ * (dataset/dataset.py:718-742): upper-left coordinates 0, I, 2I, ... <= dim-S
+ * plus one final row/col at dim-S when the stride does not land there.
+ * cs_grid_count returns the number of grid positions along one axis
+ * (tiles per bag = count(H) * count(W)); coordinate g is min(g*I, dim-S).
+ * Host-only helpers, no GPU needed.
+ * ------------------------------------------------------------------------- */
+int cs_grid_count(int dim, int tile, int interval);
+/* Fills xy_host[2*t] = row, xy_host[2*t+1] = col for all tiles of one HxW bag. */
+int cs_grid_coords_host(int H, int W, int tile, int interval, int32_t* xy_host,
+                        int64_t capacity_tiles);
+
+/* ---------------------------------------------------------------------------
+ * K1  unfold + ToTensor + Normalize.
+ * Replaces LystoTestset.__getitem__ mode "tile" / LystoDataset.__getitem__ mode 1
+ * (dataset/dataset.py:409-416, 206-214) with the transform of :78-83 / :391-397:
+ *   out[i][c][y][x] = ((float(u8)/255.f) - mean_c) / std_c        (fp32, NCHW)
+ * img:  u8 [n_bags][H][W][3]  (dense, HWC)
+ * instances inst_begin .. inst_begin+inst_count-1 of the bag range starting at
+ * bag 0 of `img` (instance i -> bag i / T, tile i % T).
+ * out:  f32 [inst_count][3][tile][tile]
+ * ------------------------------------------------------------------------- */
+int cs_unfold_normalize(const uint8_t* img, int n_bags, int H, int W, int tile,
+                        int interval, int64_t inst_begin, int64_t inst_count,
+                        float* out, void* stream);
+/* Same transform for an explicit list of tiles (LystoDataset mode 3,
+ * dataset/dataset.py:244-251): tile j is img[bag[j]][x[j]:x[j]+S, y[j]:y[j]+S]. */
+int cs_gather_normalize(const uint8_t* img, int n_bags, int H, int W, int tile,
+                        const int32_t* bag, const int32_t* x, const int32_t* y,
+                        int64_t n_tiles, float* out, void* stream);
+
+/* ---------------------------------------------------------------------------
+ * K2  tile-classifier forward.  Replaces MILResNet.forward in tile mode under
+ * model.eval() (model/resnet.py:250-269, 234-248, BasicBlock :28-43) followed by
+ * softmax(dim=1)[:,1] (inference.py:24-27).
+ *
+ * The caller folds eval-mode BatchNorm into each conv in fp32
+ * (W' = W*gamma/sqrt(var+eps), b' = beta - mean*gamma/sqrt(var+eps)) and passes
+ * HOST pointers in network order:
+ *   conv 0                 : stem 7x7/2            [64][3][7][7]
+ *   per BasicBlock, in order: conv1 3x3, conv2 3x3, then (if the block has one)
+ *                            the 1x1 downsample conv        [Cout][Cin][k][k]
+ *   fc_w [2][512], fc_b [2]: fc_tile.1 (model/resnet.py:124-127)
+ * n_convs must equal the count implied by `arch` (resnet34: 36, resnet18: 20).
+ * The library packs GEMM-ready bf16 copies and keeps the fp32 originals.
+ * ------------------------------------------------------------------------- */
+typedef struct cs_model cs_model;
+
+int cs_model_create(int arch, int n_convs, const float* const* conv_w_host,
+                    const float* const* conv_b_host, const float* fc_w_host,
+                    const float* fc_b_host, cs_model** out);
+int cs_model_destroy(cs_model* m);
+
+/* Bytes of device workspace cs_model_forward_tiles needs for batches of up to
+ * `max_batch` instances of `tile` x `tile` pixels at `precision`. */
+int64_t cs_model_workspace_bytes(const cs_model* m, int tile, int64_t max_batch,
+                                 int precision);
+
+/* Fused unfold -> CNN -> prob for instances [inst_begin, inst_begin+inst_count)
+ * of the bag array `img` (same instance numbering as cs_unfold_normalize).
+ * prob_out[j] (fp32) receives softmax(logits)[1] of instance inst_begin + j.
+ * feat_out (optional, may be NULL): fp32 [inst_count][512] pooled features
+ * avgpool(x4)+maxpool(x4) (model/resnet.py:266), the input of fc_tile — used to
+ * train fc_tile without a second encoder pass.
+ * Internally processes the range in batches of <= max_batch the workspace was
+ * sized for. */
+int cs_model_forward_tiles(cs_model* m, const uint8_t* img, int n_bags, int H, int W,
+                           int tile, int interval, int64_t inst_begin,
+                           int64_t inst_count, int precision, float* prob_out,
+                           float* feat_out, void* workspace, int64_t workspace_bytes,
+                           int64_t max_batch, void* stream);
+
+/* Same network on caller-materialised tiles (drop-in for model(x) with
+ * x = f32 [n][3][tile][tile] already normalised): writes logits f32 [n][2]. */
+int cs_model_forward_tensor(cs_model* m, const float* x, int64_t n, int tile,
+                            int precision, float* logits_out, float* feat_out,
+                            void* workspace, int64_t workspace_bytes, int64_t max_batch,
+                            void* stream);
+
+/* Number of kernels the last cs_model_forward_* call on this model launched. */
+int64_t cs_model_last_launch_count(const cs_model* m);
+
+/* ---------------------------------------------------------------------------
+ * K3  segmented ordering and adaptive top-k selection.
+ *
+ * Segments: seg_offsets i64 [n_bags+1], non-decreasing, seg_offsets[0] = 0,
+ * seg_offsets[n_bags] = N (bags may be empty — LystoDataset's bag 0 is,
+ * dataset/dataset.py:142).  If seg_offsets is NULL every bag has `uniform_T`
+ * instances.
+ *
+ * Order everywhere is numpy's  np.lexsort((probs, groups))  (inference.py:35,
+ * test_tile.py:69, evaluate.py:13): ascending bag, then ascending prob, ties in
+ * ascending instance index, NaN last, -0.0 == +0.0.
+ * ------------------------------------------------------------------------- */
+
+/* order_out i32 [N] = np.lexsort((probs, groups)). */
+int cs_lexsort_segments(const float* prob, const int64_t* seg_offsets, int64_t uniform_T,
+                        int n_bags, int32_t* order_out, void* stream);
+
+/* Replaces sample() up to the call of make_train_data (inference.py:31-42) and
+ * the pseudo-label rule of make_train_data (dataset/dataset.py:168-169):
+ *   k_b = topk_neg if labels[b]==0 else labels[b]*tiles_per_pos
+ *   keep sorted position i iff groups[i] != groups[(i + k_b) % N]     (literal,
+ *   with wrap-around)
+ * sel_idx_out   i32 [>= sum_b min(k_b, T_b)]: order[index], i.e. global instance
+ *               indices ascending by (bag, prob, index)
+ * sel_label_out u8, same length: 0 if labels[bag]==0 else 1
+ * sel_offsets_out i64 [n_bags+1]: exclusive prefix of kept counts per bag;
+ *               sel_offsets_out[n_bags] = M (total kept)
+ * capacity: number of elements sel_idx_out / sel_label_out can hold; if M exceeds
+ * it nothing beyond capacity is written and *M is still reported. */
+int cs_select_topk(const float* prob, const int64_t* seg_offsets, int64_t uniform_T,
+                   int n_bags, const int32_t* labels, int32_t tiles_per_pos,
+                   int32_t topk_neg, int32_t* sel_idx_out, uint8_t* sel_label_out,
+                   int64_t* sel_offsets_out, int64_t capacity, void* stream);
+
+/* Replaces rank() (test_tile.py:63-79, train_seg.py:234-247): keep prob > thr in
+ * lexsort order.  Outputs as cs_select_topk; sel_prob_out f32 (optional). */
+int cs_rank_threshold(const float* prob, const int64_t* seg_offsets, int64_t uniform_T,
+                      int n_bags, float threshold, int32_t* sel_idx_out,
+                      float* sel_prob_out, int64_t* sel_offsets_out, int64_t capacity,
+                      void* stream);
+
+/* ---------------------------------------------------------------------------
+ * K4  mask painting and HSV refinement.
+ * Tile j of a selection is instance sel_idx[j]; its bag and (row, col) follow
+ * from the uniform grid (H, W, tile, interval) with T tiles per bag and
+ * `bag_base` = index of the first bag that owns tiles (1 for LystoDataset, 0 for
+ * LystoTestset): bag = bag_base + idx / T.
+ * ------------------------------------------------------------------------- */
+
+/* generate_masks() painting loop (utils/image_processing.py:91-98):
+ * mask_out u8 [n_bags][H][W] must be zeroed by the caller; every kept tile sets
+ * its tile x tile square to 1. */
+int cs_paint_mask(const int32_t* sel_idx, int64_t n_sel, int H, int W, int tile,
+                  int interval, int bag_base, int n_bags, uint8_t* mask_out,
+                  void* stream);
+
+/* heatmap() painting loop (utils/image_processing.py:153-158).  Tiles arrive in
+ * ascending (bag, prob) order so the reference's last write wins = per-pixel max
+ * of the kept covering probabilities.  heat_out f32 [n_bags][H][W], zeroed by the
+ * caller; requires sel_prob >= 0. */
+int cs_paint_heatmap(const int32_t* sel_idx, const float* sel_prob, int64_t n_sel, int H,
+                     int W, int tile, int interval, int bag_base, int n_bags,
+                     float* heat_out, void* stream);
+
+/* `255 - np.uint8(255 * masks[i])` (utils/image_processing.py:165) evaluated in
+ * float64 exactly like numpy: gray_out u8 [n] = 255 - (uint8)(255.0 * (double)heat). */
+int cs_heatmap_to_gray(const float* heat, int64_t n, uint8_t* gray_out, void* stream);
+
+/* preprocess_masks() lines 117-120 (utils/image_processing.py:114-120):
+ *   V = max(R,G,B) (cv2.cvtColor(BGR2HSV) + split()[2]; channel-order free)
+ *   out = (mask != 0) & !(V > v_thresh)          -> 0/1
+ * img u8 [n_px][3], mask u8 [n_px], out u8 [n_px]; out may alias mask.
+ * The reference constant is v_thresh = 170. */
+int cs_hsv_refine(const uint8_t* img, const uint8_t* mask, int64_t n_px, int v_thresh,
+                  uint8_t* out, void* stream);
+
+/* Full 8-bit OpenCV RGB/BGR -> HSV (cv2.COLOR_BGR2HSV, H in [0,180)), bit-exact
+ * integer restatement; hsv_out u8 [n_px][3].  Channel 0 of `img` is treated as B
+ * (exactly what the reference does when it hands cv2 an RGB array). */
+int cs_bgr2hsv_u8(const uint8_t* img, int64_t n_px, uint8_t* hsv_out, void* stream);
+
+/* ---------------------------------------------------------------------------
+ * Diagnostics — used by tests/ to exercise the tcgen05 GEMM kernel and the
+ * production conv planner in isolation.  Not part of the reference surface.
+ * ------------------------------------------------------------------------- */
+
+/* out_f32[M][N] = A[M][K] . B[N][K]^T + bias[N]; A, B bf16 row-major (device).
+ * K % 64 == 0, K <= 1280, N % bn == 0, bn in {64, 128, 256}. */
+int cs_debug_gemm_bf16(const void* a_bf16, const void* b_bf16, int64_t M, int N, int K,
+                       const float* bias, int bn, float* out_f32, void* stream);
+
+/* One 3x3 / pad 1 / stride 1|2 convolution through the production planner:
+ * in_hi bf16 [n][Hi*Wi][Cin] (device), w_host fp32 OIHW (host), bias_host fp32 (host)
+ * -> out_f32 [n][Ho*Wo][Cout] (device), no ReLU.  n % 128 == 0.  Synchronises. */
+int cs_debug_conv3x3_bf16(const void* in_hi, int64_t n, int Hi, int Wi, int Cin, int Cout,
+                          int stride, const float* w_host, const float* bias_host,
+                          float* out_f32, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* CELLSEG_B200_H_ */

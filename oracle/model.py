@@ -1,0 +1,151 @@
+"""Tile-classifier forward (oracle; test infrastructure only).
+
+Restates MILResNet tile mode on CPU fp32 with the same torch ops the reference calls:
+  resnet_forward   model/resnet.py:234-248
+  BasicBlock       model/resnet.py:28-43
+  tile head        model/resnet.py:264-269  (avgpool_tile + maxpool_tile -> Flatten -> Linear)
+  prob             inference.py:24-27       (softmax(dim=1)[:, 1])
+State-dict keys are the reference's (torchvision-style + fc_tile.1.*), SURVEY Appendix B.
+"""
+import numpy as np
+import torch
+import torch.nn.functional as F
+
+LAYERS = {"resnet18": [2, 2, 2, 2], "resnet34": [3, 4, 6, 3]}
+PLANES = [64, 128, 256, 512]
+BN_EPS = 1e-5
+
+
+def _bn(sd, x, p):
+    return F.batch_norm(x, sd[p + ".running_mean"], sd[p + ".running_var"], sd[p + ".weight"],
+                        sd[p + ".bias"], training=False, eps=BN_EPS)
+
+
+def forward_features(sd, x, arch="resnet34", return_intermediate=False):
+    """x f32 [n,3,S,S] -> x4 (and x3,x2,x1); model/resnet.py:234-248 under model.eval()."""
+    x = F.conv2d(x, sd["conv1.weight"], stride=2, padding=3)
+    x = F.relu(_bn(sd, x, "bn1"))
+    x = F.max_pool2d(x, kernel_size=3, stride=2, padding=1)
+    outs = []
+    for L, nb in enumerate(LAYERS[arch], start=1):
+        for b in range(nb):
+            p = "layer%d.%d" % (L, b)
+            stride = 2 if (b == 0 and L > 1) else 1
+            residual = x
+            out = F.conv2d(x, sd[p + ".conv1.weight"], stride=stride, padding=1)
+            out = F.relu(_bn(sd, out, p + ".bn1"))
+            out = F.conv2d(out, sd[p + ".conv2.weight"], stride=1, padding=1)
+            out = _bn(sd, out, p + ".bn2")
+            if (p + ".downsample.0.weight") in sd:
+                residual = _bn(sd, F.conv2d(x, sd[p + ".downsample.0.weight"], stride=stride),
+                               p + ".downsample.1")
+            x = F.relu(out + residual)
+        outs.append(x)
+    return tuple(reversed(outs)) if return_intermediate else x
+
+
+def pooled(x4):
+    """avgpool_tile(x4) + maxpool_tile(x4), flattened (model/resnet.py:266-267)."""
+    return (F.adaptive_avg_pool2d(x4, 1) + F.adaptive_max_pool2d(x4, 1)).flatten(1)
+
+
+def forward_logits(sd, x, arch="resnet34"):
+    with torch.no_grad():
+        f = pooled(forward_features(sd, x, arch))
+        return F.linear(f, sd["fc_tile.1.weight"], sd["fc_tile.1.bias"])
+
+
+def forward_probs(sd, x, arch="resnet34", batch=1024):
+    """inference_tiles body (inference.py:19-28) on a materialised tile tensor."""
+    out = []
+    with torch.no_grad():
+        for i in range(0, x.shape[0], batch):
+            out.append(F.softmax(forward_logits(sd, x[i:i + batch], arch), dim=1)[:, 1].clone())
+    return torch.cat(out).numpy()
+
+
+# ---------------------------------------------------------------------------
+# Deterministic synthetic weights (numpy PCG64 streams are version-stable)
+# ---------------------------------------------------------------------------
+def make_state_dict(arch="resnet34", seed=0, random_bn=True):
+    """kaiming-normal convs (model/resnet.py:171-178, fan_in / leaky_relu(0) gain sqrt(2)),
+    BN gamma/beta/running stats randomised mildly so folding is exercised."""
+    rng = np.random.default_rng(seed)
+    sd = {}
+
+    def conv(name, cout, cin, k):
+        std = np.sqrt(2.0 / (cin * k * k))
+        sd[name] = torch.from_numpy((rng.standard_normal((cout, cin, k, k)) * std).astype(np.float32))
+
+    def bn(name, c):
+        if random_bn:
+            sd[name + ".weight"] = torch.from_numpy(rng.uniform(0.8, 1.2, c).astype(np.float32))
+            sd[name + ".bias"] = torch.from_numpy((rng.standard_normal(c) * 0.1).astype(np.float32))
+            sd[name + ".running_mean"] = torch.from_numpy((rng.standard_normal(c) * 0.1).astype(np.float32))
+            sd[name + ".running_var"] = torch.from_numpy(rng.uniform(0.8, 1.2, c).astype(np.float32))
+        else:
+            sd[name + ".weight"] = torch.ones(c)
+            sd[name + ".bias"] = torch.zeros(c)
+            sd[name + ".running_mean"] = torch.zeros(c)
+            sd[name + ".running_var"] = torch.ones(c)
+        sd[name + ".num_batches_tracked"] = torch.tensor(0)
+
+    conv("conv1.weight", 64, 3, 7)
+    bn("bn1", 64)
+    inplanes = 64
+    for L, nb in enumerate(LAYERS[arch], start=1):
+        planes = PLANES[L - 1]
+        for b in range(nb):
+            p = "layer%d.%d" % (L, b)
+            stride = 2 if (b == 0 and L > 1) else 1
+            conv(p + ".conv1.weight", planes, inplanes, 3)
+            bn(p + ".bn1", planes)
+            conv(p + ".conv2.weight", planes, planes, 3)
+            bn(p + ".bn2", planes)
+            if stride != 1 or inplanes != planes:
+                conv(p + ".downsample.0.weight", planes, inplanes, 1)
+                bn(p + ".downsample.1", planes)
+            inplanes = planes
+    bound = 1.0 / np.sqrt(512)
+    sd["fc_tile.1.weight"] = torch.from_numpy(rng.uniform(-bound, bound, (2, 512)).astype(np.float32))
+    sd["fc_tile.1.bias"] = torch.from_numpy(rng.uniform(-bound, bound, 2).astype(np.float32))
+    return sd
+
+
+def calibrate_head(sd, calib_x, arch="resnet34", sigma=2.0):
+    """PC-1-aligned, zero-centred fc_tile so probabilities spread over (0,1) instead of
+    saturating (SURVEY 3.5-12 / 7 'Precision gates' recipe)."""
+    with torch.no_grad():
+        f = pooled(forward_features(sd, calib_x, arch)).double().numpy()
+    mu = f.mean(0)
+    _, _, vt = np.linalg.svd(f - mu, full_matrices=False)
+    w = vt[0]
+    proj = (f - mu) @ w
+    s = sigma / proj.std()
+    W = np.stack([-w * s / 2, w * s / 2]).astype(np.float32)
+    b = np.array([(mu @ w) * s / 2, -(mu @ w) * s / 2], np.float32)
+    sd = dict(sd)
+    sd["fc_tile.1.weight"] = torch.from_numpy(W)
+    sd["fc_tile.1.bias"] = torch.from_numpy(b)
+    return sd
+
+
+def fold_bn(sd, arch="resnet34"):
+    """Eval-mode BN folded into the preceding conv, fp32:
+    s = gamma / sqrt(var + eps); W' = W * s; b' = beta - mean * s.
+    Returns [(W', b')] in network order: stem; per block conv1, conv2, [downsample]."""
+    def fold(wname, bnname):
+        w = sd[wname].float()
+        s = sd[bnname + ".weight"].float() / torch.sqrt(sd[bnname + ".running_var"].float() + BN_EPS)
+        return (w * s[:, None, None, None]).contiguous(), \
+               (sd[bnname + ".bias"].float() - sd[bnname + ".running_mean"].float() * s).contiguous()
+
+    convs = [fold("conv1.weight", "bn1")]
+    for L, nb in enumerate(LAYERS[arch], start=1):
+        for b in range(nb):
+            p = "layer%d.%d" % (L, b)
+            convs.append(fold(p + ".conv1.weight", p + ".bn1"))
+            convs.append(fold(p + ".conv2.weight", p + ".bn2"))
+            if (p + ".downsample.0.weight") in sd:
+                convs.append(fold(p + ".downsample.0.weight", p + ".downsample.1"))
+    return convs

@@ -1,0 +1,208 @@
+"""GPU parity tests: every kernel family through the C ABI against the CPU oracle."""
+import numpy as np
+import pytest
+import torch
+
+from conftest import golden
+from oracle import masks as omasks, select as oselect, synth, tiles as otiles
+
+pytestmark = pytest.mark.gpu
+
+
+def _ops():
+    from cellsegmentation_b200 import ops
+    return ops
+
+
+# ----------------------------------------------------------------------------- K4b
+@pytest.mark.parametrize("n_px", [1, 31, 32, 33, 1000, 96 * 96 * 3, 299 * 299 * 5 + 7])
+def test_hsv_refine_bit_exact(cuda, n_px):
+    ops = _ops()
+    rng = np.random.default_rng(n_px)
+    img = rng.integers(0, 256, (n_px, 3), dtype=np.uint8)
+    img[rng.uniform(size=n_px) < 0.2] = rng.integers(168, 173, 3, dtype=np.uint8)   # straddle 170
+    mask = (rng.uniform(size=n_px) < 0.5).astype(np.uint8) * rng.integers(1, 256, n_px).astype(np.uint8)
+    want = omasks.hsv_refine(img, mask).astype(np.uint8)
+    d_img, d_mask = torch.from_numpy(img).to(cuda), torch.from_numpy(mask).to(cuda)
+    got = ops.hsv_refine(d_img, d_mask).cpu().numpy()
+    assert int((got != want).sum()) == 0
+    for thr in (0, 169, 255):
+        got = ops.hsv_refine(d_img, d_mask, thr).cpu().numpy()
+        assert np.array_equal(got, omasks.hsv_refine(img, mask, thr).astype(np.uint8))
+    # in place (out aliases mask) and idempotence
+    m2 = d_mask.clone()
+    ops.hsv_refine(d_img, m2, out=m2)
+    assert np.array_equal(m2.cpu().numpy(), want)
+    ops.hsv_refine(d_img, m2, out=m2)
+    assert np.array_equal(m2.cpu().numpy(), want)
+
+
+def test_hsv_refine_unaligned_pointers(cuda):
+    ops = _ops()
+    rng = np.random.default_rng(5)
+    n = 5000
+    img = rng.integers(0, 256, (n + 1, 3), dtype=np.uint8)
+    mask = rng.integers(0, 2, n + 3, dtype=np.uint8)
+    d_img, d_mask = torch.from_numpy(img).to(cuda), torch.from_numpy(mask).to(cuda)
+    got = ops.hsv_refine(d_img[1:], d_mask[3:]).cpu().numpy()
+    assert np.array_equal(got, omasks.hsv_refine(img[1:], mask[3:]).astype(np.uint8))
+
+
+def test_hsv_refine_golden_pre_cc(cuda):
+    ops = _ops()
+    g = golden("masks.npz")
+    small = synth.make_bags(3, H=96, W=96, seed=31)
+    got = ops.hsv_refine(torch.from_numpy(small).to(cuda), torch.from_numpy(g["raw"]).to(cuda))
+    assert int((got.cpu().numpy() != g["pre_cc"]).sum()) == 0
+
+
+def test_bgr2hsv_matches_opencv(cuda):
+    import cv2
+    ops = _ops()
+    rng = np.random.default_rng(1)
+    cols = rng.integers(0, 256, (1 << 20, 1, 3), dtype=np.uint8)
+    grey = np.repeat(np.arange(256, dtype=np.uint8), 3).reshape(256, 1, 3)
+    cols = np.concatenate([cols, grey])
+    got = ops.bgr2hsv(torch.from_numpy(cols).to(cuda)).cpu().numpy()
+    assert np.array_equal(got, cv2.cvtColor(cols, cv2.COLOR_BGR2HSV))
+
+
+# ----------------------------------------------------------------------------- K1
+@pytest.mark.parametrize("S,I", [(32, 20), (32, 5), (16, 5)])
+def test_unfold_normalize_bit_exact(cuda, S, I):
+    ops = _ops()
+    bags = synth.make_bags(2, seed=3)
+    T = len(otiles.get_tiles((299, 299, 3), I, S))
+    begin, count = T - 40, 90                           # crosses the bag boundary
+    want = otiles.unfold(list(bags), I, S, begin, count)
+    got = ops.unfold_normalize(torch.from_numpy(bags).to(cuda), S, I, begin, count).cpu().numpy()
+    assert np.array_equal(got.view(np.uint32), want.view(np.uint32))
+
+
+def test_unfold_golden_transform(cuda):
+    ops = _ops()
+    g = golden("transform.npz")
+    bags = synth.make_bags(3, seed=11)
+    got = ops.unfold_normalize(torch.from_numpy(bags[1:]).to(cuda), 32, 20).cpu().numpy()
+    for j, i in enumerate(g["pick"]):
+        assert np.array_equal(got[i].view(np.uint32), g["tiles"][j].view(np.uint32))
+
+
+def test_gather_normalize(cuda):
+    ops = _ops()
+    bags = synth.make_bags(3, seed=4)
+    rng = np.random.default_rng(0)
+    n = 200
+    bag = rng.integers(0, 3, n).astype(np.int32)
+    x = rng.integers(0, 299 - 32 + 1, n).astype(np.int32)
+    y = rng.integers(0, 299 - 32 + 1, n).astype(np.int32)
+    got = ops.gather_normalize(torch.from_numpy(bags).to(cuda), 32, torch.from_numpy(bag).to(cuda),
+                               torch.from_numpy(x).to(cuda), torch.from_numpy(y).to(cuda)).cpu().numpy()
+    for j in range(n):
+        want = otiles.normalize_tile(bags[bag[j]][x[j]:x[j] + 32, y[j]:y[j] + 32])
+        assert np.array_equal(got[j].view(np.uint32), want.view(np.uint32))
+
+
+# ----------------------------------------------------------------------------- K3
+def _offsets(tileIDX, n_bags):
+    return np.concatenate([[0], np.cumsum(np.bincount(tileIDX, minlength=n_bags))]).astype(np.int64)
+
+
+@pytest.mark.parametrize("case", ["toy", "ties", "k0", "tpp3", "nan", "single", "wrapbig", "dense"])
+def test_select_topk_golden(cuda, case):
+    ops = _ops()
+    g = golden("select.npz")
+    tid, lab, p = g[case + "_tileIDX"], g[case + "_labels"], g[case + "_probs"]
+    tpp, tk = (int(v) for v in g[case + "_params"])
+    want = g[case + "_idx"]
+    off = _offsets(tid, len(lab))
+    maxT = int(np.diff(off).max())
+    idx, pl, sel_off = ops.select_topk(torch.from_numpy(p).to(cuda), torch.from_numpy(lab).to(cuda),
+                                       len(lab), maxT, tpp, tk,
+                                       seg_offsets=torch.from_numpy(off).to(cuda))
+    assert np.array_equal(idx.cpu().numpy().astype(np.int64), want)
+    assert np.array_equal(pl.cpu().numpy(), oselect.pseudo_labels(tid, lab, want))
+    kept = np.bincount(tid[want], minlength=len(lab)) if len(want) else np.zeros(len(lab), int)
+    assert np.array_equal(np.diff(sel_off.cpu().numpy()), kept)
+    # lexsort order itself
+    order = ops.lexsort_segments(torch.from_numpy(p).to(cuda), len(lab), maxT,
+                                 seg_offsets=torch.from_numpy(off).to(cuda)).cpu().numpy()
+    assert np.array_equal(order, np.lexsort((p, tid)))
+
+
+@pytest.mark.parametrize("T,n_bags", [(1, 5), (2, 3), (33, 7), (225, 16), (3025, 9), (4097, 3), (8100, 2)])
+def test_select_topk_random_uniform(cuda, T, n_bags):
+    ops = _ops()
+    rng = np.random.default_rng(T * 31 + n_bags)
+    p = rng.uniform(0, 1, T * n_bags).astype(np.float32)
+    p[rng.uniform(size=p.size) < 0.05] = np.float32(1.0)          # saturated ties
+    p[rng.uniform(size=p.size) < 0.05] = np.float32(0.0)
+    p[rng.uniform(size=p.size) < 0.01] = np.float32(-0.0)
+    lab = rng.integers(0, max(2, T // 2), n_bags).astype(np.int32)
+    lab[rng.uniform(size=n_bags) < 0.3] = 0
+    lab[-1] = T + 5                                               # k >= T on the wrapping last bag
+    tid = np.repeat(np.arange(n_bags), T)
+    for tpp, tk in [(1, 30), (2, 3), (1, 0)]:
+        want = oselect.sample_indices(tid, lab, p, tpp, tk)
+        idx, pl, _ = ops.select_topk(torch.from_numpy(p).to(cuda), torch.from_numpy(lab).to(cuda),
+                                     n_bags, T, tpp, tk)
+        assert np.array_equal(idx.cpu().numpy().astype(np.int64), want)
+        assert np.array_equal(pl.cpu().numpy(), oselect.pseudo_labels(tid, lab, want))
+
+
+def test_select_topk_ragged_with_empty_bags(cuda):
+    ops = _ops()
+    rng = np.random.default_rng(9)
+    sizes = np.array([0, 17, 0, 300, 1, 64, 0])
+    tid = np.repeat(np.arange(len(sizes)), sizes)
+    p = rng.uniform(0, 1, tid.size).astype(np.float32)
+    lab = np.array([3, 2, 5, 0, 1, 100, 2], np.int32)
+    want = oselect.sample_indices(tid, lab, p, 1, 30)
+    off = _offsets(tid, len(sizes))
+    idx, _, _ = ops.select_topk(torch.from_numpy(p).to(cuda), torch.from_numpy(lab).to(cuda),
+                                len(sizes), int(sizes.max()), 1, 30,
+                                seg_offsets=torch.from_numpy(off).to(cuda))
+    assert np.array_equal(idx.cpu().numpy().astype(np.int64), want)
+
+
+def test_rank_threshold_golden(cuda):
+    ops = _ops()
+    g = golden("rank.npz")
+    tid, p = g["tileIDX"], g["probs"]
+    off = _offsets(tid, 5)
+    idx, kp, _ = ops.rank_threshold(torch.from_numpy(p).to(cuda), 5, 225, float(g["threshold"]),
+                                    seg_offsets=torch.from_numpy(off).to(cuda))
+    idx = idx.cpu().numpy()
+    grid = np.array(otiles.get_tiles((299, 299, 3), 20, 32), np.int32)
+    assert np.array_equal(grid[idx % 225], g["tiles"])
+    assert np.array_equal(kp.cpu().numpy().view(np.uint32), g["kept_probs"].view(np.uint32))
+    assert np.array_equal(tid[idx], g["groups"])
+
+
+# ----------------------------------------------------------------------------- K4a
+def test_paint_mask_and_heatmap_golden(cuda):
+    import cv2
+    ops = _ops()
+    g = golden("masks.npz")
+    small = synth.make_bags(3, H=96, W=96, seed=31)
+    keep = torch.from_numpy(g["kept"].astype(np.int32)).to(cuda)
+    kp = torch.from_numpy(g["probs"][g["kept"]]).to(cuda)
+    raw = ops.paint_mask(keep, 3, 96, 96, 16, 5)
+    assert np.array_equal(raw.cpu().numpy(), g["raw"])
+    heat = ops.paint_heatmap(keep, kp, 3, 96, 96, 16, 5)
+    gray = ops.heatmap_to_gray(heat).cpu().numpy()
+    for i in range(3):
+        cm = cv2.applyColorMap(gray[i], cv2.COLORMAP_JET)
+        img = cv2.addWeighted(small[i], 0.5, cm, 0.5, 0)
+        assert np.array_equal(np.uint8(img), g["heat_imgs"][i])
+
+
+def test_heatmap_to_gray_all_thresholded_probs(cuda):
+    """uint8(255*p) in float64 for every float32 p in [0.9, 1] plus a sweep of [0,1]."""
+    ops = _ops()
+    lo = np.float32(0.9).view(np.uint32)
+    hi = np.float32(1.0).view(np.uint32)
+    p = np.arange(lo, hi + 1, dtype=np.uint32).view(np.float32)
+    p = np.concatenate([p, np.linspace(0, 1, 100001, dtype=np.float32)])
+    got = ops.heatmap_to_gray(torch.from_numpy(p).to(cuda)).cpu().numpy()
+    assert np.array_equal(got, omasks.heat_to_gray(p.astype(np.float64)))
