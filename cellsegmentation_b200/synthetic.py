@@ -1,0 +1,56 @@
+"""Synthetic LYSTO-shaped inputs generated on the device (there is no network for the dataset).
+
+Shapes follow dataset/dataset.py:26,59-65: 299x299x3 u8 bags with one count label each.
+"""
+import numpy as np
+import torch
+
+IMAGE_SIZE = 299
+
+
+def make_bags_device(n_bags, device, seed=0, chunk=512):
+    """u8 [n_bags,299,299,3] resident in HBM; uniform noise (compute is data independent)."""
+    g = torch.Generator(device=device)
+    g.manual_seed(1234567 + seed)
+    out = torch.empty((n_bags, IMAGE_SIZE, IMAGE_SIZE, 3), dtype=torch.uint8, device=device)
+    for b in range(0, n_bags, chunk):
+        e = min(n_bags, b + chunk)
+        out[b:e] = torch.randint(0, 256, (e - b, IMAGE_SIZE, IMAGE_SIZE, 3), dtype=torch.uint8,
+                                 device=device, generator=g)
+    return out
+
+
+def make_labels(n_bags, seed=0):
+    """LYSTO-like counts: ~30 % zeros, the rest geometric with mean ~8, capped at 300 (int32)."""
+    rng = np.random.default_rng([seed, 7919])
+    lab = rng.geometric(1.0 / 8.0, n_bags)
+    lab[rng.uniform(size=n_bags) < 0.3] = 0
+    return np.minimum(lab, 300).astype(np.int32)
+
+
+def make_resnet_weights(arch="resnet34", seed=0):
+    """Random-init BN-folded conv list + fc_tile for benchmarking: kaiming-normal convs
+    (model/resnet.py:171-175), BN at init (gamma 1, beta 0, stats 0/1 -> identity fold up to eps)."""
+    layers = {"resnet18": [2, 2, 2, 2], "resnet34": [3, 4, 6, 3]}[arch]
+    rng = np.random.default_rng(seed)
+    s = np.float32(1.0 / np.sqrt(1.0 + 1e-5))
+
+    def conv(cout, cin, k):
+        w = rng.standard_normal((cout, cin, k, k)).astype(np.float32) * np.float32(np.sqrt(2.0 / (cin * k * k)))
+        return torch.from_numpy(w * s), torch.zeros(cout)
+
+    convs = [conv(64, 3, 7)]
+    inpl = 64
+    for L, nb in enumerate(layers):
+        pl = 64 << L
+        for b in range(nb):
+            stride = 2 if (b == 0 and L > 0) else 1
+            convs.append(conv(pl, inpl, 3))
+            convs.append(conv(pl, pl, 3))
+            if stride != 1 or inpl != pl:
+                convs.append(conv(pl, inpl, 1))
+            inpl = pl
+    bound = 1.0 / np.sqrt(512)
+    fc_w = torch.from_numpy(rng.uniform(-bound, bound, (2, 512)).astype(np.float32)) * 0.05
+    fc_b = torch.zeros(2)
+    return convs, fc_w, fc_b
