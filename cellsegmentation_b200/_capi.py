@@ -36,6 +36,7 @@ _PROTOS = {
     "cs_model_create": (c_int, [c_int, c_int, POINTER(c_void_p), POINTER(c_void_p), c_void_p,
                                 c_void_p, POINTER(c_void_p)]),
     "cs_model_destroy": (c_int, [c_void_p]),
+    "cs_model_set_fc": (c_int, [c_void_p, c_void_p, c_void_p]),
     "cs_model_workspace_bytes": (c_int64, [c_void_p, c_int, c_int64, c_int]),
     "cs_model_forward_tiles": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int,
                                        c_int64, c_int64, c_int, c_void_p, c_void_p, c_void_p,
@@ -52,6 +53,10 @@ _PROTOS = {
                               c_void_p, c_void_p]),
     "cs_paint_heatmap": (c_int, [c_void_p, c_void_p, c_int64, c_int, c_int, c_int, c_int, c_int,
                                  c_int, c_void_p, c_void_p]),
+    "cs_paint_mask_xy": (c_int, [c_void_p, c_void_p, c_void_p, c_int64, c_int, c_int, c_int, c_int,
+                                 c_void_p, c_void_p]),
+    "cs_paint_heatmap_xy": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_int, c_int,
+                                    c_int, c_int, c_void_p, c_void_p]),
     "cs_heatmap_to_gray": (c_int, [c_void_p, c_int64, c_void_p, c_void_p]),
     "cs_hsv_refine": (c_int, [c_void_p, c_void_p, c_int64, c_int, c_void_p, c_void_p]),
     "cs_bgr2hsv_u8": (c_int, [c_void_p, c_int64, c_void_p, c_void_p]),

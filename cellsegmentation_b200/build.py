@@ -22,6 +22,7 @@ SOURCES = [
     "paint.cu",
     "fwd_fp32.cu",
     "fwd_tc.cu",
+    "stem_tc.cu",
     "model.cu",
 ]
 

@@ -92,6 +92,12 @@ struct StemArgs {
 };
 int launch_stem_bf16(const StemArgs& a, cudaStream_t st);
 
+// Tensor-core stem (stem_tc.cu), tile 32 only: w_bf16_dev is [64][192] packed by
+// pack_stem_weights_bf16, lut_bf16_dev the bf16 rounding of the 3x256 normalisation LUT.
+void pack_stem_weights_bf16(const float* w_oihw, uint16_t* out /* [64*192] */);
+int launch_stem_tc(const StemArgs& a, const void* w_bf16_dev, const uint16_t* lut_bf16_dev,
+                   cudaStream_t st);
+
 int launch_head_bf16(const __nv_bfloat16* x_hi, const __nv_bfloat16* x_lo, int64_t n, int P,
                      int C, const float* fc_w, const float* fc_b, float* prob_out,
                      float* logits_out, float* feat_out, cudaStream_t st);

@@ -19,147 +19,16 @@
 // applies ReLU and writes bf16 `hi` (next layer's operand) plus bf16 `lo`
 // (= value - hi) so the residual stream keeps ~16 mantissa bits.
 //
-// Warp roles (192 threads, one CTA per SM, persistent over (m_tile, n_tile)):
+// Warp roles (320 threads, one CTA per SM, persistent over (m_tile, n_tile)):
 //   warp 0 : TMA producer (one lane)          warp 1 : TMEM alloc + MMA issuer (one lane)
-//   warps 2-5 : epilogue, one TMEM lane quadrant each
+//   warps 2-9 : epilogue; warp % 4 = TMEM lane quadrant, (warp-2)/4 = column half.  The
+//   residual of the next 32-column chunk is fetched (256-bit loads) before the accumulator
+//   wait / while the current chunk is converted and stored.
 #include "fwd.cuh"
+#include "tc_ptx.cuh"
 
 namespace cs {
 namespace {
-
-// ----------------------------------------------------------------------------
-// PTX wrappers
-// ----------------------------------------------------------------------------
-__device__ __forceinline__ uint32_t smem_u32(const void* p) {
-  return (uint32_t)__cvta_generic_to_shared(p);
-}
-__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
-  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
-}
-__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
-  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes)
-               : "memory");
-}
-__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
-  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
-}
-__device__ __forceinline__ uint32_t mbar_try_wait(uint32_t bar, uint32_t parity) {
-  uint32_t ok;
-  asm volatile(
-      "{\n\t.reg .pred p;\n\t"
-      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
-      "selp.u32 %0, 1, 0, p;\n\t}"
-      : "=r"(ok)
-      : "r"(bar), "r"(parity)
-      : "memory");
-  return ok;
-}
-__device__ __forceinline__ uint64_t global_timer_ns() {
-  uint64_t t;
-  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
-  return t;
-}
-// Bounded wait: a protocol bug becomes a trapped kernel (CUDA error), not a hung GPU.
-__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
-  if (mbar_try_wait(bar, parity)) return;
-  const uint64_t t0 = global_timer_ns();
-  uint32_t spins = 0;
-  while (!mbar_try_wait(bar, parity)) {
-    if ((++spins & 0x3ff) == 0 && global_timer_ns() - t0 > 4000000000ull) __trap();
-  }
-}
-__device__ __forceinline__ void fence_barrier_init() {
-  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-}
-__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map, uint32_t bar,
-                                            int c0, int c1) {
-  asm volatile(
-      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes "
-      "[%0], [%1, {%3, %4}], [%2];" ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1)
-      : "memory");
-}
-__device__ __forceinline__ void tma_load_4d(uint32_t dst, const CUtensorMap* map, uint32_t bar,
-                                            int c0, int c1, int c2, int c3) {
-  asm volatile(
-      "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes "
-      "[%0], [%1, {%3, %4, %5, %6}], [%2];" ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1),
-      "r"(c2), "r"(c3)
-      : "memory");
-}
-__device__ __forceinline__ void prefetch_tmap(const CUtensorMap* map) {
-  asm volatile("prefetch.tensormap [%0];" ::"l"(map) : "memory");
-}
-__device__ __forceinline__ void tc_fence_before() {
-  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-}
-__device__ __forceinline__ void tc_fence_after() {
-  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-}
-__device__ __forceinline__ void tmem_alloc(uint32_t dst_smem, uint32_t cols) {
-  asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(dst_smem),
-               "r"(cols)
-               : "memory");
-  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
-}
-__device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t cols) {
-  asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(cols)
-               : "memory");
-}
-// D[tmem] (+)= A[smem] * B[smem]^T, bf16 x bf16 -> fp32, issued by one thread.
-__device__ __forceinline__ void umma_bf16(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc,
-                                          uint32_t idesc, uint32_t accumulate) {
-  asm volatile(
-      "{\n\t.reg .pred p;\n\t"
-      "setp.ne.b32 p, %4, 0;\n\t"
-      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(d_tmem),
-      "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
-      : "memory");
-}
-// Arrive on an mbarrier once every previously issued MMA has completed.
-__device__ __forceinline__ void umma_commit(uint32_t bar) {
-  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(
-                   bar)
-               : "memory");
-}
-// 32 lanes x 32 consecutive fp32 columns: thread i reads TMEM lane (base + i).
-__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
-  asm volatile(
-      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
-      "{%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,"
-      "%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31}, [%32];"
-      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]),
-        "=r"(r[7]), "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]),
-        "=r"(r[14]), "=r"(r[15]), "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]),
-        "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]), "=r"(r[25]),
-        "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
-      : "r"(taddr)
-      : "memory");
-}
-__device__ __forceinline__ void tmem_ld_wait() {
-  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-}
-
-// K-major, 128-byte-swizzled operand tile: rows of 128 B, 8-row groups 1024 B apart.
-// (start address >> 4) | SBO = 1024 B | descriptor version 1 | SWIZZLE_128B.
-__device__ __forceinline__ uint64_t umma_desc_sw128(uint32_t smem_addr) {
-  uint64_t d = (uint64_t)((smem_addr >> 4) & 0x3fffu);
-  d |= (uint64_t)(1024u >> 4) << 32;
-  d |= (uint64_t)1 << 46;
-  d |= (uint64_t)2 << 61;
-  return d;
-}
-// kind::f16 instruction descriptor: fp32 accumulate, bf16 A and B, both K-major.
-__host__ __device__ constexpr uint32_t umma_idesc_bf16(int M, int N) {
-  return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(N >> 3) << 17) |
-         ((uint32_t)(M >> 4) << 24);
-}
-
-__device__ __forceinline__ uint32_t pack_bf16x2(float a, float b) {
-  __nv_bfloat162 v = __floats2bfloat162_rn(a, b);
-  return *reinterpret_cast<uint32_t*>(&v);
-}
-__device__ __forceinline__ float bf16_lo_f(uint32_t w) { return __uint_as_float(w << 16); }
-__device__ __forceinline__ float bf16_hi_f(uint32_t w) { return __uint_as_float(w & 0xffff0000u); }
 
 // ----------------------------------------------------------------------------
 // The GEMM kernel
@@ -175,7 +44,7 @@ struct GemmCfg {
   static constexpr uint32_t kTmemCols = 2 * BN;                    // two accumulator stages
 };
 
-constexpr int kGemmThreads = 192;
+constexpr int kGemmThreads = 320;  // TMA warp, MMA warp, 8 epilogue warps
 
 template <int BN>
 __global__ void __launch_bounds__(kGemmThreads, 1)
@@ -203,7 +72,7 @@ conv_gemm_kernel(const __grid_constant__ GemmParams p) {
     }
     for (int a = 0; a < 2; ++a) {
       mbar_init(tfull_bar(a), 1);
-      mbar_init(tempty_bar(a), 128);
+      mbar_init(tempty_bar(a), 256);
     }
     fence_barrier_init();
     prefetch_tmap(&p.b_map);
@@ -276,26 +145,49 @@ conv_gemm_kernel(const __grid_constant__ GemmParams p) {
       }
     }
   } else {
-    const int quad = warp & 3;  // TMEM lanes [32*quad, 32*quad+32) belong to this warp
+    // 8 epilogue warps: TMEM lane quadrant = warp % 4, column half = (warp - 2) / 4.
+    const int quad = warp & 3;
+    const int half = (warp - 2) >> 2;
+    constexpr int kColsPerWarp = BN / 2;
+    constexpr int kChunks = kColsPerWarp / 32;   // 32-column chunks per warp: 1, 2 or 4
     const int row_in_tile = quad * 32 + lane;
+    const bool has_res_hi = p.res_hi != nullptr, has_res_lo = p.res_lo != nullptr;
     int acc = 0;
     uint32_t acc_phase = 0;
     for (int w = blockIdx.x; w < num_work; w += gridDim.x) {
       const int m_tile = w / p.num_n_tiles, n_tile = w - m_tile * p.num_n_tiles;
-      mbar_wait(tfull_bar(acc), acc_phase);
-      tc_fence_after();
       const int64_t row = (int64_t)m_tile * kGemmBM + row_in_tile;
       const bool row_ok = row < p.m_valid;
-      const int64_t off0 = row * (int64_t)p.n_total + (int64_t)n_tile * BN;
-#pragma unroll 1
-      for (int c0 = 0; c0 < BN; c0 += 32) {
+      const int col0 = n_tile * BN + half * kColsPerWarp;
+      const int64_t off0 = row * (int64_t)p.n_total + col0;
+
+      // residual of chunk c: 32 bf16 hi + 32 bf16 lo per row, fetched one chunk ahead
+      U32x8 rh[2][2], rl[2][2];
+      auto load_res = [&](int c, int slot) {
+        if (row_ok && has_res_hi) {
+          rh[slot][0] = ldg256(p.res_hi + off0 + c * 32);
+          rh[slot][1] = ldg256(p.res_hi + off0 + c * 32 + 16);
+        }
+        if (row_ok && has_res_lo) {
+          rl[slot][0] = ldg256(p.res_lo + off0 + c * 32);
+          rl[slot][1] = ldg256(p.res_lo + off0 + c * 32 + 16);
+        }
+      };
+      load_res(0, 0);
+      mbar_wait(tfull_bar(acc), acc_phase);
+      tc_fence_after();
+#pragma unroll
+      for (int c = 0; c < kChunks; ++c) {
+        const int slot = c & 1;
+        if (c + 1 < kChunks) load_res(c + 1, slot ^ 1);
         uint32_t r[32];
-        tmem_ld32(tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(acc * BN + c0), r);
+        tmem_ld32(tmem_base + ((uint32_t)(quad * 32) << 16) +
+                      (uint32_t)(acc * BN + half * kColsPerWarp + c * 32), r);
         tmem_ld_wait();
         if (row_ok) {
-          const int64_t off = off0 + c0;
+          const int64_t off = off0 + c * 32;
           float v[32];
-          const float4* b4 = reinterpret_cast<const float4*>(p.bias + n_tile * BN + c0);
+          const float4* b4 = reinterpret_cast<const float4*>(p.bias + col0 + c * 32);
 #pragma unroll
           for (int j = 0; j < 8; ++j) {
             float4 bb = __ldg(b4 + j);
@@ -304,26 +196,20 @@ conv_gemm_kernel(const __grid_constant__ GemmParams p) {
             v[4 * j + 2] = __uint_as_float(r[4 * j + 2]) + bb.z;
             v[4 * j + 3] = __uint_as_float(r[4 * j + 3]) + bb.w;
           }
-          if (p.res_hi) {
-            const uint4* rh = reinterpret_cast<const uint4*>(p.res_hi + off);
+          if (has_res_hi) {
 #pragma unroll
-            for (int j = 0; j < 4; ++j) {
-              uint4 q = __ldg(rh + j);
-              v[8 * j + 0] += bf16_lo_f(q.x); v[8 * j + 1] += bf16_hi_f(q.x);
-              v[8 * j + 2] += bf16_lo_f(q.y); v[8 * j + 3] += bf16_hi_f(q.y);
-              v[8 * j + 4] += bf16_lo_f(q.z); v[8 * j + 5] += bf16_hi_f(q.z);
-              v[8 * j + 6] += bf16_lo_f(q.w); v[8 * j + 7] += bf16_hi_f(q.w);
+            for (int j = 0; j < 16; ++j) {
+              const uint32_t q = rh[slot][j >> 3].v[j & 7];
+              v[2 * j] += bf16_lo_f(q);
+              v[2 * j + 1] += bf16_hi_f(q);
             }
           }
-          if (p.res_lo) {
-            const uint4* rl = reinterpret_cast<const uint4*>(p.res_lo + off);
+          if (has_res_lo) {
 #pragma unroll
-            for (int j = 0; j < 4; ++j) {
-              uint4 q = __ldg(rl + j);
-              v[8 * j + 0] += bf16_lo_f(q.x); v[8 * j + 1] += bf16_hi_f(q.x);
-              v[8 * j + 2] += bf16_lo_f(q.y); v[8 * j + 3] += bf16_hi_f(q.y);
-              v[8 * j + 4] += bf16_lo_f(q.z); v[8 * j + 5] += bf16_hi_f(q.z);
-              v[8 * j + 6] += bf16_lo_f(q.w); v[8 * j + 7] += bf16_hi_f(q.w);
+            for (int j = 0; j < 16; ++j) {
+              const uint32_t q = rl[slot][j >> 3].v[j & 7];
+              v[2 * j] += bf16_lo_f(q);
+              v[2 * j + 1] += bf16_hi_f(q);
             }
           }
           if (p.relu) {
@@ -336,24 +222,22 @@ conv_gemm_kernel(const __grid_constant__ GemmParams p) {
             for (int j = 0; j < 8; ++j)
               of[j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
           }
-          uint32_t hi[16];
+          U32x8 hi[2];
 #pragma unroll
-          for (int j = 0; j < 16; ++j) hi[j] = pack_bf16x2(v[2 * j], v[2 * j + 1]);
+          for (int j = 0; j < 16; ++j) hi[j >> 3].v[j & 7] = pack_bf16x2(v[2 * j], v[2 * j + 1]);
           if (p.out_hi) {
-            uint4* oh = reinterpret_cast<uint4*>(p.out_hi + off);
-#pragma unroll
-            for (int j = 0; j < 4; ++j)
-              oh[j] = make_uint4(hi[4 * j], hi[4 * j + 1], hi[4 * j + 2], hi[4 * j + 3]);
+            stg256(p.out_hi + off, hi[0]);
+            stg256(p.out_hi + off + 16, hi[1]);
           }
           if (p.out_lo) {
-            uint32_t lo[16];
+            U32x8 lo[2];
 #pragma unroll
-            for (int j = 0; j < 16; ++j)
-              lo[j] = pack_bf16x2(v[2 * j] - bf16_lo_f(hi[j]), v[2 * j + 1] - bf16_hi_f(hi[j]));
-            uint4* ol = reinterpret_cast<uint4*>(p.out_lo + off);
-#pragma unroll
-            for (int j = 0; j < 4; ++j)
-              ol[j] = make_uint4(lo[4 * j], lo[4 * j + 1], lo[4 * j + 2], lo[4 * j + 3]);
+            for (int j = 0; j < 16; ++j) {
+              const uint32_t h = hi[j >> 3].v[j & 7];
+              lo[j >> 3].v[j & 7] = pack_bf16x2(v[2 * j] - bf16_lo_f(h), v[2 * j + 1] - bf16_hi_f(h));
+            }
+            stg256(p.out_lo + off, lo[0]);
+            stg256(p.out_lo + off + 16, lo[1]);
           }
         }
       }

@@ -7,6 +7,7 @@
 // [instance][pixel (row-major y,x)][channel]; bf16 mode keeps a `hi` tensor (MMA
 // operand) and, for block outputs, a `lo` tensor (value - hi) for the residual stream.
 #include <math.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <memory>
@@ -257,10 +258,22 @@ struct TcPlan {
   const __nv_bfloat16* x4_hi = nullptr;
   const __nv_bfloat16* x4_lo = nullptr;
   int P4 = 1, C4 = 512;
-  ~TcPlan() { for (auto& l : layers) free_planned(l); }
+  uint16_t* d_stem_w = nullptr;  // [64][192] bf16 for the tensor-core stem (tile 32)
+  uint16_t* d_lut = nullptr;     // [3][256] bf16 normalisation LUT
+  ~TcPlan() {
+    for (auto& l : layers) free_planned(l);
+    if (d_stem_w) cudaFree(d_stem_w);
+    if (d_lut) cudaFree(d_lut);
+  }
 };
 
 int64_t round_up(int64_t v, int64_t a) { return (v + a - 1) / a * a; }
+
+// Diagnostics: CELLSEG_STEM=cuda routes tile-32 batches through the CUDA-core stem too.
+const bool g_force_cuda_core_stem = []() {
+  const char* e = getenv("CELLSEG_STEM");
+  return e != nullptr && strcmp(e, "cuda") == 0;
+}();
 
 int64_t act_elems(int tile) { return (int64_t)(tile / 4) * (tile / 4) * 64; }
 
@@ -349,6 +362,17 @@ int build_tc_plan(cs_model* m, int tile, int64_t max_batch, void* ws, int64_t ws
   plan->x4_lo = plan->buf_lo[xi];
   plan->P4 = H * W;
   plan->C4 = C;
+  if (tile == 32) {
+    std::vector<uint16_t> sw(64 * 192), lut(768);
+    pack_stem_weights_bf16(m->convs[0].w.data(), sw.data());
+    float lut_f[768];
+    get_norm_lut_host(lut_f);
+    for (int i = 0; i < 768; ++i) lut[i] = f32_to_bf16_rn(lut_f[i]);
+    CS_CUDA(cudaMalloc(&plan->d_stem_w, sw.size() * 2));
+    CS_CUDA(cudaMemcpy(plan->d_stem_w, sw.data(), sw.size() * 2, cudaMemcpyHostToDevice));
+    CS_CUDA(cudaMalloc(&plan->d_lut, lut.size() * 2));
+    CS_CUDA(cudaMemcpy(plan->d_lut, lut.data(), lut.size() * 2, cudaMemcpyHostToDevice));
+  }
   m->plan = std::move(plan);
   return CS_OK;
 }
@@ -362,7 +386,8 @@ int run_tc_batch(cs_model* m, const StemArgs& stem_in, int64_t count, float* pro
   sa.bias = m->convs[0].d_b;
   sa.out_hi = pl.buf_hi[0];
   sa.out_lo = pl.buf_lo[0];
-  int rc = launch_stem_bf16(sa, st);
+  int rc = (pl.tile == 32 && !g_force_cuda_core_stem) ? launch_stem_tc(sa, pl.d_stem_w, pl.d_lut, st)
+                                                      : launch_stem_bf16(sa, st);
   if (rc != CS_OK) return rc;
   m->last_launches++;
   for (PlannedConv& pc : pl.layers) {
@@ -542,6 +567,13 @@ int cs_model_destroy(cs_model* m) {
   if (m->d_fc_w) cudaFree(m->d_fc_w);
   if (m->d_fc_b) cudaFree(m->d_fc_b);
   delete m;
+  return CS_OK;
+}
+
+int cs_model_set_fc(cs_model* m, const float* fc_w_host, const float* fc_b_host) {
+  CS_REQUIRE(m && fc_w_host && fc_b_host, "cs_model_set_fc: NULL pointer");
+  CS_CUDA(cudaMemcpy(m->d_fc_w, fc_w_host, 2 * 512 * sizeof(float), cudaMemcpyHostToDevice));
+  CS_CUDA(cudaMemcpy(m->d_fc_b, fc_b_host, 2 * sizeof(float), cudaMemcpyHostToDevice));
   return CS_OK;
 }
 

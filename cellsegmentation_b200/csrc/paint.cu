@@ -30,15 +30,33 @@ __device__ __forceinline__ bool tile_origin(const Grid& g, int32_t inst, int64_t
   return inst >= 0 && *bag < g.n_bags;
 }
 
+// Explicit coordinates (the reference API hands over `tiles` and `groups` arrays).
+struct XY {
+  const int32_t* bag;
+  const int32_t* x;
+  const int32_t* y;
+};
+
+__device__ __forceinline__ bool tile_origin_xy(const Grid& g, const XY& c, int64_t j, int64_t* bag,
+                                               int* row0, int* col0) {
+  *bag = c.bag[j];
+  *row0 = c.x[j];
+  *col0 = c.y[j];
+  return *bag >= 0 && *bag < g.n_bags && *row0 >= 0 && *col0 >= 0 && *row0 + g.tile <= g.H &&
+         *col0 + g.tile <= g.W;
+}
+
 __global__ void __launch_bounds__(256)
-paint_mask_kernel(Grid g, const int32_t* __restrict__ sel, int64_t n_sel, uint8_t* __restrict__ out) {
+paint_mask_kernel(Grid g, const int32_t* __restrict__ sel, XY xy, int64_t n_sel,
+                  uint8_t* __restrict__ out) {
   int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   int lane = threadIdx.x & 31;
   int64_t n_warps = ((int64_t)gridDim.x * blockDim.x) >> 5;
   int S = g.tile;
   for (int64_t j = warp; j < n_sel; j += n_warps) {
     int64_t bag; int r0, c0;
-    if (!tile_origin(g, sel[j], &bag, &r0, &c0)) continue;
+    if (!(sel ? tile_origin(g, sel[j], &bag, &r0, &c0) : tile_origin_xy(g, xy, j, &bag, &r0, &c0)))
+      continue;
     uint8_t* base = out + (bag * g.H + r0) * (int64_t)g.W + c0;
     for (int e = lane; e < S * S; e += 32) {
       int y = e / S, x = e - y * S;
@@ -48,7 +66,7 @@ paint_mask_kernel(Grid g, const int32_t* __restrict__ sel, int64_t n_sel, uint8_
 }
 
 __global__ void __launch_bounds__(256)
-paint_heat_kernel(Grid g, const int32_t* __restrict__ sel, const float* __restrict__ prob,
+paint_heat_kernel(Grid g, const int32_t* __restrict__ sel, XY xy, const float* __restrict__ prob,
                   int64_t n_sel, float* __restrict__ out) {
   int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   int lane = threadIdx.x & 31;
@@ -56,7 +74,8 @@ paint_heat_kernel(Grid g, const int32_t* __restrict__ sel, const float* __restri
   int S = g.tile;
   for (int64_t j = warp; j < n_sel; j += n_warps) {
     int64_t bag; int r0, c0;
-    if (!tile_origin(g, sel[j], &bag, &r0, &c0)) continue;
+    if (!(sel ? tile_origin(g, sel[j], &bag, &r0, &c0) : tile_origin_xy(g, xy, j, &bag, &r0, &c0)))
+      continue;
     float p = prob[j];
     if (!(p >= 0.0f)) continue;  // negative or NaN never passes `prob > thr >= 0`
     int pi = __float_as_int(p);
@@ -105,7 +124,7 @@ int cs_paint_mask(const int32_t* sel_idx, int64_t n_sel, int H, int W, int tile,
   int rc = make_grid("cs_paint_mask", H, W, tile, interval, bag_base, n_bags, &g);
   if (rc != CS_OK) return rc;
   if (n_sel == 0) return CS_OK;
-  paint_mask_kernel<<<warp_grid(n_sel), 256, 0, cs::as_stream(stream)>>>(g, sel_idx, n_sel, mask_out);
+  paint_mask_kernel<<<warp_grid(n_sel), 256, 0, cs::as_stream(stream)>>>(g, sel_idx, XY{}, n_sel, mask_out);
   CS_LAUNCH_CHECK();
   return CS_OK;
 }
@@ -120,8 +139,36 @@ int cs_paint_heatmap(const int32_t* sel_idx, const float* sel_prob, int64_t n_se
   int rc = make_grid("cs_paint_heatmap", H, W, tile, interval, bag_base, n_bags, &g);
   if (rc != CS_OK) return rc;
   if (n_sel == 0) return CS_OK;
-  paint_heat_kernel<<<warp_grid(n_sel), 256, 0, cs::as_stream(stream)>>>(g, sel_idx, sel_prob,
+  paint_heat_kernel<<<warp_grid(n_sel), 256, 0, cs::as_stream(stream)>>>(g, sel_idx, XY{}, sel_prob,
                                                                         n_sel, heat_out);
+  CS_LAUNCH_CHECK();
+  return CS_OK;
+}
+
+int cs_paint_mask_xy(const int32_t* bag, const int32_t* x, const int32_t* y, int64_t n_sel, int H,
+                     int W, int tile, int n_bags, uint8_t* mask_out, void* stream) {
+  CS_REQUIRE(mask_out != nullptr && ((bag && x && y) || n_sel == 0), "cs_paint_mask_xy: NULL pointer");
+  CS_REQUIRE(n_sel >= 0 && tile > 0 && tile <= H && tile <= W && n_bags > 0,
+             "cs_paint_mask_xy: bad arguments");
+  if (n_sel == 0) return CS_OK;
+  Grid g{H, W, tile, 1, 1, 1, 0, n_bags};
+  paint_mask_kernel<<<warp_grid(n_sel), 256, 0, cs::as_stream(stream)>>>(g, nullptr, XY{bag, x, y},
+                                                                        n_sel, mask_out);
+  CS_LAUNCH_CHECK();
+  return CS_OK;
+}
+
+int cs_paint_heatmap_xy(const int32_t* bag, const int32_t* x, const int32_t* y, const float* prob,
+                        int64_t n_sel, int H, int W, int tile, int n_bags, float* heat_out,
+                        void* stream) {
+  CS_REQUIRE(heat_out != nullptr && ((bag && x && y && prob) || n_sel == 0),
+             "cs_paint_heatmap_xy: NULL pointer");
+  CS_REQUIRE(n_sel >= 0 && tile > 0 && tile <= H && tile <= W && n_bags > 0,
+             "cs_paint_heatmap_xy: bad arguments");
+  if (n_sel == 0) return CS_OK;
+  Grid g{H, W, tile, 1, 1, 1, 0, n_bags};
+  paint_heat_kernel<<<warp_grid(n_sel), 256, 0, cs::as_stream(stream)>>>(g, nullptr, XY{bag, x, y},
+                                                                        prob, n_sel, heat_out);
   CS_LAUNCH_CHECK();
   return CS_OK;
 }

@@ -143,6 +143,29 @@ def paint_heatmap(sel_idx, sel_prob, n_bags, H, W, tile, interval, bag_base=0, o
     return out
 
 
+def paint_mask_xy(bag, x, y, n_bags, H, W, tile, out=None):
+    """paint_mask for explicit (bag, row, col) int32 arrays."""
+    for t, nm in ((bag, "bag"), (x, "x"), (y, "y")):
+        _req_cuda(t, nm, torch.int32)
+    if out is None:
+        out = torch.zeros((n_bags, H, W), dtype=torch.uint8, device=bag.device)
+    check(lib().cs_paint_mask_xy(ptr(bag), ptr(x), ptr(y), bag.numel(), H, W, tile, n_bags, ptr(out),
+                                 cur_stream()), "cs_paint_mask_xy")
+    return out
+
+
+def paint_heatmap_xy(bag, x, y, prob, n_bags, H, W, tile, out=None):
+    """paint_heatmap for explicit (bag, row, col) int32 arrays and f32 probs."""
+    for t, nm in ((bag, "bag"), (x, "x"), (y, "y")):
+        _req_cuda(t, nm, torch.int32)
+    _req_cuda(prob, "prob", torch.float32)
+    if out is None:
+        out = torch.zeros((n_bags, H, W), dtype=torch.float32, device=bag.device)
+    check(lib().cs_paint_heatmap_xy(ptr(bag), ptr(x), ptr(y), ptr(prob), bag.numel(), H, W, tile,
+                                    n_bags, ptr(out), cur_stream()), "cs_paint_heatmap_xy")
+    return out
+
+
 def heatmap_to_gray(heat):
     """255 - np.uint8(255 * heat) with the float64 product numpy performs."""
     _req_cuda(heat, "heat", torch.float32)
@@ -200,6 +223,13 @@ class TileClassifier:
         self._h = handle
         self._ws = None
         self._ws_key = None
+
+    def set_fc(self, fc_w, fc_b):
+        """Updates fc_tile.1 on the device (the only weights MIL tile training changes)."""
+        fw = np.ascontiguousarray(fc_w.detach().cpu().numpy(), dtype=np.float32)
+        fb = np.ascontiguousarray(fc_b.detach().cpu().numpy(), dtype=np.float32)
+        with torch.cuda.device(self.device):
+            check(lib().cs_model_set_fc(self._h, fw.ctypes.data, fb.ctypes.data), "cs_model_set_fc")
 
     def close(self):
         if getattr(self, "_h", None):

@@ -1,0 +1,104 @@
+"""Heatmaps, pseudo-masks and HSV refinement (mirror of utils/image_processing.py).
+
+heatmap / generate_masks / preprocess_masks / remove_small_regions keep the reference
+signatures (utils/image_processing.py:146, 79, 114, 14).  Painting and the HSV-threshold AND run
+on the GPU (paint.cu, hsv_refine.cu); the connected-component clean-up of
+remove_small_regions is the reference's own host step (scikit-image there, scipy.ndimage here —
+SURVEY 8f N1) and PNG/CSV writing stays on the host.
+"""
+import csv
+import os
+
+import numpy as np
+import torch
+
+from . import _cc
+from .. import ops
+
+
+def _cuda_dev():
+    return torch.device("cuda", torch.cuda.current_device())
+
+
+def _imsave(path, rgb):
+    import cv2
+    cv2.imwrite(path, np.ascontiguousarray(rgb[..., ::-1]) if rgb.ndim == 3 else rgb)
+
+
+def remove_small_regions(img_bin, min_object_size, hole_area_threshold):
+    """utils/image_processing.py:14-17: remove_small_objects then remove_small_holes."""
+    return _cc.remove_small_holes(_cc.remove_small_objects(img_bin, min_object_size), hole_area_threshold)
+
+
+def _xy_tensors(tiles, groups, dev):
+    tiles = np.asarray(tiles).reshape(-1, 2).astype(np.int32)
+    g = torch.from_numpy(np.ascontiguousarray(np.asarray(groups).astype(np.int32))).to(dev)
+    x = torch.from_numpy(np.ascontiguousarray(tiles[:, 0])).to(dev)
+    y = torch.from_numpy(np.ascontiguousarray(tiles[:, 1])).to(dev)
+    return g, x, y
+
+
+def hsv_refine_batch(images_dev, masks_dev, v_thresh=170):
+    """Lines 117-120 of preprocess_masks for a whole bag array on the device (u8 0/1)."""
+    return ops.hsv_refine(images_dev, masks_dev, v_thresh)
+
+
+def preprocess_masks(img, mask):
+    """utils/image_processing.py:114-124 for one image: GPU HSV-threshold AND, host CC clean-up."""
+    dev = _cuda_dev()
+    d_img = torch.from_numpy(np.ascontiguousarray(img, dtype=np.uint8)).to(dev)
+    d_mask = torch.from_numpy(np.ascontiguousarray(np.asarray(mask) != 0).astype(np.uint8)).to(dev)
+    refined = ops.hsv_refine(d_img, d_mask, 170).cpu().numpy().astype(bool)
+    return remove_small_regions(refined, min_object_size=400, hole_area_threshold=120)
+
+
+def generate_masks(dataset, tiles, groups, preprocess, save_masks=True, output_path="./data/pseudomask"):
+    """Transform predicted pos cell regions into binary masks (utils/image_processing.py:79-111)."""
+    os.makedirs(os.path.join(output_path, "rgb"), exist_ok=True)
+    os.makedirs(os.path.join(output_path, "mask"), exist_ok=True)
+    dev = _cuda_dev()
+    n = len(dataset.images)
+    H, W = int(dataset.image_size[0]), int(dataset.image_size[1])
+    g, x, y = _xy_tensors(tiles, groups, dev)
+    masks_dev = ops.paint_mask_xy(g, x, y, n, H, W, dataset.tile_size)
+    if preprocess:
+        masks_dev = ops.hsv_refine(dataset.device_images(dev), masks_dev, 170)
+    pseudo_masks = masks_dev.cpu().numpy()
+    for i, img in enumerate(dataset.images):
+        if preprocess:
+            pseudo_masks[i] = remove_small_regions(pseudo_masks[i].astype(bool), min_object_size=400,
+                                                   hole_area_threshold=120)
+        if save_masks:
+            _imsave(os.path.join(output_path, "rgb/{:05}.png".format(i + 1)), np.uint8(img))
+            _imsave(os.path.join(output_path, "mask/{:05}.png".format(i + 1)), np.uint8(pseudo_masks[i] * 255))
+    if save_masks:
+        print("Original images & masks saved in \'{}\'.".format(output_path))
+    return pseudo_masks
+
+
+def heatmap_arrays(testset, tiles, probs, groups):
+    """u8 [n,H,W,3] blended heatmaps of heatmap() without file output."""
+    import cv2
+    dev = _cuda_dev()
+    n = len(testset.images)
+    H, W = int(testset.image_size[0]), int(testset.image_size[1])
+    g, x, y = _xy_tensors(tiles, groups, dev)
+    p = torch.from_numpy(np.ascontiguousarray(np.asarray(probs, dtype=np.float32))).to(dev)
+    heat = ops.paint_heatmap_xy(g, x, y, p, n, H, W, testset.tile_size)
+    gray = ops.heatmap_to_gray(heat).cpu().numpy()
+    out = np.empty((n, H, W, 3), np.uint8)
+    for i, img in enumerate(testset.images):
+        cm = cv2.applyColorMap(gray[i], cv2.COLORMAP_JET)          # :165
+        out[i] = cv2.addWeighted(np.asarray(img), 0.5, cm, 0.5, 0)  # :166
+    return out
+
+
+def heatmap(testset, tiles, probs, groups, csv_file, output_path):
+    """utils/image_processing.py:146-167: CSV row per kept tile + one blended PNG per image."""
+    w = csv.writer(csv_file)
+    for i, g in enumerate(groups):
+        grid = list(map(int, tiles[i]))
+        w.writerow([g, '{}'.format(grid), probs[i]])
+    imgs = heatmap_arrays(testset, tiles, probs, groups)
+    for i in range(len(testset.images)):
+        _imsave(os.path.join(output_path, "test_{:05}.png".format(i + 1)), imgs[i])

@@ -109,6 +109,9 @@ int cs_model_create(int arch, int n_convs, const float* const* conv_w_host,
                     const float* const* conv_b_host, const float* fc_w_host,
                     const float* fc_b_host, cs_model** out);
 int cs_model_destroy(cs_model* m);
+/* Replace fc_tile.1 (weight [2][512], bias [2], host pointers) after an optimizer step;
+ * the encoder is frozen in tile mode (model/resnet.py:315-319) so nothing else changes. */
+int cs_model_set_fc(cs_model* m, const float* fc_w_host, const float* fc_b_host);
 
 /* Bytes of device workspace cs_model_forward_tiles needs for batches of up to
  * `max_batch` instances of `tile` x `tile` pixels at `precision`. */
@@ -202,6 +205,15 @@ int cs_paint_mask(const int32_t* sel_idx, int64_t n_sel, int H, int W, int tile,
 int cs_paint_heatmap(const int32_t* sel_idx, const float* sel_prob, int64_t n_sel, int H,
                      int W, int tile, int interval, int bag_base, int n_bags,
                      float* heat_out, void* stream);
+
+/* Same two painting loops for explicit tile lists, the form the reference API passes
+ * around (`tiles` [n][2] = (row, col) and `groups` [n] = bag): tiles outside the image
+ * or bag range are ignored. */
+int cs_paint_mask_xy(const int32_t* bag, const int32_t* x, const int32_t* y, int64_t n_sel,
+                     int H, int W, int tile, int n_bags, uint8_t* mask_out, void* stream);
+int cs_paint_heatmap_xy(const int32_t* bag, const int32_t* x, const int32_t* y,
+                        const float* prob, int64_t n_sel, int H, int W, int tile, int n_bags,
+                        float* heat_out, void* stream);
 
 /* `255 - np.uint8(255 * masks[i])` (utils/image_processing.py:165) evaluated in
  * float64 exactly like numpy: gray_out u8 [n] = 255 - (uint8)(255.0 * (double)heat). */

@@ -1,0 +1,175 @@
+"""GPU tests of the reference-facing Python surfaces (drop-in API) against the oracle / goldens."""
+import io
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from conftest import golden
+from oracle import masks as omasks, model as omodel, select as oselect, synth, tiles as otiles
+
+pytestmark = pytest.mark.gpu
+
+
+def _model(arch, sd, cuda, precision):
+    from cellsegmentation_b200.model import nets
+    from cellsegmentation_b200.model.resnet import MILresnet18, MILresnet34
+    net = {"resnet18": MILresnet18, "resnet34": MILresnet34}[arch]()
+    missing, unexpected = net.load_state_dict(sd, strict=False)
+    assert not unexpected and not missing, (missing, unexpected)
+    net.setmode("tile")
+    net.precision = precision
+    net.max_batch = 512
+    assert "resnet34" in nets and isinstance(nets["resnet34"], type(net))
+    return net.to(cuda)
+
+
+def _trainset(n_bags=3, interval=20):
+    from cellsegmentation_b200.dataset import LystoDataset
+    bags = synth.make_bags(n_bags, seed=11)
+    return bags, LystoDataset.from_arrays(list(bags), [4, 0, 9][:n_bags], 32, interval)
+
+
+@pytest.mark.parametrize("precision,tol", [("fp32", 1e-4), ("bf16", 2e-2)])
+def test_inference_tiles_dataset_path_matches_reference_golden(cuda, precision, tol):
+    from cellsegmentation_b200.inference import inference_tiles
+    g = golden("model_resnet34.npz")
+    bags, ds = _trainset()
+    ds.setmode(1)
+    x = torch.from_numpy(otiles.unfold(list(bags[1:]), 20, 32))
+    sd = omodel.calibrate_head(omodel.make_state_dict("resnet34", seed=3), x[::3], "resnet34")
+    net = _model("resnet34", sd, cuda, precision)
+    loader = torch.utils.data.DataLoader(ds, batch_size=64, shuffle=False)
+    probs = inference_tiles(loader, net, cuda, mode="train")
+    assert probs.dtype == np.float32 and probs.shape == (450,)
+    assert np.abs(probs - g["probs"]).max() < tol          # reference's own inference_tiles output
+    # drop-in module call on a materialised batch == reference logits
+    net.eval()
+    logits = net(x[:16].to(cuda)).detach().cpu().numpy()
+    assert np.abs(logits - g["logits16"]).max() < (1e-3 if precision == "fp32" else 0.15)
+    # __getitem__ compatibility (mode 1): same tensor the reference's dataset returns
+    t, lab = ds[14]
+    gt = golden("transform.npz")
+    assert np.array_equal(t.numpy().view(np.uint32), gt["tiles"][list(gt["pick"]).index(14)].view(np.uint32))
+    assert lab == 0 or lab == ds.labels[ds.tileIDX[14]]
+
+
+def test_sample_rebuilds_reference_selection(cuda, capsys):
+    from cellsegmentation_b200.dataset import LystoDataset
+    from cellsegmentation_b200.inference import sample, sample_indices
+    g = golden("select.npz")
+    bag = synth.make_bags(1, seed=1)[0]
+    for case in ("toy", "ties", "nan", "wrapbig", "k0"):
+        lab = g[case + "_labels"]
+        ds = LystoDataset.from_arrays([bag] * len(lab), lab, 32, 20)
+        ds.setmode(1)
+        tpp, tk = (int(v) for v in g[case + "_params"])
+        idx, pl = sample_indices(ds, g[case + "_probs"], tpp, tk)
+        assert np.array_equal(idx, g[case + "_idx"])
+        assert np.array_equal(pl, oselect.pseudo_labels(g[case + "_tileIDX"], lab, g[case + "_idx"]))
+    # full sample(): same train_data as the oracle restatement of make_train_data
+    lab = g["toy_labels"]
+    ds = LystoDataset.from_arrays([bag] * len(lab), lab, 32, 20)
+    ds.setmode(1)
+    grid = otiles.get_tiles((299, 299, 3), 20, 32)
+    tiles_grid = [grid[i % 225] for i in range(len(g["toy_tileIDX"]))]
+    np.random.seed(5)
+    want, wp, wn = oselect.make_train_data(g["toy_tileIDX"], tiles_grid, lab, g["toy_idx"], 0.5)
+    np.random.seed(5)
+    sample(ds, g["toy_probs"], 1, 30, 0.5)
+    assert "Training data is sampled. (Pos samples: %d | Neg samples: %d)" % (wp, wn) in capsys.readouterr().out
+    assert [int(r[0]) for r in want] == list(ds.train_data["bag"])
+    assert [tuple(r[1]) for r in want] == list(zip(ds.train_data["x"].tolist(), ds.train_data["y"].tolist()))
+    ds.setmode(3)
+    assert len(ds) == len(want)
+    t, l = ds[0]
+    b, (x, y), wl = want[0]
+    assert np.array_equal(t.numpy(), otiles.normalize_tile(bag[x:x + 32, y:y + 32])) and l == wl
+
+
+def test_rank_and_evaluate_tile_match_reference(cuda):
+    from cellsegmentation_b200.dataset import LystoDataset
+    from cellsegmentation_b200.evaluate import evaluate_tile
+    from cellsegmentation_b200.inference import rank
+    bag = synth.make_bags(1, seed=2)[0]
+    g = golden("rank.npz")
+    ds = LystoDataset.from_arrays([bag] * 4, [1, 2, 3, 4], 32, 20)
+    tiles, probs, groups = rank(ds, g["probs"], float(g["threshold"]))
+    assert np.array_equal(tiles.astype(np.int32), g["tiles"])
+    assert np.array_equal(probs.view(np.uint32), g["kept_probs"].view(np.uint32))
+    assert np.array_equal(groups.astype(np.int32), g["groups"])
+    e = golden("evaluate.npz")
+    dse = LystoDataset.from_arrays([bag] * 5, e["labels"], 32, 20)
+    out = evaluate_tile(dse, e["probs"], int(e["params"][0]), float(e["params"][1]))
+    assert np.allclose(out, e["out"], rtol=0, atol=1e-15)
+
+
+def test_heatmap_and_generate_masks_match_reference(cuda, tmp_path):
+    import types
+    from cellsegmentation_b200 import utils
+    g = golden("masks.npz")
+    small = synth.make_bags(3, H=96, W=96, seed=31)
+    grid = np.array(otiles.get_tiles((96, 96, 3), 5, 16), np.int32)
+    T = len(grid)
+    keep = g["kept"]
+    k_tiles, k_probs, k_groups = grid[keep % T], g["probs"][keep], keep // T
+
+    class Fake:
+        images = list(small)
+        image_size = np.array([96, 96])
+        tile_size = 16
+
+        def device_images(self, dev):
+            return torch.from_numpy(small).to(dev)
+
+    fake = Fake()
+    csvf = io.StringIO(newline="")
+    utils.heatmap(fake, k_tiles, k_probs, k_groups, csvf, str(tmp_path))
+    # the golden text was read back with universal newlines; the writer emits \r\n like the reference
+    assert csvf.getvalue().replace("\r\n", "\n").encode() == g["csv"].tobytes()
+    import cv2
+    for i in range(3):
+        img = cv2.imread(os.path.join(str(tmp_path), "test_%05d.png" % (i + 1)))[..., ::-1]
+        assert np.array_equal(img, g["heat_imgs"][i])
+    raw = utils.generate_masks(fake, k_tiles, k_groups, preprocess=False, save_masks=False,
+                               output_path=str(tmp_path))
+    assert np.array_equal(raw, g["raw"])
+    full = utils.generate_masks(fake, k_tiles, k_groups, preprocess=True, save_masks=True,
+                                output_path=str(tmp_path))
+    assert np.array_equal(full.astype(np.uint8), g["full"])
+    m = cv2.imread(os.path.join(str(tmp_path), "mask", "00002.png"), cv2.IMREAD_GRAYSCALE)
+    assert np.array_equal(m, g["full"][1] * 255)
+    one = utils.preprocess_masks(small[0], g["raw"][0])
+    assert np.array_equal(one.astype(np.uint8), g["full"][0])
+
+
+def test_train_tile_updates_only_fc_tile(cuda):
+    from cellsegmentation_b200.inference import inference_tiles, sample
+    from cellsegmentation_b200.train import train_tile
+    bags, ds = _trainset()
+    ds.setmode(1)
+    x = torch.from_numpy(otiles.unfold(list(bags[1:]), 20, 32))
+    sd = omodel.calibrate_head(omodel.make_state_dict("resnet34", seed=3), x[::3], "resnet34")
+    net = _model("resnet34", sd, cuda, "bf16")
+    loader = torch.utils.data.DataLoader(ds, batch_size=64, shuffle=True)
+    probs = inference_tiles(loader, net, cuda)
+    np.random.seed(0)
+    sample(ds, probs, 1, 30, 0.5)
+    ds.setmode(3)
+    enc_before = net.layer3[2].conv1.weight.detach().clone()
+    fc_before = net.fc_tile[1].weight.detach().clone()
+    opt = torch.optim.Adam(filter(lambda p: p.requires_grad, net.parameters()), lr=1e-5, weight_decay=1e-4)
+    crit = torch.nn.CrossEntropyLoss()
+    losses = [train_tile(loader, e, 6, net, cuda, crit, opt, None, 1.) for e in range(1, 7)]
+    assert all(np.isfinite(losses)) and losses[-1] < losses[0]
+    assert torch.equal(enc_before, net.layer3[2].conv1.weight.detach())
+    assert not torch.equal(fc_before, net.fc_tile[1].weight.detach())
+    # the device-side fc follows the optimizer: probabilities change, and match the module's own head
+    ds.setmode(1)
+    probs2 = inference_tiles(loader, net, cuda)
+    assert np.abs(probs2 - probs).max() > 1e-6
+    net.eval()
+    with torch.no_grad():
+        p_mod = torch.softmax(net(x[:64].to(cuda)), 1)[:, 1].cpu().numpy()
+    assert np.abs(p_mod - probs2[:64]).max() < 1e-4
