@@ -23,6 +23,7 @@ SOURCES = [
     "fwd_fp32.cu",
     "fwd_tc.cu",
     "stem_tc.cu",
+    "conv_halo.cu",
     "model.cu",
 ]
 

@@ -1,0 +1,237 @@
+// K2b: stride-1 3x3 convolutions of the 8x8 (64 ch) and 4x4 (128 ch) stages with y-halo tiles.
+//
+// Reference: BasicBlock conv1 / conv2 of layer1 and layer2 (model/resnet.py:19-23, 28-43).
+//
+// The generic kernel (fwd_tc.cu) fetches one shifted 128-row box per tap: 9 L2 reads of the
+// same activations and 9 reads of the weights per M tile, and the launch list shows those
+// layers pinned at the L2->SM bandwidth.  Here a K step fetches ONE box per horizontal shift
+// dx that also carries a one-pixel halo in y:
+//     tensor map dims {C, W, T, H}  (instances before rows!)   box {64, W, IMG, H + 2} at
+//     (c0, dx - 1, t0, -1)  ->  shared rows ordered  r = x + W * (img + IMG * y'),  y' = y + 1
+// so the three vertical taps dy are the SAME tile read from a start address moved by
+// dy * W * IMG rows = dy * 2 KB (8x8) or dy * 4 KB (4x4): whole 1024-byte swizzle atoms,
+// i.e. just another UMMA descriptor.  TMA's out-of-bounds zero fill provides the padding in
+// x (shifted start) and y (halo rows -1 and H).  A traffic per M tile drops from 9 to 3.75
+// (8x8) / 4.5 (4x4) tiles; with 64 channels the 72 KB of weights stay resident in shared
+// memory for the whole kernel.  M row r of the accumulator is pixel (oy = r / (W*IMG),
+// img = (r / W) % IMG, ox = r % W); the epilogue maps it back to [instance][y][x][c].
+//
+// Warp roles as in fwd_tc.cu: warp 0 TMA, warp 1 MMA issue, warps 2-9 epilogue.
+#include "fwd.cuh"
+#include "gemm_epilogue.cuh"
+
+namespace cs {
+namespace {
+
+constexpr int kHaloThreads = 320;
+
+template <int BN, int W, int CCH, bool BRES>
+struct HaloCfg {
+  static constexpr int kImg = 128 / (W * W);            // instances per M tile
+  static constexpr int kRowsY = W * kImg;               // accumulator rows per output y
+  static constexpr int kHaloRows = kRowsY * (W + 2);
+  static constexpr uint32_t kABytes = kHaloRows * 128;  // 20 KB (8x8) / 24 KB (4x4)
+  static constexpr uint32_t kBTile = BN * 128;
+  static constexpr uint32_t kStageBytes = kABytes + (BRES ? 0 : 3 * kBTile);
+  static constexpr int kStages = BRES ? 5 : 3;
+  static constexpr uint32_t kBResBytes = BRES ? 9 * CCH * kBTile : 0;
+  static constexpr uint32_t kBarOffset = kStages * kStageBytes + kBResBytes;
+  static constexpr uint32_t kSmemBytes = kBarOffset + 256 + 1024;
+  static constexpr int kSteps = 3 * CCH;                // (dx, channel chunk)
+  static constexpr uint32_t kTmemCols = 2 * BN;
+  static_assert(kABytes % 1024 == 0 && kStageBytes % 1024 == 0, "stages must keep 1 KB alignment");
+  static_assert((kRowsY * 128) % 1024 == 0, "a dy shift must move whole swizzle atoms");
+};
+
+template <int BN, int W, int CCH, bool BRES>
+__global__ void __launch_bounds__(kHaloThreads, 1)
+conv_halo_kernel(const __grid_constant__ HaloParams p) {
+  using Cfg = HaloCfg<BN, W, CCH, BRES>;
+  constexpr int Cin = CCH * 64;
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t raw = smem_u32(smem_raw);
+  const uint32_t base = (raw + 1023u) & ~1023u;
+  uint8_t* base_ptr = smem_raw + (base - raw);
+  const uint32_t bres = base + Cfg::kStages * Cfg::kStageBytes;
+  const uint32_t bar_base = base + Cfg::kBarOffset;
+  auto full_bar = [&](int s) { return bar_base + 8u * s; };
+  auto empty_bar = [&](int s) { return bar_base + 8u * (Cfg::kStages + s); };
+  auto tfull_bar = [&](int a) { return bar_base + 8u * (2 * Cfg::kStages + a); };
+  auto tempty_bar = [&](int a) { return bar_base + 8u * (2 * Cfg::kStages + 2 + a); };
+  const uint32_t bres_bar = bar_base + 8u * (2 * Cfg::kStages + 4);
+  volatile uint32_t* tmem_slot =
+      reinterpret_cast<volatile uint32_t*>(base_ptr + Cfg::kBarOffset + 8 * (2 * Cfg::kStages + 5));
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+  if (warp == 0 && lane == 0) {
+    for (int s = 0; s < Cfg::kStages; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
+    for (int a = 0; a < 2; ++a) { mbar_init(tfull_bar(a), 1); mbar_init(tempty_bar(a), 256); }
+    mbar_init(bres_bar, 1);
+    fence_barrier_init();
+    prefetch_tmap(&p.a_map);
+    prefetch_tmap(&p.b_map);
+  }
+  if (warp == 1) tmem_alloc(smem_u32((const void*)tmem_slot), Cfg::kTmemCols);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      if (BRES) {
+        mbar_expect_tx(bres_bar, Cfg::kBResBytes);
+        for (int t = 0; t < 9 * CCH; ++t)   // tile index = tap * CCH + chunk = K column / 64
+          tma_load_2d(bres + t * Cfg::kBTile, &p.b_map, bres_bar, t * 64, 0);
+      }
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int m_tile = blockIdx.x; m_tile < p.num_m_tiles; m_tile += gridDim.x) {
+        for (int s = 0; s < Cfg::kSteps; ++s) {
+          const int dx = s / CCH, ch = s - dx * CCH;
+          mbar_wait(empty_bar(stage), phase ^ 1u);
+          const uint32_t a_dst = base + stage * Cfg::kStageBytes;
+          mbar_expect_tx(full_bar(stage), Cfg::kStageBytes);
+          tma_load_4d(a_dst, &p.a_map, full_bar(stage), ch * 64, dx - 1, m_tile * Cfg::kImg, -1);
+          if (!BRES) {
+            for (int dy = 0; dy < 3; ++dy)
+              tma_load_2d(a_dst + Cfg::kABytes + dy * Cfg::kBTile, &p.b_map, full_bar(stage),
+                          (dy * 3 + dx) * Cin + ch * 64, 0);
+          }
+          if (++stage == Cfg::kStages) { stage = 0; phase ^= 1u; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      constexpr uint32_t idesc = umma_idesc_bf16(128, BN);
+      if (BRES) mbar_wait(bres_bar, 0);
+      int stage = 0, acc = 0;
+      uint32_t phase = 0, acc_phase = 0;
+      for (int m_tile = blockIdx.x; m_tile < p.num_m_tiles; m_tile += gridDim.x) {
+        mbar_wait(tempty_bar(acc), acc_phase ^ 1u);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + (uint32_t)(acc * BN);
+        for (int s = 0; s < Cfg::kSteps; ++s) {
+          const int dx = s / CCH, ch = s - dx * CCH;
+          mbar_wait(full_bar(stage), phase);
+          tc_fence_after();
+          const uint32_t a_src = base + stage * Cfg::kStageBytes;
+#pragma unroll
+          for (int dy = 0; dy < 3; ++dy) {
+            const uint64_t a_desc = umma_desc_sw128(a_src + dy * (Cfg::kRowsY * 128));
+            const uint32_t b_src = BRES ? bres + ((dy * 3 + dx) * CCH + ch) * Cfg::kBTile
+                                        : a_src + Cfg::kABytes + dy * Cfg::kBTile;
+            const uint64_t b_desc = umma_desc_sw128(b_src);
+#pragma unroll
+            for (int k = 0; k < 4; ++k)
+              umma_bf16(d_tmem, a_desc + (uint64_t)(2 * k), b_desc + (uint64_t)(2 * k), idesc,
+                        (s > 0 || dy > 0 || k > 0) ? 1u : 0u);
+          }
+          umma_commit(empty_bar(stage));
+          if (++stage == Cfg::kStages) { stage = 0; phase ^= 1u; }
+        }
+        umma_commit(tfull_bar(acc));
+        acc ^= 1;
+        if (acc == 0) acc_phase ^= 1u;
+      }
+    }
+  } else {
+    const int quad = warp & 3;
+    const int half = (warp - 2) >> 2;
+    constexpr int kColsPerWarp = BN / 2;
+    const int r = quad * 32 + lane;
+    const int oy = r / Cfg::kRowsY, img = (r % Cfg::kRowsY) / W, ox = r % W;
+    const EpiArgs ea{p.bias, p.res_hi, p.res_lo, p.out_hi, p.out_lo, p.out_f32, p.relu};
+    int acc = 0;
+    uint32_t acc_phase = 0;
+    for (int m_tile = blockIdx.x; m_tile < p.num_m_tiles; m_tile += gridDim.x) {
+      const int64_t inst = (int64_t)m_tile * Cfg::kImg + img;
+      const int64_t row = inst * (W * W) + oy * W + ox;
+      const int col0 = half * kColsPerWarp;
+      epilogue_warp<kColsPerWarp / 32>(
+          ea, inst < p.n_inst, row * (int64_t)BN + col0, col0,
+          tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(acc * BN + col0), tfull_bar(acc),
+          acc_phase);
+      tc_fence_before();
+      mbar_arrive(tempty_bar(acc));
+      acc ^= 1;
+      if (acc == 0) acc_phase ^= 1u;
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, Cfg::kTmemCols);
+  }
+}
+
+template <int BN, int W, int CCH, bool BRES>
+int launch_halo(const HaloParams& p, cudaStream_t st) {
+  using Cfg = HaloCfg<BN, W, CCH, BRES>;
+  static bool attr_done[64] = {false};
+  int dev = 0;
+  CS_CUDA(cudaGetDevice(&dev));
+  if (dev >= 64 || !attr_done[dev]) {
+    CS_CUDA(cudaFuncSetAttribute(conv_halo_kernel<BN, W, CCH, BRES>,
+                                 cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg::kSmemBytes));
+    if (dev < 64) attr_done[dev] = true;
+  }
+  int grid = p.num_m_tiles < kNumSMs ? p.num_m_tiles : kNumSMs;
+  conv_halo_kernel<BN, W, CCH, BRES><<<grid, kHaloThreads, Cfg::kSmemBytes, st>>>(p);
+  CS_LAUNCH_CHECK();
+  return CS_OK;
+}
+
+}  // namespace
+
+bool halo_supported(int W, int Cin, int Cout) {
+  return (W == 8 && Cin == 64 && Cout == 64) || (W == 4 && Cin == 128 && Cout == 128);
+}
+
+int launch_conv_halo(const HaloParams& p, int W, int Cin, cudaStream_t st) {
+  if (p.num_m_tiles <= 0) return CS_OK;
+  if (W == 8 && Cin == 64) return launch_halo<64, 8, 1, true>(p, st);
+  if (W == 4 && Cin == 128) return launch_halo<128, 4, 2, false>(p, st);
+  set_error("launch_conv_halo: unsupported geometry W=%d Cin=%d", W, Cin);
+  return CS_ERR_UNSUPPORTED;
+}
+
+// {C, W, T, H} map with a {64, W, IMG, H + 2} box: instances sit between x and y in the box
+// order so that a vertical tap is a whole-atom shift of the shared-memory tile.
+int make_act_map_halo(CUtensorMap* map, const void* base, int C, int W, int H, int64_t T) {
+  typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*,
+                                    const cuuint64_t*, const cuuint64_t*, const cuuint32_t*,
+                                    const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                    CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+  static EncodeTiledFn enc = nullptr;
+  if (!enc) {
+    void* ptr = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    CS_CUDA(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &ptr, cudaEnableDefault, &qres));
+    if (qres != cudaDriverEntryPointSuccess || !ptr) {
+      set_error("cuTensorMapEncodeTiled is not available from this driver");
+      return CS_ERR_CUDA;
+    }
+    enc = reinterpret_cast<EncodeTiledFn>(ptr);
+  }
+  const int img = 128 / (W * H);
+  cuuint64_t dims[4] = {(cuuint64_t)C, (cuuint64_t)W, (cuuint64_t)T, (cuuint64_t)H};
+  cuuint64_t strides[3] = {(cuuint64_t)C * 2, (cuuint64_t)H * W * C * 2, (cuuint64_t)W * C * 2};
+  cuuint32_t box[4] = {64, (cuuint32_t)W, (cuuint32_t)img, (cuuint32_t)(H + 2)};
+  cuuint32_t estr[4] = {1, 1, 1, 1};
+  CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(base), dims, strides,
+                   box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                   CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    set_error("cuTensorMapEncodeTiled(halo C=%d W=%d H=%d T=%lld) failed: %d", C, W, H, (long long)T,
+              (int)r);
+    return CS_ERR_CUDA;
+  }
+  return CS_OK;
+}
+
+}  // namespace cs

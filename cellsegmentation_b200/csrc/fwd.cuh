@@ -76,6 +76,24 @@ int make_act_map_4d(CUtensorMap* map, const void* base, int C, int W, int H, int
 int make_mat_map_2d(CUtensorMap* map, const void* base, int64_t K, int64_t rows,
                     int64_t row_pitch_elems, int box_rows);
 
+// Stride-1 3x3 conv with y-halo tiles (conv_halo.cu): 8x8x64 and 4x4x128 stages.
+struct HaloParams {
+  CUtensorMap a_map;  // make_act_map_halo
+  CUtensorMap b_map;  // [Cout][9*Cin] K-major, box {64, Cout}
+  int num_m_tiles;    // ceil(instances / (128 / (W*W)))
+  int64_t n_inst;     // instances that exist
+  const float* bias;
+  const __nv_bfloat16* res_hi;
+  const __nv_bfloat16* res_lo;
+  __nv_bfloat16* out_hi;
+  __nv_bfloat16* out_lo;
+  float* out_f32;
+  int relu;
+};
+bool halo_supported(int W, int Cin, int Cout);
+int launch_conv_halo(const HaloParams& p, int W, int Cin, cudaStream_t st);
+int make_act_map_halo(CUtensorMap* map, const void* base, int C, int W, int H, int64_t T);
+
 struct StemArgs {
   // source A: u8 images + uniform grid
   const uint8_t* img;

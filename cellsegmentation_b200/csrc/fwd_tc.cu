@@ -25,7 +25,7 @@
 //   residual of the next 32-column chunk is fetched (256-bit loads) before the accumulator
 //   wait / while the current chunk is converted and stored.
 #include "fwd.cuh"
-#include "tc_ptx.cuh"
+#include "gemm_epilogue.cuh"
 
 namespace cs {
 namespace {
@@ -149,98 +149,18 @@ conv_gemm_kernel(const __grid_constant__ GemmParams p) {
     const int quad = warp & 3;
     const int half = (warp - 2) >> 2;
     constexpr int kColsPerWarp = BN / 2;
-    constexpr int kChunks = kColsPerWarp / 32;   // 32-column chunks per warp: 1, 2 or 4
     const int row_in_tile = quad * 32 + lane;
-    const bool has_res_hi = p.res_hi != nullptr, has_res_lo = p.res_lo != nullptr;
+    const EpiArgs ea{p.bias, p.res_hi, p.res_lo, p.out_hi, p.out_lo, p.out_f32, p.relu};
     int acc = 0;
     uint32_t acc_phase = 0;
     for (int w = blockIdx.x; w < num_work; w += gridDim.x) {
       const int m_tile = w / p.num_n_tiles, n_tile = w - m_tile * p.num_n_tiles;
       const int64_t row = (int64_t)m_tile * kGemmBM + row_in_tile;
-      const bool row_ok = row < p.m_valid;
       const int col0 = n_tile * BN + half * kColsPerWarp;
-      const int64_t off0 = row * (int64_t)p.n_total + col0;
-
-      // residual of chunk c: 32 bf16 hi + 32 bf16 lo per row, fetched one chunk ahead
-      U32x8 rh[2][2], rl[2][2];
-      auto load_res = [&](int c, int slot) {
-        if (row_ok && has_res_hi) {
-          rh[slot][0] = ldg256(p.res_hi + off0 + c * 32);
-          rh[slot][1] = ldg256(p.res_hi + off0 + c * 32 + 16);
-        }
-        if (row_ok && has_res_lo) {
-          rl[slot][0] = ldg256(p.res_lo + off0 + c * 32);
-          rl[slot][1] = ldg256(p.res_lo + off0 + c * 32 + 16);
-        }
-      };
-      load_res(0, 0);
-      mbar_wait(tfull_bar(acc), acc_phase);
-      tc_fence_after();
-#pragma unroll
-      for (int c = 0; c < kChunks; ++c) {
-        const int slot = c & 1;
-        if (c + 1 < kChunks) load_res(c + 1, slot ^ 1);
-        uint32_t r[32];
-        tmem_ld32(tmem_base + ((uint32_t)(quad * 32) << 16) +
-                      (uint32_t)(acc * BN + half * kColsPerWarp + c * 32), r);
-        tmem_ld_wait();
-        if (row_ok) {
-          const int64_t off = off0 + c * 32;
-          float v[32];
-          const float4* b4 = reinterpret_cast<const float4*>(p.bias + col0 + c * 32);
-#pragma unroll
-          for (int j = 0; j < 8; ++j) {
-            float4 bb = __ldg(b4 + j);
-            v[4 * j + 0] = __uint_as_float(r[4 * j + 0]) + bb.x;
-            v[4 * j + 1] = __uint_as_float(r[4 * j + 1]) + bb.y;
-            v[4 * j + 2] = __uint_as_float(r[4 * j + 2]) + bb.z;
-            v[4 * j + 3] = __uint_as_float(r[4 * j + 3]) + bb.w;
-          }
-          if (has_res_hi) {
-#pragma unroll
-            for (int j = 0; j < 16; ++j) {
-              const uint32_t q = rh[slot][j >> 3].v[j & 7];
-              v[2 * j] += bf16_lo_f(q);
-              v[2 * j + 1] += bf16_hi_f(q);
-            }
-          }
-          if (has_res_lo) {
-#pragma unroll
-            for (int j = 0; j < 16; ++j) {
-              const uint32_t q = rl[slot][j >> 3].v[j & 7];
-              v[2 * j] += bf16_lo_f(q);
-              v[2 * j + 1] += bf16_hi_f(q);
-            }
-          }
-          if (p.relu) {
-#pragma unroll
-            for (int j = 0; j < 32; ++j) v[j] = fmaxf(v[j], 0.f);
-          }
-          if (p.out_f32) {
-            float4* of = reinterpret_cast<float4*>(p.out_f32 + off);
-#pragma unroll
-            for (int j = 0; j < 8; ++j)
-              of[j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
-          }
-          U32x8 hi[2];
-#pragma unroll
-          for (int j = 0; j < 16; ++j) hi[j >> 3].v[j & 7] = pack_bf16x2(v[2 * j], v[2 * j + 1]);
-          if (p.out_hi) {
-            stg256(p.out_hi + off, hi[0]);
-            stg256(p.out_hi + off + 16, hi[1]);
-          }
-          if (p.out_lo) {
-            U32x8 lo[2];
-#pragma unroll
-            for (int j = 0; j < 16; ++j) {
-              const uint32_t h = hi[j >> 3].v[j & 7];
-              lo[j >> 3].v[j & 7] = pack_bf16x2(v[2 * j] - bf16_lo_f(h), v[2 * j + 1] - bf16_hi_f(h));
-            }
-            stg256(p.out_lo + off, lo[0]);
-            stg256(p.out_lo + off + 16, lo[1]);
-          }
-        }
-      }
+      epilogue_warp<kColsPerWarp / 32>(
+          ea, row < p.m_valid, row * (int64_t)p.n_total + col0, col0,
+          tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(acc * BN + half * kColsPerWarp),
+          tfull_bar(acc), acc_phase);
       tc_fence_before();
       mbar_arrive(tempty_bar(acc));
       acc ^= 1;

@@ -27,6 +27,12 @@ uint16_t f32_to_bf16_rn(float f) {
   return (uint16_t)(u >> 16);
 }
 
+// Diagnostics: CELLSEG_HALO=0 keeps every shifted-box conv on the generic kernel.
+const bool g_disable_halo = []() {
+  const char* e = getenv("CELLSEG_HALO");
+  return e != nullptr && strcmp(e, "0") == 0;
+}();
+
 struct ConvW {
   int cin = 0, cout = 0, k = 0, stride = 1, pad = 0;
   std::vector<float> w;  // OIHW, BN folded
@@ -49,6 +55,9 @@ struct PlannedConv {
   int BN = 0;
   bool dense = false;
   int Po = 0;  // output pixels per instance
+  bool halo = false;  // stride-1 3x3 on 8x8x64 / 4x4x128: y-halo kernel (conv_halo.cu)
+  HaloParams hp;
+  int halo_W = 0, halo_Cin = 0;
   __nv_bfloat16* d_B = nullptr;
   float* d_bias = nullptr;
 };
@@ -244,8 +253,38 @@ int plan_conv(const ConvGeom& g, const float* w_oihw, const float* bias, const C
   rc = make_mat_map_2d(&pc.p.b_map, pc.d_B, K_cat, pc.p.n_total, K_cat, pc.BN);
   if (rc != CS_OK) { free_planned(pc); return rc; }
   pc.p.bias = pc.d_bias;
+  if (!pc.dense && !gds && g.stride == 1 && g.Hi == g.Wi && halo_supported(g.Wi, g.Cin, g.Cout) &&
+      !g_disable_halo) {
+    rc = make_act_map_halo(&pc.hp.a_map, in_hi, g.Cin, g.Wi, g.Hi, b_pad);
+    if (rc != CS_OK) { free_planned(pc); return rc; }
+    pc.hp.b_map = pc.p.b_map;
+    pc.hp.bias = pc.d_bias;
+    pc.halo = true;
+    pc.halo_W = g.Wi;
+    pc.halo_Cin = g.Cin;
+  }
   *out = pc;
   return CS_OK;
+}
+
+// Launches one planned convolution for `count` instances (pointers / relu taken from pc.p).
+int launch_planned(const PlannedConv& pc, int64_t count, float* out_f32, cudaStream_t st) {
+  if (pc.halo) {
+    HaloParams hp = pc.hp;
+    hp.res_hi = pc.p.res_hi; hp.res_lo = pc.p.res_lo;
+    hp.out_hi = pc.p.out_hi; hp.out_lo = pc.p.out_lo;
+    hp.out_f32 = out_f32;
+    hp.relu = pc.p.relu;
+    hp.n_inst = count;
+    hp.num_m_tiles = (int)ceil_div<int64_t>(count, kGemmBM / pc.Po);
+    return launch_conv_halo(hp, pc.halo_W, pc.halo_Cin, st);
+  }
+  GemmParams p = pc.p;
+  int64_t rows = pc.dense ? count : count * pc.Po;
+  p.m_valid = rows;
+  p.num_m_tiles = (int)ceil_div<int64_t>(rows, kGemmBM);
+  p.out_f32 = out_f32;
+  return launch_conv_gemm(p, pc.BN, st);
 }
 
 struct TcPlan {
@@ -391,11 +430,7 @@ int run_tc_batch(cs_model* m, const StemArgs& stem_in, int64_t count, float* pro
   if (rc != CS_OK) return rc;
   m->last_launches++;
   for (PlannedConv& pc : pl.layers) {
-    GemmParams p = pc.p;
-    int64_t rows = pc.dense ? count : count * pc.Po;
-    p.m_valid = rows;
-    p.num_m_tiles = (int)ceil_div<int64_t>(rows, kGemmBM);
-    rc = launch_conv_gemm(p, pc.BN, st);
+    rc = launch_planned(pc, count, nullptr, st);
     if (rc != CS_OK) return rc;
     m->last_launches++;
   }
@@ -728,13 +763,8 @@ int cs_debug_conv3x3_bf16(const void* in_hi, int64_t n, int Hi, int Wi, int Cin,
   rc = plan_conv(g, w_host, bias_host, nullptr, nullptr, nullptr,
                  reinterpret_cast<const __nv_bfloat16*>(in_hi), nullptr, n, &pc);
   if (rc != CS_OK) return rc;
-  GemmParams p = pc.p;
-  int64_t rows = pc.dense ? n : n * pc.Po;
-  p.m_valid = rows;
-  p.num_m_tiles = (int)ceil_div<int64_t>(rows, kGemmBM);
-  p.out_f32 = out_f32;
-  p.relu = 0;
-  rc = launch_conv_gemm(p, pc.BN, as_stream(stream));
+  pc.p.relu = 0;
+  rc = launch_planned(pc, n, out_f32, as_stream(stream));
   cudaError_t e = cudaStreamSynchronize(as_stream(stream));
   free_planned(pc);
   if (rc != CS_OK) return rc;
