@@ -117,6 +117,7 @@ stem_tc_kernel(const __grid_constant__ StemTcParams p) {
     // the global-load latency is hidden behind the im2col build of the current instance.
     uint32_t pre[24];
     const bool from_img = a.x == nullptr;
+    const int sy = tid >> 2, sq = tid & 3;
     auto prefetch = [&](int64_t t) {
       if (from_img) {
         int64_t inst = a.inst_begin + t;
@@ -125,29 +126,19 @@ stem_tc_kernel(const __grid_constant__ StemTcParams p) {
         int gy = tl / a.grid_w, gx = tl - gy * a.grid_w;
         int row0 = grid_coord(gy, a.H, kS, a.interval), col0 = grid_coord(gx, a.W, kS, a.interval);
         const uint8_t* src = a.img + ((bag * a.H + row0) * (int64_t)a.W + col0) * 3;
+        // thread -> tile row sy and a 24-element quarter sq of that row (8 pixels x 3 channels)
+        const uint8_t* rowp = src + (int64_t)sy * a.W * 3 + 24 * sq;
 #pragma unroll
-        for (int i = 0; i < 24; ++i) {
-          int e = tid + 128 * i;             // 0..3071 : y*96 + x*3 + c
-          int y = e / 96, r = e - y * 96;
-          pre[i] = __ldg(src + (int64_t)y * a.W * 3 + r);
-        }
+        for (int i = 0; i < 24; ++i) pre[i] = __ldg(rowp + i);
       } else {
-        const float* src = a.x + t * (int64_t)(3 * kS * kS);  // NCHW fp32, already normalised
+        const float* src = a.x + t * (int64_t)(3 * kS * kS) + sy * kS + 8 * sq;  // NCHW fp32
 #pragma unroll
-        for (int i = 0; i < 24; ++i) {
-          int e = tid + 128 * i;
-          int y = e / 96, r = e - y * 96;
-          int x = r / 3, c = r - x * 3;
-          pre[i] = __float_as_uint(__ldg(src + (c * kS + y) * kS + x));
-        }
+        for (int i = 0; i < 24; ++i)   // element i = pixel i/3, channel i%3
+          pre[i] = __float_as_uint(__ldg(src + (i % 3) * kS * kS + i / 3));
       }
     };
     auto staged_value = [&](int i) -> uint16_t {
-      if (from_img) {
-        int e = tid + 128 * i;
-        int r = e % 96;
-        return lut[(r % 3) * 256 + pre[i]];
-      }
+      if (from_img) return lut[(i % 3) * 256 + pre[i]];
       __nv_bfloat16 h = __float2bfloat16_rn(__uint_as_float(pre[i]));
       return *reinterpret_cast<uint16_t*>(&h);
     };
@@ -159,11 +150,11 @@ stem_tc_kernel(const __grid_constant__ StemTcParams p) {
     for (; t < n_inst; t += gridDim.x, ++it) {
       const int buf = it & 1;
       uint8_t* in_g = bp + Smem::in + buf * kInBytes;
+      {
+        // padded row sy + 3, elements 9 + 24*sq .. (3 pad pixels * 3 channels = 9)
+        uint16_t* dstp = reinterpret_cast<uint16_t*>(in_g + (sy + 3) * kInPitch) + 9 + 24 * sq;
 #pragma unroll
-      for (int i = 0; i < 24; ++i) {
-        int e = tid + 128 * i;
-        int y = e / 96, r = e - y * 96;
-        *reinterpret_cast<uint16_t*>(in_g + (y + 3) * kInPitch + (9 + r) * 2) = staged_value(i);  // (3 px)*3 ch = 9
+        for (int i = 0; i < 24; ++i) dstp[i] = staged_value(i);
       }
       named_bar(1, 128);
       if (t + gridDim.x < n_inst) prefetch(t + gridDim.x);
@@ -261,32 +252,39 @@ stem_tc_kernel(const __grid_constant__ StemTcParams p) {
         if (++acc == 4) { acc = 0; acc_phase ^= 1u; }
       }
       named_bar(2, 128);
-      // maxpool 3x3 / 2, pad 1 over the 16x16 map (values >= 0 after ReLU)
-#pragma unroll 1
-      for (int o = etid; o < 64 * 16; o += 128) {
-        const int c4 = o & 15, pp = o >> 4;
-        const int py = pp >> 3, px = pp & 7;
-        float4 mx = make_float4(0.f, 0.f, 0.f, 0.f);
+      // maxpool 3x3 / 2, pad 1 over the 16x16 map.  Values are >= 0 after ReLU, so the padding
+      // is "max with 0" and clamping a window index re-reads an element already in the window.
+      // Each thread owns one (output column px, channel quad c4) and slides down the 16 conv
+      // rows: 3 loads per row, every row shared by two vertically adjacent outputs.
+      {
+        const int c4 = etid & 15, px = etid >> 4;
+        const int ixa = (2 * px - 1) < 0 ? 0 : 2 * px - 1, ixb = 2 * px, ixc = 2 * px + 1;
+        const float* pa = conv_s + ixa * 64 + ((c4 ^ ixa) << 2);
+        const float* pb = conv_s + ixb * 64 + ((c4 ^ ixb) << 2);
+        const float* pc = conv_s + ixc * 64 + ((c4 ^ ixc) << 2);
+        auto hmax = [&](int iy) {
+          const float4 u = *reinterpret_cast<const float4*>(pa + iy * 16 * 64);
+          const float4 v = *reinterpret_cast<const float4*>(pb + iy * 16 * 64);
+          const float4 w = *reinterpret_cast<const float4*>(pc + iy * 16 * 64);
+          return make_float4(fmaxf(fmaxf(u.x, v.x), w.x), fmaxf(fmaxf(u.y, v.y), w.y),
+                             fmaxf(fmaxf(u.z, v.z), w.z), fmaxf(fmaxf(u.w, v.w), w.w));
+        };
+        float4 prev = make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
-        for (int dy = 0; dy < 3; ++dy) {
-          const int iy = 2 * py - 1 + dy;
-          if (iy < 0) continue;
-#pragma unroll
-          for (int dx = 0; dx < 3; ++dx) {
-            const int ix = 2 * px - 1 + dx;
-            if (ix < 0) continue;
-            const float4 v = *reinterpret_cast<const float4*>(conv_s + (iy * 16 + ix) * 64 + ((c4 ^ ix) << 2));
-            mx.x = fmaxf(mx.x, v.x); mx.y = fmaxf(mx.y, v.y);
-            mx.z = fmaxf(mx.z, v.z); mx.w = fmaxf(mx.w, v.w);
+        for (int py = 0; py < 8; ++py) {
+          const float4 h0 = hmax(2 * py), h1 = hmax(2 * py + 1);
+          float4 mx;
+          mx.x = fmaxf(fmaxf(prev.x, h0.x), h1.x); mx.y = fmaxf(fmaxf(prev.y, h0.y), h1.y);
+          mx.z = fmaxf(fmaxf(prev.z, h0.z), h1.z); mx.w = fmaxf(fmaxf(prev.w, h0.w), h1.w);
+          prev = h1;
+          const uint32_t h0p = pack_bf16x2(mx.x, mx.y), h1p = pack_bf16x2(mx.z, mx.w);
+          const int64_t off = (t * 64 + (py * 8 + px)) * 64 + c4 * 4;
+          *reinterpret_cast<uint2*>(a.out_hi + off) = make_uint2(h0p, h1p);
+          if (a.out_lo) {
+            const uint32_t l0 = pack_bf16x2(mx.x - bf16_lo_f(h0p), mx.y - bf16_hi_f(h0p));
+            const uint32_t l1 = pack_bf16x2(mx.z - bf16_lo_f(h1p), mx.w - bf16_hi_f(h1p));
+            *reinterpret_cast<uint2*>(a.out_lo + off) = make_uint2(l0, l1);
           }
-        }
-        const uint32_t h0 = pack_bf16x2(mx.x, mx.y), h1 = pack_bf16x2(mx.z, mx.w);
-        const int64_t off = (t * 64 + pp) * 64 + c4 * 4;
-        *reinterpret_cast<uint2*>(a.out_hi + off) = make_uint2(h0, h1);
-        if (a.out_lo) {
-          const uint32_t l0 = pack_bf16x2(mx.x - bf16_lo_f(h0), mx.y - bf16_hi_f(h0));
-          const uint32_t l1 = pack_bf16x2(mx.z - bf16_lo_f(h1), mx.w - bf16_hi_f(h1));
-          *reinterpret_cast<uint2*>(a.out_lo + off) = make_uint2(l0, l1);
         }
       }
       named_bar(2, 128);
