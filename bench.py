@@ -205,6 +205,44 @@ def main():
     sel_ms = sum(e[1].elapsed_time(e[2]) for e in evs) / args.steps
     gpu_launches = launches[0]
 
+    # ---- side kernels at the full config size, timed alone on this stream (rank 0 reports):
+    #      K3 select over 20 000 bags x 3025 probabilities, K4b HSV refine over the resident bags
+    def time_alone(fn, reps=5):
+        fn(); torch.cuda.synchronize()
+        ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(reps)]
+        flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+        for a, b in ev:
+            flush.zero_()                      # > L2: evict the operands between repetitions
+            a.record(); fn(); b.record()
+        torch.cuda.synchronize()
+        return min(a.elapsed_time(b) for a, b in ev)
+
+    side = {}
+    if rank == 0:
+        nb_sel = 20000
+        g = torch.Generator(device=dev); g.manual_seed(7)
+        p_all = torch.rand(nb_sel * T_PER_BAG, device=dev, generator=g)
+        lab_all = torch.from_numpy(synthetic.make_labels(nb_sel, seed=3)).to(dev)
+        sel_out = {}
+
+        def run_sel():
+            sel_out["r"] = ops.select_topk(p_all, lab_all, nb_sel, T_PER_BAG, 1, 30, capacity=nb_sel * 330)
+        ms = time_alone(run_sel)
+        m_kept = int(sel_out["r"][0].numel())
+        sel_bytes = 4.0 * p_all.numel() + 5.0 * m_kept + 4.0 * nb_sel
+        side["select_20k"] = {"bound": "hbm", "bags": nb_sel, "instances": int(p_all.numel()), "kept": m_kept,
+                              "ms": ms, "instances_per_s": p_all.numel() / (ms * 1e-3),
+                              "achieved": sel_bytes / (ms * 1e-3) / 1e9, "unit": "GB/s",
+                              "note": "3 launches (count, scan, sort+emit) + one .item() sync inside the timing"}
+        del p_all, sel_out
+        masks = (torch.rand((resident, H, H), device=dev, generator=g) < 0.3).to(torch.uint8)
+        out_m = torch.empty_like(masks)
+        ms = time_alone(lambda: ops.hsv_refine(bags, masks, 170, out=out_m))
+        side["hsv_refine"] = {"bound": "hbm", "bags": resident, "ms": ms, "masks_per_s": resident / (ms * 1e-3),
+                              "achieved": 5.0 * masks.numel() / (ms * 1e-3) / 1e9, "unit": "GB/s",
+                              "bytes_per_mask": 5 * H * H}
+        del masks, out_m
+
     # ---- end to end: host (pinned) bags -> H2D -> score + select -> D2H of the selection
     host = torch.empty((B, H, H, 3), dtype=torch.uint8).pin_memory()
     host.copy_(bags[:B].cpu())
@@ -274,6 +312,10 @@ def main():
                                     "peak": pk["hbm_gbs"], "unit": "GB/s",
                                     "frac": SELECT_BYTES_PER_INST * n_inst / (sel_ms * 1e-3) / 1e9 / pk["hbm_gbs"]}},
         }
+        for k, v in side.items():
+            v["peak"] = pk["hbm_gbs"]
+            v["frac"] = v["achieved"] / pk["hbm_gbs"]
+            out["roofline"][k] = v
         if not args.no_cpu_baseline:
             from oracle import model as omodel
             torch.set_num_threads(os.cpu_count())

@@ -87,7 +87,8 @@ conv_halo_kernel(const __grid_constant__ HaloParams p) {
       }
       int stage = 0;
       uint32_t phase = 0;
-      for (int m_tile = blockIdx.x; m_tile < p.num_m_tiles; m_tile += gridDim.x) {
+      for (int mi = blockIdx.x; mi < p.num_m_tiles; mi += gridDim.x) {
+        const int m_tile = p.reverse ? p.num_m_tiles - 1 - mi : mi;
         for (int s = 0; s < Cfg::kSteps; ++s) {
           const int dx = s / CCH, ch = s - dx * CCH;
           mbar_wait(empty_bar(stage), phase ^ 1u);
@@ -109,7 +110,8 @@ conv_halo_kernel(const __grid_constant__ HaloParams p) {
       if (BRES) mbar_wait(bres_bar, 0);
       int stage = 0, acc = 0;
       uint32_t phase = 0, acc_phase = 0;
-      for (int m_tile = blockIdx.x; m_tile < p.num_m_tiles; m_tile += gridDim.x) {
+      for (int mi = blockIdx.x; mi < p.num_m_tiles; mi += gridDim.x) {
+        const int m_tile = p.reverse ? p.num_m_tiles - 1 - mi : mi;
         mbar_wait(tempty_bar(acc), acc_phase ^ 1u);
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + (uint32_t)(acc * BN);
@@ -146,7 +148,8 @@ conv_halo_kernel(const __grid_constant__ HaloParams p) {
     const EpiArgs ea{p.bias, p.res_hi, p.res_lo, p.out_hi, p.out_lo, p.out_f32, p.relu};
     int acc = 0;
     uint32_t acc_phase = 0;
-    for (int m_tile = blockIdx.x; m_tile < p.num_m_tiles; m_tile += gridDim.x) {
+    for (int mi = blockIdx.x; mi < p.num_m_tiles; mi += gridDim.x) {
+        const int m_tile = p.reverse ? p.num_m_tiles - 1 - mi : mi;
       const int64_t inst = (int64_t)m_tile * Cfg::kImg + img;
       const int64_t row = inst * (W * W) + oy * W + ox;
       const int col0 = half * kColsPerWarp;

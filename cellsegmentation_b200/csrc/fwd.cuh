@@ -54,6 +54,7 @@ struct GemmParams {
   int a_mode;         // 0: 2-D {k, row}; 1: 4-D {c, x, y, tile}
   int units_per_mtile;  // 4-D mode: tiles (instances) per 128-row M tile
   int num_m_tiles, num_n_tiles;
+  int reverse;        // walk work items from the last to the first (L2 snake order between layers)
   int n_total;        // output row pitch, elements
   int64_t m_valid;    // rows that exist
   const float* bias;  // [n_total]
@@ -81,6 +82,7 @@ struct HaloParams {
   CUtensorMap a_map;  // make_act_map_halo
   CUtensorMap b_map;  // [Cout][9*Cin] K-major, box {64, Cout}
   int num_m_tiles;    // ceil(instances / (128 / (W*W)))
+  int reverse;        // walk M tiles from the last to the first
   int64_t n_inst;     // instances that exist
   const float* bias;
   const __nv_bfloat16* res_hi;

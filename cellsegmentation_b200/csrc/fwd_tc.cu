@@ -91,7 +91,8 @@ conv_gemm_kernel(const __grid_constant__ GemmParams p) {
       int stage = 0;
       uint32_t phase = 0;
       for (int w = blockIdx.x; w < num_work; w += gridDim.x) {
-        const int m_tile = w / p.num_n_tiles, n_tile = w - m_tile * p.num_n_tiles;
+        const int wi = p.reverse ? num_work - 1 - w : w;
+        const int m_tile = wi / p.num_n_tiles, n_tile = wi - m_tile * p.num_n_tiles;
         const int var = p.n_variants > 1 ? n_tile : 0;
         const int ns = p.n_steps[var];
         for (int s = 0; s < ns; ++s) {
@@ -118,7 +119,8 @@ conv_gemm_kernel(const __grid_constant__ GemmParams p) {
       int acc = 0;
       uint32_t acc_phase = 0;
       for (int w = blockIdx.x; w < num_work; w += gridDim.x) {
-        const int m_tile = w / p.num_n_tiles, n_tile = w - m_tile * p.num_n_tiles;
+        const int wi = p.reverse ? num_work - 1 - w : w;
+        const int m_tile = wi / p.num_n_tiles, n_tile = wi - m_tile * p.num_n_tiles;
         const int var = p.n_variants > 1 ? n_tile : 0;
         const int ns = p.n_steps[var];
         mbar_wait(tempty_bar(acc), acc_phase ^ 1u);
@@ -154,7 +156,8 @@ conv_gemm_kernel(const __grid_constant__ GemmParams p) {
     int acc = 0;
     uint32_t acc_phase = 0;
     for (int w = blockIdx.x; w < num_work; w += gridDim.x) {
-      const int m_tile = w / p.num_n_tiles, n_tile = w - m_tile * p.num_n_tiles;
+      const int wi = p.reverse ? num_work - 1 - w : w;
+      const int m_tile = wi / p.num_n_tiles, n_tile = wi - m_tile * p.num_n_tiles;
       const int64_t row = (int64_t)m_tile * kGemmBM + row_in_tile;
       const int col0 = n_tile * BN + half * kColsPerWarp;
       epilogue_warp<kColsPerWarp / 32>(

@@ -27,6 +27,11 @@ uint16_t f32_to_bf16_rn(float f) {
   return (uint16_t)(u >> 16);
 }
 
+const bool g_snake = []() {
+  const char* e = getenv("CELLSEG_SNAKE");
+  return !(e != nullptr && strcmp(e, "0") == 0);
+}();
+
 // Diagnostics: CELLSEG_HALO=0 keeps every shifted-box conv on the generic kernel.
 const bool g_disable_halo = []() {
   const char* e = getenv("CELLSEG_HALO");
@@ -268,7 +273,8 @@ int plan_conv(const ConvGeom& g, const float* w_oihw, const float* bias, const C
 }
 
 // Launches one planned convolution for `count` instances (pointers / relu taken from pc.p).
-int launch_planned(const PlannedConv& pc, int64_t count, float* out_f32, cudaStream_t st) {
+int launch_planned(const PlannedConv& pc, int64_t count, float* out_f32, cudaStream_t st,
+                   int reverse = 0) {
   if (pc.halo) {
     HaloParams hp = pc.hp;
     hp.res_hi = pc.p.res_hi; hp.res_lo = pc.p.res_lo;
@@ -276,6 +282,7 @@ int launch_planned(const PlannedConv& pc, int64_t count, float* out_f32, cudaStr
     hp.out_f32 = out_f32;
     hp.relu = pc.p.relu;
     hp.n_inst = count;
+    hp.reverse = reverse;
     hp.num_m_tiles = (int)ceil_div<int64_t>(count, kGemmBM / pc.Po);
     return launch_conv_halo(hp, pc.halo_W, pc.halo_Cin, st);
   }
@@ -284,6 +291,7 @@ int launch_planned(const PlannedConv& pc, int64_t count, float* out_f32, cudaStr
   p.m_valid = rows;
   p.num_m_tiles = (int)ceil_div<int64_t>(rows, kGemmBM);
   p.out_f32 = out_f32;
+  p.reverse = reverse;
   return launch_conv_gemm(p, pc.BN, st);
 }
 
@@ -429,8 +437,11 @@ int run_tc_batch(cs_model* m, const StemArgs& stem_in, int64_t count, float* pro
                                                       : launch_stem_bf16(sa, st);
   if (rc != CS_OK) return rc;
   m->last_launches++;
+  int li = 0;
   for (PlannedConv& pc : pl.layers) {
-    rc = launch_planned(pc, count, nullptr, st);
+    // snake order: odd layers walk their tiles backwards, starting with the rows the previous
+    // layer wrote last (still L2 resident when a batch's activations exceed L2)
+    rc = launch_planned(pc, count, nullptr, st, g_snake ? (++li & 1) : 0);
     if (rc != CS_OK) return rc;
     m->last_launches++;
   }
