@@ -22,6 +22,7 @@ SOURCES = [
     "paint.cu",
     "fwd_fp32.cu",
     "fwd_tc.cu",
+    "conv_gemm.cu",
     "stem_tc.cu",
     "conv_halo.cu",
     "model.cu",

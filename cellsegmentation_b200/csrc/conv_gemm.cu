@@ -1,0 +1,292 @@
+// K2 (bf16 mode): the generic implicit-GEMM convolution kernel on tcgen05 tensor cores.
+//
+// Reference: BasicBlock.forward (model/resnet.py:28-43) and resnet_forward (:234-248) under
+// eval-mode BN folded into the conv (model.cu does the folding/packing/planning).
+//
+//   out[r][n] = act( bias[n] + sum_steps A_step[r][0:64] . B[n][b_k : b_k+64]  (+ residual) )
+//
+// A is never materialised as im2col.  A K step is a TMA box:
+//   4-D mode  rows = (instance, oy, ox): box {64 ch, W, H, instances} fetched at the tap's pixel
+//             shift (dx, dy); out-of-image pixels are zero-filled by TMA = the conv's padding.
+//             Stride-2 convs read one of four parity-phase maps of the input.
+//   2-D mode  rows = instances, columns = (pixel, channel): maps with <= 2x2 outputs become dense
+//             GEMMs whose all-zero K blocks were dropped on the host.
+// Operands land in shared memory in the 128-byte-swizzled K-major layout UMMA expects;
+// accumulators live in TMEM (two stages: the epilogue of tile i overlaps the MMAs of tile i+1).
+//
+// Clusters (CL = 2): the launch list showed every layer pinned at the L2 -> SM bandwidth, and
+// the weight tile B is the larger operand.  Two CTAs of a cluster take neighbouring M tiles of
+// the same N tile and walk the K steps in lockstep; each loads half of B and multicasts it to
+// both, so a CTA pulls A + B/2 per step instead of A + B.  A stage is released by a multicast
+// tcgen05.commit to both CTAs' "empty" barriers (count = CL).
+//
+// Warp roles (320 threads, one CTA per SM, persistent):
+//   warp 0 : TMA producer (one lane)          warp 1 : TMEM alloc + MMA issuer (one lane)
+//   warps 2-9 : epilogue; warp % 4 = TMEM lane quadrant, (warp-2)/4 = column half.
+#include "fwd.cuh"
+#include "gemm_epilogue.cuh"
+
+namespace cs {
+namespace {
+
+template <int BN>
+struct GemmCfg {
+  static constexpr int kStages = BN == 256 ? 3 : (BN == 128 ? 4 : 5);
+  static constexpr uint32_t kABytes = kGemmBM * kGemmBK * 2;  // 16 KB
+  static constexpr uint32_t kBBytes = BN * kGemmBK * 2;
+  static constexpr uint32_t kStageBytes = kABytes + kBBytes;
+  static constexpr uint32_t kStagingOffset = kStages * kStageBytes;   // epilogue staging sets
+  static constexpr uint32_t kBarOffset = kStagingOffset + kEpiStagingBytes;
+  static constexpr uint32_t kSmemBytes = kBarOffset + 256 + 1024;  // barriers + align slack
+  static constexpr int kChunks = BN / 64;                          // 64-column epilogue chunks
+  static constexpr uint32_t kTmemCols = 2 * BN;                    // two accumulator stages
+};
+
+constexpr int kGemmThreads = 352;  // TMA warp, MMA warp, 8 epilogue warps, epilogue DMA warp
+
+template <int BN, int CL>
+__global__ void __launch_bounds__(kGemmThreads, 1)
+conv_gemm_kernel(const __grid_constant__ GemmParams p) {
+  using Cfg = GemmCfg<BN>;
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t raw = smem_u32(smem_raw);
+  const uint32_t base = (raw + 1023u) & ~1023u;
+  uint8_t* base_ptr = smem_raw + (base - raw);
+  const uint32_t bar_base = base + Cfg::kBarOffset;
+  auto full_bar = [&](int s) { return bar_base + 8u * s; };
+  auto empty_bar = [&](int s) { return bar_base + 8u * (Cfg::kStages + s); };
+  auto tfull_bar = [&](int a) { return bar_base + 8u * (2 * Cfg::kStages + a); };
+  auto tempty_bar = [&](int a) { return bar_base + 8u * (2 * Cfg::kStages + 2 + a); };
+  EpiBars ebars;
+  for (int s = 0; s < 2; ++s) {
+    ebars.res_full[s] = bar_base + 8u * (2 * Cfg::kStages + 4 + s);
+    ebars.out_ready[s] = bar_base + 8u * (2 * Cfg::kStages + 6 + s);
+  }
+  volatile uint32_t* tmem_slot =
+      reinterpret_cast<volatile uint32_t*>(base_ptr + Cfg::kBarOffset + 8 * (2 * Cfg::kStages + 8));
+  const uint32_t staging = base + Cfg::kStagingOffset;
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int rank = CL > 1 ? (int)cluster_ctarank() : 0;
+  constexpr uint16_t kMask = (uint16_t)((1u << CL) - 1u);
+
+  if (warp == 0 && lane == 0) {
+    for (int s = 0; s < Cfg::kStages; ++s) {
+      mbar_init(full_bar(s), 1);
+      mbar_init(empty_bar(s), CL);
+    }
+    for (int a = 0; a < 2; ++a) {
+      mbar_init(tfull_bar(a), 1);
+      mbar_init(tempty_bar(a), kEpiThreads);
+    }
+    epi_bars_init(ebars);
+    fence_barrier_init();
+    prefetch_tmap(&p.b_map);
+    prefetch_tmap(&p.a_map[0]);
+  }
+  if (warp == 1) tmem_alloc(smem_u32((const void*)tmem_slot), Cfg::kTmemCols);
+  tc_fence_before();
+  __syncthreads();
+  if (CL > 1) cluster_sync_all();   // peers' barriers are initialised before any remote arrive
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  // Work items of a cluster: (group of CL consecutive M tiles, N tile); CTA `rank` owns M tile
+  // group*CL + rank.  CTAs whose M tile does not exist still run the protocol (zero-filled A,
+  // stores predicated off).
+  const int m_groups = (p.num_m_tiles + CL - 1) / CL;
+  const int num_work = m_groups * p.num_n_tiles;
+  const int first = blockIdx.x / CL, step_w = gridDim.x / CL;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int w = first; w < num_work; w += step_w) {
+        const int wi = p.reverse ? num_work - 1 - w : w;
+        const int m_tile = (wi / p.num_n_tiles) * CL + rank, n_tile = wi % p.num_n_tiles;
+        const int var = p.n_variants > 1 ? n_tile : 0;
+        const int ns = p.n_steps[var];
+        for (int s = 0; s < ns; ++s) {
+          const KStep st = p.steps[var][s];
+          mbar_wait(empty_bar(stage), phase ^ 1u);
+          const uint32_t a_dst = base + stage * Cfg::kStageBytes;
+          const uint32_t b_dst = a_dst + Cfg::kABytes;
+          mbar_expect_tx(full_bar(stage), Cfg::kStageBytes);
+          if (p.a_mode == 0)
+            tma_load_2d(a_dst, &p.a_map[st.map], full_bar(stage), st.a_c0, m_tile * kGemmBM);
+          else
+            tma_load_4d(a_dst, &p.a_map[st.map], full_bar(stage), st.a_c0, st.dx, st.dy,
+                        m_tile * p.units_per_mtile);
+          if (CL == 1) {
+            tma_load_2d(b_dst, &p.b_map, full_bar(stage), st.b_k, n_tile * BN);
+          } else {
+            // this CTA's slice of the B tile, delivered to every CTA of the cluster
+            constexpr int kSliceRows = BN / CL;
+            tma_load_2d_mcast(b_dst + rank * (kSliceRows * 128), &p.b_map, full_bar(stage), st.b_k,
+                              n_tile * BN + rank * kSliceRows, kMask);
+          }
+          if (++stage == Cfg::kStages) { stage = 0; phase ^= 1u; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      constexpr uint32_t idesc = umma_idesc_bf16(kGemmBM, BN);
+      int stage = 0;
+      uint32_t phase = 0;
+      int acc = 0;
+      uint32_t acc_phase = 0;
+      for (int w = first; w < num_work; w += step_w) {
+        const int wi = p.reverse ? num_work - 1 - w : w;
+        const int n_tile = wi % p.num_n_tiles;
+        const int var = p.n_variants > 1 ? n_tile : 0;
+        const int ns = p.n_steps[var];
+        mbar_wait(tempty_bar(acc), acc_phase ^ 1u);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + (uint32_t)(acc * BN);
+        for (int s = 0; s < ns; ++s) {
+          mbar_wait(full_bar(stage), phase);
+          tc_fence_after();
+          const uint32_t a_src = base + stage * Cfg::kStageBytes;
+          const uint64_t a_desc = umma_desc_sw128(a_src);
+          const uint64_t b_desc = umma_desc_sw128(a_src + Cfg::kABytes);
+#pragma unroll
+          for (int k = 0; k < kGemmBK / 16; ++k) {
+            // +32 B per K=16 slice inside the 128-byte swizzle row: +2 in (addr >> 4)
+            umma_bf16(d_tmem, a_desc + (uint64_t)(2 * k), b_desc + (uint64_t)(2 * k), idesc,
+                      (s > 0 || k > 0) ? 1u : 0u);
+          }
+          // frees the stage when these MMAs retire -- in every CTA that wrote into it
+          if (CL == 1) umma_commit(empty_bar(stage));
+          else umma_commit_mcast(empty_bar(stage), kMask);
+          if (++stage == Cfg::kStages) { stage = 0; phase ^= 1u; }
+        }
+        umma_commit(tfull_bar(acc));  // accumulator complete -> epilogue
+        acc ^= 1;
+        if (acc == 0) acc_phase ^= 1u;
+      }
+    }
+  } else if (warp < 2 + kEpiWarps) {
+    // 8 epilogue warps: TMEM lane quadrant = warp % 4, column half of each 64-column chunk =
+    // (warp - 2) / 4.  They only touch TMEM and the shared-memory staging sets.
+    const int quad = warp & 3;
+    const int half = (warp - 2) >> 2;
+    const int r = quad * 32 + lane;
+    const EpiArgs ea{p.bias, p.res_hi != nullptr, p.res_lo != nullptr, p.out_hi != nullptr,
+                     p.out_lo != nullptr, p.out_f32, p.relu};
+    int acc = 0;
+    uint32_t acc_phase = 0;
+    int64_t q = 0;
+    for (int w = first; w < num_work; w += step_w) {
+      const int wi = p.reverse ? num_work - 1 - w : w;
+      const int m_tile = (wi / p.num_n_tiles) * CL + rank, n_tile = wi % p.num_n_tiles;
+      const int64_t row = (int64_t)m_tile * kGemmBM + r;
+      mbar_wait(tfull_bar(acc), acc_phase);
+      tc_fence_after();
+#pragma unroll 1
+      for (int c = 0; c < Cfg::kChunks; ++c, ++q) {
+        const int s = (int)(q & 1);
+        mbar_wait(ebars.res_full[s], (uint32_t)((q >> 1) & 1));
+        const int col = n_tile * BN + c * 64 + half * 32;
+        epi_chunk(ea, staging + s * kEpiSetBytes, r, half,
+                  tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(acc * BN + c * 64 + half * 32),
+                  col, row < p.m_valid, row * (int64_t)p.n_total + col);
+        fence_async_shared();
+        mbar_arrive(ebars.out_ready[s]);
+      }
+      tc_fence_before();
+      mbar_arrive(tempty_bar(acc));
+      acc ^= 1;
+      if (acc == 0) acc_phase ^= 1u;
+    }
+  } else if (lane == 0) {
+    // epilogue DMA thread: residual tiles in, result tiles out, one 64-column chunk at a time
+    int n_items = 0;
+    for (int w = first; w < num_work; w += step_w) ++n_items;
+    auto coords = [&](int64_t q, int* col, int* row) {
+      const int item = (int)(q / Cfg::kChunks), c = (int)(q % Cfg::kChunks);
+      const int w = first + item * step_w;
+      const int wi = p.reverse ? num_work - 1 - w : w;
+      const int m_tile = (wi / p.num_n_tiles) * CL + rank, n_tile = wi % p.num_n_tiles;
+      *col = n_tile * BN + c * 64;
+      *row = m_tile * kGemmBM;
+    };
+    const bool rh = p.res_hi != nullptr, rl = p.res_lo != nullptr;
+    const bool oh = p.out_hi != nullptr, ol = p.out_lo != nullptr;
+    epi_dma_loop(
+        (int64_t)n_items * Cfg::kChunks, staging, ebars,
+        (rh ? kEpiTileBytes : 0u) + (rl ? kEpiTileBytes : 0u), oh || ol,
+        [&](int64_t q, uint32_t set, uint32_t bar) {
+          int col, row;
+          coords(q, &col, &row);
+          if (rh) tma_load_2d(set, &p.res_hi_map, bar, col, row);
+          if (rl) tma_load_2d(set + kEpiTileBytes, &p.res_lo_map, bar, col, row);
+        },
+        [&](int64_t q, uint32_t set) {
+          int col, row;
+          coords(q, &col, &row);
+          if (oh) tma_store_2d(&p.out_hi_map, set, col, row);
+          if (ol) tma_store_2d(&p.out_lo_map, set + kEpiTileBytes, col, row);
+        });
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (CL > 1) cluster_sync_all();   // no CTA leaves while a peer may still write into it
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, Cfg::kTmemCols);
+  }
+}
+
+template <int BN, int CL>
+int launch_gemm_bn(const GemmParams& p, cudaStream_t st) {
+  using Cfg = GemmCfg<BN>;
+  static bool attr_done[64] = {false};
+  int dev = 0;
+  CS_CUDA(cudaGetDevice(&dev));
+  if (dev >= 64 || !attr_done[dev]) {
+    CS_CUDA(cudaFuncSetAttribute(conv_gemm_kernel<BN, CL>,
+                                 cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg::kSmemBytes));
+    if (dev < 64) attr_done[dev] = true;
+  }
+  const int m_groups = (p.num_m_tiles + CL - 1) / CL;
+  const int work = m_groups * p.num_n_tiles;
+  int clusters = work < kNumSMs / CL ? work : kNumSMs / CL;
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3((unsigned)(clusters * CL));
+  cfg.blockDim = dim3(kGemmThreads);
+  cfg.dynamicSmemBytes = Cfg::kSmemBytes;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = CL;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  CS_CUDA(cudaLaunchKernelEx(&cfg, conv_gemm_kernel<BN, CL>, p));
+  return CS_OK;
+}
+
+}  // namespace
+
+int launch_conv_gemm(const GemmParams& p, int BN, cudaStream_t st) {
+  if (p.num_m_tiles <= 0 || p.num_n_tiles <= 0) return CS_OK;
+  const int cl = p.cluster > 1 ? 2 : 1;
+  switch (BN * 10 + cl) {
+    case 641: return launch_gemm_bn<64, 1>(p, st);
+    case 1281: return launch_gemm_bn<128, 1>(p, st);
+    case 2561: return launch_gemm_bn<256, 1>(p, st);
+    case 642: return launch_gemm_bn<64, 2>(p, st);
+    case 1282: return launch_gemm_bn<128, 2>(p, st);
+    case 2562: return launch_gemm_bn<256, 2>(p, st);
+    default:
+      set_error("launch_conv_gemm: unsupported N tile %d", BN);
+      return CS_ERR_UNSUPPORTED;
+  }
+}
+
+}  // namespace cs

@@ -23,7 +23,7 @@
 namespace cs {
 namespace {
 
-constexpr int kHaloThreads = 320;
+constexpr int kHaloThreads = 352;  // TMA warp, MMA warp, 8 epilogue warps, epilogue DMA warp
 
 template <int BN, int W, int CCH, bool BRES>
 struct HaloCfg {
@@ -33,9 +33,11 @@ struct HaloCfg {
   static constexpr uint32_t kABytes = kHaloRows * 128;  // 20 KB (8x8) / 24 KB (4x4)
   static constexpr uint32_t kBTile = BN * 128;
   static constexpr uint32_t kStageBytes = kABytes + (BRES ? 0 : 3 * kBTile);
-  static constexpr int kStages = BRES ? 5 : 3;
+  static constexpr int kStages = BRES ? 4 : 2;
   static constexpr uint32_t kBResBytes = BRES ? 9 * CCH * kBTile : 0;
-  static constexpr uint32_t kBarOffset = kStages * kStageBytes + kBResBytes;
+  static constexpr uint32_t kStagingOffset = kStages * kStageBytes + kBResBytes;
+  static constexpr uint32_t kBarOffset = kStagingOffset + kEpiStagingBytes;
+  static constexpr int kChunks = BN / 64;
   static constexpr uint32_t kSmemBytes = kBarOffset + 256 + 1024;
   static constexpr int kSteps = 3 * CCH;                // (dx, channel chunk)
   static constexpr uint32_t kTmemCols = 2 * BN;
@@ -59,15 +61,22 @@ conv_halo_kernel(const __grid_constant__ HaloParams p) {
   auto tfull_bar = [&](int a) { return bar_base + 8u * (2 * Cfg::kStages + a); };
   auto tempty_bar = [&](int a) { return bar_base + 8u * (2 * Cfg::kStages + 2 + a); };
   const uint32_t bres_bar = bar_base + 8u * (2 * Cfg::kStages + 4);
+  EpiBars ebars;
+  for (int s = 0; s < 2; ++s) {
+    ebars.res_full[s] = bar_base + 8u * (2 * Cfg::kStages + 5 + s);
+    ebars.out_ready[s] = bar_base + 8u * (2 * Cfg::kStages + 7 + s);
+  }
   volatile uint32_t* tmem_slot =
-      reinterpret_cast<volatile uint32_t*>(base_ptr + Cfg::kBarOffset + 8 * (2 * Cfg::kStages + 5));
+      reinterpret_cast<volatile uint32_t*>(base_ptr + Cfg::kBarOffset + 8 * (2 * Cfg::kStages + 9));
+  const uint32_t staging = base + Cfg::kStagingOffset;
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
   if (warp == 0 && lane == 0) {
     for (int s = 0; s < Cfg::kStages; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
-    for (int a = 0; a < 2; ++a) { mbar_init(tfull_bar(a), 1); mbar_init(tempty_bar(a), 256); }
+    for (int a = 0; a < 2; ++a) { mbar_init(tfull_bar(a), 1); mbar_init(tempty_bar(a), kEpiThreads); }
     mbar_init(bres_bar, 1);
+    epi_bars_init(ebars);
     fence_barrier_init();
     prefetch_tmap(&p.a_map);
     prefetch_tmap(&p.b_map);
@@ -139,29 +148,67 @@ conv_halo_kernel(const __grid_constant__ HaloParams p) {
         if (acc == 0) acc_phase ^= 1u;
       }
     }
-  } else {
+  } else if (warp < 2 + kEpiWarps) {
     const int quad = warp & 3;
     const int half = (warp - 2) >> 2;
-    constexpr int kColsPerWarp = BN / 2;
     const int r = quad * 32 + lane;
     const int oy = r / Cfg::kRowsY, img = (r % Cfg::kRowsY) / W, ox = r % W;
-    const EpiArgs ea{p.bias, p.res_hi, p.res_lo, p.out_hi, p.out_lo, p.out_f32, p.relu};
+    const EpiArgs ea{p.bias, p.res_hi != nullptr, p.res_lo != nullptr, p.out_hi != nullptr,
+                     p.out_lo != nullptr, p.out_f32, p.relu};
     int acc = 0;
     uint32_t acc_phase = 0;
+    int64_t q = 0;
     for (int mi = blockIdx.x; mi < p.num_m_tiles; mi += gridDim.x) {
-        const int m_tile = p.reverse ? p.num_m_tiles - 1 - mi : mi;
+      const int m_tile = p.reverse ? p.num_m_tiles - 1 - mi : mi;
       const int64_t inst = (int64_t)m_tile * Cfg::kImg + img;
       const int64_t row = inst * (W * W) + oy * W + ox;
-      const int col0 = half * kColsPerWarp;
-      epilogue_warp<kColsPerWarp / 32>(
-          ea, inst < p.n_inst, row * (int64_t)BN + col0, col0,
-          tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(acc * BN + col0), tfull_bar(acc),
-          acc_phase);
+      mbar_wait(tfull_bar(acc), acc_phase);
+      tc_fence_after();
+#pragma unroll 1
+      for (int c = 0; c < Cfg::kChunks; ++c, ++q) {
+        const int s = (int)(q & 1);
+        mbar_wait(ebars.res_full[s], (uint32_t)((q >> 1) & 1));
+        const int col = c * 64 + half * 32;
+        epi_chunk(ea, staging + s * kEpiSetBytes, r, half,
+                  tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(acc * BN + col), col,
+                  inst < p.n_inst, row * (int64_t)BN + col);
+        fence_async_shared();
+        mbar_arrive(ebars.out_ready[s]);
+      }
       tc_fence_before();
       mbar_arrive(tempty_bar(acc));
       acc ^= 1;
       if (acc == 0) acc_phase ^= 1u;
     }
+  } else if (lane == 0) {
+    // epilogue DMA thread: tiles move as {64 ch, W, IMG, H} boxes of the {C, W, T, H} maps, i.e.
+    // in accumulator row order
+    int n_items = 0;
+    for (int mi = blockIdx.x; mi < p.num_m_tiles; mi += gridDim.x) ++n_items;
+    auto coords = [&](int64_t q, int* c0, int* t0) {
+      const int item = (int)(q / Cfg::kChunks), c = (int)(q % Cfg::kChunks);
+      const int mi = blockIdx.x + item * gridDim.x;
+      const int m_tile = p.reverse ? p.num_m_tiles - 1 - mi : mi;
+      *c0 = c * 64;
+      *t0 = m_tile * Cfg::kImg;
+    };
+    const bool rh = p.res_hi != nullptr, rl = p.res_lo != nullptr;
+    const bool oh = p.out_hi != nullptr, ol = p.out_lo != nullptr;
+    epi_dma_loop(
+        (int64_t)n_items * Cfg::kChunks, staging, ebars,
+        (rh ? kEpiTileBytes : 0u) + (rl ? kEpiTileBytes : 0u), oh || ol,
+        [&](int64_t q, uint32_t set, uint32_t bar) {
+          int c0, t0;
+          coords(q, &c0, &t0);
+          if (rh) tma_load_4d(set, &p.res_hi_map, bar, c0, 0, t0, 0);
+          if (rl) tma_load_4d(set + kEpiTileBytes, &p.res_lo_map, bar, c0, 0, t0, 0);
+        },
+        [&](int64_t q, uint32_t set) {
+          int c0, t0;
+          coords(q, &c0, &t0);
+          if (oh) tma_store_4d(&p.out_hi_map, set, c0, 0, t0, 0);
+          if (ol) tma_store_4d(&p.out_lo_map, set + kEpiTileBytes, c0, 0, t0, 0);
+        });
   }
 
   tc_fence_before();
@@ -205,7 +252,8 @@ int launch_conv_halo(const HaloParams& p, int W, int Cin, cudaStream_t st) {
 
 // {C, W, T, H} map with a {64, W, IMG, H + 2} box: instances sit between x and y in the box
 // order so that a vertical tap is a whole-atom shift of the shared-memory tile.
-int make_act_map_halo(CUtensorMap* map, const void* base, int C, int W, int H, int64_t T) {
+int make_act_map_halo(CUtensorMap* map, const void* base, int C, int W, int H, int64_t T,
+                      int halo) {
   typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*,
                                     const cuuint64_t*, const cuuint64_t*, const cuuint32_t*,
                                     const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
@@ -224,7 +272,7 @@ int make_act_map_halo(CUtensorMap* map, const void* base, int C, int W, int H, i
   const int img = 128 / (W * H);
   cuuint64_t dims[4] = {(cuuint64_t)C, (cuuint64_t)W, (cuuint64_t)T, (cuuint64_t)H};
   cuuint64_t strides[3] = {(cuuint64_t)C * 2, (cuuint64_t)H * W * C * 2, (cuuint64_t)W * C * 2};
-  cuuint32_t box[4] = {64, (cuuint32_t)W, (cuuint32_t)img, (cuuint32_t)(H + 2)};
+  cuuint32_t box[4] = {64, (cuuint32_t)W, (cuuint32_t)img, (cuuint32_t)(H + 2 * halo)};
   cuuint32_t estr[4] = {1, 1, 1, 1};
   CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(base), dims, strides,
                    box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,

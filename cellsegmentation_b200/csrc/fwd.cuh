@@ -55,15 +55,18 @@ struct GemmParams {
   int units_per_mtile;  // 4-D mode: tiles (instances) per 128-row M tile
   int num_m_tiles, num_n_tiles;
   int reverse;        // walk work items from the last to the first (L2 snake order between layers)
+  int cluster;        // 1, or 2: CTA pairs share the B tile by TMA multicast (b_map box = BN/2 rows)
   int n_total;        // output row pitch, elements
   int64_t m_valid;    // rows that exist
   const float* bias;  // [n_total]
   const __nv_bfloat16* res_hi;  // nullable
   const __nv_bfloat16* res_lo;  // nullable
-  __nv_bfloat16* out_hi;
-  __nv_bfloat16* out_lo;  // nullable
+  __nv_bfloat16* out_hi;        // nullable
+  __nv_bfloat16* out_lo;        // nullable
   float* out_f32;         // nullable: raw fp32 result (diagnostics)
   int relu;
+  // TMA views of the four tensors above: {n_total, rows} with a {64, 128} box (make_mat_map_2d)
+  CUtensorMap res_hi_map, res_lo_map, out_hi_map, out_lo_map;
 };
 
 // BN (the CTA's N tile) must be 64, 128 or 256.
@@ -91,10 +94,13 @@ struct HaloParams {
   __nv_bfloat16* out_lo;
   float* out_f32;
   int relu;
+  // TMA views {C, W, T, H}, box {64, W, IMG, H} (make_act_map_halo with halo = 0)
+  CUtensorMap res_hi_map, res_lo_map, out_hi_map, out_lo_map;
 };
 bool halo_supported(int W, int Cin, int Cout);
 int launch_conv_halo(const HaloParams& p, int W, int Cin, cudaStream_t st);
-int make_act_map_halo(CUtensorMap* map, const void* base, int C, int W, int H, int64_t T);
+int make_act_map_halo(CUtensorMap* map, const void* base, int C, int W, int H, int64_t T,
+                      int halo /* 1: box H+2 rows for the A operand, 0: H rows for epilogue tiles */);
 
 struct StemArgs {
   // source A: u8 images + uniform grid

@@ -1,183 +1,10 @@
-// K2 (bf16 mode): implicit-GEMM convolutions on tcgen05 tensor cores.
-//
-// Reference: BasicBlock.forward (model/resnet.py:28-43) and resnet_forward (:234-248)
-// under eval-mode BN folded into the conv (see model.cu for the folding/packing).
-//
-// Every 3x3 / 1x1 convolution of the encoder is one launch of conv_gemm_kernel:
-//   out[r][n] = act( bias[n] + sum_steps A_step[r][0:64] . B[n][b_k : b_k+64]  (+ residual) )
-// A is never materialised as im2col.  A K step is a TMA box:
-//   4-D mode  rows = (instance, oy, ox): box {64 ch, W, H, instances} fetched at the
-//             tap's pixel shift (dx, dy); out-of-image pixels are zero-filled by TMA,
-//             which is exactly the conv's zero padding.  Stride-2 convs read one of
-//             four parity-phase maps of the input.
-//   2-D mode  rows = instances, columns = (pixel, channel): small maps (<= 2x2
-//             outputs) become dense GEMMs whose all-zero K blocks were dropped on the
-//             host, so taps that only ever see padding cost nothing.
-// Operands land in shared memory in the 128-byte-swizzled K-major layout UMMA
-// expects; accumulators live in TMEM (two stages, so the epilogue of tile i overlaps
-// the MMAs of tile i+1); the epilogue adds the folded-BN bias and the residual,
-// applies ReLU and writes bf16 `hi` (next layer's operand) plus bf16 `lo`
-// (= value - hi) so the residual stream keeps ~16 mantissa bits.
-//
-// Warp roles (320 threads, one CTA per SM, persistent over (m_tile, n_tile)):
-//   warp 0 : TMA producer (one lane)          warp 1 : TMEM alloc + MMA issuer (one lane)
-//   warps 2-9 : epilogue; warp % 4 = TMEM lane quadrant, (warp-2)/4 = column half.  The
-//   residual of the next 32-column chunk is fetched (256-bit loads) before the accumulator
-//   wait / while the current chunk is converted and stored.
+// K2 (bf16 mode) support code: CUDA-core stem (tile 16), tile head, TMA descriptor builders.
+// The tensor-core kernels live in conv_gemm.cu, conv_halo.cu and stem_tc.cu.
 #include "fwd.cuh"
 #include "gemm_epilogue.cuh"
 
 namespace cs {
 namespace {
-
-// ----------------------------------------------------------------------------
-// The GEMM kernel
-// ----------------------------------------------------------------------------
-template <int BN>
-struct GemmCfg {
-  static constexpr int kStages = BN == 256 ? 4 : (BN == 128 ? 6 : 8);
-  static constexpr uint32_t kABytes = kGemmBM * kGemmBK * 2;  // 16 KB
-  static constexpr uint32_t kBBytes = BN * kGemmBK * 2;
-  static constexpr uint32_t kStageBytes = kABytes + kBBytes;
-  static constexpr uint32_t kBarOffset = kStages * kStageBytes;
-  static constexpr uint32_t kSmemBytes = kBarOffset + 256 + 1024;  // barriers + align slack
-  static constexpr uint32_t kTmemCols = 2 * BN;                    // two accumulator stages
-};
-
-constexpr int kGemmThreads = 320;  // TMA warp, MMA warp, 8 epilogue warps
-
-template <int BN>
-__global__ void __launch_bounds__(kGemmThreads, 1)
-conv_gemm_kernel(const __grid_constant__ GemmParams p) {
-  using Cfg = GemmCfg<BN>;
-  extern __shared__ uint8_t smem_raw[];
-  const uint32_t raw = smem_u32(smem_raw);
-  const uint32_t base = (raw + 1023u) & ~1023u;
-  uint8_t* base_ptr = smem_raw + (base - raw);
-  const uint32_t bar_base = base + Cfg::kBarOffset;
-  auto full_bar = [&](int s) { return bar_base + 8u * s; };
-  auto empty_bar = [&](int s) { return bar_base + 8u * (Cfg::kStages + s); };
-  auto tfull_bar = [&](int a) { return bar_base + 8u * (2 * Cfg::kStages + a); };
-  auto tempty_bar = [&](int a) { return bar_base + 8u * (2 * Cfg::kStages + 2 + a); };
-  volatile uint32_t* tmem_slot =
-      reinterpret_cast<volatile uint32_t*>(base_ptr + Cfg::kBarOffset + 8 * (2 * Cfg::kStages + 4));
-
-  const int warp = threadIdx.x >> 5;
-  const int lane = threadIdx.x & 31;
-
-  if (warp == 0 && lane == 0) {
-    for (int s = 0; s < Cfg::kStages; ++s) {
-      mbar_init(full_bar(s), 1);
-      mbar_init(empty_bar(s), 1);
-    }
-    for (int a = 0; a < 2; ++a) {
-      mbar_init(tfull_bar(a), 1);
-      mbar_init(tempty_bar(a), 256);
-    }
-    fence_barrier_init();
-    prefetch_tmap(&p.b_map);
-    prefetch_tmap(&p.a_map[0]);
-  }
-  if (warp == 1) tmem_alloc(smem_u32((const void*)tmem_slot), Cfg::kTmemCols);
-  tc_fence_before();
-  __syncthreads();
-  tc_fence_after();
-  const uint32_t tmem_base = *tmem_slot;
-
-  const int num_work = p.num_m_tiles * p.num_n_tiles;
-
-  if (warp == 0) {
-    if (lane == 0) {
-      int stage = 0;
-      uint32_t phase = 0;
-      for (int w = blockIdx.x; w < num_work; w += gridDim.x) {
-        const int wi = p.reverse ? num_work - 1 - w : w;
-        const int m_tile = wi / p.num_n_tiles, n_tile = wi - m_tile * p.num_n_tiles;
-        const int var = p.n_variants > 1 ? n_tile : 0;
-        const int ns = p.n_steps[var];
-        for (int s = 0; s < ns; ++s) {
-          const KStep st = p.steps[var][s];
-          mbar_wait(empty_bar(stage), phase ^ 1u);
-          const uint32_t a_dst = base + stage * Cfg::kStageBytes;
-          const uint32_t b_dst = a_dst + Cfg::kABytes;
-          mbar_expect_tx(full_bar(stage), Cfg::kStageBytes);
-          if (p.a_mode == 0)
-            tma_load_2d(a_dst, &p.a_map[st.map], full_bar(stage), st.a_c0, m_tile * kGemmBM);
-          else
-            tma_load_4d(a_dst, &p.a_map[st.map], full_bar(stage), st.a_c0, st.dx, st.dy,
-                        m_tile * p.units_per_mtile);
-          tma_load_2d(b_dst, &p.b_map, full_bar(stage), st.b_k, n_tile * BN);
-          if (++stage == Cfg::kStages) { stage = 0; phase ^= 1u; }
-        }
-      }
-    }
-  } else if (warp == 1) {
-    if (lane == 0) {
-      constexpr uint32_t idesc = umma_idesc_bf16(kGemmBM, BN);
-      int stage = 0;
-      uint32_t phase = 0;
-      int acc = 0;
-      uint32_t acc_phase = 0;
-      for (int w = blockIdx.x; w < num_work; w += gridDim.x) {
-        const int wi = p.reverse ? num_work - 1 - w : w;
-        const int m_tile = wi / p.num_n_tiles, n_tile = wi - m_tile * p.num_n_tiles;
-        const int var = p.n_variants > 1 ? n_tile : 0;
-        const int ns = p.n_steps[var];
-        mbar_wait(tempty_bar(acc), acc_phase ^ 1u);
-        tc_fence_after();
-        const uint32_t d_tmem = tmem_base + (uint32_t)(acc * BN);
-        for (int s = 0; s < ns; ++s) {
-          mbar_wait(full_bar(stage), phase);
-          tc_fence_after();
-          const uint32_t a_src = base + stage * Cfg::kStageBytes;
-          const uint64_t a_desc = umma_desc_sw128(a_src);
-          const uint64_t b_desc = umma_desc_sw128(a_src + Cfg::kABytes);
-#pragma unroll
-          for (int k = 0; k < kGemmBK / 16; ++k) {
-            // +32 B per K=16 slice inside the 128-byte swizzle row: +2 in (addr >> 4)
-            umma_bf16(d_tmem, a_desc + (uint64_t)(2 * k), b_desc + (uint64_t)(2 * k), idesc,
-                      (s > 0 || k > 0) ? 1u : 0u);
-          }
-          umma_commit(empty_bar(stage));  // frees the smem stage when these MMAs retire
-          if (++stage == Cfg::kStages) { stage = 0; phase ^= 1u; }
-        }
-        umma_commit(tfull_bar(acc));  // accumulator complete -> epilogue
-        acc ^= 1;
-        if (acc == 0) acc_phase ^= 1u;
-      }
-    }
-  } else {
-    // 8 epilogue warps: TMEM lane quadrant = warp % 4, column half = (warp - 2) / 4.
-    const int quad = warp & 3;
-    const int half = (warp - 2) >> 2;
-    constexpr int kColsPerWarp = BN / 2;
-    const int row_in_tile = quad * 32 + lane;
-    const EpiArgs ea{p.bias, p.res_hi, p.res_lo, p.out_hi, p.out_lo, p.out_f32, p.relu};
-    int acc = 0;
-    uint32_t acc_phase = 0;
-    for (int w = blockIdx.x; w < num_work; w += gridDim.x) {
-      const int wi = p.reverse ? num_work - 1 - w : w;
-      const int m_tile = wi / p.num_n_tiles, n_tile = wi - m_tile * p.num_n_tiles;
-      const int64_t row = (int64_t)m_tile * kGemmBM + row_in_tile;
-      const int col0 = n_tile * BN + half * kColsPerWarp;
-      epilogue_warp<kColsPerWarp / 32>(
-          ea, row < p.m_valid, row * (int64_t)p.n_total + col0, col0,
-          tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(acc * BN + half * kColsPerWarp),
-          tfull_bar(acc), acc_phase);
-      tc_fence_before();
-      mbar_arrive(tempty_bar(acc));
-      acc ^= 1;
-      if (acc == 0) acc_phase ^= 1u;
-    }
-  }
-
-  tc_fence_before();
-  __syncthreads();
-  if (warp == 1) {
-    tc_fence_after();
-    tmem_dealloc(tmem_base, Cfg::kTmemCols);
-  }
-}
 
 // ----------------------------------------------------------------------------
 // Stem (v1, CUDA cores): unfold + normalise + conv7x7/2 + bias + ReLU + maxpool3x3/2.
@@ -382,37 +209,7 @@ int get_encoder(EncodeTiledFn* fn) {
   return CS_OK;
 }
 
-template <int BN>
-int launch_gemm_bn(const GemmParams& p, cudaStream_t st) {
-  using Cfg = GemmCfg<BN>;
-  static bool attr_done[64] = {false};
-  int dev = 0;
-  CS_CUDA(cudaGetDevice(&dev));
-  if (dev >= 64 || !attr_done[dev]) {
-    CS_CUDA(cudaFuncSetAttribute(conv_gemm_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                 (int)Cfg::kSmemBytes));
-    if (dev < 64) attr_done[dev] = true;
-  }
-  int work = p.num_m_tiles * p.num_n_tiles;
-  int grid = work < kNumSMs ? work : kNumSMs;
-  conv_gemm_kernel<BN><<<grid, kGemmThreads, Cfg::kSmemBytes, st>>>(p);
-  CS_LAUNCH_CHECK();
-  return CS_OK;
-}
-
 }  // namespace
-
-int launch_conv_gemm(const GemmParams& p, int BN, cudaStream_t st) {
-  if (p.num_m_tiles <= 0 || p.num_n_tiles <= 0) return CS_OK;
-  switch (BN) {
-    case 64: return launch_gemm_bn<64>(p, st);
-    case 128: return launch_gemm_bn<128>(p, st);
-    case 256: return launch_gemm_bn<256>(p, st);
-    default:
-      set_error("launch_conv_gemm: unsupported N tile %d", BN);
-      return CS_ERR_UNSUPPORTED;
-  }
-}
 
 int make_act_map_4d(CUtensorMap* map, const void* base, int C, int W, int H, int64_t T,
                     int64_t stride_x_elems, int64_t stride_y_elems, int64_t stride_t_elems,

@@ -32,6 +32,12 @@ const bool g_snake = []() {
   return !(e != nullptr && strcmp(e, "0") == 0);
 }();
 
+// CELLSEG_CLUSTER=1 disables the 2-CTA B multicast of the generic GEMM kernel.
+const int g_cluster = []() {
+  const char* e = getenv("CELLSEG_CLUSTER");
+  return (e != nullptr && strcmp(e, "1") == 0) ? 1 : 2;
+}();
+
 // Diagnostics: CELLSEG_HALO=0 keeps every shifted-box conv on the generic kernel.
 const bool g_disable_halo = []() {
   const char* e = getenv("CELLSEG_HALO");
@@ -255,14 +261,16 @@ int plan_conv(const ConvGeom& g, const float* w_oihw, const float* bias, const C
   CS_CUDA(cudaMemcpy(pc.d_B, B.data(), B.size() * sizeof(uint16_t), cudaMemcpyHostToDevice));
   CS_CUDA(cudaMalloc(&pc.d_bias, bias_full.size() * sizeof(float)));
   CS_CUDA(cudaMemcpy(pc.d_bias, bias_full.data(), bias_full.size() * sizeof(float), cudaMemcpyHostToDevice));
-  rc = make_mat_map_2d(&pc.p.b_map, pc.d_B, K_cat, pc.p.n_total, K_cat, pc.BN);
+  pc.p.cluster = g_cluster;
+  rc = make_mat_map_2d(&pc.p.b_map, pc.d_B, K_cat, pc.p.n_total, K_cat, pc.BN / pc.p.cluster);
   if (rc != CS_OK) { free_planned(pc); return rc; }
   pc.p.bias = pc.d_bias;
   if (!pc.dense && !gds && g.stride == 1 && g.Hi == g.Wi && halo_supported(g.Wi, g.Cin, g.Cout) &&
       !g_disable_halo) {
-    rc = make_act_map_halo(&pc.hp.a_map, in_hi, g.Cin, g.Wi, g.Hi, b_pad);
+    rc = make_act_map_halo(&pc.hp.a_map, in_hi, g.Cin, g.Wi, g.Hi, b_pad, 1);
     if (rc != CS_OK) { free_planned(pc); return rc; }
-    pc.hp.b_map = pc.p.b_map;
+    rc = make_mat_map_2d(&pc.hp.b_map, pc.d_B, K_cat, pc.p.n_total, K_cat, pc.BN);
+    if (rc != CS_OK) { free_planned(pc); return rc; }
     pc.hp.bias = pc.d_bias;
     pc.halo = true;
     pc.halo_W = g.Wi;
@@ -272,11 +280,33 @@ int plan_conv(const ConvGeom& g, const float* w_oihw, const float* bias, const C
   return CS_OK;
 }
 
+// Builds the TMA views of the residual / output tensors once their pointers are known.
+int finalize_io_maps(PlannedConv& pc, int64_t b_pad) {
+  int rc = CS_OK;
+  if (pc.halo) {
+    const int W = pc.halo_W, C = pc.p.n_total;
+    if (pc.p.res_hi && (rc = make_act_map_halo(&pc.hp.res_hi_map, pc.p.res_hi, C, W, W, b_pad, 0))) return rc;
+    if (pc.p.res_lo && (rc = make_act_map_halo(&pc.hp.res_lo_map, pc.p.res_lo, C, W, W, b_pad, 0))) return rc;
+    if (pc.p.out_hi && (rc = make_act_map_halo(&pc.hp.out_hi_map, pc.p.out_hi, C, W, W, b_pad, 0))) return rc;
+    if (pc.p.out_lo && (rc = make_act_map_halo(&pc.hp.out_lo_map, pc.p.out_lo, C, W, W, b_pad, 0))) return rc;
+    return CS_OK;
+  }
+  const int64_t rows = pc.dense ? b_pad : b_pad * pc.Po;
+  const int64_t N = pc.p.n_total;
+  if (pc.p.res_hi && (rc = make_mat_map_2d(&pc.p.res_hi_map, pc.p.res_hi, N, rows, N, kGemmBM))) return rc;
+  if (pc.p.res_lo && (rc = make_mat_map_2d(&pc.p.res_lo_map, pc.p.res_lo, N, rows, N, kGemmBM))) return rc;
+  if (pc.p.out_hi && (rc = make_mat_map_2d(&pc.p.out_hi_map, pc.p.out_hi, N, rows, N, kGemmBM))) return rc;
+  if (pc.p.out_lo && (rc = make_mat_map_2d(&pc.p.out_lo_map, pc.p.out_lo, N, rows, N, kGemmBM))) return rc;
+  return CS_OK;
+}
+
 // Launches one planned convolution for `count` instances (pointers / relu taken from pc.p).
 int launch_planned(const PlannedConv& pc, int64_t count, float* out_f32, cudaStream_t st,
                    int reverse = 0) {
   if (pc.halo) {
     HaloParams hp = pc.hp;
+    hp.res_hi_map = pc.hp.res_hi_map; hp.res_lo_map = pc.hp.res_lo_map;
+    hp.out_hi_map = pc.hp.out_hi_map; hp.out_lo_map = pc.hp.out_lo_map;
     hp.res_hi = pc.p.res_hi; hp.res_lo = pc.p.res_lo;
     hp.out_hi = pc.p.out_hi; hp.out_lo = pc.p.out_lo;
     hp.out_f32 = out_f32;
@@ -383,6 +413,8 @@ int build_tc_plan(cs_model* m, int tile, int64_t max_batch, void* ws, int64_t ws
     p1.p.out_lo = nullptr;
     p1.p.res_hi = p1.p.res_lo = nullptr;
     p1.p.relu = 1;
+    rc = finalize_io_maps(p1, plan->b_pad);
+    if (rc != CS_OK) return rc;
     plan->layers.push_back(p1);
     if (b.ds >= 0) {
       const ConvW& cd = m->convs[b.ds];
@@ -401,6 +433,8 @@ int build_tc_plan(cs_model* m, int tile, int64_t max_batch, void* ws, int64_t ws
     p2.p.out_hi = plan->buf_hi[1 - xi];
     p2.p.out_lo = plan->buf_lo[1 - xi];
     p2.p.relu = 1;
+    rc = finalize_io_maps(p2, plan->b_pad);
+    if (rc != CS_OK) return rc;
     plan->layers.push_back(p2);
     xi = 1 - xi;
     H = Ho; W = Wo; C = b.cout;
@@ -740,7 +774,8 @@ int cs_debug_gemm_bf16(const void* a_bf16, const void* b_bf16, int64_t M, int N,
   memset(&p, 0, sizeof(p));
   rc = make_mat_map_2d(&p.a_map[0], a_bf16, K, M, K, kGemmBM);
   if (rc != CS_OK) return rc;
-  rc = make_mat_map_2d(&p.b_map, b_bf16, K, N, K, bn);
+  p.cluster = g_cluster;
+  rc = make_mat_map_2d(&p.b_map, b_bf16, K, N, K, bn / p.cluster);
   if (rc != CS_OK) return rc;
   p.n_variants = 1;
   p.n_steps[0] = K / 64;
