@@ -31,13 +31,20 @@ namespace {
 
 template <int BN>
 struct GemmCfg {
-  static constexpr int kStages = BN == 256 ? 3 : (BN == 128 ? 4 : 5);
+  static constexpr int kMaxStages = 8;
   static constexpr uint32_t kABytes = kGemmBM * kGemmBK * 2;  // 16 KB
   static constexpr uint32_t kBBytes = BN * kGemmBK * 2;
   static constexpr uint32_t kStageBytes = kABytes + kBBytes;
-  static constexpr uint32_t kStagingOffset = kStages * kStageBytes;   // epilogue staging sets
-  static constexpr uint32_t kBarOffset = kStagingOffset + kEpiStagingBytes;
-  static constexpr uint32_t kSmemBytes = kBarOffset + 256 + 1024;  // barriers + align slack
+  static constexpr uint32_t kSmemLimit = 227 * 1024;
+  // Shared memory: [stages x (A|B)] [staging: 2 sets of hi(+lo) tiles] [barriers]; the stage
+  // count is whatever fits once the epilogue staging (16 or 32 KB per set) is reserved.
+  static constexpr int stages_for(uint32_t set_bytes) {
+    int s = (int)((kSmemLimit - 1024 - 256 - 2 * set_bytes) / kStageBytes);
+    return s > kMaxStages ? kMaxStages : s;
+  }
+  static constexpr uint32_t smem_bytes(int stages, uint32_t set_bytes) {
+    return stages * kStageBytes + 2 * set_bytes + 256 + 1024;
+  }
   static constexpr int kChunks = BN / 64;                          // 64-column epilogue chunks
   static constexpr uint32_t kTmemCols = 2 * BN;                    // two accumulator stages
 };
@@ -52,19 +59,22 @@ conv_gemm_kernel(const __grid_constant__ GemmParams p) {
   const uint32_t raw = smem_u32(smem_raw);
   const uint32_t base = (raw + 1023u) & ~1023u;
   uint8_t* base_ptr = smem_raw + (base - raw);
-  const uint32_t bar_base = base + Cfg::kBarOffset;
+  const int n_stages = p.stages;
+  const uint32_t set_bytes = p.epi_set_bytes;                 // 16 KB (hi only) or 32 KB (hi + lo)
+  const uint32_t staging = base + n_stages * Cfg::kStageBytes;
+  const uint32_t bar_off = n_stages * Cfg::kStageBytes + 2 * set_bytes;
+  const uint32_t bar_base = base + bar_off;
   auto full_bar = [&](int s) { return bar_base + 8u * s; };
-  auto empty_bar = [&](int s) { return bar_base + 8u * (Cfg::kStages + s); };
-  auto tfull_bar = [&](int a) { return bar_base + 8u * (2 * Cfg::kStages + a); };
-  auto tempty_bar = [&](int a) { return bar_base + 8u * (2 * Cfg::kStages + 2 + a); };
+  auto empty_bar = [&](int s) { return bar_base + 8u * (Cfg::kMaxStages + s); };
+  auto tfull_bar = [&](int a) { return bar_base + 8u * (2 * Cfg::kMaxStages + a); };
+  auto tempty_bar = [&](int a) { return bar_base + 8u * (2 * Cfg::kMaxStages + 2 + a); };
   EpiBars ebars;
   for (int s = 0; s < 2; ++s) {
-    ebars.res_full[s] = bar_base + 8u * (2 * Cfg::kStages + 4 + s);
-    ebars.out_ready[s] = bar_base + 8u * (2 * Cfg::kStages + 6 + s);
+    ebars.res_full[s] = bar_base + 8u * (2 * Cfg::kMaxStages + 4 + s);
+    ebars.out_ready[s] = bar_base + 8u * (2 * Cfg::kMaxStages + 6 + s);
   }
   volatile uint32_t* tmem_slot =
-      reinterpret_cast<volatile uint32_t*>(base_ptr + Cfg::kBarOffset + 8 * (2 * Cfg::kStages + 8));
-  const uint32_t staging = base + Cfg::kStagingOffset;
+      reinterpret_cast<volatile uint32_t*>(base_ptr + bar_off + 8 * (2 * Cfg::kMaxStages + 8));
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -72,7 +82,7 @@ conv_gemm_kernel(const __grid_constant__ GemmParams p) {
   constexpr uint16_t kMask = (uint16_t)((1u << CL) - 1u);
 
   if (warp == 0 && lane == 0) {
-    for (int s = 0; s < Cfg::kStages; ++s) {
+    for (int s = 0; s < n_stages; ++s) {
       mbar_init(full_bar(s), 1);
       mbar_init(empty_bar(s), CL);
     }
@@ -127,7 +137,7 @@ conv_gemm_kernel(const __grid_constant__ GemmParams p) {
             tma_load_2d_mcast(b_dst + rank * (kSliceRows * 128), &p.b_map, full_bar(stage), st.b_k,
                               n_tile * BN + rank * kSliceRows, kMask);
           }
-          if (++stage == Cfg::kStages) { stage = 0; phase ^= 1u; }
+          if (++stage == n_stages) { stage = 0; phase ^= 1u; }
         }
       }
     }
@@ -161,7 +171,7 @@ conv_gemm_kernel(const __grid_constant__ GemmParams p) {
           // frees the stage when these MMAs retire -- in every CTA that wrote into it
           if (CL == 1) umma_commit(empty_bar(stage));
           else umma_commit_mcast(empty_bar(stage), kMask);
-          if (++stage == Cfg::kStages) { stage = 0; phase ^= 1u; }
+          if (++stage == n_stages) { stage = 0; phase ^= 1u; }
         }
         umma_commit(tfull_bar(acc));  // accumulator complete -> epilogue
         acc ^= 1;
@@ -190,7 +200,7 @@ conv_gemm_kernel(const __grid_constant__ GemmParams p) {
         const int s = (int)(q & 1);
         mbar_wait(ebars.res_full[s], (uint32_t)((q >> 1) & 1));
         const int col = n_tile * BN + c * 64 + half * 32;
-        epi_chunk(ea, staging + s * kEpiSetBytes, r, half,
+        epi_chunk(ea, staging + s * set_bytes, r, half,
                   tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(acc * BN + c * 64 + half * 32),
                   col, row < p.m_valid, row * (int64_t)p.n_total + col);
         fence_async_shared();
@@ -216,7 +226,7 @@ conv_gemm_kernel(const __grid_constant__ GemmParams p) {
     const bool rh = p.res_hi != nullptr, rl = p.res_lo != nullptr;
     const bool oh = p.out_hi != nullptr, ol = p.out_lo != nullptr;
     epi_dma_loop(
-        (int64_t)n_items * Cfg::kChunks, staging, ebars,
+        (int64_t)n_items * Cfg::kChunks, staging, set_bytes, ebars,
         (rh ? kEpiTileBytes : 0u) + (rl ? kEpiTileBytes : 0u), oh || ol,
         [&](int64_t q, uint32_t set, uint32_t bar) {
           int col, row;
@@ -249,16 +259,20 @@ int launch_gemm_bn(const GemmParams& p, cudaStream_t st) {
   CS_CUDA(cudaGetDevice(&dev));
   if (dev >= 64 || !attr_done[dev]) {
     CS_CUDA(cudaFuncSetAttribute(conv_gemm_kernel<BN, CL>,
-                                 cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg::kSmemBytes));
+                                 cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg::kSmemLimit));
     if (dev < 64) attr_done[dev] = true;
   }
+  GemmParams q = p;
+  q.epi_set_bytes = (p.out_lo || p.res_lo) ? kEpiSetBytes : kEpiTileBytes;
+  q.stages = Cfg::stages_for(q.epi_set_bytes);
+  const uint32_t smem = Cfg::smem_bytes(q.stages, q.epi_set_bytes);
   const int m_groups = (p.num_m_tiles + CL - 1) / CL;
   const int work = m_groups * p.num_n_tiles;
   int clusters = work < kNumSMs / CL ? work : kNumSMs / CL;
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3((unsigned)(clusters * CL));
   cfg.blockDim = dim3(kGemmThreads);
-  cfg.dynamicSmemBytes = Cfg::kSmemBytes;
+  cfg.dynamicSmemBytes = smem;
   cfg.stream = st;
   cudaLaunchAttribute attr[1];
   attr[0].id = cudaLaunchAttributeClusterDimension;
@@ -267,7 +281,7 @@ int launch_gemm_bn(const GemmParams& p, cudaStream_t st) {
   attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr;
   cfg.numAttrs = 1;
-  CS_CUDA(cudaLaunchKernelEx(&cfg, conv_gemm_kernel<BN, CL>, p));
+  CS_CUDA(cudaLaunchKernelEx(&cfg, conv_gemm_kernel<BN, CL>, q));
   return CS_OK;
 }
 

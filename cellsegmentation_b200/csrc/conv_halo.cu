@@ -195,7 +195,7 @@ conv_halo_kernel(const __grid_constant__ HaloParams p) {
     const bool rh = p.res_hi != nullptr, rl = p.res_lo != nullptr;
     const bool oh = p.out_hi != nullptr, ol = p.out_lo != nullptr;
     epi_dma_loop(
-        (int64_t)n_items * Cfg::kChunks, staging, ebars,
+        (int64_t)n_items * Cfg::kChunks, staging, kEpiSetBytes, ebars,
         (rh ? kEpiTileBytes : 0u) + (rl ? kEpiTileBytes : 0u), oh || ol,
         [&](int64_t q, uint32_t set, uint32_t bar) {
           int c0, t0;

@@ -130,14 +130,15 @@ __device__ __forceinline__ void epi_bars_init(const EpiBars& b) {
 // chunk q (or nothing), store(q, set_addr) the TMA stores.  res_bytes = bytes the loads of one
 // chunk deliver (0: no residual, the set is handed over with a plain arrive).
 template <class LoadFn, class StoreFn>
-__device__ __forceinline__ void epi_dma_loop(int64_t Q, uint32_t staging, const EpiBars& bars,
+__device__ __forceinline__ void epi_dma_loop(int64_t Q, uint32_t staging, uint32_t set_bytes,
+                                             const EpiBars& bars,
                                              uint32_t res_bytes, bool any_store, LoadFn load,
                                              StoreFn store) {
   auto hand_over = [&](int64_t q) {
     const int s = (int)(q & 1);
     if (res_bytes) {
       mbar_expect_tx(bars.res_full[s], res_bytes);
-      load(q, staging + s * kEpiSetBytes, bars.res_full[s]);
+      load(q, staging + s * set_bytes, bars.res_full[s]);
     } else {
       mbar_arrive(bars.res_full[s]);
     }
@@ -148,7 +149,7 @@ __device__ __forceinline__ void epi_dma_loop(int64_t Q, uint32_t staging, const 
     const int s = (int)(q & 1);
     mbar_wait(bars.out_ready[s], (uint32_t)((q >> 1) & 1));
     if (any_store) {
-      store(q, staging + s * kEpiSetBytes);
+      store(q, staging + s * set_bytes);
       bulk_commit_group();
     }
     if (q + 2 < Q) {
