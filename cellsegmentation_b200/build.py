@@ -19,6 +19,7 @@ SOURCES = [
     "hsv_refine.cu",
     "unfold.cu",
     "select_topk.cu",
+    "select_fast.cu",
     "paint.cu",
     "fwd_fp32.cu",
     "fwd_tc.cu",

@@ -10,6 +10,8 @@
 // Algorithmic bytes: 3 (img) + 1 (mask) read + 1 written = 5 B / pixel.
 // Layout: one thread owns 32 consecutive pixels = three 32-byte image loads, one
 // 32-byte mask load, one 32-byte store; all streaming (evict-first) accesses.
+#include <stdlib.h>
+
 #include "common.cuh"
 
 namespace {
@@ -58,23 +60,47 @@ __device__ __forceinline__ uint32_t refine4(uint32_t w0, uint32_t w1, uint32_t w
 }
 
 constexpr int kPxPerThread = 32;
+constexpr int kPxPerWarp = 32 * kPxPerThread;   // 1024 pixels = 3072 image bytes per warp block
+constexpr int kWarpsPerCta = 8;
 
-__global__ void __launch_bounds__(256)
+// One warp = one block of 1024 pixels.  The three image loads are fully coalesced (lane l
+// takes bytes [k*1024 + 32 l, +32) of the 3072-byte block: 8 full lines per instruction);
+// letting every lane read its own 96 contiguous bytes instead makes each instruction touch all
+// 24 lines of the block (3x the L2 tag look-ups) and capped the kernel at 67 % of copy speed.
+// The bytes are redistributed through a per-warp 3 KB shared-memory slab so that lane l ends up
+// with the 96 bytes of its 32 pixels.
+__global__ void __launch_bounds__(kWarpsPerCta * 32)
 hsv_refine_vec_kernel(const u32x8* __restrict__ img, const u32x8* mask, u32x8* out,
-                      int64_t n_vec, uint32_t thr4) {
-  int64_t stride = (int64_t)gridDim.x * blockDim.x;
-  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n_vec; i += stride) {
-    u32x8 a = ld_stream(img + 3 * i);
-    u32x8 b = ld_stream(img + 3 * i + 1);
-    u32x8 c = ld_stream(img + 3 * i + 2);
-    u32x8 m = ld_stream_rw(mask + i);
+                      int64_t n_blocks, uint32_t thr4) {
+  __shared__ __align__(32) uint32_t slab[kWarpsPerCta][768];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  uint32_t* my = slab[warp];
+  const int64_t stride = (int64_t)gridDim.x * kWarpsPerCta;
+  for (int64_t bi = (int64_t)blockIdx.x * kWarpsPerCta + warp; bi < n_blocks; bi += stride) {
+    const u32x8* src = img + bi * 96;
+    u32x8 a = ld_stream(src + lane);
+    u32x8 b = ld_stream(src + 32 + lane);
+    u32x8 c = ld_stream(src + 64 + lane);
+    u32x8 m = ld_stream_rw(mask + bi * 32 + lane);
+    uint4* s4 = reinterpret_cast<uint4*>(my);
+    s4[2 * lane] = make_uint4(a.v[0], a.v[1], a.v[2], a.v[3]);
+    s4[2 * lane + 1] = make_uint4(a.v[4], a.v[5], a.v[6], a.v[7]);
+    s4[64 + 2 * lane] = make_uint4(b.v[0], b.v[1], b.v[2], b.v[3]);
+    s4[64 + 2 * lane + 1] = make_uint4(b.v[4], b.v[5], b.v[6], b.v[7]);
+    s4[128 + 2 * lane] = make_uint4(c.v[0], c.v[1], c.v[2], c.v[3]);
+    s4[128 + 2 * lane + 1] = make_uint4(c.v[4], c.v[5], c.v[6], c.v[7]);
+    __syncwarp();
     uint32_t w[24];
 #pragma unroll
-    for (int j = 0; j < 8; ++j) { w[j] = a.v[j]; w[8 + j] = b.v[j]; w[16 + j] = c.v[j]; }
+    for (int j = 0; j < 6; ++j) {
+      const uint4 q = s4[6 * lane + j];   // this lane's 96 bytes
+      w[4 * j] = q.x; w[4 * j + 1] = q.y; w[4 * j + 2] = q.z; w[4 * j + 3] = q.w;
+    }
+    __syncwarp();
     u32x8 o;
 #pragma unroll
     for (int j = 0; j < 8; ++j) o.v[j] = refine4(w[3 * j], w[3 * j + 1], w[3 * j + 2], m.v[j], thr4);
-    st_stream(out + i, o);
+    st_stream(out + bi * 32 + lane, o);
   }
 }
 
@@ -145,17 +171,23 @@ int cs_hsv_refine(const uint8_t* img, const uint8_t* mask, int64_t n_px, int v_t
   if (n_px == 0) return CS_OK;
   cudaStream_t st = cs::as_stream(stream);
   bool aligned = (((uintptr_t)img | (uintptr_t)mask | (uintptr_t)out) & 31u) == 0;
-  int64_t n_vec = aligned ? n_px / kPxPerThread : 0;
+  int64_t n_vec = aligned ? n_px / kPxPerWarp : 0;   // full 1024-pixel warp blocks
   if (n_vec > 0) {
     uint32_t thr4 = (uint32_t)v_thresh * 0x01010101u;
     // 8 resident CTAs of 256 threads per SM; grid-stride over the rest.
-    int64_t want = cs::ceil_div<int64_t>(n_vec, 256);
-    int grid = (int)(want < (int64_t)cs::kNumSMs * 8 * 4 ? want : (int64_t)cs::kNumSMs * 8 * 4);
+    int64_t want = cs::ceil_div<int64_t>(n_vec, kWarpsPerCta);
+    static const int ctas_per_sm = []() {
+      const char* e = getenv("CELLSEG_HSV_CTAS_PER_SM");   // tuning knob (profiles/tune_hsv.py)
+      int v = e ? atoi(e) : 0;
+      return v > 0 ? v : 32;
+    }();
+    int64_t cap = (int64_t)cs::kNumSMs * ctas_per_sm;
+    int grid = (int)(want < cap ? want : cap);
     hsv_refine_vec_kernel<<<grid, 256, 0, st>>>((const u32x8*)img, (const u32x8*)mask,
                                                (u32x8*)out, n_vec, thr4);
     CS_LAUNCH_CHECK();
   }
-  int64_t done = n_vec * kPxPerThread;
+  int64_t done = n_vec * kPxPerWarp;
   if (done < n_px) {
     int64_t rem = n_px - done;
     int grid = (int)(cs::ceil_div<int64_t>(rem, 256) < 148 * 16 ? cs::ceil_div<int64_t>(rem, 256)

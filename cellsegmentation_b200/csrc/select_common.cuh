@@ -1,0 +1,70 @@
+// Types shared by the exact per-bag sort (select_topk.cu) and the register-resident fast path
+// (select_fast.cu).
+#pragma once
+#include "common.cuh"
+
+namespace cs {
+
+struct Segs {
+  const int64_t* offsets;  // nullptr -> uniform
+  int64_t uniform_T;
+  int n_bags;
+  __device__ __forceinline__ int64_t start(int b) const {
+    return offsets ? offsets[b] : (int64_t)b * uniform_T;
+  }
+  __device__ __forceinline__ int64_t total() const {
+    return offsets ? offsets[n_bags] : (int64_t)n_bags * uniform_T;
+  }
+};
+
+__device__ __forceinline__ int pow2_ceil(int v) {
+  int p = 1;
+  while (p < v) p <<= 1;
+  return p;
+}
+
+// Kept ranks of one bag under the literal predicate: [a1,b1) U [a2,b2).
+struct Kept {
+  int a1, b1, a2, b2;
+  __device__ __forceinline__ int count() const { return (b1 - a1) + (b2 - a2); }
+};
+
+__device__ __forceinline__ Kept kept_ranges(int64_t s, int64_t T, int64_t N, int64_t k) {
+  Kept r{0, 0, 0, 0};
+  if (T <= 0 || N <= 0) return r;
+  int64_t kp = k % N;
+  int64_t J0 = N - kp - s;
+  int64_t a1 = T - kp > 0 ? T - kp : 0;
+  int64_t b1 = T < J0 ? T : J0;
+  int64_t a2 = J0 > 0 ? J0 : 0;
+  int64_t b2 = T < N - kp ? T : N - kp;
+  if (b1 < a1) b1 = a1;
+  if (b2 < a2) b2 = a2;
+  r.a1 = (int)a1; r.b1 = (int)b1; r.a2 = (int)a2; r.b2 = (int)b2;
+  return r;
+}
+
+__device__ __forceinline__ int64_t bag_k(const int32_t* labels, int b, int32_t tiles_per_pos,
+                                         int32_t topk_neg) {
+  int32_t c = labels[b];
+  return c == 0 ? (int64_t)topk_neg : (int64_t)c * (int64_t)tiles_per_pos;
+}
+
+struct EmitArgs {
+  const int32_t* labels;
+  int32_t tiles_per_pos, topk_neg;
+  float thr;
+  int32_t* idx_out;
+  uint8_t* label_out;
+  float* prob_out;
+  const int64_t* out_offsets;  // [n_bags+1]
+  int64_t capacity;
+  const int32_t* fb_count;      // exact kernel after the fast path: number of declined bags ...
+  const int32_t* fb_list;       // ... and their indices (nullptr: process every bag)
+};
+
+
+int launch_select_fast(const Segs& segs, const float* prob, const EmitArgs& ea, int64_t max_T,
+                       int32_t* fb_count, int32_t* fb_list, cudaStream_t st, bool* handled);
+
+}  // namespace cs

@@ -21,57 +21,17 @@
 // Normal case: the last min(k,T) ranks.  k' = 0 keeps nothing (also k = N).
 //
 // Algorithmic bytes: 4 B/instance read + 5 B per kept instance + 4 B/bag label.
+#include <stdlib.h>
+
 #include "common.cuh"
+#include "select_common.cuh"
+
+using namespace cs;
 
 namespace {
 
 constexpr int kThreads = 512;
 constexpr int kMaxSegPow2 = 32768;  // 6 B * 32768 = 192 KB of shared memory
-
-struct Segs {
-  const int64_t* offsets;  // nullptr -> uniform
-  int64_t uniform_T;
-  int n_bags;
-  __device__ __forceinline__ int64_t start(int b) const {
-    return offsets ? offsets[b] : (int64_t)b * uniform_T;
-  }
-  __device__ __forceinline__ int64_t total() const {
-    return offsets ? offsets[n_bags] : (int64_t)n_bags * uniform_T;
-  }
-};
-
-__device__ __forceinline__ int pow2_ceil(int v) {
-  int p = 1;
-  while (p < v) p <<= 1;
-  return p;
-}
-
-// Kept ranks of one bag under the literal predicate: [a1,b1) U [a2,b2).
-struct Kept {
-  int a1, b1, a2, b2;
-  __device__ __forceinline__ int count() const { return (b1 - a1) + (b2 - a2); }
-};
-
-__device__ __forceinline__ Kept kept_ranges(int64_t s, int64_t T, int64_t N, int64_t k) {
-  Kept r{0, 0, 0, 0};
-  if (T <= 0 || N <= 0) return r;
-  int64_t kp = k % N;
-  int64_t J0 = N - kp - s;
-  int64_t a1 = T - kp > 0 ? T - kp : 0;
-  int64_t b1 = T < J0 ? T : J0;
-  int64_t a2 = J0 > 0 ? J0 : 0;
-  int64_t b2 = T < N - kp ? T : N - kp;
-  if (b1 < a1) b1 = a1;
-  if (b2 < a2) b2 = a2;
-  r.a1 = (int)a1; r.b1 = (int)b1; r.a2 = (int)a2; r.b2 = (int)b2;
-  return r;
-}
-
-__device__ __forceinline__ int64_t bag_k(const int32_t* labels, int b, int32_t tiles_per_pos,
-                                         int32_t topk_neg) {
-  int32_t c = labels[b];
-  return c == 0 ? (int64_t)topk_neg : (int64_t)c * (int64_t)tiles_per_pos;
-}
 
 // ---- per-bag kept counts ----------------------------------------------------
 __global__ void select_count_kernel(Segs segs, const int32_t* __restrict__ labels,
@@ -102,64 +62,61 @@ rank_count_kernel(Segs segs, const float* __restrict__ prob, float thr,
 }
 
 // In-place exclusive scan of counts[0..n) into offsets[0..n]; offsets[n] = total.
-// One CTA; n_bags is at most ~1e5, so a serial-over-chunks block scan is enough.
+// One CTA of 32 warps; warp w owns the contiguous slice [w*per, (w+1)*per) and walks it 32
+// elements at a time (coalesced loads, shuffle scan, running carry); the 32 slice totals are
+// scanned by warp 0 and added in a second coalesced pass.
 __global__ void __launch_bounds__(1024)
 exclusive_scan_kernel(int64_t* __restrict__ data, int n) {
   __shared__ int64_t warp_tot[32];
-  __shared__ int64_t carry;
-  if (threadIdx.x == 0) carry = 0;
-  __syncthreads();
-  for (int base = 0; base < n; base += 1024) {
-    int i = base + threadIdx.x;
-    int64_t v = i < n ? data[i] : 0;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int per = ((n + 31) / 32 + 31) / 32 * 32;        // slice length, multiple of 32
+  const int lo = min(warp * per, n), hi = min(lo + per, n);
+  int64_t carry = 0;
+  for (int base = lo; base < hi; base += 32) {
+    const int i = base + lane;
+    const int64_t v = i < hi ? data[i] : 0;
     int64_t x = v;
+#pragma unroll
     for (int o = 1; o < 32; o <<= 1) {
-      int64_t y = __shfl_up_sync(0xffffffffu, x, o);
-      if ((threadIdx.x & 31) >= o) x += y;
+      const int64_t y = __shfl_up_sync(0xffffffffu, x, o);
+      if (lane >= o) x += y;
     }
-    if ((threadIdx.x & 31) == 31) warp_tot[threadIdx.x >> 5] = x;
-    __syncthreads();
-    if (threadIdx.x < 32) {
-      int64_t w = warp_tot[threadIdx.x];
-      int64_t xs = w;
-      for (int o = 1; o < 32; o <<= 1) {
-        int64_t y = __shfl_up_sync(0xffffffffu, xs, o);
-        if (threadIdx.x >= o) xs += y;
-      }
-      warp_tot[threadIdx.x] = xs - w;  // exclusive warp prefix
-    }
-    __syncthreads();
-    int64_t excl = carry + warp_tot[threadIdx.x >> 5] + (x - v);
-    if (i < n) data[i] = excl;
-    __syncthreads();
-    if (threadIdx.x == 1023) carry = excl + v;
-    __syncthreads();
+    if (i < hi) data[i] = carry + x - v;                  // exclusive within the slice
+    carry += __shfl_sync(0xffffffffu, x, 31);
   }
-  if (threadIdx.x == 0) data[n] = carry;
+  if (lane == 0) warp_tot[warp] = carry;
+  __syncthreads();
+  if (warp == 0) {
+    const int64_t w = warp_tot[lane];
+    int64_t xs = w;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const int64_t y = __shfl_up_sync(0xffffffffu, xs, o);
+      if (lane >= o) xs += y;
+    }
+    warp_tot[lane] = xs - w;                              // exclusive prefix of the slice totals
+    if (lane == 31) data[n] = xs;
+  }
+  __syncthreads();
+  const int64_t off = warp_tot[warp];
+  if (off != 0)
+    for (int i = lo + lane; i < hi; i += 32) data[i] += off;
 }
 
 // ---- per-bag sort + emit ----------------------------------------------------
 enum Mode { kLexsort = 0, kSelect = 1, kRank = 2 };
 
-struct EmitArgs {
-  const int32_t* labels;
-  int32_t tiles_per_pos, topk_neg;
-  float thr;
-  int32_t* idx_out;
-  uint8_t* label_out;
-  float* prob_out;
-  const int64_t* out_offsets;  // [n_bags+1]
-  int64_t capacity;
-};
-
 template <int kMode>
 __global__ void __launch_bounds__(kThreads)
 seg_sort_kernel(Segs segs, const float* __restrict__ prob, EmitArgs ea) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
-  const int b = blockIdx.x;
+  // Either every bag (one CTA each) or, after the fast path, only the bags it declined.
+  const int n_items = ea.fb_list != nullptr ? *ea.fb_count : segs.n_bags;
+  for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
+  const int b = ea.fb_list != nullptr ? ea.fb_list[item] : item;
   const int64_t s = segs.start(b);
   const int T = (int)(segs.start(b + 1) - s);
-  if (T <= 0) return;
+  if (T <= 0) continue;
   const int P = pow2_ceil(T);
   uint32_t* key = reinterpret_cast<uint32_t*>(smem_raw);
   uint16_t* idx = reinterpret_cast<uint16_t*>(smem_raw + (size_t)P * 4);
@@ -227,9 +184,15 @@ seg_sort_kernel(Segs segs, const float* __restrict__ prob, EmitArgs ea) {
       }
     }
   }
+  __syncthreads();   // shared memory is reused by the next item
+  }
 }
 
-int64_t* g_scan_dummy = nullptr;
+// Diagnostics: CELLSEG_SELECT_FAST=0 routes every bag through the exact sort kernel.
+const bool g_disable_fast = []() {
+  const char* e = getenv("CELLSEG_SELECT_FAST");
+  return e != nullptr && e[0] == '0';
+}();
 
 struct SegHostInfo {
   int max_pow2;
@@ -262,7 +225,8 @@ int launch_sort(const Segs& segs, const float* prob, const EmitArgs& ea, int64_t
                                  cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSegPow2 * 6));
     if (dev < 64) attr_set[dev][kMode] = true;
   }
-  seg_sort_kernel<kMode><<<segs.n_bags, kThreads, smem, st>>>(segs, prob, ea);
+  const int grid = ea.fb_list != nullptr ? (segs.n_bags < 148 * 4 ? segs.n_bags : 148 * 4) : segs.n_bags;
+  seg_sort_kernel<kMode><<<grid, kThreads, smem, st>>>(segs, prob, ea);
   CS_LAUNCH_CHECK();
   return CS_OK;
 }
@@ -299,8 +263,11 @@ int cs_lexsort_segments(const float* prob, const int64_t* seg_offsets, int64_t u
 int cs_select_topk(const float* prob, const int64_t* seg_offsets, int64_t uniform_T, int n_bags,
                    const int32_t* labels, int32_t tiles_per_pos, int32_t topk_neg,
                    int32_t* sel_idx_out, uint8_t* sel_label_out, int64_t* sel_offsets_out,
-                   int64_t capacity, void* stream) {
+                   int64_t capacity, void* workspace, int64_t workspace_bytes, void* stream) {
   int rc = check_segs("cs_select_topk", prob, seg_offsets, uniform_T, n_bags);
+  CS_REQUIRE(workspace != nullptr && workspace_bytes >= cs_select_workspace_bytes(n_bags),
+             "cs_select_topk: workspace too small (need %lld bytes)",
+             (long long)cs_select_workspace_bytes(n_bags));
   if (rc != CS_OK) return rc;
   CS_REQUIRE(labels && sel_idx_out && sel_label_out && sel_offsets_out,
              "cs_select_topk: NULL pointer");
@@ -321,8 +288,23 @@ int cs_select_topk(const float* prob, const int64_t* seg_offsets, int64_t unifor
   ea.label_out = sel_label_out;
   ea.out_offsets = sel_offsets_out;
   ea.capacity = capacity;
+  // register-resident warp-per-bag path first; bags it declines are flagged and ordered exactly
+  int32_t* fb_count = static_cast<int32_t*>(workspace);
+  int32_t* fb_list = fb_count + 64;
+  bool handled = false;
+  if (!g_disable_fast) {
+    CS_CUDA(cudaMemsetAsync(fb_count, 0, sizeof(int32_t), st));
+    rc = launch_select_fast(segs, prob, ea, uniform_T, fb_count, fb_list, st, &handled);
+    if (rc != CS_OK) return rc;
+  }
+  if (handled) {
+    ea.fb_count = fb_count;
+    ea.fb_list = fb_list;
+  }
   return launch_sort<kSelect>(segs, prob, ea, uniform_T, st);
 }
+
+int64_t cs_select_workspace_bytes(int n_bags) { return n_bags > 0 ? 256 + 4 * (int64_t)n_bags : 0; }
 
 int cs_rank_threshold(const float* prob, const int64_t* seg_offsets, int64_t uniform_T, int n_bags,
                       float threshold, int32_t* sel_idx_out, float* sel_prob_out,

@@ -96,8 +96,11 @@ def select_topk(prob, labels, n_bags, uniform_T, tiles_per_pos, topk_neg, seg_of
     idx = torch.empty(capacity, dtype=torch.int32, device=prob.device)
     lab = torch.empty(capacity, dtype=torch.uint8, device=prob.device)
     off = torch.empty(n_bags + 1, dtype=torch.int64, device=prob.device)
+    ws = torch.empty(max(int(lib().cs_select_workspace_bytes(n_bags)), 1), dtype=torch.uint8,
+                     device=prob.device)
     check(lib().cs_select_topk(ptr(prob), so, T, n_bags, ptr(labels), int(tiles_per_pos),
-                               int(topk_neg), ptr(idx), ptr(lab), ptr(off), capacity, cur_stream()),
+                               int(topk_neg), ptr(idx), ptr(lab), ptr(off), capacity, ptr(ws),
+                               ws.numel(), cur_stream()),
           "cs_select_topk")
     M = int(off[-1].item())
     if M > capacity:

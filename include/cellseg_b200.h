@@ -174,7 +174,11 @@ int cs_lexsort_segments(const float* prob, const int64_t* seg_offsets, int64_t u
 int cs_select_topk(const float* prob, const int64_t* seg_offsets, int64_t uniform_T,
                    int n_bags, const int32_t* labels, int32_t tiles_per_pos,
                    int32_t topk_neg, int32_t* sel_idx_out, uint8_t* sel_label_out,
-                   int64_t* sel_offsets_out, int64_t capacity, void* stream);
+                   int64_t* sel_offsets_out, int64_t capacity, void* workspace,
+                   int64_t workspace_bytes, void* stream);
+/* Bytes of device workspace cs_select_topk needs (the list of bags the register-resident
+ * fast path hands to the exact per-bag sort). */
+int64_t cs_select_workspace_bytes(int n_bags);
 
 /* Replaces rank() (test_tile.py:63-79, train_seg.py:234-247): keep prob > thr in
  * lexsort order.  Outputs as cs_select_topk; sel_prob_out f32 (optional). */
