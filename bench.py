@@ -235,13 +235,30 @@ def main():
                               "achieved": sel_bytes / (ms * 1e-3) / 1e9, "unit": "GB/s",
                               "note": "3 launches (count, scan, sort+emit) + one .item() sync inside the timing"}
         del p_all, sel_out
-        masks = (torch.rand((resident, H, H), device=dev, generator=g) < 0.3).to(torch.uint8)
+        # K4b at the config-5 size class: 8000 bags (3.6 GB of traffic per launch, >> L2)
+        nb_m = max(resident, 8000)
+        imgs_m = bags if nb_m == resident else synthetic.make_bags_device(nb_m, dev, seed=99)
+        blob = torch.rand((nb_m, H // 13 + 1, H // 13 + 1), device=dev, generator=g) < 0.45
+        masks = blob.repeat_interleave(13, 1).repeat_interleave(13, 2)[:, :H, :H].contiguous().to(torch.uint8)
         out_m = torch.empty_like(masks)
-        ms = time_alone(lambda: ops.hsv_refine(bags, masks, 170, out=out_m))
-        side["hsv_refine"] = {"bound": "hbm", "bags": resident, "ms": ms, "masks_per_s": resident / (ms * 1e-3),
+        ms = time_alone(lambda: ops.hsv_refine(imgs_m, masks, 170, out=out_m))
+        side["hsv_refine"] = {"bound": "hbm", "bags": nb_m, "ms": ms, "masks_per_s": nb_m / (ms * 1e-3),
                               "achieved": 5.0 * masks.numel() / (ms * 1e-3) / 1e9, "unit": "GB/s",
                               "bytes_per_mask": 5 * H * H}
-        del masks, out_m
+        # N1: connected-component clean-up of the refined masks (2000 bags), and the whole
+        # preprocess_masks chain (HSV AND + clean-up) in masks/s
+        nb_c = 2000
+        cc_in = out_m[:nb_c].clone()
+        work = torch.empty_like(cc_in)
+
+        def run_cc():
+            work.copy_(cc_in)
+            ops.remove_small_regions(work, 400, 120)
+        ms_cc = time_alone(run_cc, reps=3)
+        side["remove_small_regions"] = {"bags": nb_c, "ms": ms_cc, "masks_per_s": nb_c / (ms_cc * 1e-3),
+                                        "note": "includes a device copy of the 2000 input masks"}
+        side["preprocess_masks_chain"] = {"masks_per_s": 1.0 / (ms / nb_m * 1e-3 + ms_cc / nb_c * 1e-3)}
+        del masks, out_m, cc_in, work
 
     # ---- end to end: host (pinned) bags -> H2D -> score + select -> D2H of the selection
     host = torch.empty((B, H, H, 3), dtype=torch.uint8).pin_memory()
@@ -313,8 +330,9 @@ def main():
                                     "frac": SELECT_BYTES_PER_INST * n_inst / (sel_ms * 1e-3) / 1e9 / pk["hbm_gbs"]}},
         }
         for k, v in side.items():
-            v["peak"] = pk["hbm_gbs"]
-            v["frac"] = v["achieved"] / pk["hbm_gbs"]
+            if "achieved" in v:
+                v["peak"] = pk["hbm_gbs"]
+                v["frac"] = v["achieved"] / pk["hbm_gbs"]
             out["roofline"][k] = v
         if not args.no_cpu_baseline:
             from oracle import model as omodel

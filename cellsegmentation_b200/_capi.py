@@ -61,6 +61,9 @@ _PROTOS = {
     "cs_heatmap_to_gray": (c_int, [c_void_p, c_int64, c_void_p, c_void_p]),
     "cs_hsv_refine": (c_int, [c_void_p, c_void_p, c_int64, c_int, c_void_p, c_void_p]),
     "cs_bgr2hsv_u8": (c_int, [c_void_p, c_int64, c_void_p, c_void_p]),
+    "cs_cc_workspace_bytes": (c_int64, [c_int, c_int, c_int]),
+    "cs_remove_small_regions": (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p, c_int64,
+                                        c_void_p]),
     "cs_debug_gemm_bf16": (c_int, [c_void_p, c_void_p, c_int64, c_int, c_int, c_void_p, c_int,
                                    c_void_p, c_void_p]),
     "cs_debug_conv3x3_bf16": (c_int, [c_void_p, c_int64, c_int, c_int, c_int, c_int, c_int,

@@ -21,6 +21,7 @@ SOURCES = [
     "select_topk.cu",
     "select_fast.cu",
     "paint.cu",
+    "cc.cu",
     "fwd_fp32.cu",
     "fwd_tc.cu",
     "conv_gemm.cu",

@@ -192,6 +192,20 @@ def hsv_refine(img, mask, v_thresh=170, out=None):
     return out
 
 
+def remove_small_regions(mask, min_object_size, hole_area_threshold):
+    """remove_small_regions (utils/image_processing.py:14-17) on u8 [n,H,W] masks, in place (0/1)."""
+    _req_cuda(mask, "mask", torch.uint8)
+    if mask.dim() == 2:
+        mask = mask.unsqueeze(0)
+    n, H, W = mask.shape
+    nbytes = lib().cs_cc_workspace_bytes(n, H, W)
+    ws = torch.empty(nbytes, dtype=torch.uint8, device=mask.device)
+    check(lib().cs_remove_small_regions(ptr(mask), n, H, W, int(min_object_size),
+                                        int(hole_area_threshold), ptr(ws), nbytes, cur_stream()),
+          "cs_remove_small_regions")
+    return mask
+
+
 def bgr2hsv(img):
     """cv2.cvtColor(img, cv2.COLOR_BGR2HSV) for u8 [...,3], bit-exact."""
     _req_cuda(img, "img", torch.uint8)

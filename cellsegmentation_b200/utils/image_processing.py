@@ -1,10 +1,9 @@
 """Heatmaps, pseudo-masks and HSV refinement (mirror of utils/image_processing.py).
 
 heatmap / generate_masks / preprocess_masks / remove_small_regions keep the reference
-signatures (utils/image_processing.py:146, 79, 114, 14).  Painting and the HSV-threshold AND run
-on the GPU (paint.cu, hsv_refine.cu); the connected-component clean-up of
-remove_small_regions is the reference's own host step (scikit-image there, scipy.ndimage here —
-SURVEY 8f N1) and PNG/CSV writing stays on the host.
+signatures (utils/image_processing.py:146, 79, 114, 14).  Painting, the HSV-threshold AND and the
+connected-component clean-up of remove_small_regions run on the GPU (paint.cu, hsv_refine.cu,
+cc.cu); the JET colour map / blend (cv2) and PNG/CSV writing stay on the host.
 """
 import csv
 import os
@@ -12,7 +11,6 @@ import os
 import numpy as np
 import torch
 
-from . import _cc
 from .. import ops
 
 
@@ -26,8 +24,9 @@ def _imsave(path, rgb):
 
 
 def remove_small_regions(img_bin, min_object_size, hole_area_threshold):
-    """utils/image_processing.py:14-17: remove_small_objects then remove_small_holes."""
-    return _cc.remove_small_holes(_cc.remove_small_objects(img_bin, min_object_size), hole_area_threshold)
+    """utils/image_processing.py:14-17: remove_small_objects then remove_small_holes (bool [H,W])."""
+    d = torch.from_numpy(np.ascontiguousarray(np.asarray(img_bin) != 0).astype(np.uint8)).to(_cuda_dev())
+    return ops.remove_small_regions(d, min_object_size, hole_area_threshold)[0].cpu().numpy().astype(bool)
 
 
 def _xy_tensors(tiles, groups, dev):
@@ -48,8 +47,8 @@ def preprocess_masks(img, mask):
     dev = _cuda_dev()
     d_img = torch.from_numpy(np.ascontiguousarray(img, dtype=np.uint8)).to(dev)
     d_mask = torch.from_numpy(np.ascontiguousarray(np.asarray(mask) != 0).astype(np.uint8)).to(dev)
-    refined = ops.hsv_refine(d_img, d_mask, 170).cpu().numpy().astype(bool)
-    return remove_small_regions(refined, min_object_size=400, hole_area_threshold=120)
+    refined = ops.hsv_refine(d_img, d_mask, 170)
+    return ops.remove_small_regions(refined, 400, 120)[0].cpu().numpy().astype(bool)
 
 
 def generate_masks(dataset, tiles, groups, preprocess, save_masks=True, output_path="./data/pseudomask"):
@@ -61,13 +60,11 @@ def generate_masks(dataset, tiles, groups, preprocess, save_masks=True, output_p
     H, W = int(dataset.image_size[0]), int(dataset.image_size[1])
     g, x, y = _xy_tensors(tiles, groups, dev)
     masks_dev = ops.paint_mask_xy(g, x, y, n, H, W, dataset.tile_size)
-    if preprocess:
+    if preprocess:      # preprocess_masks for every bag at once (:100-102, :114-124)
         masks_dev = ops.hsv_refine(dataset.device_images(dev), masks_dev, 170)
+        masks_dev = ops.remove_small_regions(masks_dev, 400, 120)
     pseudo_masks = masks_dev.cpu().numpy()
     for i, img in enumerate(dataset.images):
-        if preprocess:
-            pseudo_masks[i] = remove_small_regions(pseudo_masks[i].astype(bool), min_object_size=400,
-                                                   hole_area_threshold=120)
         if save_masks:
             _imsave(os.path.join(output_path, "rgb/{:05}.png".format(i + 1)), np.uint8(img))
             _imsave(os.path.join(output_path, "mask/{:05}.png".format(i + 1)), np.uint8(pseudo_masks[i] * 255))

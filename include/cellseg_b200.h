@@ -236,6 +236,15 @@ int cs_hsv_refine(const uint8_t* img, const uint8_t* mask, int64_t n_px, int v_t
  * (exactly what the reference does when it hands cv2 an RGB array). */
 int cs_bgr2hsv_u8(const uint8_t* img, int64_t n_px, uint8_t* hsv_out, void* stream);
 
+/* remove_small_regions() (utils/image_processing.py:14-17): skimage 0.19
+ * remove_small_objects(min_size) then remove_small_holes(area_threshold), both 4-connected:
+ * components with size < threshold are flipped.  mask u8 [n_bags][H][W] (non-zero =
+ * foreground) is rewritten in place as 0/1.  A threshold of 0 skips that step. */
+int64_t cs_cc_workspace_bytes(int n_bags, int H, int W);
+int cs_remove_small_regions(uint8_t* mask, int n_bags, int H, int W, int min_object_size,
+                            int hole_area_threshold, void* workspace, int64_t workspace_bytes,
+                            void* stream);
+
 /* ---------------------------------------------------------------------------
  * Diagnostics — used by tests/ to exercise the tcgen05 GEMM kernel and the
  * production conv planner in isolation.  Not part of the reference surface.

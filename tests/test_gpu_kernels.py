@@ -206,3 +206,22 @@ def test_heatmap_to_gray_all_thresholded_probs(cuda):
     p = np.concatenate([p, np.linspace(0, 1, 100001, dtype=np.float32)])
     got = ops.heatmap_to_gray(torch.from_numpy(p).to(cuda)).cpu().numpy()
     assert np.array_equal(got, omasks.heat_to_gray(p.astype(np.float64)))
+
+
+# ----------------------------------------------------------------------------- N1 connected components
+@pytest.mark.parametrize("H,W,density,seed", [(299, 299, 0.5, 0), (299, 299, 0.62, 1), (96, 96, 0.55, 2),
+                                               (64, 48, 0.4, 3), (299, 299, 0.9, 4), (17, 301, 0.5, 5)])
+def test_remove_small_regions_bit_exact(cuda, H, W, density, seed):
+    ops = _ops()
+    rng = np.random.default_rng(seed)
+    n = 5
+    # blobs + salt noise: components of all sizes around the 400 / 120 thresholds
+    coarse = rng.uniform(size=(n, H // 7 + 2, W // 7 + 2)) < density
+    m = np.kron(coarse, np.ones((7, 7), bool))[:, :H, :W]
+    m ^= rng.uniform(size=m.shape) < 0.03
+    m[0] = 0
+    m[1] = 1
+    for mo, ha in [(400, 120), (30, 9), (0, 120), (400, 0), (1, 1)]:
+        want = np.stack([omasks.remove_small_regions(x, mo, ha) for x in m]).astype(np.uint8)
+        got = ops.remove_small_regions(torch.from_numpy(m.astype(np.uint8) * 3).to(cuda), mo, ha)
+        assert int((got.cpu().numpy() != want).sum()) == 0, (mo, ha)
