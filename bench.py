@@ -36,7 +36,7 @@ def parse():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--bags-per-step", type=int, default=1024, help="bags scored per step per GPU")
     ap.add_argument("--resident-bags", type=int, default=0, help="bags resident in HBM per GPU (0: auto)")
-    ap.add_argument("--max-batch", type=int, default=18944, help="instances per forward batch")
+    ap.add_argument("--max-batch", type=int, default=37888, help="instances per forward batch")
     ap.add_argument("--ref-bags", type=int, default=2, help="bags per step of the CPU reference arm")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     return ap.parse_args()

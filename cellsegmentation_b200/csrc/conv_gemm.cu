@@ -101,6 +101,8 @@ conv_gemm_kernel(const __grid_constant__ GemmParams p) {
   if (CL > 1) cluster_sync_all();   // peers' barriers are initialised before any remote arrive
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  pdl_launch_dependents();   // the next layer may start its prologue on SMs that free up
+  pdl_wait();                // ... and this one touches activations only after its producer is done
 
   // Work items of a cluster: (group of CL consecutive M tiles, N tile); CTA `rank` owns M tile
   // group*CL + rank.  CTAs whose M tile does not exist still run the protocol (zero-filled A,
@@ -269,19 +271,8 @@ int launch_gemm_bn(const GemmParams& p, cudaStream_t st) {
   const int m_groups = (p.num_m_tiles + CL - 1) / CL;
   const int work = m_groups * p.num_n_tiles;
   int clusters = work < kNumSMs / CL ? work : kNumSMs / CL;
-  cudaLaunchConfig_t cfg = {};
-  cfg.gridDim = dim3((unsigned)(clusters * CL));
-  cfg.blockDim = dim3(kGemmThreads);
-  cfg.dynamicSmemBytes = smem;
-  cfg.stream = st;
-  cudaLaunchAttribute attr[1];
-  attr[0].id = cudaLaunchAttributeClusterDimension;
-  attr[0].val.clusterDim.x = CL;
-  attr[0].val.clusterDim.y = 1;
-  attr[0].val.clusterDim.z = 1;
-  cfg.attrs = attr;
-  cfg.numAttrs = 1;
-  CS_CUDA(cudaLaunchKernelEx(&cfg, conv_gemm_kernel<BN, CL>, q));
+  CS_CUDA(launch_pdl(conv_gemm_kernel<BN, CL>, dim3((unsigned)(clusters * CL)), dim3(kGemmThreads), smem, st,
+                     CL, q));
   return CS_OK;
 }
 

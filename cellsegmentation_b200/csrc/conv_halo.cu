@@ -86,14 +86,16 @@ conv_halo_kernel(const __grid_constant__ HaloParams p) {
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  pdl_launch_dependents();
 
   if (warp == 0) {
     if (lane == 0) {
-      if (BRES) {
+      if (BRES) {   // weights are constants: fetch them while the previous layer still drains
         mbar_expect_tx(bres_bar, Cfg::kBResBytes);
         for (int t = 0; t < 9 * CCH; ++t)   // tile index = tap * CCH + chunk = K column / 64
           tma_load_2d(bres + t * Cfg::kBTile, &p.b_map, bres_bar, t * 64, 0);
       }
+      pdl_wait();
       int stage = 0;
       uint32_t phase = 0;
       for (int mi = blockIdx.x; mi < p.num_m_tiles; mi += gridDim.x) {
@@ -149,6 +151,7 @@ conv_halo_kernel(const __grid_constant__ HaloParams p) {
       }
     }
   } else if (warp < 2 + kEpiWarps) {
+    pdl_wait();
     const int quad = warp & 3;
     const int half = (warp - 2) >> 2;
     const int r = quad * 32 + lane;
@@ -181,6 +184,7 @@ conv_halo_kernel(const __grid_constant__ HaloParams p) {
       if (acc == 0) acc_phase ^= 1u;
     }
   } else if (lane == 0) {
+    pdl_wait();
     // epilogue DMA thread: tiles move as {64 ch, W, IMG, H} boxes of the {C, W, T, H} maps, i.e.
     // in accumulator row order
     int n_items = 0;
@@ -231,8 +235,8 @@ int launch_halo(const HaloParams& p, cudaStream_t st) {
     if (dev < 64) attr_done[dev] = true;
   }
   int grid = p.num_m_tiles < kNumSMs ? p.num_m_tiles : kNumSMs;
-  conv_halo_kernel<BN, W, CCH, BRES><<<grid, kHaloThreads, Cfg::kSmemBytes, st>>>(p);
-  CS_LAUNCH_CHECK();
+  CS_CUDA(launch_pdl(conv_halo_kernel<BN, W, CCH, BRES>, dim3((unsigned)grid), dim3(kHaloThreads),
+                     Cfg::kSmemBytes, st, 1, p));
   return CS_OK;
 }
 

@@ -150,6 +150,8 @@ head_bf16_kernel(const __nv_bfloat16* __restrict__ x_hi, const __nv_bfloat16* __
                  int64_t n, int P, int C, const float* __restrict__ fc_w,
                  const float* __restrict__ fc_b, float* __restrict__ prob_out,
                  float* __restrict__ logits_out, float* __restrict__ feat_out) {
+  pdl_launch_dependents();
+  pdl_wait();
   int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   int lane = threadIdx.x & 31;
   if (warp >= n) return;
@@ -288,9 +290,8 @@ int launch_head_bf16(const __nv_bfloat16* x_hi, const __nv_bfloat16* x_lo, int64
                      float* feat_out, cudaStream_t st) {
   if (n <= 0) return CS_OK;
   int64_t blocks = ceil_div<int64_t>(n * 32, 256);
-  head_bf16_kernel<<<(unsigned)blocks, 256, 0, st>>>(x_hi, x_lo, n, P, C, fc_w, fc_b, prob_out,
-                                                    logits_out, feat_out);
-  CS_LAUNCH_CHECK();
+  CS_CUDA(launch_pdl(head_bf16_kernel, dim3((unsigned)blocks), dim3(256), 0, st, 1, x_hi, x_lo, n, P, C,
+                     fc_w, fc_b, prob_out, logits_out, feat_out));
   return CS_OK;
 }
 

@@ -106,6 +106,8 @@ stem_tc_kernel(const __grid_constant__ StemTcParams p) {
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  pdl_launch_dependents();
+  pdl_wait();   // the output buffers may still be read by the previous batch's kernels
 
   const int64_t n_inst = a.count;
 
@@ -340,8 +342,7 @@ int launch_stem_tc(const StemArgs& a, const void* w_bf16_dev, const uint16_t* lu
   p.a = a;
   p.lut_bf16 = lut_bf16_dev;
   int grid = (int)(a.count < kNumSMs ? a.count : kNumSMs);
-  stem_tc_kernel<<<grid, kThreads, Smem::total + 1024, st>>>(p);
-  CS_LAUNCH_CHECK();
+  CS_CUDA(launch_pdl(stem_tc_kernel, dim3((unsigned)grid), dim3(kThreads), Smem::total + 1024, st, 1, p));
   return CS_OK;
 }
 

@@ -60,6 +60,15 @@ __device__ __forceinline__ void tma_load_4d(uint32_t dst, const CUtensorMap* map
       "r"(c2), "r"(c3)
       : "memory");
 }
+// Programmatic dependent launch: a kernel launched with the PDL attribute may start while its
+// predecessor drains; pdl_wait() blocks until the predecessor grid has completed and its
+// memory is visible (call it before touching any data another kernel produces), and
+// pdl_launch_dependents() lets the successor begin its own prologue.
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_launch_dependents() {
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+}
+
 // TMA stores (shared -> global, bulk async-group completion) and their bookkeeping.
 __device__ __forceinline__ void tma_store_2d(const CUtensorMap* map, uint32_t src, int c0, int c1) {
   asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];" ::"l"(map),

@@ -270,7 +270,7 @@ class TileClassifier:
         return self._ws
 
     def forward_tiles(self, img, tile, interval, inst_begin=0, inst_count=None, precision="bf16",
-                      max_batch=18944, want_features=False, prob_out=None):
+                      max_batch=37888, want_features=False, prob_out=None):
         """Fused unfold -> CNN -> softmax[:,1] over instances of the resident u8 bag array."""
         _req_cuda(img, "img", torch.uint8)
         Nb, H, W, _ = img.shape
@@ -288,7 +288,7 @@ class TileClassifier:
               "cs_model_forward_tiles")
         return (prob_out, feat) if want_features else prob_out
 
-    def forward_tensor(self, x, precision="bf16", max_batch=18944, want_features=False):
+    def forward_tensor(self, x, precision="bf16", max_batch=37888, want_features=False):
         """Drop-in for model(x): x f32 [n,3,S,S] normalised tiles -> logits f32 [n,2]."""
         _req_cuda(x, "x", torch.float32)
         n, _, S, _ = x.shape

@@ -173,3 +173,50 @@ def test_train_tile_updates_only_fc_tile(cuda):
     with torch.no_grad():
         p_mod = torch.softmax(net(x[:64].to(cuda)), 1)[:, 1].cpu().numpy()
     assert np.abs(p_mod - probs2[:64]).max() < 1e-4
+
+
+def test_train_tile_matches_reference_loop_fp32(cuda):
+    """One epoch of train_tile (SGD, loader order) against the oracle restatement of
+    train/train.py:12-48: mean loss and the updated fc_tile within fp32 tolerance."""
+    from oracle import train as otrain
+    from cellsegmentation_b200.inference import inference_tiles, sample
+    from cellsegmentation_b200.train import train_tile
+    bags, ds = _trainset()
+    ds.setmode(1)
+    x = torch.from_numpy(otiles.unfold(list(bags[1:]), 20, 32))
+    sd = omodel.calibrate_head(omodel.make_state_dict("resnet34", seed=3), x[::3], "resnet34")
+    net = _model("resnet34", sd, cuda, "fp32")
+    loader = torch.utils.data.DataLoader(ds, batch_size=16, shuffle=False)
+    probs = inference_tiles(loader, net, cuda)
+    np.random.seed(1)
+    sample(ds, probs, 1, 30, 0.5)
+    ds.setmode(3)
+    td = ds.train_data
+    tiles = torch.stack([torch.from_numpy(otiles.normalize_tile(bags[r["bag"]][r["x"]:r["x"] + 32, r["y"]:r["y"] + 32]))
+                         for r in td])
+    labels = torch.from_numpy(td["label"].copy())
+    want_loss, want_w, want_b = otrain.train_tile_epoch(sd, tiles, labels, 16, lr=1e-6)
+    opt = torch.optim.SGD(filter(lambda p: p.requires_grad, net.parameters()), lr=1e-6)
+    got_loss = train_tile(loader, 1, 1, net, cuda, torch.nn.CrossEntropyLoss(), opt, None, 1.)
+    assert abs(got_loss - want_loss) < 1e-4 * max(1.0, abs(want_loss))
+    assert (net.fc_tile[1].weight.detach().cpu() - want_w).abs().max() < 1e-6
+    assert (net.fc_tile[1].bias.detach().cpu() - want_b).abs().max() < 1e-6
+    assert (net.fc_tile[1].weight.detach().cpu() - sd["fc_tile.1.weight"]).abs().max() > 0
+
+
+def test_mil_epoch_single_process_equals_sample_plus_train_tile(cuda):
+    from cellsegmentation_b200.inference import sample_indices, inference_tiles
+    from cellsegmentation_b200.mil import mil_epoch, select_global
+    bags, ds = _trainset()
+    x = torch.from_numpy(otiles.unfold(list(bags[1:]), 20, 32))
+    sd = omodel.calibrate_head(omodel.make_state_dict("resnet34", seed=3), x[::3], "resnet34")
+    net = _model("resnet34", sd, cuda, "bf16")
+    ds.setmode(1)
+    loader = torch.utils.data.DataLoader(ds, batch_size=64, shuffle=False)
+    probs = inference_tiles(loader, net, cuda)
+    want_idx, want_pl = sample_indices(ds, probs, 1, 30)
+    gidx, glab = select_global(ds, net, cuda, 1, 30)
+    assert np.array_equal(gidx, want_idx) and np.array_equal(glab, want_pl)
+    opt = torch.optim.SGD(filter(lambda p: p.requires_grad, net.parameters()), lr=1e-6)
+    loss, pos, neg = mil_epoch(ds, net, cuda, torch.nn.CrossEntropyLoss(), opt, 1, 30, 0.5, 16, seed=3)
+    assert np.isfinite(loss) and pos + neg == len(ds.train_data)
