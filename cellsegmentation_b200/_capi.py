@@ -13,7 +13,7 @@ LIB_PATH = os.path.join(_HERE, "csrc", "libcellseg_b200.so")
 CS_OK = 0
 CS_PREC_FP32 = 0
 CS_PREC_BF16 = 1
-CS_ARCH = {"resnet18": 0, "resnet34": 1}
+CS_ARCH = {"resnet18": 0, "resnet34": 1, "resnet50": 2, "resnext50_32x4d": 3}
 
 
 class CellSegError(RuntimeError):
@@ -36,6 +36,7 @@ _PROTOS = {
     "cs_model_create": (c_int, [c_int, c_int, POINTER(c_void_p), POINTER(c_void_p), c_void_p,
                                 c_void_p, POINTER(c_void_p)]),
     "cs_model_destroy": (c_int, [c_void_p]),
+    "cs_model_feature_dim": (c_int, [c_void_p]),
     "cs_model_set_fc": (c_int, [c_void_p, c_void_p, c_void_p]),
     "cs_model_workspace_bytes": (c_int64, [c_void_p, c_int, c_int64, c_int]),
     "cs_model_forward_tiles": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int,
@@ -66,8 +67,8 @@ _PROTOS = {
                                         c_void_p]),
     "cs_debug_gemm_bf16": (c_int, [c_void_p, c_void_p, c_int64, c_int, c_int, c_void_p, c_int,
                                    c_void_p, c_void_p]),
-    "cs_debug_conv3x3_bf16": (c_int, [c_void_p, c_int64, c_int, c_int, c_int, c_int, c_int,
-                                      c_void_p, c_void_p, c_void_p, c_void_p]),
+    "cs_debug_conv_bf16": (c_int, [c_void_p, c_int64, c_int, c_int, c_int, c_int, c_int, c_int, c_int,
+                                   c_void_p, c_void_p, c_void_p, c_void_p]),
 }
 
 EXPORTED = tuple(_PROTOS)

@@ -126,17 +126,18 @@ conv_gemm_kernel(const __grid_constant__ GemmParams p) {
           const uint32_t a_dst = base + stage * Cfg::kStageBytes;
           const uint32_t b_dst = a_dst + Cfg::kABytes;
           mbar_expect_tx(full_bar(stage), Cfg::kStageBytes);
-          if (p.a_mode == 0)
-            tma_load_2d(a_dst, &p.a_map[st.map], full_bar(stage), st.a_c0, m_tile * kGemmBM);
+          const int mp = st.map();
+          if (((p.a_mode >> mp) & 1) == 0)
+            tma_load_2d(a_dst, &p.a_map[mp], full_bar(stage), st.a_c0(), m_tile * kGemmBM);
           else
-            tma_load_4d(a_dst, &p.a_map[st.map], full_bar(stage), st.a_c0, st.dx, st.dy,
+            tma_load_4d(a_dst, &p.a_map[mp], full_bar(stage), st.a_c0(), st.dx(), st.dy(),
                         m_tile * p.units_per_mtile);
           if (CL == 1) {
-            tma_load_2d(b_dst, &p.b_map, full_bar(stage), st.b_k, n_tile * BN);
+            tma_load_2d(b_dst, &p.b_map, full_bar(stage), st.b_k(), n_tile * BN);
           } else {
             // this CTA's slice of the B tile, delivered to every CTA of the cluster
             constexpr int kSliceRows = BN / CL;
-            tma_load_2d_mcast(b_dst + rank * (kSliceRows * 128), &p.b_map, full_bar(stage), st.b_k,
+            tma_load_2d_mcast(b_dst + rank * (kSliceRows * 128), &p.b_map, full_bar(stage), st.b_k(),
                               n_tile * BN + rank * kSliceRows, kMask);
           }
           if (++stage == n_stages) { stage = 0; phase ^= 1u; }

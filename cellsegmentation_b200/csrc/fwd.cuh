@@ -33,16 +33,27 @@ int launch_head_fp32(const float* x4, int64_t n, int P, int C, const float* fc_w
 // ---------------------------------------------------------------------------
 constexpr int kGemmBM = 128;       // UMMA M (rows per CTA tile)
 constexpr int kGemmBK = 64;        // bf16 elements per K step = one 128-byte swizzle row
-constexpr int kMaxSteps = 20;      // K steps per (layer, n-variant)
-constexpr int kMaxVariants = 4;
+constexpr int kMaxSteps = 40;      // K steps per (layer, n-variant)
+constexpr int kMaxVariants = 8;
 
-// One K step of 64 channels: which A box to fetch and which B columns it meets.
+// One K step of 64 channels, packed: which A box to fetch and which B columns it meets.
+//   bits  0-9  : A coordinate 0 / 64 (channel chunk, or K-column chunk in 2-D mode)
+//   bits 10-19 : B coordinate 0 / 64 (K-column chunk)
+//   bits 20-21 : dx + 1, bits 22-23 : dy + 1   (4-D maps: pixel shift in {-1, 0, +1})
+//   bits 24-25 : A tensor map index
 struct KStep {
-  int16_t a_c0;  // A coordinate 0 (channel, or K column in 2-D mode), elements
-  int16_t b_k;   // B coordinate 0 (K column), elements
-  int8_t dx, dy; // 4-D mode: A coordinates 1 and 2 (pixel shift; may be -1)
-  uint8_t map;   // A tensor map index
-  uint8_t pad_;
+  uint32_t v;
+  __host__ __device__ int a_c0() const { return (int)(v & 1023u) * 64; }
+  __host__ __device__ int b_k() const { return (int)((v >> 10) & 1023u) * 64; }
+  __host__ __device__ int dx() const { return (int)((v >> 20) & 3u) - 1; }
+  __host__ __device__ int dy() const { return (int)((v >> 22) & 3u) - 1; }
+  __host__ __device__ int map() const { return (int)((v >> 24) & 3u); }
+  static KStep make(int a_c0, int b_k, int dx, int dy, int map) {
+    KStep s;
+    s.v = (uint32_t)(a_c0 / 64) | ((uint32_t)(b_k / 64) << 10) | ((uint32_t)(dx + 1) << 20) |
+          ((uint32_t)(dy + 1) << 22) | ((uint32_t)map << 24);
+    return s;
+  }
 };
 
 struct GemmParams {
@@ -51,7 +62,7 @@ struct GemmParams {
   KStep steps[kMaxVariants][kMaxSteps];
   int n_steps[kMaxVariants];
   int n_variants;     // 1: every n-tile walks steps[0]; else steps[n_tile]
-  int a_mode;         // 0: 2-D {k, row}; 1: 4-D {c, x, y, tile}
+  int a_mode;         // bit i set: A map i is 4-D {c, x, y, tile}; clear: 2-D {k, row}
   int units_per_mtile;  // 4-D mode: tiles (instances) per 128-row M tile
   int num_m_tiles, num_n_tiles;
   int reverse;        // walk work items from the last to the first (L2 snake order between layers)

@@ -1,11 +1,12 @@
 // Model object for the tile classifier: weight packing, per-layer GEMM planning and the
 // forward drivers behind cs_model_forward_tiles / cs_model_forward_tensor.
 //
-// Reference network: MILResNet with BasicBlock (model/resnet.py:15-43, 81-127, 179-193,
-// 234-269); ctor layer counts from MILresnet18/34 (:336-352).  The caller has folded
-// eval-mode BN into every conv (fp32).  Activation layout on the device is
-// [instance][pixel (row-major y,x)][channel]; bf16 mode keeps a `hi` tensor (MMA
-// operand) and, for block outputs, a `lo` tensor (value - hi) for the residual stream.
+// Reference networks: MILResNet with BasicBlock or Bottleneck (model/resnet.py:15-79, 81-127,
+// 179-193, 234-269; ctors :336-361) and MILResNeXt with grouped Bottleneck
+// (model/resnext.py:67-113, 305-340, 418-442).  The caller has folded eval-mode BN into every
+// conv (fp32).  Activation layout on the device is [instance][pixel (row-major y,x)][channel];
+// bf16 mode keeps a `hi` tensor (MMA operand) and, for block outputs, a `lo` tensor
+// (value - hi) for the residual stream.
 #include <math.h>
 #include <stdlib.h>
 #include <string.h>
@@ -27,46 +28,39 @@ uint16_t f32_to_bf16_rn(float f) {
   return (uint16_t)(u >> 16);
 }
 
-const bool g_snake = []() {
-  const char* e = getenv("CELLSEG_SNAKE");
-  return !(e != nullptr && strcmp(e, "0") == 0);
-}();
-
-// CELLSEG_CLUSTER=1 disables the 2-CTA B multicast of the generic GEMM kernel.
-const int g_cluster = []() {
-  const char* e = getenv("CELLSEG_CLUSTER");
-  return (e != nullptr && strcmp(e, "1") == 0) ? 1 : 2;
-}();
-
-// Diagnostics: CELLSEG_HALO=0 keeps every shifted-box conv on the generic kernel.
-const bool g_disable_halo = []() {
-  const char* e = getenv("CELLSEG_HALO");
-  return e != nullptr && strcmp(e, "0") == 0;
-}();
+bool env_is(const char* name, const char* value) {
+  const char* e = getenv(name);
+  return e != nullptr && strcmp(e, value) == 0;
+}
+const bool g_snake = !env_is("CELLSEG_SNAKE", "0");          // alternate the tile walk per layer
+const int g_cluster = env_is("CELLSEG_CLUSTER", "2") ? 2 : 1;  // 2-CTA B multicast (no gain measured)
+const bool g_disable_halo = env_is("CELLSEG_HALO", "0");     // diagnostics: generic kernel only
+const bool g_force_cuda_core_stem = env_is("CELLSEG_STEM", "cuda");
 
 struct ConvW {
-  int cin = 0, cout = 0, k = 0, stride = 1, pad = 0;
-  std::vector<float> w;  // OIHW, BN folded
+  int cin = 0, cout = 0, k = 0, stride = 1, pad = 0, groups = 1;
+  std::vector<float> w;  // dense OIHW [cout][cin][k][k], BN folded, zeros outside the groups
   std::vector<float> b;  // [cout]
   float* d_w32 = nullptr;  // [k*k*cin][cout]
   float* d_b = nullptr;
 };
 
 struct BlockDesc {
-  int conv1, conv2, ds;  // indices into convs; ds = -1 when the block has no downsample
-  int cin, cout, stride;
+  bool bottleneck;
+  int conv1, conv2, conv3, ds;  // indices into convs; conv3 / ds = -1 when absent
+  int cin, width, cout, stride;
 };
 
 struct ConvGeom {
-  int Hi, Wi, Cin, Ho, Wo, Cout, k, stride, pad;
+  int Hi, Wi, Cin, Ho, Wo, Cout, k, stride, pad, groups;
 };
 
 struct PlannedConv {
   GemmParams p;
   int BN = 0;
-  bool dense = false;
-  int Po = 0;  // output pixels per instance
-  bool halo = false;  // stride-1 3x3 on 8x8x64 / 4x4x128: y-halo kernel (conv_halo.cu)
+  bool dense = false;  // rows = instances (else rows = instances x output pixels)
+  int Po = 0;          // output pixels per instance
+  bool halo = false;   // stride-1 3x3 on 8x8x64 / 4x4x128: y-halo kernel (conv_halo.cu)
   HaloParams hp;
   int halo_W = 0, halo_Cin = 0;
   __nv_bfloat16* d_B = nullptr;
@@ -80,10 +74,21 @@ void free_planned(PlannedConv& pc) {
   pc.d_bias = nullptr;
 }
 
-// Builds the GEMM description of one convolution (optionally with the block's 1x1
-// stride-2 downsample fused as extra K steps reading `ds_in_hi`).
+// One candidate K step before it is known which N tiles need it.
+struct StepCand {
+  int a_c0, b_k, dx, dy, map;
+};
+
+// Builds the GEMM description of one convolution (optionally with a 1x1 downsample of the
+// block input fused as extra K steps reading `ds_in_hi`).
 //   in_hi     : conv input  [b_pad][Hi*Wi][Cin] bf16
 //   ds_in_hi  : block input [b_pad][Hx*Wx][Cx]  bf16 (only when gds != nullptr)
+// Forms:
+//   3x3, >= 16 output pixels : shifted boxes, rows = (instance, oy, ox), 4-D A maps
+//   3x3, <= 4 output pixels  : dense, rows = instances, N = (out pixel, co), K = (in pixel, ci)
+//   1x1                      : pointwise, rows = (instance, pixel); stride 2 reads parity phase 0
+// For every N tile only the K steps whose weight block is not identically zero are kept:
+// padding-only taps of the dense form and the off-diagonal blocks of grouped convs cost nothing.
 int plan_conv(const ConvGeom& g, const float* w_oihw, const float* bias, const ConvGeom* gds,
               const float* wds_oihw, const float* bds, const __nv_bfloat16* in_hi,
               const __nv_bfloat16* ds_in_hi, int64_t b_pad, PlannedConv* out) {
@@ -102,34 +107,60 @@ int plan_conv(const ConvGeom& g, const float* w_oihw, const float* bias, const C
   }
   std::vector<float> bias_full;
   std::vector<uint16_t> B;
+  std::vector<StepCand> cands;
   int64_t K_cat = 0;
   int rc;
+  const int kk = g.k * g.k;
 
-  if (Po >= 16) {
-    // ---- shifted-box form: rows = (instance, oy, ox)
-    if (kGemmBM % Po != 0 || g.Cout > 256 || g.k != 3 || g.pad != 1 ||
-        (g.stride != 1 && g.stride != 2) || (g.stride == 2 && (g.Hi != 2 * g.Ho || g.Wi != 2 * g.Wo))) {
-      set_error("plan_conv: unsupported shifted-box geometry Ho=%d Wo=%d Cout=%d k=%d s=%d", g.Ho,
-                g.Wo, g.Cout, g.k, g.stride);
+  if (g.k == 1 || Po >= 16) {
+    // ---- rows = (instance, oy, ox): shifted boxes (3x3) or pointwise (1x1)
+    const bool pointwise = g.k == 1;
+    if (!pointwise && (kGemmBM % Po != 0 || g.k != 3 || g.pad != 1)) {
+      set_error("plan_conv: unsupported shifted-box geometry Ho=%d Wo=%d k=%d", g.Ho, g.Wo, g.k);
+      return CS_ERR_UNSUPPORTED;
+    }
+    // (a strided 1x1 only reads phase (0,0), so odd input sizes such as 1x1 -> 1x1 are fine)
+    if ((g.stride != 1 && g.stride != 2) ||
+        (g.stride == 2 && !pointwise && (g.Hi != 2 * g.Ho || g.Wi != 2 * g.Wo)) ||
+        (g.stride == 2 && kGemmBM % Po != 0)) {
+      set_error("plan_conv: unsupported stride geometry Hi=%d Ho=%d s=%d", g.Hi, g.Ho, g.stride);
       return CS_ERR_UNSUPPORTED;
     }
     pc.dense = false;
-    pc.BN = g.Cout;
-    pc.p.a_mode = 1;
-    pc.p.units_per_mtile = kGemmBM / Po;
-    pc.p.num_n_tiles = 1;
-    pc.p.n_variants = 1;
+    pc.BN = (g.groups > 1 && !pointwise) ? 64 : (g.Cout >= 256 ? 256 : g.Cout);
     pc.p.n_total = g.Cout;
-    const int K_main = 9 * g.Cin;
+    const int K_main = kk * g.Cin;
     K_cat = K_main + (gds ? gds->Cin : 0);
-    int ns = 0;
     int n_maps = 0;
-    if (g.stride == 1) {
+    if (pointwise && g.stride == 1) {
+      // A = the activation matrix itself: [b_pad * Pi rows][Cin]
+      rc = make_mat_map_2d(&pc.p.a_map[0], in_hi, g.Cin, b_pad * Pi, g.Cin, kGemmBM);
+      if (rc != CS_OK) return rc;
+      n_maps = 1;
+      for (int c0 = 0; c0 < g.Cin; c0 += 64) cands.push_back({c0, c0, 0, 0, 0});
+    } else if (pointwise) {
+      // 1x1 stride 2: parity phase (0,0) of the input, no shift
+      pc.p.a_mode |= 1;
+      pc.p.units_per_mtile = kGemmBM / Po;
+      rc = make_act_map_4d(&pc.p.a_map[0], in_hi, g.Cin, g.Wo, g.Ho, b_pad, 2 * g.Cin,
+                           (int64_t)2 * g.Wi * g.Cin, (int64_t)Pi * g.Cin, g.Wo, g.Ho, kGemmBM / Po);
+      if (rc != CS_OK) return rc;
+      n_maps = 1;
+      for (int c0 = 0; c0 < g.Cin; c0 += 64) cands.push_back({c0, c0, 0, 0, 0});
+    } else if (g.stride == 1) {
+      pc.p.a_mode |= 1;
+      pc.p.units_per_mtile = kGemmBM / Po;
       rc = make_act_map_4d(&pc.p.a_map[0], in_hi, g.Cin, g.Wi, g.Hi, b_pad, g.Cin,
                            (int64_t)g.Wi * g.Cin, (int64_t)Pi * g.Cin, g.Wo, g.Ho, kGemmBM / Po);
       if (rc != CS_OK) return rc;
       n_maps = 1;
+      for (int dy = 0; dy < 3; ++dy)
+        for (int dx = 0; dx < 3; ++dx)
+          for (int c0 = 0; c0 < g.Cin; c0 += 64)
+            cands.push_back({c0, (dy * 3 + dx) * g.Cin + c0, dx - 1, dy - 1, 0});
     } else {
+      pc.p.a_mode |= 0xF;
+      pc.p.units_per_mtile = kGemmBM / Po;
       for (int a = 0; a < 2; ++a)
         for (int b = 0; b < 2; ++b) {
           rc = make_act_map_4d(&pc.p.a_map[a * 2 + b], in_hi + ((int64_t)a * g.Wi + b) * g.Cin,
@@ -138,45 +169,36 @@ int plan_conv(const ConvGeom& g, const float* w_oihw, const float* bias, const C
           if (rc != CS_OK) return rc;
         }
       n_maps = 4;
-    }
-    for (int dy = 0; dy < 3; ++dy)
-      for (int dx = 0; dx < 3; ++dx)
-        for (int c0 = 0; c0 < g.Cin; c0 += 64) {
-          if (ns >= kMaxSteps) { set_error("plan_conv: too many K steps"); return CS_ERR_UNSUPPORTED; }
-          KStep& st = pc.p.steps[0][ns++];
-          st.a_c0 = (int16_t)c0;
-          st.b_k = (int16_t)((dy * 3 + dx) * g.Cin + c0);
-          if (g.stride == 1) {
-            st.map = 0; st.dx = (int8_t)(dx - 1); st.dy = (int8_t)(dy - 1);
-          } else {
+      for (int dy = 0; dy < 3; ++dy)
+        for (int dx = 0; dx < 3; ++dx)
+          for (int c0 = 0; c0 < g.Cin; c0 += 64) {
             // iy = 2*oy + dy - 1: dy=0 -> phase 1 shift -1; dy=1 -> phase 0; dy=2 -> phase 1
-            int pa = (dy == 1) ? 0 : 1, pb = (dx == 1) ? 0 : 1;
-            st.map = (uint8_t)(pa * 2 + pb);
-            st.dy = (int8_t)(dy == 0 ? -1 : 0);
-            st.dx = (int8_t)(dx == 0 ? -1 : 0);
+            const int pa = (dy == 1) ? 0 : 1, pb = (dx == 1) ? 0 : 1;
+            cands.push_back({c0, (dy * 3 + dx) * g.Cin + c0, dx == 0 ? -1 : 0, dy == 0 ? -1 : 0,
+                             pa * 2 + pb});
           }
-        }
+    }
     if (gds) {
       if (n_maps >= 4) { set_error("plan_conv: no free A map for the downsample"); return CS_ERR_UNSUPPORTED; }
-      // 1x1 stride-2 conv on the block input: parity phase (0,0), no shift.
-      rc = make_act_map_4d(&pc.p.a_map[n_maps], ds_in_hi, gds->Cin, g.Wo, g.Ho, b_pad, 2 * gds->Cin,
-                           (int64_t)2 * gds->Wi * gds->Cin, (int64_t)gds->Hi * gds->Wi * gds->Cin,
-                           g.Wo, g.Ho, kGemmBM / Po);
-      if (rc != CS_OK) return rc;
-      for (int c0 = 0; c0 < gds->Cin; c0 += 64) {
-        if (ns >= kMaxSteps) { set_error("plan_conv: too many K steps"); return CS_ERR_UNSUPPORTED; }
-        KStep& st = pc.p.steps[0][ns++];
-        st.a_c0 = (int16_t)c0; st.b_k = (int16_t)(K_main + c0);
-        st.map = (uint8_t)n_maps; st.dx = 0; st.dy = 0;
+      if (gds->stride == 1) {
+        rc = make_mat_map_2d(&pc.p.a_map[n_maps], ds_in_hi, gds->Cin, b_pad * gds->Hi * gds->Wi,
+                             gds->Cin, kGemmBM);
+      } else {
+        pc.p.a_mode |= 1 << n_maps;
+        pc.p.units_per_mtile = kGemmBM / Po;
+        rc = make_act_map_4d(&pc.p.a_map[n_maps], ds_in_hi, gds->Cin, g.Wo, g.Ho, b_pad, 2 * gds->Cin,
+                             (int64_t)2 * gds->Wi * gds->Cin, (int64_t)gds->Hi * gds->Wi * gds->Cin,
+                             g.Wo, g.Ho, kGemmBM / Po);
       }
+      if (rc != CS_OK) return rc;
+      for (int c0 = 0; c0 < gds->Cin; c0 += 64) cands.push_back({c0, K_main + c0, 0, 0, n_maps});
     }
-    pc.p.n_steps[0] = ns;
-    // B[co][(dy*3+dx)*Cin + ci] (+ [K_main + ci] for the downsample)
+    // B[co][tap*Cin + ci] (+ [K_main + ci] for the downsample)
     B.assign((size_t)g.Cout * K_cat, 0);
     for (int co = 0; co < g.Cout; ++co) {
       for (int ci = 0; ci < g.Cin; ++ci)
-        for (int t = 0; t < 9; ++t)
-          B[(size_t)co * K_cat + t * g.Cin + ci] = f32_to_bf16_rn(w_oihw[((size_t)co * g.Cin + ci) * 9 + t]);
+        for (int t = 0; t < kk; ++t)
+          B[(size_t)co * K_cat + t * g.Cin + ci] = f32_to_bf16_rn(w_oihw[((size_t)co * g.Cin + ci) * kk + t]);
       if (gds)
         for (int ci = 0; ci < gds->Cin; ++ci)
           B[(size_t)co * K_cat + K_main + ci] = f32_to_bf16_rn(wds_oihw[(size_t)co * gds->Cin + ci]);
@@ -188,19 +210,12 @@ int plan_conv(const ConvGeom& g, const float* w_oihw, const float* bias, const C
     pc.dense = true;
     const int N_total = Po * g.Cout;
     pc.BN = (N_total % 256 == 0) ? 256 : (N_total % 128 == 0 ? 128 : 64);
-    pc.p.a_mode = 0;
     pc.p.units_per_mtile = kGemmBM;
-    pc.p.num_n_tiles = N_total / pc.BN;
     pc.p.n_total = N_total;
-    if (pc.p.num_n_tiles > kMaxVariants) {
-      set_error("plan_conv: %d N tiles exceed %d variants", pc.p.num_n_tiles, kMaxVariants);
-      return CS_ERR_UNSUPPORTED;
-    }
-    pc.p.n_variants = pc.p.num_n_tiles;
     const int64_t K_main = (int64_t)Pi * g.Cin;
     const int64_t K_ds = gds ? (int64_t)gds->Hi * gds->Wi * gds->Cin : 0;
     K_cat = K_main + K_ds;
-    if (K_cat > 32767) { set_error("plan_conv: dense K %lld too large", (long long)K_cat); return CS_ERR_UNSUPPORTED; }
+    if (K_cat > 65535) { set_error("plan_conv: dense K %lld too large", (long long)K_cat); return CS_ERR_UNSUPPORTED; }
     rc = make_mat_map_2d(&pc.p.a_map[0], in_hi, K_main, b_pad, K_main, kGemmBM);
     if (rc != CS_OK) return rc;
     if (gds) {
@@ -218,8 +233,8 @@ int plan_conv(const ConvGeom& g, const float* w_oihw, const float* bias, const C
             const int pi = iy * g.Wi + ix;
             for (int co = 0; co < g.Cout; ++co) {
               uint16_t* dst = &B[((size_t)po * g.Cout + co) * K_cat + (size_t)pi * g.Cin];
-              const float* src = &w_oihw[(size_t)co * g.Cin * g.k * g.k + dy * g.k + dx];
-              for (int ci = 0; ci < g.Cin; ++ci) dst[ci] = f32_to_bf16_rn(src[(size_t)ci * g.k * g.k]);
+              const float* src = &w_oihw[(size_t)co * g.Cin * kk + dy * g.k + dx];
+              for (int ci = 0; ci < g.Cin; ++ci) dst[ci] = f32_to_bf16_rn(src[(size_t)ci * kk]);
             }
           }
         if (gds) {
@@ -230,31 +245,46 @@ int plan_conv(const ConvGeom& g, const float* w_oihw, const float* bias, const C
           }
         }
       }
-    // K steps per N tile: only 64-wide K blocks with a non-zero weight in that tile
-    for (int nt = 0; nt < pc.p.num_n_tiles; ++nt) {
-      int ns = 0;
-      for (int64_t kb = 0; kb < K_cat; kb += 64) {
-        bool any = false;
-        for (int n = nt * pc.BN; n < (nt + 1) * pc.BN && !any; ++n)
-          for (int kk = 0; kk < 64; ++kk)
-            if ((B[(size_t)n * K_cat + kb + kk] & 0x7fff) != 0) { any = true; break; }
-        if (!any) continue;
-        if (ns >= kMaxSteps) { set_error("plan_conv: too many dense K steps"); return CS_ERR_UNSUPPORTED; }
-        KStep& st = pc.p.steps[nt][ns++];
-        st.b_k = (int16_t)kb;
-        if (kb < K_main) { st.map = 0; st.a_c0 = (int16_t)kb; }
-        else { st.map = 1; st.a_c0 = (int16_t)(kb - K_main); }
-        st.dx = st.dy = 0;
-      }
-      if (ns == 0) {  // all-zero weights: keep one step so the accumulator is defined
-        KStep& st = pc.p.steps[nt][ns++];
-        st.b_k = 0; st.map = 0; st.a_c0 = 0; st.dx = st.dy = 0;
-      }
-      pc.p.n_steps[nt] = ns;
-    }
+    for (int64_t kb = 0; kb < K_cat; kb += 64)
+      cands.push_back(kb < K_main ? StepCand{(int)kb, (int)kb, 0, 0, 0}
+                                  : StepCand{(int)(kb - K_main), (int)kb, 0, 0, 1});
     bias_full.resize(N_total);
     for (int po = 0; po < Po; ++po)
       for (int co = 0; co < g.Cout; ++co) bias_full[(size_t)po * g.Cout + co] = bias[co] + (gds ? bds[co] : 0.f);
+  }
+
+  // ---- K steps per N tile: drop weight blocks that are identically zero
+  pc.p.num_n_tiles = pc.p.n_total / pc.BN;
+  std::vector<std::vector<KStep>> per_tile(pc.p.num_n_tiles);
+  for (int nt = 0; nt < pc.p.num_n_tiles; ++nt) {
+    for (const StepCand& c : cands) {
+      bool any = false;
+      for (int n = nt * pc.BN; n < (nt + 1) * pc.BN && !any; ++n) {
+        const uint16_t* row = &B[(size_t)n * K_cat + c.b_k];
+        for (int q = 0; q < 64; ++q)
+          if ((row[q] & 0x7fff) != 0) { any = true; break; }
+      }
+      if (any) per_tile[nt].push_back(KStep::make(c.a_c0, c.b_k, c.dx, c.dy, c.map));
+    }
+    if (per_tile[nt].empty()) per_tile[nt].push_back(KStep::make(0, 0, 0, 0, 0));  // all-zero weights
+    if ((int)per_tile[nt].size() > kMaxSteps) {
+      set_error("plan_conv: %d K steps exceed %d", (int)per_tile[nt].size(), kMaxSteps);
+      return CS_ERR_UNSUPPORTED;
+    }
+  }
+  bool same = true;
+  for (int nt = 1; nt < pc.p.num_n_tiles && same; ++nt) {
+    same = per_tile[nt].size() == per_tile[0].size();
+    for (size_t i = 0; same && i < per_tile[nt].size(); ++i) same = per_tile[nt][i].v == per_tile[0][i].v;
+  }
+  pc.p.n_variants = same ? 1 : pc.p.num_n_tiles;
+  if (pc.p.n_variants > kMaxVariants) {
+    set_error("plan_conv: %d N tiles with different K steps exceed %d variants", pc.p.n_variants, kMaxVariants);
+    return CS_ERR_UNSUPPORTED;
+  }
+  for (int v = 0; v < pc.p.n_variants; ++v) {
+    pc.p.n_steps[v] = (int)per_tile[v].size();
+    for (size_t i = 0; i < per_tile[v].size(); ++i) pc.p.steps[v][i] = per_tile[v][i];
   }
 
   CS_CUDA(cudaMalloc(&pc.d_B, B.size() * sizeof(uint16_t)));
@@ -265,8 +295,8 @@ int plan_conv(const ConvGeom& g, const float* w_oihw, const float* bias, const C
   rc = make_mat_map_2d(&pc.p.b_map, pc.d_B, K_cat, pc.p.n_total, K_cat, pc.BN / pc.p.cluster);
   if (rc != CS_OK) { free_planned(pc); return rc; }
   pc.p.bias = pc.d_bias;
-  if (!pc.dense && !gds && g.stride == 1 && g.Hi == g.Wi && halo_supported(g.Wi, g.Cin, g.Cout) &&
-      !g_disable_halo) {
+  if (!pc.dense && !gds && g.k == 3 && g.groups == 1 && g.stride == 1 && g.Hi == g.Wi &&
+      halo_supported(g.Wi, g.Cin, g.Cout) && !g_disable_halo) {
     rc = make_act_map_halo(&pc.hp.a_map, in_hi, g.Cin, g.Wi, g.Hi, b_pad, 1);
     if (rc != CS_OK) { free_planned(pc); return rc; }
     rc = make_mat_map_2d(&pc.hp.b_map, pc.d_B, K_cat, pc.p.n_total, K_cat, pc.BN);
@@ -305,8 +335,6 @@ int launch_planned(const PlannedConv& pc, int64_t count, float* out_f32, cudaStr
                    int reverse = 0) {
   if (pc.halo) {
     HaloParams hp = pc.hp;
-    hp.res_hi_map = pc.hp.res_hi_map; hp.res_lo_map = pc.hp.res_lo_map;
-    hp.out_hi_map = pc.hp.out_hi_map; hp.out_lo_map = pc.hp.out_lo_map;
     hp.res_hi = pc.p.res_hi; hp.res_lo = pc.p.res_lo;
     hp.out_hi = pc.p.out_hi; hp.out_lo = pc.p.out_lo;
     hp.out_f32 = out_f32;
@@ -329,9 +357,10 @@ struct TcPlan {
   int tile = 0;
   int64_t max_batch = 0, b_pad = 0;
   void* ws = nullptr;
-  std::vector<PlannedConv> layers;  // conv1, conv2 of every block in order
-  __nv_bfloat16* buf_hi[3] = {nullptr, nullptr, nullptr};
-  __nv_bfloat16* buf_lo[2] = {nullptr, nullptr};
+  std::vector<PlannedConv> layers;  // every conv launch of the encoder in order
+  __nv_bfloat16* x_hi[2] = {nullptr, nullptr};   // block input / output (ping-pong)
+  __nv_bfloat16* x_lo[2] = {nullptr, nullptr};
+  __nv_bfloat16* mid[2] = {nullptr, nullptr};    // conv1 / conv2 outputs inside a block
   const __nv_bfloat16* x4_hi = nullptr;
   const __nv_bfloat16* x4_lo = nullptr;
   int P4 = 1, C4 = 512;
@@ -346,19 +375,7 @@ struct TcPlan {
 
 int64_t round_up(int64_t v, int64_t a) { return (v + a - 1) / a * a; }
 
-// Diagnostics: CELLSEG_STEM=cuda routes tile-32 batches through the CUDA-core stem too.
-const bool g_force_cuda_core_stem = []() {
-  const char* e = getenv("CELLSEG_STEM");
-  return e != nullptr && strcmp(e, "cuda") == 0;
-}();
-
-int64_t act_elems(int tile) { return (int64_t)(tile / 4) * (tile / 4) * 64; }
-
 constexpr int64_t kFp32Chunk = 4096;
-
-int64_t fp32_floats_per_inst(int tile) {
-  return (int64_t)3 * tile * tile + (int64_t)(tile / 2) * (tile / 2) * 64 + 4 * act_elems(tile);
-}
 
 }  // namespace
 }  // namespace cs
@@ -379,68 +396,122 @@ struct cs_model {
 namespace cs {
 namespace {
 
+// Largest block-level activation (elements per instance) at this tile size: x buffers hold
+// block inputs / outputs, mid buffers the conv1 / conv2 outputs.
+void act_sizes(const cs_model* m, int tile, int64_t* x_elems, int64_t* mid_elems) {
+  int H = tile / 4;
+  int64_t xe = (int64_t)H * H * 64, me = 0;
+  for (const BlockDesc& b : m->blocks) {
+    const int Ho = (H + 2 - 3) / b.stride + 1;
+    // conv1 keeps the input resolution in a Bottleneck (stride sits on conv2), halves it in a BasicBlock
+    const int64_t m1 = b.bottleneck ? (int64_t)H * H * b.width : (int64_t)Ho * Ho * b.width;
+    const int64_t m2 = (int64_t)Ho * Ho * b.width;
+    if (m1 > me) me = m1;
+    if (m2 > me) me = m2;
+    const int64_t y = (int64_t)Ho * Ho * b.cout;
+    if (y > xe) xe = y;
+    H = Ho;
+  }
+  *x_elems = xe;
+  *mid_elems = me;
+}
+
+int64_t fp32_floats_per_inst(const cs_model* m, int tile) {
+  int64_t xe, me;
+  act_sizes(m, tile, &xe, &me);
+  // input tile + stem conv output + x, y, ds + two mids
+  return (int64_t)3 * tile * tile + (int64_t)(tile / 2) * (tile / 2) * 64 + 3 * xe + 2 * me;
+}
+
 int build_tc_plan(cs_model* m, int tile, int64_t max_batch, void* ws, int64_t ws_bytes) {
   auto plan = std::make_unique<TcPlan>();
   plan->tile = tile;
   plan->max_batch = max_batch;
   plan->b_pad = round_up(max_batch, kGemmBM);
   plan->ws = ws;
-  const int64_t E = act_elems(tile);
-  const int64_t buf_bytes = round_up(plan->b_pad * E * 2, 1024);
-  if (ws_bytes < 5 * buf_bytes + 1024) {
+  int64_t xe, me;
+  act_sizes(m, tile, &xe, &me);
+  const int64_t xb = round_up(plan->b_pad * xe * 2, 1024), mb = round_up(plan->b_pad * me * 2, 1024);
+  if (ws_bytes < 4 * xb + 2 * mb + 1024) {
     set_error("bf16 workspace too small: %lld < %lld", (long long)ws_bytes,
-              (long long)(5 * buf_bytes + 1024));
+              (long long)(4 * xb + 2 * mb + 1024));
     return CS_ERR_WORKSPACE;
   }
   uintptr_t base = round_up((int64_t)(uintptr_t)ws, 1024);
-  for (int i = 0; i < 3; ++i) plan->buf_hi[i] = reinterpret_cast<__nv_bfloat16*>(base + i * buf_bytes);
-  for (int i = 0; i < 2; ++i) plan->buf_lo[i] = reinterpret_cast<__nv_bfloat16*>(base + (3 + i) * buf_bytes);
+  for (int i = 0; i < 2; ++i) {
+    plan->x_hi[i] = reinterpret_cast<__nv_bfloat16*>(base + i * xb);
+    plan->x_lo[i] = reinterpret_cast<__nv_bfloat16*>(base + (2 + i) * xb);
+    plan->mid[i] = reinterpret_cast<__nv_bfloat16*>(base + 4 * xb + i * mb);
+  }
+  const int64_t bp = plan->b_pad;
+  auto push = [&](PlannedConv& pc, const __nv_bfloat16* rh, const __nv_bfloat16* rl, __nv_bfloat16* oh,
+                  __nv_bfloat16* ol, int relu) {
+    pc.p.res_hi = rh; pc.p.res_lo = rl; pc.p.out_hi = oh; pc.p.out_lo = ol; pc.p.relu = relu;
+    int rc = finalize_io_maps(pc, bp);
+    if (rc != CS_OK) { free_planned(pc); return rc; }
+    plan->layers.push_back(pc);
+    return (int)CS_OK;
+  };
 
-  // x lives in (hi[xi], lo[xi]); mid in hi[2]; y in (hi[1-xi], lo[1-xi])
-  int xi = 0;
+  int xi = 0;   // x lives in (x_hi[xi], x_lo[xi]); the block writes (x_hi[1-xi], x_lo[1-xi])
   int H = tile / 4, W = tile / 4, C = 64;
   for (const BlockDesc& b : m->blocks) {
+    const int Ho = (H + 2 - 3) / b.stride + 1, Wo = (W + 2 - 3) / b.stride + 1;
     const ConvW& c1 = m->convs[b.conv1];
     const ConvW& c2 = m->convs[b.conv2];
-    const int Ho = (H + 2 - 3) / b.stride + 1, Wo = (W + 2 - 3) / b.stride + 1;
-    ConvGeom g1{H, W, C, Ho, Wo, b.cout, 3, b.stride, 1};
-    ConvGeom g2{Ho, Wo, b.cout, Ho, Wo, b.cout, 3, 1, 1};
-    PlannedConv p1, p2;
-    int rc = plan_conv(g1, c1.w.data(), c1.b.data(), nullptr, nullptr, nullptr, plan->buf_hi[xi],
-                       nullptr, plan->b_pad, &p1);
-    if (rc != CS_OK) return rc;
-    p1.p.out_hi = plan->buf_hi[2];
-    p1.p.out_lo = nullptr;
-    p1.p.res_hi = p1.p.res_lo = nullptr;
-    p1.p.relu = 1;
-    rc = finalize_io_maps(p1, plan->b_pad);
-    if (rc != CS_OK) return rc;
-    plan->layers.push_back(p1);
-    if (b.ds >= 0) {
-      const ConvW& cd = m->convs[b.ds];
-      ConvGeom gd{H, W, C, Ho, Wo, b.cout, 1, b.stride, 0};
-      rc = plan_conv(g2, c2.w.data(), c2.b.data(), &gd, cd.w.data(), cd.b.data(), plan->buf_hi[2],
-                     plan->buf_hi[xi], plan->b_pad, &p2);
+    PlannedConv p;
+    int rc;
+    if (!b.bottleneck) {
+      ConvGeom g1{H, W, C, Ho, Wo, b.cout, 3, b.stride, 1, 1};
+      ConvGeom g2{Ho, Wo, b.cout, Ho, Wo, b.cout, 3, 1, 1, 1};
+      rc = plan_conv(g1, c1.w.data(), c1.b.data(), nullptr, nullptr, nullptr, plan->x_hi[xi], nullptr, bp, &p);
       if (rc != CS_OK) return rc;
-      p2.p.res_hi = p2.p.res_lo = nullptr;
+      if ((rc = push(p, nullptr, nullptr, plan->mid[0], nullptr, 1)) != CS_OK) return rc;
+      if (b.ds >= 0) {   // downsample fused into conv2 as extra K steps
+        const ConvW& cd = m->convs[b.ds];
+        ConvGeom gd{H, W, C, Ho, Wo, b.cout, 1, b.stride, 0, 1};
+        rc = plan_conv(g2, c2.w.data(), c2.b.data(), &gd, cd.w.data(), cd.b.data(), plan->mid[0],
+                       plan->x_hi[xi], bp, &p);
+        if (rc != CS_OK) return rc;
+        rc = push(p, nullptr, nullptr, plan->x_hi[1 - xi], plan->x_lo[1 - xi], 1);
+      } else {
+        rc = plan_conv(g2, c2.w.data(), c2.b.data(), nullptr, nullptr, nullptr, plan->mid[0], nullptr, bp, &p);
+        if (rc != CS_OK) return rc;
+        rc = push(p, plan->x_hi[xi], plan->x_lo[xi], plan->x_hi[1 - xi], plan->x_lo[1 - xi], 1);
+      }
+      if (rc != CS_OK) return rc;
     } else {
-      rc = plan_conv(g2, c2.w.data(), c2.b.data(), nullptr, nullptr, nullptr, plan->buf_hi[2],
-                     nullptr, plan->b_pad, &p2);
+      const ConvW& c3 = m->convs[b.conv3];
+      ConvGeom g1{H, W, C, H, W, b.width, 1, 1, 0, 1};
+      ConvGeom g2{H, W, b.width, Ho, Wo, b.width, 3, b.stride, 1, c2.groups};
+      ConvGeom g3{Ho, Wo, b.width, Ho, Wo, b.cout, 1, 1, 0, 1};
+      rc = plan_conv(g1, c1.w.data(), c1.b.data(), nullptr, nullptr, nullptr, plan->x_hi[xi], nullptr, bp, &p);
       if (rc != CS_OK) return rc;
-      p2.p.res_hi = plan->buf_hi[xi];
-      p2.p.res_lo = plan->buf_lo[xi];
+      if ((rc = push(p, nullptr, nullptr, plan->mid[0], nullptr, 1)) != CS_OK) return rc;
+      rc = plan_conv(g2, c2.w.data(), c2.b.data(), nullptr, nullptr, nullptr, plan->mid[0], nullptr, bp, &p);
+      if (rc != CS_OK) return rc;
+      if ((rc = push(p, nullptr, nullptr, plan->mid[1], nullptr, 1)) != CS_OK) return rc;
+      if (b.ds >= 0) {   // downsample as its own launch into y, then conv3 adds y in place
+        const ConvW& cd = m->convs[b.ds];
+        ConvGeom gd{H, W, C, Ho, Wo, b.cout, 1, b.stride, 0, 1};
+        rc = plan_conv(gd, cd.w.data(), cd.b.data(), nullptr, nullptr, nullptr, plan->x_hi[xi], nullptr, bp, &p);
+        if (rc != CS_OK) return rc;
+        if ((rc = push(p, nullptr, nullptr, plan->x_hi[1 - xi], plan->x_lo[1 - xi], 0)) != CS_OK) return rc;
+        rc = plan_conv(g3, c3.w.data(), c3.b.data(), nullptr, nullptr, nullptr, plan->mid[1], nullptr, bp, &p);
+        if (rc != CS_OK) return rc;
+        rc = push(p, plan->x_hi[1 - xi], plan->x_lo[1 - xi], plan->x_hi[1 - xi], plan->x_lo[1 - xi], 1);
+      } else {
+        rc = plan_conv(g3, c3.w.data(), c3.b.data(), nullptr, nullptr, nullptr, plan->mid[1], nullptr, bp, &p);
+        if (rc != CS_OK) return rc;
+        rc = push(p, plan->x_hi[xi], plan->x_lo[xi], plan->x_hi[1 - xi], plan->x_lo[1 - xi], 1);
+      }
+      if (rc != CS_OK) return rc;
     }
-    p2.p.out_hi = plan->buf_hi[1 - xi];
-    p2.p.out_lo = plan->buf_lo[1 - xi];
-    p2.p.relu = 1;
-    rc = finalize_io_maps(p2, plan->b_pad);
-    if (rc != CS_OK) return rc;
-    plan->layers.push_back(p2);
     xi = 1 - xi;
     H = Ho; W = Wo; C = b.cout;
   }
-  plan->x4_hi = plan->buf_hi[xi];
-  plan->x4_lo = plan->buf_lo[xi];
+  plan->x4_hi = plan->x_hi[xi];
+  plan->x4_lo = plan->x_lo[xi];
   plan->P4 = H * W;
   plan->C4 = C;
   if (tile == 32) {
@@ -465,8 +536,8 @@ int run_tc_batch(cs_model* m, const StemArgs& stem_in, int64_t count, float* pro
   sa.count = count;
   sa.w = m->convs[0].d_w32;
   sa.bias = m->convs[0].d_b;
-  sa.out_hi = pl.buf_hi[0];
-  sa.out_lo = pl.buf_lo[0];
+  sa.out_hi = pl.x_hi[0];
+  sa.out_lo = pl.x_lo[0];
   int rc = (pl.tile == 32 && !g_force_cuda_core_stem) ? launch_stem_tc(sa, pl.d_stem_w, pl.d_lut, st)
                                                       : launch_stem_bf16(sa, st);
   if (rc != CS_OK) return rc;
@@ -491,10 +562,14 @@ int run_fp32_batch(cs_model* m, const float* x_in, int tile, int64_t count, floa
                    float* prob_out, float* logits_out, float* feat_out, cudaStream_t st) {
   const int S = tile;
   const int Hc = S / 2, Hp = S / 4;
+  int64_t xe, me;
+  act_sizes(m, tile, &xe, &me);
   float* c1 = ws_f;
-  float* bufs[4];
   float* q = c1 + count * (int64_t)Hc * Hc * 64;
-  for (int i = 0; i < 4; ++i) { bufs[i] = q; q += count * act_elems(tile); }
+  float* xb[3];   // x, y, ds
+  for (int i = 0; i < 3; ++i) { xb[i] = q; q += count * xe; }
+  float* mid[2];
+  for (int i = 0; i < 2; ++i) { mid[i] = q; q += count * me; }
   const ConvW& stem = m->convs[0];
   ConvF32Args a{};
   a.in = x_in; a.in_sn = (int64_t)3 * S * S; a.in_sc = (int64_t)S * S; a.in_sy = S; a.in_sx = 1;
@@ -503,45 +578,40 @@ int run_fp32_batch(cs_model* m, const float* x_in, int tile, int64_t count, floa
   a.M = count * Hc * Hc; a.relu = 1;
   int rc = launch_conv_fp32(a, st);
   if (rc != CS_OK) return rc;
-  rc = launch_maxpool_fp32(c1, bufs[0], count, Hc, Hc, 64, st);
+  rc = launch_maxpool_fp32(c1, xb[0], count, Hc, Hc, 64, st);
   if (rc != CS_OK) return rc;
   m->last_launches += 2;
+  auto conv = [&](const ConvW& w, const float* in, int H, int W, int Cin, int Ho, int Wo, const float* res,
+                  float* out, int relu) {
+    ConvF32Args c{};
+    c.in = in; c.in_sn = (int64_t)H * W * Cin; c.in_sc = 1; c.in_sy = (int64_t)W * Cin; c.in_sx = Cin;
+    c.Hi = H; c.Wi = W; c.Cin = Cin; c.Ho = Ho; c.Wo = Wo; c.Cout = w.cout; c.k = w.k; c.stride = w.stride;
+    c.pad = w.pad; c.w = w.d_w32; c.bias = w.d_b; c.residual = res; c.out = out; c.M = count * Ho * Wo;
+    c.relu = relu;
+    m->last_launches++;
+    return launch_conv_fp32(c, st);
+  };
   int xi = 0, H = Hp, W = Hp, C = 64;
   for (const BlockDesc& b : m->blocks) {
-    const ConvW& w1 = m->convs[b.conv1];
-    const ConvW& w2 = m->convs[b.conv2];
     const int Ho = (H + 2 - 3) / b.stride + 1, Wo = (W + 2 - 3) / b.stride + 1;
-    float* x = bufs[xi];
-    float* mid = bufs[2];
-    float* dsb = bufs[3];
-    float* y = bufs[1 - xi];
-    ConvF32Args c{};
-    c.in = x; c.in_sn = (int64_t)H * W * C; c.in_sc = 1; c.in_sy = (int64_t)W * C; c.in_sx = C;
-    c.Hi = H; c.Wi = W; c.Cin = C; c.Ho = Ho; c.Wo = Wo; c.Cout = b.cout; c.k = 3; c.stride = b.stride; c.pad = 1;
-    c.w = w1.d_w32; c.bias = w1.d_b; c.residual = nullptr; c.out = mid; c.M = count * Ho * Wo; c.relu = 1;
-    rc = launch_conv_fp32(c, st);
-    if (rc != CS_OK) return rc;
-    m->last_launches++;
+    float* x = xb[xi];
+    float* y = xb[1 - xi];
     const float* res = x;
     if (b.ds >= 0) {
-      const ConvW& wd = m->convs[b.ds];
-      ConvF32Args d = c;
-      d.k = 1; d.pad = 0; d.w = wd.d_w32; d.bias = wd.d_b; d.out = dsb; d.relu = 0;
-      rc = launch_conv_fp32(d, st);
-      if (rc != CS_OK) return rc;
-      m->last_launches++;
-      res = dsb;
+      if ((rc = conv(m->convs[b.ds], x, H, W, C, Ho, Wo, nullptr, xb[2], 0)) != CS_OK) return rc;
+      res = xb[2];
     }
-    ConvF32Args e{};
-    e.in = mid; e.in_sn = (int64_t)Ho * Wo * b.cout; e.in_sc = 1; e.in_sy = (int64_t)Wo * b.cout; e.in_sx = b.cout;
-    e.Hi = Ho; e.Wi = Wo; e.Cin = b.cout; e.Ho = Ho; e.Wo = Wo; e.Cout = b.cout; e.k = 3; e.stride = 1; e.pad = 1;
-    e.w = w2.d_w32; e.bias = w2.d_b; e.residual = res; e.out = y; e.M = count * Ho * Wo; e.relu = 1;
-    rc = launch_conv_fp32(e, st);
-    if (rc != CS_OK) return rc;
-    m->last_launches++;
+    if (!b.bottleneck) {
+      if ((rc = conv(m->convs[b.conv1], x, H, W, C, Ho, Wo, nullptr, mid[0], 1)) != CS_OK) return rc;
+      if ((rc = conv(m->convs[b.conv2], mid[0], Ho, Wo, b.cout, Ho, Wo, res, y, 1)) != CS_OK) return rc;
+    } else {
+      if ((rc = conv(m->convs[b.conv1], x, H, W, C, H, W, nullptr, mid[0], 1)) != CS_OK) return rc;
+      if ((rc = conv(m->convs[b.conv2], mid[0], H, W, b.width, Ho, Wo, nullptr, mid[1], 1)) != CS_OK) return rc;
+      if ((rc = conv(m->convs[b.conv3], mid[1], Ho, Wo, b.width, Ho, Wo, res, y, 1)) != CS_OK) return rc;
+    }
     xi = 1 - xi; H = Ho; W = Wo; C = b.cout;
   }
-  rc = launch_head_fp32(bufs[xi], count, H * W, C, m->d_fc_w, m->d_fc_b, prob_out, logits_out,
+  rc = launch_head_fp32(xb[xi], count, H * W, C, m->d_fc_w, m->d_fc_b, prob_out, logits_out,
                         feat_out, st);
   if (rc != CS_OK) return rc;
   m->last_launches++;
@@ -581,31 +651,49 @@ int cs_model_create(int arch, int n_convs, const float* const* conv_w_host,
   *out = nullptr;
   CS_REQUIRE(conv_w_host && conv_b_host && fc_w_host && fc_b_host, "cs_model_create: NULL weights");
   std::vector<int> layers;
-  if (arch == CS_ARCH_RESNET18) layers = {2, 2, 2, 2};
-  else if (arch == CS_ARCH_RESNET34) layers = {3, 4, 6, 3};
-  else { set_error("cs_model_create: unknown arch %d", arch); return CS_ERR_UNSUPPORTED; }
+  bool bottleneck = false;
+  int groups = 1, width_per_group = 64;
+  switch (arch) {
+    case CS_ARCH_RESNET18: layers = {2, 2, 2, 2}; break;
+    case CS_ARCH_RESNET34: layers = {3, 4, 6, 3}; break;
+    case CS_ARCH_RESNET50: layers = {3, 4, 6, 3}; bottleneck = true; break;
+    case CS_ARCH_RESNEXT50_32X4D: layers = {3, 4, 6, 3}; bottleneck = true; groups = 32; width_per_group = 4; break;
+    default: set_error("cs_model_create: unknown arch %d", arch); return CS_ERR_UNSUPPORTED;
+  }
   int rc = cs_check_device();
   if (rc != CS_OK) return rc;
 
   auto m = std::make_unique<cs_model>();
   m->arch = arch;
-  auto add_conv = [&](int cin, int cout, int k, int stride, int pad) {
-    ConvW c; c.cin = cin; c.cout = cout; c.k = k; c.stride = stride; c.pad = pad;
+  auto add_conv = [&](int cin, int cout, int k, int stride, int pad, int grp) {
+    ConvW c; c.cin = cin; c.cout = cout; c.k = k; c.stride = stride; c.pad = pad; c.groups = grp;
     m->convs.push_back(std::move(c));
     return (int)m->convs.size() - 1;
   };
-  add_conv(3, 64, 7, 2, 3);
+  add_conv(3, 64, 7, 2, 3, 1);
   int inplanes = 64;
   const int planes[4] = {64, 128, 256, 512};
+  const int expansion = bottleneck ? 4 : 1;
   for (int L = 0; L < 4; ++L)
     for (int bi = 0; bi < layers[L]; ++bi) {
       int stride = (bi == 0 && L > 0) ? 2 : 1;
       BlockDesc b;
-      b.cin = inplanes; b.cout = planes[L]; b.stride = stride;
-      b.conv1 = add_conv(inplanes, planes[L], 3, stride, 1);
-      b.conv2 = add_conv(planes[L], planes[L], 3, 1, 1);
-      b.ds = (stride != 1 || inplanes != planes[L]) ? add_conv(inplanes, planes[L], 1, stride, 0) : -1;
-      inplanes = planes[L];
+      b.bottleneck = bottleneck;
+      b.cin = inplanes; b.cout = planes[L] * expansion; b.stride = stride;
+      b.conv3 = -1;
+      if (!bottleneck) {
+        b.width = planes[L];
+        b.conv1 = add_conv(inplanes, planes[L], 3, stride, 1, 1);
+        b.conv2 = add_conv(planes[L], planes[L], 3, 1, 1, 1);
+      } else {
+        // model/resnext.py:81: width = int(planes * (base_width / 64.)) * groups; stride on conv2
+        b.width = (planes[L] * width_per_group / 64) * groups;
+        b.conv1 = add_conv(inplanes, b.width, 1, 1, 0, 1);
+        b.conv2 = add_conv(b.width, b.width, 3, stride, 1, groups);
+        b.conv3 = add_conv(b.width, b.cout, 1, 1, 0, 1);
+      }
+      b.ds = (stride != 1 || inplanes != b.cout) ? add_conv(inplanes, b.cout, 1, stride, 0, 1) : -1;
+      inplanes = b.cout;
       m->blocks.push_back(b);
     }
   CS_REQUIRE((int)m->convs.size() == n_convs, "cs_model_create: arch %d has %d convs, got %d", arch,
@@ -613,12 +701,20 @@ int cs_model_create(int arch, int n_convs, const float* const* conv_w_host,
   for (int i = 0; i < n_convs; ++i) {
     ConvW& c = m->convs[i];
     CS_REQUIRE(conv_w_host[i] && conv_b_host[i], "cs_model_create: conv %d weights NULL", i);
-    size_t nw = (size_t)c.cout * c.cin * c.k * c.k;
-    c.w.assign(conv_w_host[i], conv_w_host[i] + nw);
+    const int kk = c.k * c.k;
+    const int cin_g = c.cin / c.groups, cout_g = c.cout / c.groups;
+    // torch layout [cout][cin/groups][k][k] -> dense [cout][cin][k][k] (zeros outside the group)
+    c.w.assign((size_t)c.cout * c.cin * kk, 0.f);
+    for (int co = 0; co < c.cout; ++co) {
+      const int grp = co / cout_g;
+      for (int cl = 0; cl < cin_g; ++cl)
+        memcpy(&c.w[((size_t)co * c.cin + grp * cin_g + cl) * kk],
+               &conv_w_host[i][((size_t)co * cin_g + cl) * kk], kk * sizeof(float));
+    }
     c.b.assign(conv_b_host[i], conv_b_host[i] + c.cout);
     // fp32 device layout [(dy*k+dx)*cin + ci][cout]
+    const size_t nw = c.w.size();
     std::vector<float> t(nw);
-    const int kk = c.k * c.k;
     for (int co = 0; co < c.cout; ++co)
       for (int ci = 0; ci < c.cin; ++ci)
         for (int tp = 0; tp < kk; ++tp)
@@ -628,9 +724,9 @@ int cs_model_create(int arch, int n_convs, const float* const* conv_w_host,
     CS_CUDA(cudaMalloc(&c.d_b, c.cout * sizeof(float)));
     CS_CUDA(cudaMemcpy(c.d_b, c.b.data(), c.cout * sizeof(float), cudaMemcpyHostToDevice));
   }
-  m->feat_dim = 512;
-  CS_CUDA(cudaMalloc(&m->d_fc_w, 2 * 512 * sizeof(float)));
-  CS_CUDA(cudaMemcpy(m->d_fc_w, fc_w_host, 2 * 512 * sizeof(float), cudaMemcpyHostToDevice));
+  m->feat_dim = 512 * expansion;
+  CS_CUDA(cudaMalloc(&m->d_fc_w, 2 * m->feat_dim * sizeof(float)));
+  CS_CUDA(cudaMemcpy(m->d_fc_w, fc_w_host, 2 * m->feat_dim * sizeof(float), cudaMemcpyHostToDevice));
   CS_CUDA(cudaMalloc(&m->d_fc_b, 2 * sizeof(float)));
   CS_CUDA(cudaMemcpy(m->d_fc_b, fc_b_host, 2 * sizeof(float), cudaMemcpyHostToDevice));
   *out = m.release();
@@ -650,23 +746,25 @@ int cs_model_destroy(cs_model* m) {
   return CS_OK;
 }
 
+int cs_model_feature_dim(const cs_model* m) { return m ? m->feat_dim : 0; }
+
 int cs_model_set_fc(cs_model* m, const float* fc_w_host, const float* fc_b_host) {
   CS_REQUIRE(m && fc_w_host && fc_b_host, "cs_model_set_fc: NULL pointer");
-  CS_CUDA(cudaMemcpy(m->d_fc_w, fc_w_host, 2 * 512 * sizeof(float), cudaMemcpyHostToDevice));
+  CS_CUDA(cudaMemcpy(m->d_fc_w, fc_w_host, 2 * m->feat_dim * sizeof(float), cudaMemcpyHostToDevice));
   CS_CUDA(cudaMemcpy(m->d_fc_b, fc_b_host, 2 * sizeof(float), cudaMemcpyHostToDevice));
   return CS_OK;
 }
 
 int64_t cs_model_workspace_bytes(const cs_model* m, int tile, int64_t max_batch, int precision) {
-  (void)m;
-  if (max_batch <= 0 || (tile != 16 && tile != 32)) return 0;
-  // fp32 chunk buffers are needed in both modes only when the fp32 path runs
+  if (!m || max_batch <= 0 || (tile != 16 && tile != 32)) return 0;
   if (precision == CS_PREC_FP32) {
     int64_t chunk = max_batch < kFp32Chunk ? max_batch : kFp32Chunk;
-    return chunk * fp32_floats_per_inst(tile) * 4 + 4096;
+    return chunk * fp32_floats_per_inst(m, tile) * 4 + 4096;
   }
+  int64_t xe, me;
+  act_sizes(m, tile, &xe, &me);
   int64_t b_pad = round_up(max_batch, kGemmBM);
-  return 5 * round_up(b_pad * act_elems(tile) * 2, 1024) + 4096;
+  return 4 * round_up(b_pad * xe * 2, 1024) + 2 * round_up(b_pad * me * 2, 1024) + 4096;
 }
 
 int cs_model_forward_tiles(cs_model* m, const uint8_t* img, int n_bags, int H, int W, int tile,
@@ -762,7 +860,7 @@ int64_t cs_model_last_launch_count(const cs_model* m) { return m ? m->last_launc
 // ---------------------------------------------------------------------------
 
 // out_f32[M][N] = A[M][K] . B[N][K]^T + bias[N];  A, B bf16 (device), K multiple of 64 and
-// <= 1280, N multiple of bn, bn in {64,128,256}.
+// <= 2560, N multiple of bn, bn in {64,128,256}.
 int cs_debug_gemm_bf16(const void* a_bf16, const void* b_bf16, int64_t M, int N, int K,
                        const float* bias, int bn, float* out_f32, void* stream) {
   CS_REQUIRE(a_bf16 && b_bf16 && bias && out_f32, "cs_debug_gemm_bf16: NULL pointer");
@@ -779,10 +877,7 @@ int cs_debug_gemm_bf16(const void* a_bf16, const void* b_bf16, int64_t M, int N,
   if (rc != CS_OK) return rc;
   p.n_variants = 1;
   p.n_steps[0] = K / 64;
-  for (int s = 0; s < K / 64; ++s) {
-    p.steps[0][s].a_c0 = (int16_t)(s * 64);
-    p.steps[0][s].b_k = (int16_t)(s * 64);
-  }
+  for (int s = 0; s < K / 64; ++s) p.steps[0][s] = KStep::make(s * 64, s * 64, 0, 0, 0);
   p.a_mode = 0;
   p.units_per_mtile = kGemmBM;
   p.num_m_tiles = (int)ceil_div<int64_t>(M, kGemmBM);
@@ -794,19 +889,29 @@ int cs_debug_gemm_bf16(const void* a_bf16, const void* b_bf16, int64_t M, int N,
   return launch_conv_gemm(p, bn, as_stream(stream));
 }
 
-// One 3x3 conv (pad 1, stride 1|2) through plan_conv: in_hi bf16 [n][Hi*Wi][Cin] (device),
-// w_host fp32 OIHW, bias_host fp32 -> out_f32 [n][Ho*Wo][Cout] (device), no ReLU.
-// n must be a multiple of 128.
-int cs_debug_conv3x3_bf16(const void* in_hi, int64_t n, int Hi, int Wi, int Cin, int Cout,
-                          int stride, const float* w_host, const float* bias_host,
-                          float* out_f32, void* stream) {
-  CS_REQUIRE(in_hi && w_host && bias_host && out_f32, "cs_debug_conv3x3_bf16: NULL pointer");
-  CS_REQUIRE(n > 0 && n % kGemmBM == 0, "cs_debug_conv3x3_bf16: n must be a positive multiple of 128");
+// One k x k conv (k = 3: pad 1; k = 1: pad 0; stride 1|2; `groups` groups with the torch weight
+// layout [Cout][Cin/groups][k][k]) through plan_conv: in_hi bf16 [n][Hi*Wi][Cin] (device),
+// w_host / bias_host fp32 (host) -> out_f32 [n][Ho*Wo][Cout] (device), no ReLU.  n % 128 == 0.
+int cs_debug_conv_bf16(const void* in_hi, int64_t n, int Hi, int Wi, int Cin, int Cout, int k,
+                       int stride, int groups, const float* w_host, const float* bias_host,
+                       float* out_f32, void* stream) {
+  CS_REQUIRE(in_hi && w_host && bias_host && out_f32, "cs_debug_conv_bf16: NULL pointer");
+  CS_REQUIRE(n > 0 && n % kGemmBM == 0, "cs_debug_conv_bf16: n must be a positive multiple of 128");
+  CS_REQUIRE((k == 1 || k == 3) && groups >= 1 && Cin % groups == 0 && Cout % groups == 0,
+             "cs_debug_conv_bf16: bad k / groups");
   int rc = cs_check_device();
   if (rc != CS_OK) return rc;
-  ConvGeom g{Hi, Wi, Cin, (Hi + 2 - 3) / stride + 1, (Wi + 2 - 3) / stride + 1, Cout, 3, stride, 1};
+  const int pad = k == 3 ? 1 : 0, kk = k * k;
+  const int Ho = (Hi + 2 * pad - k) / stride + 1, Wo = (Wi + 2 * pad - k) / stride + 1;
+  std::vector<float> dense((size_t)Cout * Cin * kk, 0.f);
+  const int cin_g = Cin / groups, cout_g = Cout / groups;
+  for (int co = 0; co < Cout; ++co)
+    for (int cl = 0; cl < cin_g; ++cl)
+      memcpy(&dense[((size_t)co * Cin + (co / cout_g) * cin_g + cl) * kk],
+             &w_host[((size_t)co * cin_g + cl) * kk], kk * sizeof(float));
+  ConvGeom g{Hi, Wi, Cin, Ho, Wo, Cout, k, stride, pad, groups};
   PlannedConv pc;
-  rc = plan_conv(g, w_host, bias_host, nullptr, nullptr, nullptr,
+  rc = plan_conv(g, dense.data(), bias_host, nullptr, nullptr, nullptr,
                  reinterpret_cast<const __nv_bfloat16*>(in_hi), nullptr, n, &pc);
   if (rc != CS_OK) return rc;
   pc.p.relu = 0;

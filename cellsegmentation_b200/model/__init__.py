@@ -1,9 +1,11 @@
 """`nets` registry (mirror of model/__init__.py:5-13).  The reference instantiates every
 backbone with pretrained=True at import time (needs the network); here entries are built
 lazily with random init and weights come from load_state_dict()."""
-from .resnet import MILResNet, MILresnet18, MILresnet34
+from .resnet import MILResNet, MILresnet18, MILresnet34, MILresnet50
+from .resnext import MILResNeXt, MILresnext50_32x4d
 
-_CTORS = {"resnet18": MILresnet18, "resnet34": MILresnet34}
+_CTORS = {"resnet18": MILresnet18, "resnet34": MILresnet34, "resnet50": MILresnet50,
+          "resnext50_32x4d": MILresnext50_32x4d}
 
 
 class _Nets(dict):

@@ -2,7 +2,7 @@
 on the sm_100a kernels.
 
 Same module tree and state_dict keys as the reference for the encoder and the tile head
-(conv1, bn1, layer{1..4}.{b}.{conv1,bn1,conv2,bn2,downsample.{0,1}}, fc_tile.1.*), the same
+(conv1, bn1, layer{1..4}.{b}.{conv1,bn1,conv2,bn2,[conv3,bn3,]downsample.{0,1}}, fc_tile.1.*), the same
 prefix tuples and setmode() contract (model/resnet.py:83-106, 308-333), so reference
 checkpoints load with the same `load_state_dict(..., strict=False)` calls the scripts make.
 
@@ -17,7 +17,7 @@ import torch.nn as nn
 
 from .. import ops
 
-__all__ = ["MILresnet18", "MILresnet34", "MILResNet", "BasicBlock"]
+__all__ = ["MILresnet18", "MILresnet34", "MILresnet50", "MILResNet", "BasicBlock", "Bottleneck"]
 
 BN_EPS = 1e-5
 
@@ -25,13 +25,34 @@ BN_EPS = 1e-5
 class BasicBlock(nn.Module):
     expansion = 1
 
-    def __init__(self, inplanes, planes, stride=1, downsample=None):
+    def __init__(self, inplanes, planes, stride=1, downsample=None, groups=1, base_width=64):
         super().__init__()
+        if groups != 1 or base_width != 64:
+            raise ValueError("BasicBlock only supports groups=1 and base_width=64")   # model/resnext.py:35-36
         self.conv1 = nn.Conv2d(inplanes, planes, kernel_size=3, stride=stride, padding=1, bias=False)
         self.bn1 = nn.BatchNorm2d(planes)
         self.relu = nn.ReLU(inplace=True)
         self.conv2 = nn.Conv2d(planes, planes, kernel_size=3, padding=1, bias=False)
         self.bn2 = nn.BatchNorm2d(planes)
+        self.downsample = downsample
+        self.stride = stride
+
+
+class Bottleneck(nn.Module):
+    """model/resnet.py:46-78 (groups=1, base_width=64) and model/resnext.py:67-113 (grouped 3x3,
+    stride on conv2)."""
+    expansion = 4
+
+    def __init__(self, inplanes, planes, stride=1, downsample=None, groups=1, base_width=64):
+        super().__init__()
+        width = int(planes * (base_width / 64.)) * groups
+        self.conv1 = nn.Conv2d(inplanes, width, kernel_size=1, bias=False)
+        self.bn1 = nn.BatchNorm2d(width)
+        self.conv2 = nn.Conv2d(width, width, kernel_size=3, stride=stride, padding=1, groups=groups, bias=False)
+        self.bn2 = nn.BatchNorm2d(width)
+        self.conv3 = nn.Conv2d(width, planes * self.expansion, kernel_size=1, bias=False)
+        self.bn3 = nn.BatchNorm2d(planes * self.expansion)
+        self.relu = nn.ReLU(inplace=True)
         self.downsample = downsample
         self.stride = stride
 
@@ -46,11 +67,14 @@ def _fold(conv, bn):
 
 class MILResNet(nn.Module):
 
-    def __init__(self, encoder, block, layers, num_classes=1000, expansion=1):
+    def __init__(self, encoder, block, layers, num_classes=1000, expansion=1, groups=1, width_per_group=64):
         super().__init__()
-        if block is not BasicBlock:
-            raise NotImplementedError("only BasicBlock encoders (resnet18/34) have sm_100a kernels so far")
+        if encoder not in ops._capi.CS_ARCH:
+            raise NotImplementedError("encoder %r has no sm_100a kernels (available: %s)"
+                                      % (encoder, sorted(ops._capi.CS_ARCH)))
         self.encoder_name = encoder
+        self.groups = groups
+        self.base_width = width_per_group
         self.mode = None
         self.encoder_prefix = ("conv1", "bn1", "relu", "layer1", "layer2", "layer3", "layer4")
         self.image_module_prefix = ("fc_image_cls", "fc_image_reg")
@@ -87,10 +111,10 @@ class MILResNet(nn.Module):
             downsample = nn.Sequential(
                 nn.Conv2d(self.inplanes, planes * block.expansion, kernel_size=1, stride=stride, bias=False),
                 nn.BatchNorm2d(planes * block.expansion))
-        layers = [block(self.inplanes, planes, stride, downsample)]
+        layers = [block(self.inplanes, planes, stride, downsample, self.groups, self.base_width)]
         self.inplanes = planes * block.expansion
         for _ in range(1, blocks):
-            layers.append(block(self.inplanes, planes))
+            layers.append(block(self.inplanes, planes, groups=self.groups, base_width=self.base_width))
         return nn.Sequential(*layers)
 
     # ---- requires_grad groups (model/resnet.py:196-232, 308-333) ----------------------------
@@ -114,12 +138,15 @@ class MILResNet(nn.Module):
 
     # ---- device classifier ------------------------------------------------------------------
     def folded_convs(self):
-        """[(W', b')] in the order cs_model_create expects: stem; per block conv1, conv2, [downsample]."""
+        """[(W', b')] in the order cs_model_create expects: stem; per block conv1, conv2, [conv3],
+        [downsample]."""
         convs = [_fold(self.conv1, self.bn1)]
         for layer in (self.layer1, self.layer2, self.layer3, self.layer4):
             for blk in layer:
                 convs.append(_fold(blk.conv1, blk.bn1))
                 convs.append(_fold(blk.conv2, blk.bn2))
+                if hasattr(blk, "conv3"):
+                    convs.append(_fold(blk.conv3, blk.bn3))
                 if blk.downsample is not None:
                     convs.append(_fold(blk.downsample[0], blk.downsample[1]))
         return convs
@@ -142,7 +169,8 @@ class MILResNet(nn.Module):
         key = (str(device), self._encoder_version())
         fc = self.fc_tile[1]
         if fc.out_features != 2:
-            raise ops._capi.CellSegError("fc_tile must have 2 outputs (MILresnet18/34 set this)")
+            raise ops._capi.CellSegError("fc_tile must have 2 outputs (the MILres* constructors set this; pass "
+                                         "num_classes=2 to a bare MILResNet / MILResNeXt)")
         if self._clf is None or self._clf_key != key:
             if self._clf is not None:
                 self._clf.close()
@@ -156,7 +184,7 @@ class MILResNet(nn.Module):
         return self._clf
 
     def encode(self, x):
-        """Pooled 512-d features avgpool(x4)+maxpool(x4) (model/resnet.py:266), no grad."""
+        """Pooled 512*expansion-d features avgpool(x4)+maxpool(x4) (model/resnet.py:266), no grad."""
         with torch.no_grad():
             _, feat = self.classifier(x.device).forward_tensor(
                 x.contiguous().float(), precision=self.precision, max_batch=self.max_batch,
@@ -191,4 +219,12 @@ def MILresnet34(pretrained=False, **kwargs):
         raise RuntimeError("no network access: load weights with load_state_dict() instead")
     model = MILResNet("resnet34", BasicBlock, [3, 4, 6, 3], **kwargs)
     model.fc_tile[1] = nn.Linear(model.fc_tile[1].in_features, 2)   # model/resnet.py:351
+    return model
+
+
+def MILresnet50(pretrained=False, **kwargs):
+    if pretrained:
+        raise RuntimeError("no network access: load weights with load_state_dict() instead")
+    model = MILResNet("resnet50", Bottleneck, [3, 4, 6, 3], expansion=4, **kwargs)
+    model.fc_tile[1] = nn.Linear(model.fc_tile[1].in_features, 2)   # model/resnet.py:360
     return model

@@ -217,13 +217,14 @@ def bgr2hsv(img):
 class TileClassifier:
     """Device-side tile classifier built from BN-folded fp32 conv weights.
 
-    convs: list of (weight [Cout,Cin,k,k], bias [Cout]) CPU float32 tensors in network order
-    (stem; per BasicBlock conv1, conv2, [downsample]); fc_w [2,512], fc_b [2].
+    convs: list of (weight [Cout,Cin/groups,k,k], bias [Cout]) CPU float32 tensors in network order
+    (stem; per BasicBlock conv1, conv2, [downsample]; per Bottleneck conv1, conv2, conv3,
+    [downsample]); fc_w [2,F], fc_b [2] with F = 512 or 2048.
     """
 
     def __init__(self, arch, convs, fc_w, fc_b, device=None):
         if arch not in _capi.CS_ARCH:
-            raise _capi.CellSegError("arch %r has no sm_100a kernels (resnet18 / resnet34)" % arch)
+            raise _capi.CellSegError("arch %r has no sm_100a kernels (%s)" % (arch, sorted(_capi.CS_ARCH)))
         self.arch = arch
         self.device = torch.device("cuda", torch.cuda.current_device()) if device is None else device
         ws = [np.ascontiguousarray(w.detach().cpu().numpy(), dtype=np.float32) for w, _ in convs]
@@ -238,6 +239,7 @@ class TileClassifier:
             check(lib().cs_model_create(_capi.CS_ARCH[arch], n, wp, bp, fw.ctypes.data, fb.ctypes.data,
                                         ctypes.byref(handle)), "cs_model_create")
         self._h = handle
+        self.feature_dim = int(lib().cs_model_feature_dim(handle))
         self._ws = None
         self._ws_key = None
 
@@ -281,7 +283,7 @@ class TileClassifier:
         ws = self._workspace(tile, max_batch, prec)
         if prob_out is None:
             prob_out = torch.empty(inst_count, dtype=torch.float32, device=img.device)
-        feat = torch.empty((inst_count, 512), dtype=torch.float32, device=img.device) if want_features else None
+        feat = torch.empty((inst_count, self.feature_dim), dtype=torch.float32, device=img.device) if want_features else None
         check(lib().cs_model_forward_tiles(self._h, ptr(img), Nb, H, W, tile, interval, inst_begin,
                                            inst_count, prec, ptr(prob_out), ptr(feat), ptr(ws),
                                            ws.numel(), max_batch, cur_stream()),
@@ -295,7 +297,7 @@ class TileClassifier:
         prec = PRECISIONS[precision]
         ws = self._workspace(S, max_batch, prec)
         logits = torch.empty((n, 2), dtype=torch.float32, device=x.device)
-        feat = torch.empty((n, 512), dtype=torch.float32, device=x.device) if want_features else None
+        feat = torch.empty((n, self.feature_dim), dtype=torch.float32, device=x.device) if want_features else None
         check(lib().cs_model_forward_tensor(self._h, ptr(x), n, S, prec, ptr(logits), ptr(feat),
                                             ptr(ws), ws.numel(), max_batch, cur_stream()),
               "cs_model_forward_tensor")
@@ -319,16 +321,18 @@ def debug_gemm_bf16(a, b, bias, bn):
     return out
 
 
-def debug_conv3x3_bf16(x_hi, w, bias, stride):
-    """x_hi bf16 [n,H,W,Cin] (cuda), w f32 [Cout,Cin,3,3] (cpu), bias f32 [Cout] (cpu) -> f32 [n,Ho,Wo,Cout]."""
+def debug_conv_bf16(x_hi, w, bias, stride, groups=1):
+    """x_hi bf16 [n,H,W,Cin] (cuda), w f32 [Cout,Cin/groups,k,k] (cpu), bias f32 [Cout] (cpu)
+    -> f32 [n,Ho,Wo,Cout] through the production planner + tcgen05 kernels (k = 1 or 3)."""
     _req_cuda(x_hi, "x_hi", torch.bfloat16)
     n, H, W, Cin = x_hi.shape
-    Cout = w.shape[0]
-    Ho, Wo = (H + 2 - 3) // stride + 1, (W + 2 - 3) // stride + 1
+    Cout, k = w.shape[0], w.shape[2]
+    pad = 1 if k == 3 else 0
+    Ho, Wo = (H + 2 * pad - k) // stride + 1, (W + 2 * pad - k) // stride + 1
     wn = np.ascontiguousarray(w.detach().cpu().numpy(), dtype=np.float32)
     bn_ = np.ascontiguousarray(bias.detach().cpu().numpy(), dtype=np.float32)
     out = torch.zeros((n, Ho, Wo, Cout), dtype=torch.float32, device=x_hi.device)
-    check(lib().cs_debug_conv3x3_bf16(ptr(x_hi), n, H, W, Cin, Cout, stride, wn.ctypes.data,
-                                      bn_.ctypes.data, ptr(out), cur_stream()),
-          "cs_debug_conv3x3_bf16")
+    check(lib().cs_debug_conv_bf16(ptr(x_hi), n, H, W, Cin, Cout, k, stride, groups, wn.ctypes.data,
+                                   bn_.ctypes.data, ptr(out), cur_stream()),
+          "cs_debug_conv_bf16")
     return out

@@ -45,8 +45,10 @@ typedef enum cs_precision {
 } cs_precision;
 
 typedef enum cs_arch {
-  CS_ARCH_RESNET18 = 0, /* model/resnet.py:336-343  BasicBlock [2,2,2,2] */
-  CS_ARCH_RESNET34 = 1  /* model/resnet.py:346-352  BasicBlock [3,4,6,3] */
+  CS_ARCH_RESNET18 = 0,        /* model/resnet.py:336-343   BasicBlock [2,2,2,2] */
+  CS_ARCH_RESNET34 = 1,        /* model/resnet.py:346-352   BasicBlock [3,4,6,3] */
+  CS_ARCH_RESNET50 = 2,        /* model/resnet.py:355-361   Bottleneck [3,4,6,3] */
+  CS_ARCH_RESNEXT50_32X4D = 3  /* model/resnext.py:418-428  Bottleneck [3,4,6,3], groups 32 x 4 */
 } cs_arch;
 
 /* Library version: major*10000 + minor*100 + patch. */
@@ -99,8 +101,12 @@ int cs_gather_normalize(const uint8_t* img, int n_bags, int H, int W, int tile,
  *   conv 0                 : stem 7x7/2            [64][3][7][7]
  *   per BasicBlock, in order: conv1 3x3, conv2 3x3, then (if the block has one)
  *                            the 1x1 downsample conv        [Cout][Cin][k][k]
- *   fc_w [2][512], fc_b [2]: fc_tile.1 (model/resnet.py:124-127)
- * n_convs must equal the count implied by `arch` (resnet34: 36, resnet18: 20).
+ *   per Bottleneck, in order: conv1 1x1, conv2 3x3 (grouped: [W][W/groups][3][3], the torch
+ *                            layout), conv3 1x1, then the 1x1 downsample conv if present
+ *   fc_w [2][F], fc_b [2]  : fc_tile.1 (model/resnet.py:124-127), F = 512 (BasicBlock nets)
+ *                            or 2048 (Bottleneck nets) = cs_model_feature_dim()
+ * n_convs must equal the count implied by `arch` (resnet18: 20, resnet34: 36,
+ * resnet50 / resnext50_32x4d: 53).
  * The library packs GEMM-ready bf16 copies and keeps the fp32 originals.
  * ------------------------------------------------------------------------- */
 typedef struct cs_model cs_model;
@@ -109,7 +115,9 @@ int cs_model_create(int arch, int n_convs, const float* const* conv_w_host,
                     const float* const* conv_b_host, const float* fc_w_host,
                     const float* fc_b_host, cs_model** out);
 int cs_model_destroy(cs_model* m);
-/* Replace fc_tile.1 (weight [2][512], bias [2], host pointers) after an optimizer step;
+/* Length F of the pooled feature vector / fc_tile input (512 or 2048). */
+int cs_model_feature_dim(const cs_model* m);
+/* Replace fc_tile.1 (weight [2][F], bias [2], host pointers) after an optimizer step;
  * the encoder is frozen in tile mode (model/resnet.py:315-319) so nothing else changes. */
 int cs_model_set_fc(cs_model* m, const float* fc_w_host, const float* fc_b_host);
 
@@ -121,7 +129,7 @@ int64_t cs_model_workspace_bytes(const cs_model* m, int tile, int64_t max_batch,
 /* Fused unfold -> CNN -> prob for instances [inst_begin, inst_begin+inst_count)
  * of the bag array `img` (same instance numbering as cs_unfold_normalize).
  * prob_out[j] (fp32) receives softmax(logits)[1] of instance inst_begin + j.
- * feat_out (optional, may be NULL): fp32 [inst_count][512] pooled features
+ * feat_out (optional, may be NULL): fp32 [inst_count][F] pooled features
  * avgpool(x4)+maxpool(x4) (model/resnet.py:266), the input of fc_tile — used to
  * train fc_tile without a second encoder pass.
  * Internally processes the range in batches of <= max_batch the workspace was
@@ -251,16 +259,17 @@ int cs_remove_small_regions(uint8_t* mask, int n_bags, int H, int W, int min_obj
  * ------------------------------------------------------------------------- */
 
 /* out_f32[M][N] = A[M][K] . B[N][K]^T + bias[N]; A, B bf16 row-major (device).
- * K % 64 == 0, K <= 1280, N % bn == 0, bn in {64, 128, 256}. */
+ * K % 64 == 0, K <= 2560, N % bn == 0, bn in {64, 128, 256}. */
 int cs_debug_gemm_bf16(const void* a_bf16, const void* b_bf16, int64_t M, int N, int K,
                        const float* bias, int bn, float* out_f32, void* stream);
 
-/* One 3x3 / pad 1 / stride 1|2 convolution through the production planner:
- * in_hi bf16 [n][Hi*Wi][Cin] (device), w_host fp32 OIHW (host), bias_host fp32 (host)
+/* One k x k convolution (k = 3: pad 1, k = 1: pad 0; stride 1|2; `groups` groups, torch weight
+ * layout [Cout][Cin/groups][k][k]) through the production planner:
+ * in_hi bf16 [n][Hi*Wi][Cin] (device), w_host / bias_host fp32 (host)
  * -> out_f32 [n][Ho*Wo][Cout] (device), no ReLU.  n % 128 == 0.  Synchronises. */
-int cs_debug_conv3x3_bf16(const void* in_hi, int64_t n, int Hi, int Wi, int Cin, int Cout,
-                          int stride, const float* w_host, const float* bias_host,
-                          float* out_f32, void* stream);
+int cs_debug_conv_bf16(const void* in_hi, int64_t n, int Hi, int Wi, int Cin, int Cout, int k,
+                       int stride, int groups, const float* w_host, const float* bias_host,
+                       float* out_f32, void* stream);
 
 #ifdef __cplusplus
 }

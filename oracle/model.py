@@ -3,6 +3,7 @@
 Restates MILResNet tile mode on CPU fp32 with the same torch ops the reference calls:
   resnet_forward   model/resnet.py:234-248
   BasicBlock       model/resnet.py:28-43
+  Bottleneck       model/resnet.py:60-78 (resnet50), model/resnext.py:93-113 (grouped 3x3)
   tile head        model/resnet.py:264-269  (avgpool_tile + maxpool_tile -> Flatten -> Linear)
   prob             inference.py:24-27       (softmax(dim=1)[:, 1])
 State-dict keys are the reference's (torchvision-style + fc_tile.1.*), SURVEY Appendix B.
@@ -11,8 +12,15 @@ import numpy as np
 import torch
 import torch.nn.functional as F
 
-LAYERS = {"resnet18": [2, 2, 2, 2], "resnet34": [3, 4, 6, 3]}
+LAYERS = {"resnet18": [2, 2, 2, 2], "resnet34": [3, 4, 6, 3], "resnet50": [3, 4, 6, 3],
+          "resnext50_32x4d": [3, 4, 6, 3]}
+# (groups, width_per_group) of the Bottleneck nets; model/resnet.py:355-361, model/resnext.py:418-428
+BOTTLENECK = {"resnet50": (1, 64), "resnext50_32x4d": (32, 4)}
 PLANES = [64, 128, 256, 512]
+
+
+def feature_dim(arch):
+    return 2048 if arch in BOTTLENECK else 512
 BN_EPS = 1e-5
 
 
@@ -32,10 +40,17 @@ def forward_features(sd, x, arch="resnet34", return_intermediate=False):
             p = "layer%d.%d" % (L, b)
             stride = 2 if (b == 0 and L > 1) else 1
             residual = x
-            out = F.conv2d(x, sd[p + ".conv1.weight"], stride=stride, padding=1)
-            out = F.relu(_bn(sd, out, p + ".bn1"))
-            out = F.conv2d(out, sd[p + ".conv2.weight"], stride=1, padding=1)
-            out = _bn(sd, out, p + ".bn2")
+            if arch in BOTTLENECK:
+                out = F.relu(_bn(sd, F.conv2d(x, sd[p + ".conv1.weight"]), p + ".bn1"))
+                out = F.conv2d(out, sd[p + ".conv2.weight"], stride=stride, padding=1,
+                               groups=BOTTLENECK[arch][0])
+                out = F.relu(_bn(sd, out, p + ".bn2"))
+                out = _bn(sd, F.conv2d(out, sd[p + ".conv3.weight"]), p + ".bn3")
+            else:
+                out = F.conv2d(x, sd[p + ".conv1.weight"], stride=stride, padding=1)
+                out = F.relu(_bn(sd, out, p + ".bn1"))
+                out = F.conv2d(out, sd[p + ".conv2.weight"], stride=1, padding=1)
+                out = _bn(sd, out, p + ".bn2")
             if (p + ".downsample.0.weight") in sd:
                 residual = _bn(sd, F.conv2d(x, sd[p + ".downsample.0.weight"], stride=stride),
                                p + ".downsample.1")
@@ -98,6 +113,20 @@ def make_state_dict(arch="resnet34", seed=0, random_bn=True):
         for b in range(nb):
             p = "layer%d.%d" % (L, b)
             stride = 2 if (b == 0 and L > 1) else 1
+            if arch in BOTTLENECK:
+                groups, wpg = BOTTLENECK[arch]
+                width = int(planes * (wpg / 64.)) * groups
+                conv(p + ".conv1.weight", width, inplanes, 1)
+                bn(p + ".bn1", width)
+                conv(p + ".conv2.weight", width, width // groups, 3)
+                bn(p + ".bn2", width)
+                conv(p + ".conv3.weight", planes * 4, width, 1)
+                bn(p + ".bn3", planes * 4)
+                if stride != 1 or inplanes != planes * 4:
+                    conv(p + ".downsample.0.weight", planes * 4, inplanes, 1)
+                    bn(p + ".downsample.1", planes * 4)
+                inplanes = planes * 4
+                continue
             conv(p + ".conv1.weight", planes, inplanes, 3)
             bn(p + ".bn1", planes)
             conv(p + ".conv2.weight", planes, planes, 3)
@@ -106,8 +135,9 @@ def make_state_dict(arch="resnet34", seed=0, random_bn=True):
                 conv(p + ".downsample.0.weight", planes, inplanes, 1)
                 bn(p + ".downsample.1", planes)
             inplanes = planes
-    bound = 1.0 / np.sqrt(512)
-    sd["fc_tile.1.weight"] = torch.from_numpy(rng.uniform(-bound, bound, (2, 512)).astype(np.float32))
+    fd = feature_dim(arch)
+    bound = 1.0 / np.sqrt(fd)
+    sd["fc_tile.1.weight"] = torch.from_numpy(rng.uniform(-bound, bound, (2, fd)).astype(np.float32))
     sd["fc_tile.1.bias"] = torch.from_numpy(rng.uniform(-bound, bound, 2).astype(np.float32))
     return sd
 
@@ -133,7 +163,7 @@ def calibrate_head(sd, calib_x, arch="resnet34", sigma=2.0):
 def fold_bn(sd, arch="resnet34"):
     """Eval-mode BN folded into the preceding conv, fp32:
     s = gamma / sqrt(var + eps); W' = W * s; b' = beta - mean * s.
-    Returns [(W', b')] in network order: stem; per block conv1, conv2, [downsample]."""
+    Returns [(W', b')] in network order: stem; per block conv1, conv2, [conv3], [downsample]."""
     def fold(wname, bnname):
         w = sd[wname].float()
         s = sd[bnname + ".weight"].float() / torch.sqrt(sd[bnname + ".running_var"].float() + BN_EPS)
@@ -146,6 +176,8 @@ def fold_bn(sd, arch="resnet34"):
             p = "layer%d.%d" % (L, b)
             convs.append(fold(p + ".conv1.weight", p + ".bn1"))
             convs.append(fold(p + ".conv2.weight", p + ".bn2"))
+            if (p + ".conv3.weight") in sd:
+                convs.append(fold(p + ".conv3.weight", p + ".bn3"))
             if (p + ".downsample.0.weight") in sd:
                 convs.append(fold(p + ".downsample.0.weight", p + ".downsample.1"))
     return convs

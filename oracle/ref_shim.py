@@ -69,9 +69,13 @@ def import_reference():
     return ns
 
 
-def load_reference_resnet():
-    """model/resnet.py alone (needs only torch)."""
-    spec = importlib.util.spec_from_file_location("ref_resnet", os.path.join(REF_ROOT, "model", "resnet.py"))
+def load_reference_module(name):
+    """model/<name>.py alone (resnet.py / resnext.py need only torch)."""
+    spec = importlib.util.spec_from_file_location("ref_" + name, os.path.join(REF_ROOT, "model", name + ".py"))
     mod = importlib.util.module_from_spec(spec)
     spec.loader.exec_module(mod)
     return mod
+
+
+def load_reference_resnet():
+    return load_reference_module("resnet")

@@ -45,9 +45,42 @@ def extract_nested_rank():
     raise RuntimeError("rank() not found in test_tile.py")
 
 
+def gen_model(ref, ds, arch):
+    """Model forward through the reference classes + inference_tiles."""
+    if arch.startswith("resnext"):
+        net = getattr(ref_shim.load_reference_module("resnext"), "MIL" + arch)(num_classes=2)
+    else:
+        net = getattr(ref_shim.load_reference_module("resnet"), "MIL" + arch)()
+    sd = omodel.make_state_dict(arch, seed=3)
+    ds.setmode(1)
+    calib = torch.stack([ds[i][0] for i in range(0, len(ds), 3)])
+    sd = omodel.calibrate_head(sd, calib, arch)
+    missing, unexpected = net.load_state_dict(sd, strict=False)
+    assert not unexpected and all(not k.startswith(net.encoder_prefix + net.tile_module_prefix)
+                                  for k in missing), (missing, unexpected)
+    net.setmode("tile")
+    net.eval()
+    loader = torch.utils.data.DataLoader(ds, batch_size=64, shuffle=False, num_workers=0)
+    import contextlib
+    with contextlib.redirect_stderr(io.StringIO()):
+        probs = ref.inference.inference_tiles(loader, net, torch.device("cpu"), mode="train")
+    fwd = net.resnext_forward if arch.startswith("resnext") else net.resnet_forward
+    with torch.no_grad():
+        x16 = torch.stack([ds[i][0] for i in range(16)])
+        logits = net(x16).numpy()
+        x4, x3, x2, x1 = fwd(x16, True)
+    save("model_%s.npz" % arch, probs=probs.astype(np.float32), logits16=logits,
+         x1_sum=x1.double().sum(dim=(1, 2, 3)).numpy(), x2_sum=x2.double().sum(dim=(1, 2, 3)).numpy(),
+         x3_sum=x3.double().sum(dim=(1, 2, 3)).numpy(), x4=x4.numpy().reshape(16, -1))
+
+
 def main():
     ref = ref_shim.import_reference()
-    resnet = ref_shim.load_reference_resnet()
+    if len(sys.argv) > 1:          # python make_golden.py resnet50 ...: only those model fixtures
+        ds = ref_dataset(ref, synth.make_bags(3, seed=11), [4, 0, 9], 32, 20)
+        for arch in sys.argv[1:]:
+            gen_model(ref, ds, arch)
+        return
 
     # 1. tile grids -----------------------------------------------------------------
     grids = {}
@@ -69,28 +102,8 @@ def main():
          n=np.array(len(ds)))
 
     # 3. model forward through the reference classes + inference_tiles ----------------
-    for arch in ("resnet34", "resnet18"):
-        sd = omodel.make_state_dict(arch, seed=3)
-        ds.setmode(1)
-        calib = torch.stack([ds[i][0] for i in range(0, len(ds), 3)])
-        sd = omodel.calibrate_head(sd, calib, arch)
-        net = getattr(resnet, "MIL" + arch)()
-        missing, unexpected = net.load_state_dict(sd, strict=False)
-        assert not unexpected and all(not k.startswith(net.encoder_prefix + net.tile_module_prefix)
-                                      for k in missing), (missing, unexpected)
-        net.setmode("tile")
-        net.eval()
-        loader = torch.utils.data.DataLoader(ds, batch_size=64, shuffle=False, num_workers=0)
-        import contextlib
-        with contextlib.redirect_stderr(io.StringIO()):
-            probs = ref.inference.inference_tiles(loader, net, torch.device("cpu"), mode="train")
-        with torch.no_grad():
-            x16 = torch.stack([ds[i][0] for i in range(16)])
-            logits = net(x16).numpy()
-            x4, x3, x2, x1 = net.resnet_forward(x16, True)
-        save("model_%s.npz" % arch, probs=probs.astype(np.float32), logits16=logits,
-             x1_sum=x1.double().sum(dim=(1, 2, 3)).numpy(), x2_sum=x2.double().sum(dim=(1, 2, 3)).numpy(),
-             x3_sum=x3.double().sum(dim=(1, 2, 3)).numpy(), x4=x4.numpy().reshape(16, -1))
+    for arch in ("resnet34", "resnet18", "resnet50", "resnext50_32x4d"):
+        gen_model(ref, ds, arch)
 
     # 4. sample(): capture the idxs handed to make_train_data -------------------------
     cases = {}

@@ -14,14 +14,16 @@ pytestmark = pytest.mark.gpu
 
 def _model(arch, sd, cuda, precision):
     from cellsegmentation_b200.model import nets
-    from cellsegmentation_b200.model.resnet import MILresnet18, MILresnet34
-    net = {"resnet18": MILresnet18, "resnet34": MILresnet34}[arch]()
+    from cellsegmentation_b200.model.resnet import MILresnet18, MILresnet34, MILresnet50
+    from cellsegmentation_b200.model.resnext import MILresnext50_32x4d
+    net = {"resnet18": MILresnet18, "resnet34": MILresnet34, "resnet50": MILresnet50,
+           "resnext50_32x4d": MILresnext50_32x4d}[arch]()
     missing, unexpected = net.load_state_dict(sd, strict=False)
     assert not unexpected and not missing, (missing, unexpected)
     net.setmode("tile")
     net.precision = precision
     net.max_batch = 512
-    assert "resnet34" in nets and isinstance(nets["resnet34"], type(net))
+    assert arch in nets and type(nets[arch]) is type(net)
     return net.to(cuda)
 
 
@@ -53,6 +55,27 @@ def test_inference_tiles_dataset_path_matches_reference_golden(cuda, precision, 
     gt = golden("transform.npz")
     assert np.array_equal(t.numpy().view(np.uint32), gt["tiles"][list(gt["pick"]).index(14)].view(np.uint32))
     assert lab == 0 or lab == ds.labels[ds.tileIDX[14]]
+
+
+@pytest.mark.parametrize("arch", ["resnet50", "resnext50_32x4d"])
+def test_bottleneck_nets_match_reference_golden(cuda, arch):
+    """BASELINE config 4 (encoder swap): reference state_dict keys load, module call == golden."""
+    from cellsegmentation_b200.inference import inference_tiles
+    g = golden("model_%s.npz" % arch)
+    bags, ds = _trainset()
+    ds.setmode(1)
+    x = torch.from_numpy(otiles.unfold(list(bags[1:]), 20, 32))
+    sd = omodel.calibrate_head(omodel.make_state_dict(arch, seed=3), x[::3], arch)
+    for precision, tol, ltol in (("fp32", 1e-4, 2e-3), ("bf16", 2e-2, 0.2)):
+        net = _model(arch, sd, cuda, precision)
+        net.eval()
+        loader = torch.utils.data.DataLoader(ds, batch_size=64, shuffle=False)
+        probs = inference_tiles(loader, net, cuda, mode="train")
+        assert np.abs(probs - g["probs"]).max() < tol
+        logits = net(x[:16].to(cuda)).detach().cpu().numpy()
+        assert np.abs(logits - g["logits16"]).max() < ltol
+        feat = net.encode(x[:16].to(cuda))
+        assert feat.shape == (16, 2048)
 
 
 def test_sample_rebuilds_reference_selection(cuda, capsys):
