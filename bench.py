@@ -259,6 +259,24 @@ def main():
                                         "note": "includes a device copy of the 2000 input masks"}
         side["preprocess_masks_chain"] = {"masks_per_s": 1.0 / (ms / nb_m * 1e-3 + ms_cc / nb_c * 1e-3)}
         del masks, out_m, cc_in, work
+        # configs[3]: ResNeXt-50 32x4d backbone at a denser tile stride (interval 3 -> 8100
+        # instances per bag), score + select, timed alone on a 64-bag slice
+        nb_x, iv_x = 64, 3
+        t_x = ((H - TILE + iv_x - 1) // iv_x + 1) ** 2
+        cx, fwx, fbx = synthetic.make_resnet_weights("resnext50_32x4d", seed=0)
+        clf_x = ops.TileClassifier("resnext50_32x4d", cx, fwx, fbx, device=dev)
+        prob_x = torch.empty(nb_x * t_x, dtype=torch.float32, device=dev)
+
+        def run_x():
+            clf_x.forward_tiles(bags[:nb_x], TILE, iv_x, precision="bf16", max_batch=args.max_batch // 2,
+                                prob_out=prob_x)
+            ops.select_topk(prob_x, labels[:nb_x], nb_x, t_x, 1, 30, capacity=nb_x * 330)
+        ms_x = time_alone(run_x, reps=3)
+        side["resnext50_32x4d_dense_stride"] = {
+            "workload": "configs[3]: ResNeXt-50 32x4d, tile 32 interval 3 (%d instances/bag), %d bags" % (t_x, nb_x),
+            "ms": ms_x, "instances_per_s": nb_x * t_x / (ms_x * 1e-3), "launches": clf_x.last_launch_count + 3}
+        clf_x.close()
+        del prob_x
 
     # ---- end to end: host (pinned) bags -> H2D -> score + select -> D2H of the selection
     host = torch.empty((B, H, H, 3), dtype=torch.uint8).pin_memory()

@@ -25,7 +25,7 @@ SOURCES = [
     "fwd_fp32.cu",
     "fwd_tc.cu",
     "conv_gemm.cu",
-    "stem_tc.cu",
+    "stem_tc.cu", "stem_win.cu",
     "conv_halo.cu",
     "model.cu",
 ]

@@ -137,6 +137,13 @@ void pack_stem_weights_bf16(const float* w_oihw, uint16_t* out /* [64*192] */);
 int launch_stem_tc(const StemArgs& a, const void* w_bf16_dev, const uint16_t* lut_bf16_dev,
                    cudaStream_t st);
 
+// Window-form tensor-core stem (stem_win.cu), tile 32 only: no im2col, the padded bf16 image is
+// the UMMA operand.  w_packed_dev holds stem_win_weight_bytes() bytes from pack_stem_weights_win.
+int stem_win_weight_bytes();
+void pack_stem_weights_win(const float* w_oihw, uint16_t* out);
+int launch_stem_win(const StemArgs& a, const void* w_packed_dev, const uint16_t* lut_bf16_dev,
+                    cudaStream_t st);
+
 int launch_head_bf16(const __nv_bfloat16* x_hi, const __nv_bfloat16* x_lo, int64_t n, int P,
                      int C, const float* fc_w, const float* fc_b, float* prob_out,
                      float* logits_out, float* feat_out, cudaStream_t st);

@@ -36,6 +36,7 @@ const bool g_snake = !env_is("CELLSEG_SNAKE", "0");          // alternate the ti
 const int g_cluster = env_is("CELLSEG_CLUSTER", "2") ? 2 : 1;  // 2-CTA B multicast (no gain measured)
 const bool g_disable_halo = env_is("CELLSEG_HALO", "0");     // diagnostics: generic kernel only
 const bool g_force_cuda_core_stem = env_is("CELLSEG_STEM", "cuda");
+const bool g_im2col_stem = env_is("CELLSEG_STEM", "im2col");   // first tensor-core stem (stem_tc.cu)
 
 struct ConvW {
   int cin = 0, cout = 0, k = 0, stride = 1, pad = 0, groups = 1;
@@ -365,10 +366,12 @@ struct TcPlan {
   const __nv_bfloat16* x4_lo = nullptr;
   int P4 = 1, C4 = 512;
   uint16_t* d_stem_w = nullptr;  // [64][192] bf16 for the tensor-core stem (tile 32)
+  uint16_t* d_stem_w2 = nullptr; // window-form stem weights (stem_win.cu)
   uint16_t* d_lut = nullptr;     // [3][256] bf16 normalisation LUT
   ~TcPlan() {
     for (auto& l : layers) free_planned(l);
     if (d_stem_w) cudaFree(d_stem_w);
+    if (d_stem_w2) cudaFree(d_stem_w2);
     if (d_lut) cudaFree(d_lut);
   }
 };
@@ -454,6 +457,7 @@ int build_tc_plan(cs_model* m, int tile, int64_t max_batch, void* ws, int64_t ws
   };
 
   int xi = 0;   // x lives in (x_hi[xi], x_lo[xi]); the block writes (x_hi[1-xi], x_lo[1-xi])
+  bool x_has_lo = false;   // the stem writes the bf16 stream only (see stem_win.cu)
   int H = tile / 4, W = tile / 4, C = 64;
   for (const BlockDesc& b : m->blocks) {
     const int Ho = (H + 2 - 3) / b.stride + 1, Wo = (W + 2 - 3) / b.stride + 1;
@@ -477,7 +481,8 @@ int build_tc_plan(cs_model* m, int tile, int64_t max_batch, void* ws, int64_t ws
       } else {
         rc = plan_conv(g2, c2.w.data(), c2.b.data(), nullptr, nullptr, nullptr, plan->mid[0], nullptr, bp, &p);
         if (rc != CS_OK) return rc;
-        rc = push(p, plan->x_hi[xi], plan->x_lo[xi], plan->x_hi[1 - xi], plan->x_lo[1 - xi], 1);
+        rc = push(p, plan->x_hi[xi], x_has_lo ? plan->x_lo[xi] : nullptr, plan->x_hi[1 - xi],
+                  plan->x_lo[1 - xi], 1);
       }
       if (rc != CS_OK) return rc;
     } else {
@@ -503,11 +508,13 @@ int build_tc_plan(cs_model* m, int tile, int64_t max_batch, void* ws, int64_t ws
       } else {
         rc = plan_conv(g3, c3.w.data(), c3.b.data(), nullptr, nullptr, nullptr, plan->mid[1], nullptr, bp, &p);
         if (rc != CS_OK) return rc;
-        rc = push(p, plan->x_hi[xi], plan->x_lo[xi], plan->x_hi[1 - xi], plan->x_lo[1 - xi], 1);
+        rc = push(p, plan->x_hi[xi], x_has_lo ? plan->x_lo[xi] : nullptr, plan->x_hi[1 - xi],
+                  plan->x_lo[1 - xi], 1);
       }
       if (rc != CS_OK) return rc;
     }
     xi = 1 - xi;
+    x_has_lo = true;
     H = Ho; W = Wo; C = b.cout;
   }
   plan->x4_hi = plan->x_hi[xi];
@@ -522,6 +529,10 @@ int build_tc_plan(cs_model* m, int tile, int64_t max_batch, void* ws, int64_t ws
     for (int i = 0; i < 768; ++i) lut[i] = f32_to_bf16_rn(lut_f[i]);
     CS_CUDA(cudaMalloc(&plan->d_stem_w, sw.size() * 2));
     CS_CUDA(cudaMemcpy(plan->d_stem_w, sw.data(), sw.size() * 2, cudaMemcpyHostToDevice));
+    std::vector<uint16_t> sw2(stem_win_weight_bytes() / 2);
+    pack_stem_weights_win(m->convs[0].w.data(), sw2.data());
+    CS_CUDA(cudaMalloc(&plan->d_stem_w2, sw2.size() * 2));
+    CS_CUDA(cudaMemcpy(plan->d_stem_w2, sw2.data(), sw2.size() * 2, cudaMemcpyHostToDevice));
     CS_CUDA(cudaMalloc(&plan->d_lut, lut.size() * 2));
     CS_CUDA(cudaMemcpy(plan->d_lut, lut.data(), lut.size() * 2, cudaMemcpyHostToDevice));
   }
@@ -537,9 +548,13 @@ int run_tc_batch(cs_model* m, const StemArgs& stem_in, int64_t count, float* pro
   sa.w = m->convs[0].d_w32;
   sa.bias = m->convs[0].d_b;
   sa.out_hi = pl.x_hi[0];
-  sa.out_lo = pl.x_lo[0];
-  int rc = (pl.tile == 32 && !g_force_cuda_core_stem) ? launch_stem_tc(sa, pl.d_stem_w, pl.d_lut, st)
-                                                      : launch_stem_bf16(sa, st);
+  sa.out_lo = nullptr;   // bf16 stream only; the first block's residual add reads x_hi alone
+  int rc;
+  if (pl.tile == 32 && !g_force_cuda_core_stem)
+    rc = g_im2col_stem ? launch_stem_tc(sa, pl.d_stem_w, pl.d_lut, st)
+                       : launch_stem_win(sa, pl.d_stem_w2, pl.d_lut, st);
+  else
+    rc = launch_stem_bf16(sa, st);
   if (rc != CS_OK) return rc;
   m->last_launches++;
   int li = 0;

@@ -1,0 +1,412 @@
+// K1+K2a fused on tensor cores, window form: unfold + normalise + conv7x7/2 + BN bias + ReLU +
+// maxpool3x3/2 for 32x32 tiles without ever materialising im2col rows.
+//
+// Reference: crop/ToTensor/Normalize (dataset/dataset.py:409-416, 78-83) and
+// conv1 -> bn1 -> relu -> maxpool (model/resnet.py:236-239), eval-mode BN folded.
+//
+// The tile is staged once as a zero-padded, normalised bf16 image of 4-channel pixels
+// (8 bytes: r, g, b, 0), rows of kPitch bytes.  For a fixed kernel row ky the inputs of conv
+// pixel (oy, ox) are the 8 consecutive padded pixels starting at column 2*ox (K = 8 px x 4 ch
+// = 32; kernel column kx sits in slot kx + 1, slot 0 and channel 3 carry zero weights).  Two
+// neighbouring EVEN (or ODD) conv columns are 4 padded pixels = 32 bytes apart, so the 128 rows
+//   r = oy * 8 + j   <->   conv pixel (oy, 2*j + b),  b = 0 | 1
+// of one UMMA M tile are exactly a K-major SWIZZLE_32B operand whose 8-row groups are two image
+// rows apart (SBO = 2 * kPitch): the descriptor's start address walks ky (kPitch), b (16 B)
+// and the K half (32 B); rows of the operand overlap in memory.  tcgen05.mma applies the
+// swizzle XOR on absolute shared-memory address bits (tools/umma_probe.cu), so the producers
+// only have to store every 16-byte chunk at its swizzled address.  Per instance: 2 M tiles
+// (b = 0, 1) x 7 ky x 2 K halves = 28 MMAs of 128x64x16, against 12 KB of staging writes
+// instead of the 96 KB im2col build of the first version.
+//
+// TMEM lane r of accumulators b = 0, 1 holds conv pixels (oy, 2j) and (oy, 2j + 1): the
+// horizontal 3-window of pooled column j is (lane j-1: b1), (own b0), (own b1) -- one shuffle
+// -- and the vertical one two more shuffles (rows oy-1, oy+1), the row above a warp's first
+// row coming from the neighbouring epilogue warp through 2 KB of shared memory.  Bias and ReLU
+// The bias is added in fp32 and the sums rounded to bf16 before the window max (rounding is
+// monotonic, so this equals rounding last); the window runs on packed bf16x2 pairs.  The stem
+// output carries no low half: dropping it moves max|dp| by < 2e-3 (the first residual add
+// then reads the bf16 value only).  The [64 px][64 ch] tile leaves through a swizzled staging
+// buffer and one TMA store.
+//
+// Warp roles (288 threads, one CTA per SM, persistent over instances):
+//   warps 0-3 producers   warps 4-7 epilogue (TMEM lane quarter = warp & 3)   warp 8 MMA issue
+#include "fwd.cuh"
+#include "tc_ptx.cuh"
+
+namespace cs {
+namespace {
+
+constexpr int kS = 32;                 // tile side
+constexpr int kRows = kS + 6;          // padded rows (3 above, 3 below)
+constexpr int kPitch = 320;            // bytes per padded row: 40 px x 8 B (4 left, 32, 4 right)
+constexpr int kImgBytes = 12288;       // kRows * kPitch = 12160, rounded to 256
+constexpr int kStages = 4;             // staged images in flight
+constexpr int kAccs = 4;               // TMEM buffers (one instance = 128 columns)
+constexpr int kWBytes = 14 * 2048;     // [ky][khalf][64 n][16 k] bf16, SWIZZLE_32B rows of 32 B
+constexpr int kOutTile = 64 * 128;     // [64 px][64 ch] bf16, SWIZZLE_128B
+constexpr int kThreads = 288;
+
+struct Smem {
+  static constexpr uint32_t img = 0;
+  static constexpr uint32_t w = img + kStages * kImgBytes;
+  static constexpr uint32_t out = w + kWBytes;                  // 2 staging sets
+  static constexpr uint32_t xch = out + 2 * kOutTile;           // [4 warps][32 ch pairs][8 px]
+  static constexpr uint32_t bias = xch + 4 * 1024;              // 64 fp32
+  static constexpr uint32_t bars = bias + 64 * 4;
+  static constexpr uint32_t total = bars + 256;
+};
+static_assert(Smem::w % 1024 == 0 && Smem::out % 1024 == 0, "swizzled regions must stay aligned");
+
+struct StemWinParams {
+  CUtensorMap hi_map;           // [count*64 rows][64 ch] bf16, box {64, 64}, SWIZZLE_128B
+  StemArgs a;
+  const uint16_t* w_packed;     // kWBytes / 2 bf16, logical (unswizzled) order
+  float norm_a[3], norm_b[3];   // normalised value of byte v in channel c = fma(v, a[c], b[c])
+};
+
+__device__ __forceinline__ void named_bar(int id, int n) {
+  asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(n) : "memory");
+}
+// SWIZZLE_32B: 16-byte chunk bit (4) ^= address bit 7
+__device__ __forceinline__ uint32_t swz32(uint32_t addr) { return addr ^ ((addr >> 3) & 16u); }
+
+__device__ __forceinline__ uint64_t desc_sw32(uint32_t addr, uint32_t sbo) {
+  uint64_t d = (uint64_t)((addr >> 4) & 0x3fffu);
+  d |= (uint64_t)1 << 16;                       // LBO (unused: K extent = one swizzle row)
+  d |= (uint64_t)((sbo >> 4) & 0x3fffu) << 32;
+  d |= (uint64_t)1 << 46;
+  d |= (uint64_t)6 << 61;                       // SWIZZLE_32B
+  return d;
+}
+
+__global__ void __launch_bounds__(kThreads, 1)
+stem_win_kernel(const __grid_constant__ StemWinParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t raw = smem_u32(smem_raw);
+  const uint32_t base = (raw + 1023u) & ~1023u;
+  uint8_t* bp = smem_raw + (base - raw);
+  const uint32_t bars = base + Smem::bars;
+  auto full_bar = [&](int s) { return bars + 8u * s; };                     // kStages
+  auto empty_bar = [&](int s) { return bars + 8u * (kStages + s); };        // kStages
+  auto tfull_bar = [&](int q) { return bars + 8u * (2 * kStages + q); };    // kAccs
+  auto tempty_bar = [&](int q) { return bars + 8u * (2 * kStages + kAccs + q); };
+  volatile uint32_t* tmem_slot =
+      reinterpret_cast<volatile uint32_t*>(bp + Smem::bars + 8 * (2 * kStages + 2 * kAccs));
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, tid = threadIdx.x;
+  const StemArgs& a = p.a;
+
+  // one-time init: zero the staged images (borders stay zero), weights to their swizzled
+  // places, bias
+  for (int i = tid; i < kStages * kImgBytes / 16; i += kThreads)
+    reinterpret_cast<uint4*>(bp + Smem::img)[i] = make_uint4(0, 0, 0, 0);
+  for (int i = tid; i < kWBytes / 16; i += kThreads) {
+    const uint4 v = reinterpret_cast<const uint4*>(p.w_packed)[i];
+    const uint32_t dst = swz32(base + Smem::w + 16u * i);
+    *reinterpret_cast<uint4*>(bp + (dst - base)) = v;
+  }
+  for (int i = tid; i < 64; i += kThreads) reinterpret_cast<float*>(bp + Smem::bias)[i] = a.bias[i];
+  if (tid == 0) {
+    for (int s = 0; s < kStages; ++s) { mbar_init(full_bar(s), 128); mbar_init(empty_bar(s), 1); }
+    for (int q = 0; q < kAccs; ++q) { mbar_init(tfull_bar(q), 1); mbar_init(tempty_bar(q), 128); }
+    fence_barrier_init();
+    prefetch_tmap(&p.hi_map);
+  }
+  if (warp == 8) tmem_alloc(smem_u32((const void*)tmem_slot), 512);
+  fence_async_shared();
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  pdl_launch_dependents();
+  pdl_wait();   // the output buffers may still be read by the previous batch's kernels
+
+  const int64_t n_inst = a.count;
+
+  if (warp < 4) {
+    // ================= producers: u8 / fp32 tile -> padded bf16x4 image =================
+    // Image source: a thread owns 24 bytes (8 px) of one tile row and fetches the 7 aligned
+    // words that cover them (byte loads cost 26 L1 sector look-ups per request); the bytes are
+    // normalised with one FMA each, which rounds to the same bf16 as the reference's
+    // (v/255 - mean)/std for all 3 x 256 inputs (checked on the host at launch).
+    // The raw words of the next kDepth instances are kept in flight in registers so that the
+    // global-load latency (the whole per-instance budget is ~1500 cycles) never stalls staging.
+    constexpr int kDepth = 4;
+    uint32_t pre[kDepth][7];
+    uint32_t sh[kDepth];
+    uint32_t pref[24];
+    const bool from_img = a.x == nullptr;
+    const int sy = tid >> 2, sq = tid & 3;   // tile row, 8-pixel quarter of that row
+    auto prefetch_img = [&](uint32_t (&w)[7], uint32_t& shift, int64_t t) {
+      int64_t inst = a.inst_begin + t;
+      int64_t bag = inst / a.tiles_per_bag;
+      int tl = (int)(inst - bag * a.tiles_per_bag);
+      int gy = tl / a.grid_w, gx = tl - gy * a.grid_w;
+      int row0 = grid_coord(gy, a.H, kS, a.interval), col0 = grid_coord(gx, a.W, kS, a.interval);
+      const uint8_t* rowp = a.img + ((bag * a.H + row0 + sy) * (int64_t)a.W + col0 + 8 * sq) * 3;
+      const uintptr_t pa = reinterpret_cast<uintptr_t>(rowp);
+      const uint32_t* wp = reinterpret_cast<const uint32_t*>(pa & ~(uintptr_t)3);
+      shift = (uint32_t)(pa & 3) * 8u;
+#pragma unroll
+      for (int k = 0; k < 6; ++k) w[k] = __ldg(wp + k);
+      w[6] = shift ? __ldg(wp + 6) : 0u;
+    };
+    auto prefetch_x = [&](int64_t t) {
+      const float* src = a.x + t * (int64_t)(3 * kS * kS) + sy * kS + 8 * sq;  // NCHW fp32
+#pragma unroll
+      for (int i = 0; i < 24; ++i)   // element i = pixel i/3, channel i%3
+        pref[i] = __float_as_uint(__ldg(src + (i % 3) * kS * kS + i / 3));
+    };
+    int stage = 0;
+    uint32_t phase = 0;
+    int64_t t = blockIdx.x;
+    const int64_t step = gridDim.x;
+    if (from_img) {
+#pragma unroll
+      for (int u = 0; u < kDepth; ++u)
+        if (t + u * step < n_inst) prefetch_img(pre[u], sh[u], t + u * step);
+    } else if (t < n_inst) {
+      prefetch_x(t);
+    }
+    // padded row sy + 3, padded pixel 4 + 8*sq: four 16-byte chunks (2 pixels each)
+    const uint32_t dst_off = (uint32_t)((sy + 3) * kPitch + (4 + 8 * sq) * 8);
+    while (t < n_inst) {
+#pragma unroll
+      for (int u = 0; u < kDepth; ++u) {
+        if (t >= n_inst) break;
+        float f[24];
+        if (from_img) {
+#pragma unroll
+          for (int k = 0; k < 6; ++k) {
+            const uint32_t word = __funnelshift_r(pre[u][k], pre[u][k + 1], sh[u]);
+#pragma unroll
+            for (int m = 0; m < 4; ++m) {
+              const int i = 4 * k + m;
+              f[i] = fmaf((float)((word >> (8 * m)) & 0xffu), p.norm_a[i % 3], p.norm_b[i % 3]);
+            }
+          }
+          if (t + kDepth * step < n_inst) prefetch_img(pre[u], sh[u], t + kDepth * step);
+        } else {
+#pragma unroll
+          for (int i = 0; i < 24; ++i) f[i] = __uint_as_float(pref[i]);
+          if (t + step < n_inst) prefetch_x(t + step);
+        }
+        mbar_wait(empty_bar(stage), phase ^ 1u);
+        const uint32_t dst = base + Smem::img + stage * kImgBytes + dst_off;
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+          uint4 v;
+          v.x = pack_bf16x2(f[6 * c + 0], f[6 * c + 1]);
+          v.y = pack_bf16x2(f[6 * c + 2], 0.f);
+          v.z = pack_bf16x2(f[6 * c + 3], f[6 * c + 4]);
+          v.w = pack_bf16x2(f[6 * c + 5], 0.f);
+          sts128v(swz32(dst + 16u * c), v);
+        }
+        fence_async_shared();
+        mbar_arrive(full_bar(stage));
+        if (++stage == kStages) { stage = 0; phase ^= 1u; }
+        t += step;
+      }
+    }
+  } else if (warp == 8) {
+    // ================= MMA issue =================
+    if (lane == 0) {
+      constexpr uint32_t idesc = umma_idesc_bf16(128, 64);
+      int stage = 0, acc = 0;
+      uint32_t phase = 0, acc_phase = 0;
+      for (int64_t t = blockIdx.x; t < n_inst; t += gridDim.x) {
+        mbar_wait(tempty_bar(acc), acc_phase ^ 1u);
+        mbar_wait(full_bar(stage), phase);
+        tc_fence_after();
+        const uint32_t img = base + Smem::img + stage * kImgBytes;
+#pragma unroll
+        for (int b = 0; b < 2; ++b) {
+          const uint32_t d_tmem = tmem_base + (uint32_t)(acc * 128 + b * 64);
+#pragma unroll
+          for (int ky = 0; ky < 7; ++ky) {
+#pragma unroll
+            for (int s = 0; s < 2; ++s) {
+              const uint64_t ad = desc_sw32(img + ky * kPitch + b * 16 + s * 32, 2 * kPitch);
+              const uint64_t bd = desc_sw32(base + Smem::w + (ky * 2 + s) * 2048, 256);
+              umma_bf16(d_tmem, ad, bd, idesc, (ky > 0 || s > 0) ? 1u : 0u);
+            }
+          }
+        }
+        umma_commit(empty_bar(stage));
+        umma_commit(tfull_bar(acc));
+        if (++stage == kStages) { stage = 0; phase ^= 1u; }
+        if (++acc == kAccs) { acc = 0; acc_phase ^= 1u; }
+      }
+    }
+  } else {
+    // ================= epilogue: bias, bf16 pack, pool in registers, ReLU, TMA store ========
+    // Rounding is monotonic, so bf16(max_i(c_i) + b) == max_i bf16(c_i + b): the bias is added
+    // in fp32, the sums are rounded once to bf16 and the whole 3x3 window runs on packed
+    // bf16x2 pairs (half the shuffles and max instructions), bit-identical to rounding last.
+    const int q = warp & 3;                    // TMEM lanes 32q .. 32q+31: conv rows 4q .. 4q+3
+    const int etid = q * 32 + lane;
+    const int j = lane & 7, oyl = lane >> 3;   // pooled column, conv row within the warp
+    const float* bias_s = reinterpret_cast<const float*>(bp + Smem::bias);
+    uint32_t* xch = reinterpret_cast<uint32_t*>(bp + Smem::xch);
+    constexpr uint32_t kNegInf2 = 0xff80ff80u;
+    const bool active = (oyl & 1) == 0;        // even conv rows produce pooled rows 2q, 2q+1
+    const int prow = (2 * q + (oyl >> 1)) * 8 + j;   // row of the [64 px][64 ch] output tile
+    int acc = 0;
+    uint32_t acc_phase = 0;
+    int it = 0;
+    for (int64_t t = blockIdx.x; t < n_inst; t += gridDim.x, ++it) {
+      mbar_wait(tfull_bar(acc), acc_phase);
+      tc_fence_after();
+      const uint32_t t_addr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * 128);
+      // horizontal 3-max of conv row oy at pooled column j, 32 channel pairs
+      uint32_t hp[32];
+#pragma unroll
+      for (int c0 = 0; c0 < 64; c0 += 32) {
+        uint32_t r0[32], r1[32];
+        tmem_ld32(t_addr + (uint32_t)c0, r0);
+        tmem_ld32(t_addr + (uint32_t)(64 + c0), r1);
+        tmem_ld_wait();
+#pragma unroll
+        for (int c = 0; c < 32; c += 4) {
+          const float4 bq = *reinterpret_cast<const float4*>(bias_s + c0 + c);
+          const float bv[4] = {bq.x, bq.y, bq.z, bq.w};
+#pragma unroll
+          for (int e = 0; e < 4; e += 2) {
+            const uint32_t p0 = pack_bf16x2(__uint_as_float(r0[c + e]) + bv[e],
+                                            __uint_as_float(r0[c + e + 1]) + bv[e + 1]);
+            const uint32_t p1 = pack_bf16x2(__uint_as_float(r1[c + e]) + bv[e],
+                                            __uint_as_float(r1[c + e + 1]) + bv[e + 1]);
+            uint32_t left = __shfl_up_sync(0xffffffffu, p1, 1);
+            if (j == 0) left = kNegInf2;
+            hp[(c0 + c + e) >> 1] = max_bf16x2(max_bf16x2(p0, p1), left);
+          }
+        }
+      }
+      tc_fence_before();
+      mbar_arrive(tempty_bar(acc));
+      if (++acc == kAccs) { acc = 0; acc_phase ^= 1u; }
+      // the last conv row of this warp is the row above the next warp's first row
+      if (oyl == 3 && q < 3) {
+#pragma unroll
+        for (int k = 0; k < 32; ++k) xch[(q * 32 + k) * 8 + j] = hp[k];
+      }
+      // the staging set of this instance must have been read by the TMA store issued two
+      // instances ago (thread 0 issues every store; only the latest group may stay in flight)
+      const int set = it & 1;
+      if (etid == 0) bulk_wait_read_1();
+      named_bar(2, 128);
+      const uint32_t out_s = base + Smem::out + (uint32_t)(set * kOutTile) + prow * 128;
+#pragma unroll
+      for (int c8 = 0; c8 < 8; ++c8) {
+        uint32_t v[4];
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          const int k = c8 * 4 + e;
+          const uint32_t dn = __shfl_down_sync(0xffffffffu, hp[k], 8);
+          uint32_t up = __shfl_up_sync(0xffffffffu, hp[k], 8);
+          if (oyl == 0) up = q > 0 ? xch[((q - 1) * 32 + k) * 8 + j] : kNegInf2;
+          v[e] = max_bf16x2(max_bf16x2(max_bf16x2(hp[k], dn), up), 0u);   // window max, ReLU
+        }
+        if (active) sts128v(out_s + (uint32_t)((c8 ^ (prow & 7)) << 4), make_uint4(v[0], v[1], v[2], v[3]));
+      }
+      fence_async_shared();
+      named_bar(2, 128);
+      if (etid == 0) {
+        tma_store_2d(&p.hi_map, base + Smem::out + (uint32_t)(set * kOutTile), 0, (int)(t * 64));
+        bulk_commit_group();
+      }
+    }
+    if (etid == 0) bulk_wait_all();
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 8) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, 512);
+  }
+}
+
+uint16_t bf16_rn_host(float f) {
+  uint32_t u;
+  memcpy(&u, &f, 4);
+  uint32_t lsb = (u >> 16) & 1u;
+  u += 0x7fffu + lsb;
+  return (uint16_t)(u >> 16);
+}
+
+struct NormConst { float a[3], b[3]; bool ok; };
+NormConst make_norm_const() {
+  const double mean[3] = {(double)0.485f, (double)0.456f, (double)0.406f};
+  const double stdv[3] = {(double)0.229f, (double)0.224f, (double)0.225f};
+  NormConst nc;
+  float lut[768];
+  get_norm_lut_host(lut);
+  nc.ok = true;
+  for (int c = 0; c < 3; ++c) {
+    nc.a[c] = (float)(1.0 / (255.0 * stdv[c]));
+    nc.b[c] = (float)(-mean[c] / stdv[c]);
+    for (int v = 0; v < 256; ++v)
+      if (bf16_rn_host(fmaf((float)v, nc.a[c], nc.b[c])) != bf16_rn_host(lut[c * 256 + v])) nc.ok = false;
+  }
+  return nc;
+}
+
+}  // namespace
+
+// Host: packs the folded stem weights [64][3][7][7] into bf16 [ky 7][khalf 2][n 64][16]:
+// k = slot * 4 + c with slot = kx + 1 - 4 * khalf (slot 0 of half 0 and channel 3 stay zero).
+void pack_stem_weights_win(const float* w_oihw, uint16_t* out) {
+  memset(out, 0, kWBytes);
+  for (int co = 0; co < 64; ++co)
+    for (int c = 0; c < 3; ++c)
+      for (int ky = 0; ky < 7; ++ky)
+        for (int kx = 0; kx < 7; ++kx) {
+          const int slot = kx + 1, s = slot >> 2, sl = slot & 3;
+          out[((ky * 2 + s) * 64 + co) * 16 + sl * 4 + c] =
+              bf16_rn_host(w_oihw[((co * 3 + c) * 7 + ky) * 7 + kx]);
+        }
+}
+
+int stem_win_weight_bytes() { return kWBytes; }
+
+int launch_stem_win(const StemArgs& a, const void* w_packed_dev, const uint16_t* lut_bf16_dev,
+                    cudaStream_t st) {
+  if (a.tile != kS) {
+    set_error("tensor-core stem supports tile 32 only (got %d)", a.tile);
+    return CS_ERR_UNSUPPORTED;
+  }
+  static bool attr_done[64] = {false};
+  int dev = 0;
+  CS_CUDA(cudaGetDevice(&dev));
+  if (dev >= 64 || !attr_done[dev]) {
+    CS_CUDA(cudaFuncSetAttribute(stem_win_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                 (int)(Smem::total + 1024)));
+    if (dev < 64) attr_done[dev] = true;
+  }
+  if (a.count <= 0) return CS_OK;
+  StemWinParams p;
+  int rc = make_mat_map_2d(&p.hi_map, a.out_hi, 64, a.count * 64, 64, 64);
+  if (rc != CS_OK) return rc;
+  if (a.out_lo) {
+    set_error("stem_win writes the bf16 stream only (out_lo must be NULL)");
+    return CS_ERR_INVALID_ARG;
+  }
+  p.a = a;
+  p.w_packed = reinterpret_cast<const uint16_t*>(w_packed_dev);
+  (void)lut_bf16_dev;
+  {
+    // fma(v, a, b) must round to the same bf16 as the reference's (v/255 - mean)/std (the LUT)
+    static const NormConst nc = make_norm_const();
+    if (!nc.ok) {
+      set_error("stem_win: FMA normalisation does not reproduce the bf16 LUT");
+      return CS_ERR_UNSUPPORTED;
+    }
+    for (int c = 0; c < 3; ++c) { p.norm_a[c] = nc.a[c]; p.norm_b[c] = nc.b[c]; }
+  }
+  int grid = (int)(a.count < kNumSMs ? a.count : kNumSMs);
+  CS_CUDA(launch_pdl(stem_win_kernel, dim3((unsigned)grid), dim3(kThreads), Smem::total + 1024, st, 1, p));
+  return CS_OK;
+}
+
+}  // namespace cs

@@ -89,6 +89,10 @@ __device__ __forceinline__ void bulk_commit_group() {
 __device__ __forceinline__ void bulk_wait_read_all() {
   asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
 }
+// ... same, but the most recently committed group may still be in flight.
+__device__ __forceinline__ void bulk_wait_read_1() {
+  asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
+}
 // ... and until they are complete (writes visible) -- before the kernel exits.
 __device__ __forceinline__ void bulk_wait_all() {
   asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
@@ -220,6 +224,11 @@ __device__ __forceinline__ void stg256(void* p, const U32x8& r) {
 __device__ __forceinline__ uint32_t pack_bf16x2(float a, float b) {
   __nv_bfloat162 v = __floats2bfloat162_rn(a, b);
   return *reinterpret_cast<uint32_t*>(&v);
+}
+__device__ __forceinline__ uint32_t max_bf16x2(uint32_t a, uint32_t b) {
+  uint32_t r;
+  asm("max.bf16x2 %0, %1, %2;" : "=r"(r) : "r"(a), "r"(b));
+  return r;
 }
 __device__ __forceinline__ float bf16_lo_f(uint32_t w) { return __uint_as_float(w << 16); }
 __device__ __forceinline__ float bf16_hi_f(uint32_t w) { return __uint_as_float(w & 0xffff0000u); }

@@ -31,7 +31,9 @@ def make_labels(n_bags, seed=0):
 def make_resnet_weights(arch="resnet34", seed=0):
     """Random-init BN-folded conv list + fc_tile for benchmarking: kaiming-normal convs
     (model/resnet.py:171-175), BN at init (gamma 1, beta 0, stats 0/1 -> identity fold up to eps)."""
-    layers = {"resnet18": [2, 2, 2, 2], "resnet34": [3, 4, 6, 3]}[arch]
+    layers = {"resnet18": [2, 2, 2, 2], "resnet34": [3, 4, 6, 3], "resnet50": [3, 4, 6, 3],
+              "resnext50_32x4d": [3, 4, 6, 3]}[arch]
+    bottleneck = {"resnet50": (1, 64), "resnext50_32x4d": (32, 4)}.get(arch)   # (groups, width/group)
     rng = np.random.default_rng(seed)
     s = np.float32(1.0 / np.sqrt(1.0 + 1e-5))
 
@@ -45,12 +47,23 @@ def make_resnet_weights(arch="resnet34", seed=0):
         pl = 64 << L
         for b in range(nb):
             stride = 2 if (b == 0 and L > 0) else 1
+            if bottleneck:
+                groups, wpg = bottleneck
+                width = pl * wpg // 64 * groups
+                convs.append(conv(width, inpl, 1))
+                convs.append(conv(width, width // groups, 3))
+                convs.append(conv(pl * 4, width, 1))
+                if stride != 1 or inpl != pl * 4:
+                    convs.append(conv(pl * 4, inpl, 1))
+                inpl = pl * 4
+                continue
             convs.append(conv(pl, inpl, 3))
             convs.append(conv(pl, pl, 3))
             if stride != 1 or inpl != pl:
                 convs.append(conv(pl, inpl, 1))
             inpl = pl
-    bound = 1.0 / np.sqrt(512)
-    fc_w = torch.from_numpy(rng.uniform(-bound, bound, (2, 512)).astype(np.float32)) * 0.05
+    fd = 2048 if bottleneck else 512
+    bound = 1.0 / np.sqrt(fd)
+    fc_w = torch.from_numpy(rng.uniform(-bound, bound, (2, fd)).astype(np.float32)) * 0.05
     fc_b = torch.zeros(2)
     return convs, fc_w, fc_b
