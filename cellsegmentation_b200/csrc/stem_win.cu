@@ -18,18 +18,20 @@
 // (b = 0, 1) x 7 ky x 2 K halves = 28 MMAs of 128x64x16, against 12 KB of staging writes
 // instead of the 96 KB im2col build of the first version.
 //
-// TMEM lane r of accumulators b = 0, 1 holds conv pixels (oy, 2j) and (oy, 2j + 1): the
-// horizontal 3-window of pooled column j is (lane j-1: b1), (own b0), (own b1) -- one shuffle
-// -- and the vertical one two more shuffles (rows oy-1, oy+1), the row above a warp's first
-// row coming from the neighbouring epilogue warp through 2 KB of shared memory.  Bias and ReLU
+// TMEM lane r of accumulators b = 0, 1 holds conv pixels (oy, 2j) and (oy, 2j + 1).  Read with
+// tcgen05.ld.16x256b a thread owns all four conv rows of its warp at one pooled column, so the
+// vertical windows reduce in registers, the horizontal one needs a single shuffle (column
+// 2j - 1 lives four lanes down) and only the conv row above a warp's first row comes from the
+// neighbouring epilogue warp through 1 KB of shared memory.  Bias and ReLU
 // The bias is added in fp32 and the sums rounded to bf16 before the window max (rounding is
 // monotonic, so this equals rounding last); the window runs on packed bf16x2 pairs.  The stem
 // output carries no low half: dropping it moves max|dp| by < 2e-3 (the first residual add
 // then reads the bf16 value only).  The [64 px][64 ch] tile leaves through a swizzled staging
 // buffer and one TMA store.
 //
-// Warp roles (288 threads, one CTA per SM, persistent over instances):
-//   warps 0-3 producers   warps 4-7 epilogue (TMEM lane quarter = warp & 3)   warp 8 MMA issue
+// Warp roles (416 threads, one CTA per SM, persistent over instances):
+//   warps 0-3 producers   warps 4-11 epilogue (TMEM lane quarter = warp & 3, channel half =
+//   (warp - 4) >> 2)   warp 12 MMA issue
 #include "fwd.cuh"
 #include "tc_ptx.cuh"
 
@@ -44,14 +46,16 @@ constexpr int kStages = 4;             // staged images in flight
 constexpr int kAccs = 4;               // TMEM buffers (one instance = 128 columns)
 constexpr int kWBytes = 14 * 2048;     // [ky][khalf][64 n][16 k] bf16, SWIZZLE_32B rows of 32 B
 constexpr int kOutTile = 64 * 128;     // [64 px][64 ch] bf16, SWIZZLE_128B
-constexpr int kThreads = 288;
+constexpr int kEpiWarps = 8;           // two per TMEM lane quarter, 32 channels each
+constexpr int kMmaWarp = 4 + kEpiWarps;
+constexpr int kThreads = 32 * (kMmaWarp + 1);
 
 struct Smem {
   static constexpr uint32_t img = 0;
   static constexpr uint32_t w = img + kStages * kImgBytes;
   static constexpr uint32_t out = w + kWBytes;                  // 2 staging sets
-  static constexpr uint32_t xch = out + 2 * kOutTile;           // [4 warps][32 ch pairs][8 px]
-  static constexpr uint32_t bias = xch + 4 * 1024;              // 64 fp32
+  static constexpr uint32_t xch = out + 2 * kOutTile;           // [3 quarters][2 halves][8 words][32 lanes]
+  static constexpr uint32_t bias = xch + 6 * 1024;              // 64 fp32 (unused by the epilogue)
   static constexpr uint32_t bars = bias + 64 * 4;
   static constexpr uint32_t total = bars + 256;
 };
@@ -64,6 +68,9 @@ struct StemWinParams {
   float norm_a[3], norm_b[3];   // normalised value of byte v in channel c = fma(v, a[c], b[c])
 };
 
+__device__ __forceinline__ void sts32(uint32_t addr, uint32_t v) {
+  asm volatile("st.shared.u32 [%0], %1;" ::"r"(addr), "r"(v) : "memory");
+}
 __device__ __forceinline__ void named_bar(int id, int n) {
   asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(n) : "memory");
 }
@@ -108,11 +115,11 @@ stem_win_kernel(const __grid_constant__ StemWinParams p) {
   for (int i = tid; i < 64; i += kThreads) reinterpret_cast<float*>(bp + Smem::bias)[i] = a.bias[i];
   if (tid == 0) {
     for (int s = 0; s < kStages; ++s) { mbar_init(full_bar(s), 128); mbar_init(empty_bar(s), 1); }
-    for (int q = 0; q < kAccs; ++q) { mbar_init(tfull_bar(q), 1); mbar_init(tempty_bar(q), 128); }
+    for (int q = 0; q < kAccs; ++q) { mbar_init(tfull_bar(q), 1); mbar_init(tempty_bar(q), 32 * kEpiWarps); }
     fence_barrier_init();
     prefetch_tmap(&p.hi_map);
   }
-  if (warp == 8) tmem_alloc(smem_u32((const void*)tmem_slot), 512);
+  if (warp == kMmaWarp) tmem_alloc(smem_u32((const void*)tmem_slot), 512);
   fence_async_shared();
   tc_fence_before();
   __syncthreads();
@@ -208,7 +215,7 @@ stem_win_kernel(const __grid_constant__ StemWinParams p) {
         t += step;
       }
     }
-  } else if (warp == 8) {
+  } else if (warp == kMmaWarp) {
     // ================= MMA issue =================
     if (lane == 0) {
       constexpr uint32_t idesc = umma_idesc_bf16(128, 64);
@@ -241,76 +248,86 @@ stem_win_kernel(const __grid_constant__ StemWinParams p) {
   } else {
     // ================= epilogue: bias, bf16 pack, pool in registers, ReLU, TMA store ========
     // Rounding is monotonic, so bf16(max_i(c_i) + b) == max_i bf16(c_i + b): the bias is added
-    // in fp32, the sums are rounded once to bf16 and the whole 3x3 window runs on packed
-    // bf16x2 pairs (half the shuffles and max instructions), bit-identical to rounding last.
+    // in fp32, the sums are rounded once to bf16 and the 3x3 window runs on packed bf16x2 pairs.
+    // tcgen05.ld.16x256b hands thread T (g = T/4, t = T%4) the conv pixels (oy, 2g + b) of the
+    // FOUR conv rows of this warp for channel pairs (8i + 2t, 8i + 2t + 1): both pooled rows of
+    // the warp reduce vertically in registers, the column to the left is one shuffle (lane - 4)
+    // and only conv row 4q - 1 comes from the warp above through shared memory.
     const int q = warp & 3;                    // TMEM lanes 32q .. 32q+31: conv rows 4q .. 4q+3
-    const int etid = q * 32 + lane;
-    const int j = lane & 7, oyl = lane >> 3;   // pooled column, conv row within the warp
-    const float* bias_s = reinterpret_cast<const float*>(bp + Smem::bias);
+    const int half = (warp - 4) >> 2;          // channels 32*half .. 32*half+31
+    const int etid = (warp - 4) * 32 + lane;
+    const int g = lane >> 2, tq = lane & 3;    // pooled column, channel-pair slot
     uint32_t* xch = reinterpret_cast<uint32_t*>(bp + Smem::xch);
     constexpr uint32_t kNegInf2 = 0xff80ff80u;
-    const bool active = (oyl & 1) == 0;        // even conv rows produce pooled rows 2q, 2q+1
-    const int prow = (2 * q + (oyl >> 1)) * 8 + j;   // row of the [64 px][64 ch] output tile
+    float bias_r[4][2];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      bias_r[i][0] = a.bias[half * 32 + 8 * i + 2 * tq];
+      bias_r[i][1] = a.bias[half * 32 + 8 * i + 2 * tq + 1];
+    }
     int acc = 0;
     uint32_t acc_phase = 0;
     int it = 0;
     for (int64_t t = blockIdx.x; t < n_inst; t += gridDim.x, ++it) {
       mbar_wait(tfull_bar(acc), acc_phase);
       tc_fence_after();
-      const uint32_t t_addr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * 128);
-      // horizontal 3-max of conv row oy at pooled column j, 32 channel pairs
-      uint32_t hp[32];
+      // P[row 0..3][b][i]: bf16x2 of (conv + bias) at conv row 4q + row, column 2g + b
+      uint32_t P[4][2][4];
 #pragma unroll
-      for (int c0 = 0; c0 < 64; c0 += 32) {
-        uint32_t r0[32], r1[32];
-        tmem_ld32(t_addr + (uint32_t)c0, r0);
-        tmem_ld32(t_addr + (uint32_t)(64 + c0), r1);
+      for (int w = 0; w < 2; ++w) {
+        uint32_t r0[16], r1[16];
+        const uint32_t t_addr = tmem_base + ((uint32_t)(q * 32 + w * 16) << 16) +
+                                (uint32_t)(acc * 128 + half * 32);
+        tmem_ld_16x256b_x4(t_addr, r0);
+        tmem_ld_16x256b_x4(t_addr + 64u, r1);
         tmem_ld_wait();
 #pragma unroll
-        for (int c = 0; c < 32; c += 4) {
-          const float4 bq = *reinterpret_cast<const float4*>(bias_s + c0 + c);
-          const float bv[4] = {bq.x, bq.y, bq.z, bq.w};
+        for (int i = 0; i < 4; ++i)
 #pragma unroll
-          for (int e = 0; e < 4; e += 2) {
-            const uint32_t p0 = pack_bf16x2(__uint_as_float(r0[c + e]) + bv[e],
-                                            __uint_as_float(r0[c + e + 1]) + bv[e + 1]);
-            const uint32_t p1 = pack_bf16x2(__uint_as_float(r1[c + e]) + bv[e],
-                                            __uint_as_float(r1[c + e + 1]) + bv[e + 1]);
-            uint32_t left = __shfl_up_sync(0xffffffffu, p1, 1);
-            if (j == 0) left = kNegInf2;
-            hp[(c0 + c + e) >> 1] = max_bf16x2(max_bf16x2(p0, p1), left);
+          for (int h = 0; h < 2; ++h) {
+            P[2 * w + h][0][i] = pack_bf16x2(__uint_as_float(r0[4 * i + 2 * h]) + bias_r[i][0],
+                                             __uint_as_float(r0[4 * i + 2 * h + 1]) + bias_r[i][1]);
+            P[2 * w + h][1][i] = pack_bf16x2(__uint_as_float(r1[4 * i + 2 * h]) + bias_r[i][0],
+                                             __uint_as_float(r1[4 * i + 2 * h + 1]) + bias_r[i][1]);
           }
-        }
       }
       tc_fence_before();
       mbar_arrive(tempty_bar(acc));
       if (++acc == kAccs) { acc = 0; acc_phase ^= 1u; }
-      // the last conv row of this warp is the row above the next warp's first row
-      if (oyl == 3 && q < 3) {
+      // conv row 4q + 3 is the row above the next warp's first pooled window
+      if (q < 3) {
 #pragma unroll
-        for (int k = 0; k < 32; ++k) xch[(q * 32 + k) * 8 + j] = hp[k];
+        for (int b = 0; b < 2; ++b)
+#pragma unroll
+          for (int i = 0; i < 4; ++i) xch[((q * 2 + half) * 8 + b * 4 + i) * 32 + lane] = P[3][b][i];
       }
       // the staging set of this instance must have been read by the TMA store issued two
       // instances ago (thread 0 issues every store; only the latest group may stay in flight)
       const int set = it & 1;
       if (etid == 0) bulk_wait_read_1();
-      named_bar(2, 128);
-      const uint32_t out_s = base + Smem::out + (uint32_t)(set * kOutTile) + prow * 128;
+      named_bar(2, 32 * kEpiWarps);
+      const uint32_t out_s = base + Smem::out + (uint32_t)(set * kOutTile) + 4u * tq;
 #pragma unroll
-      for (int c8 = 0; c8 < 8; ++c8) {
-        uint32_t v[4];
+      for (int i = 0; i < 4; ++i) {
+        uint32_t v0[2], v1[2];
 #pragma unroll
-        for (int e = 0; e < 4; ++e) {
-          const int k = c8 * 4 + e;
-          const uint32_t dn = __shfl_down_sync(0xffffffffu, hp[k], 8);
-          uint32_t up = __shfl_up_sync(0xffffffffu, hp[k], 8);
-          if (oyl == 0) up = q > 0 ? xch[((q - 1) * 32 + k) * 8 + j] : kNegInf2;
-          v[e] = max_bf16x2(max_bf16x2(max_bf16x2(hp[k], dn), up), 0u);   // window max, ReLU
+        for (int b = 0; b < 2; ++b) {
+          const uint32_t above = q > 0 ? xch[(((q - 1) * 2 + half) * 8 + b * 4 + i) * 32 + lane] : kNegInf2;
+          v0[b] = max3_bf16x2(P[0][b][i], P[1][b][i], above);
+          v1[b] = max3_bf16x2(P[1][b][i], P[2][b][i], P[3][b][i]);
         }
-        if (active) sts128v(out_s + (uint32_t)((c8 ^ (prow & 7)) << 4), make_uint4(v[0], v[1], v[2], v[3]));
+        uint32_t l0 = __shfl_up_sync(0xffffffffu, v0[1], 4);
+        uint32_t l1 = __shfl_up_sync(0xffffffffu, v1[1], 4);
+        if (g == 0) { l0 = kNegInf2; l1 = kNegInf2; }
+        const uint32_t o0 = max_bf16x2(max3_bf16x2(v0[0], v0[1], l0), 0u);   // window max, ReLU
+        const uint32_t o1 = max_bf16x2(max3_bf16x2(v1[0], v1[1], l1), 0u);
+        // pooled rows 2q, 2q+1, column g: tile row prow = py * 8 + g, 16-byte chunk half*4 + i
+        const uint32_t chunk = (uint32_t)(((half * 4 + i) ^ g) << 4);
+        sts32(out_s + (uint32_t)((2 * q) * 8 + g) * 128u + chunk, o0);
+        sts32(out_s + (uint32_t)((2 * q + 1) * 8 + g) * 128u + chunk, o1);
       }
       fence_async_shared();
-      named_bar(2, 128);
+      named_bar(2, 32 * kEpiWarps);
       if (etid == 0) {
         tma_store_2d(&p.hi_map, base + Smem::out + (uint32_t)(set * kOutTile), 0, (int)(t * 64));
         bulk_commit_group();
@@ -321,7 +338,7 @@ stem_win_kernel(const __grid_constant__ StemWinParams p) {
 
   tc_fence_before();
   __syncthreads();
-  if (warp == 8) {
+  if (warp == kMmaWarp) {
     tc_fence_after();
     tmem_dealloc(tmem_base, 512);
   }

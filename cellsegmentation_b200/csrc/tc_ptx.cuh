@@ -186,6 +186,18 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
       : "r"(taddr)
       : "memory");
 }
+// 16 TMEM lanes x 32 columns in the mma C-fragment layout (tools/tmem_ld_probe.cu): thread T of
+// the warp gets r[4i + 2h + e] = (lane T/4 + 8h, column 8i + 2(T%4) + e) of the 16-lane window
+// at the address' lane (a multiple of 16 inside the warp's own 32-lane quarter).
+__device__ __forceinline__ void tmem_ld_16x256b_x4(uint32_t taddr, uint32_t (&r)[16]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.16x256b.x4.b32 "
+      "{%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]),
+        "=r"(r[7]), "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]),
+        "=r"(r[14]), "=r"(r[15])
+      : "r"(taddr));
+}
 __device__ __forceinline__ void tmem_ld_wait() {
   asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 }
@@ -229,6 +241,9 @@ __device__ __forceinline__ uint32_t max_bf16x2(uint32_t a, uint32_t b) {
   uint32_t r;
   asm("max.bf16x2 %0, %1, %2;" : "=r"(r) : "r"(a), "r"(b));
   return r;
+}
+__device__ __forceinline__ uint32_t max3_bf16x2(uint32_t a, uint32_t b, uint32_t c) {
+  return max_bf16x2(max_bf16x2(a, b), c);
 }
 __device__ __forceinline__ float bf16_lo_f(uint32_t w) { return __uint_as_float(w << 16); }
 __device__ __forceinline__ float bf16_hi_f(uint32_t w) { return __uint_as_float(w & 0xffff0000u); }
