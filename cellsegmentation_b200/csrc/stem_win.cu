@@ -226,15 +226,16 @@ stem_win_kernel(const __grid_constant__ StemWinParams p) {
         mbar_wait(full_bar(stage), phase);
         tc_fence_after();
         const uint32_t img = base + Smem::img + stage * kImgBytes;
+        // consecutive MMAs alternate between the two accumulators (b = 0, 1)
 #pragma unroll
-        for (int b = 0; b < 2; ++b) {
-          const uint32_t d_tmem = tmem_base + (uint32_t)(acc * 128 + b * 64);
+        for (int ky = 0; ky < 7; ++ky) {
 #pragma unroll
-          for (int ky = 0; ky < 7; ++ky) {
+          for (int s = 0; s < 2; ++s) {
+            const uint64_t bd = desc_sw32(base + Smem::w + (ky * 2 + s) * 2048, 256);
 #pragma unroll
-            for (int s = 0; s < 2; ++s) {
+            for (int b = 0; b < 2; ++b) {
+              const uint32_t d_tmem = tmem_base + (uint32_t)(acc * 128 + b * 64);
               const uint64_t ad = desc_sw32(img + ky * kPitch + b * 16 + s * 32, 2 * kPitch);
-              const uint64_t bd = desc_sw32(base + Smem::w + (ky * 2 + s) * 2048, 256);
               umma_bf16(d_tmem, ad, bd, idesc, (ky > 0 || s > 0) ? 1u : 0u);
             }
           }
