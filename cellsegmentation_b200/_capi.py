@@ -13,7 +13,7 @@ LIB_PATH = os.path.join(_HERE, "csrc", "libcellseg_b200.so")
 CS_OK = 0
 CS_PREC_FP32 = 0
 CS_PREC_BF16 = 1
-CS_ARCH = {"resnet18": 0, "resnet34": 1, "resnet50": 2, "resnext50_32x4d": 3}
+CS_ARCH = {"resnet18": 0, "resnet34": 1, "resnet50": 2, "resnext50_32x4d": 3, "resnext101_32x8d": 4}
 
 
 class CellSegError(RuntimeError):
@@ -59,6 +59,7 @@ _PROTOS = {
                                  c_void_p, c_void_p]),
     "cs_paint_heatmap_xy": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_int, c_int,
                                     c_int, c_int, c_void_p, c_void_p]),
+    "cs_heatmap_blend": (c_int, [c_void_p, c_void_p, c_void_p, c_int64, c_void_p, c_void_p]),
     "cs_heatmap_to_gray": (c_int, [c_void_p, c_int64, c_void_p, c_void_p]),
     "cs_hsv_refine": (c_int, [c_void_p, c_void_p, c_int64, c_int, c_void_p, c_void_p]),
     "cs_bgr2hsv_u8": (c_int, [c_void_p, c_int64, c_void_p, c_void_p]),

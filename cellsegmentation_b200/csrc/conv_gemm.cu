@@ -119,9 +119,11 @@ conv_gemm_kernel(const __grid_constant__ GemmParams p) {
         const int wi = p.reverse ? num_work - 1 - w : w;
         const int m_tile = (wi / p.num_n_tiles) * CL + rank, n_tile = wi % p.num_n_tiles;
         const int var = p.n_variants > 1 ? n_tile : 0;
-        const int ns = p.n_steps[var];
+        const uint32_t* ext = p.ext_steps ? p.ext_steps + (size_t)var * (kMaxSteps + 1) : nullptr;
+        const int ns = ext ? (int)__ldg(ext) : p.n_steps[var];
         for (int s = 0; s < ns; ++s) {
-          const KStep st = p.steps[var][s];
+          KStep st;
+          if (ext) st.v = __ldg(ext + 1 + s); else st = p.steps[var][s];
           mbar_wait(empty_bar(stage), phase ^ 1u);
           const uint32_t a_dst = base + stage * Cfg::kStageBytes;
           const uint32_t b_dst = a_dst + Cfg::kABytes;
@@ -155,7 +157,7 @@ conv_gemm_kernel(const __grid_constant__ GemmParams p) {
         const int wi = p.reverse ? num_work - 1 - w : w;
         const int n_tile = wi % p.num_n_tiles;
         const int var = p.n_variants > 1 ? n_tile : 0;
-        const int ns = p.n_steps[var];
+        const int ns = p.ext_steps ? (int)__ldg(p.ext_steps + (size_t)var * (kMaxSteps + 1)) : p.n_steps[var];
         mbar_wait(tempty_bar(acc), acc_phase ^ 1u);
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + (uint32_t)(acc * BN);

@@ -62,6 +62,9 @@ struct GemmParams {
   KStep steps[kMaxVariants][kMaxSteps];
   int n_steps[kMaxVariants];
   int n_variants;     // 1: every n-tile walks steps[0]; else steps[n_tile]
+  // more than kMaxVariants step lists (wide grouped convs): device table
+  // [n_variants][kMaxSteps + 1] of u32, entry 0 = step count; nullptr otherwise
+  const uint32_t* ext_steps;
   int a_mode;         // bit i set: A map i is 4-D {c, x, y, tile}; clear: 2-D {k, row}
   int units_per_mtile;  // 4-D mode: tiles (instances) per 128-row M tile
   int num_m_tiles, num_n_tiles;

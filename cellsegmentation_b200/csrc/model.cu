@@ -66,13 +66,16 @@ struct PlannedConv {
   int halo_W = 0, halo_Cin = 0;
   __nv_bfloat16* d_B = nullptr;
   float* d_bias = nullptr;
+  uint32_t* d_ext_steps = nullptr;
 };
 
 void free_planned(PlannedConv& pc) {
   if (pc.d_B) cudaFree(pc.d_B);
   if (pc.d_bias) cudaFree(pc.d_bias);
+  if (pc.d_ext_steps) cudaFree(pc.d_ext_steps);
   pc.d_B = nullptr;
   pc.d_bias = nullptr;
+  pc.d_ext_steps = nullptr;
 }
 
 // One candidate K step before it is known which N tiles need it.
@@ -279,13 +282,22 @@ int plan_conv(const ConvGeom& g, const float* w_oihw, const float* bias, const C
     for (size_t i = 0; same && i < per_tile[nt].size(); ++i) same = per_tile[nt][i].v == per_tile[0][i].v;
   }
   pc.p.n_variants = same ? 1 : pc.p.num_n_tiles;
+  pc.p.ext_steps = nullptr;
   if (pc.p.n_variants > kMaxVariants) {
-    set_error("plan_conv: %d N tiles with different K steps exceed %d variants", pc.p.n_variants, kMaxVariants);
-    return CS_ERR_UNSUPPORTED;
-  }
-  for (int v = 0; v < pc.p.n_variants; ++v) {
-    pc.p.n_steps[v] = (int)per_tile[v].size();
-    for (size_t i = 0; i < per_tile[v].size(); ++i) pc.p.steps[v][i] = per_tile[v][i];
+    // wide grouped convs: the per-tile step lists live in device memory
+    std::vector<uint32_t> ext((size_t)pc.p.n_variants * (kMaxSteps + 1), 0u);
+    for (int v = 0; v < pc.p.n_variants; ++v) {
+      ext[(size_t)v * (kMaxSteps + 1)] = (uint32_t)per_tile[v].size();
+      for (size_t i = 0; i < per_tile[v].size(); ++i) ext[(size_t)v * (kMaxSteps + 1) + 1 + i] = per_tile[v][i].v;
+    }
+    CS_CUDA(cudaMalloc(&pc.d_ext_steps, ext.size() * sizeof(uint32_t)));
+    CS_CUDA(cudaMemcpy(pc.d_ext_steps, ext.data(), ext.size() * sizeof(uint32_t), cudaMemcpyHostToDevice));
+    pc.p.ext_steps = pc.d_ext_steps;
+  } else {
+    for (int v = 0; v < pc.p.n_variants; ++v) {
+      pc.p.n_steps[v] = (int)per_tile[v].size();
+      for (size_t i = 0; i < per_tile[v].size(); ++i) pc.p.steps[v][i] = per_tile[v][i];
+    }
   }
 
   CS_CUDA(cudaMalloc(&pc.d_B, B.size() * sizeof(uint16_t)));
@@ -673,6 +685,7 @@ int cs_model_create(int arch, int n_convs, const float* const* conv_w_host,
     case CS_ARCH_RESNET34: layers = {3, 4, 6, 3}; break;
     case CS_ARCH_RESNET50: layers = {3, 4, 6, 3}; bottleneck = true; break;
     case CS_ARCH_RESNEXT50_32X4D: layers = {3, 4, 6, 3}; bottleneck = true; groups = 32; width_per_group = 4; break;
+    case CS_ARCH_RESNEXT101_32X8D: layers = {3, 4, 23, 3}; bottleneck = true; groups = 32; width_per_group = 8; break;
     default: set_error("cs_model_create: unknown arch %d", arch); return CS_ERR_UNSUPPORTED;
   }
   int rc = cs_check_device();
@@ -891,6 +904,7 @@ int cs_debug_gemm_bf16(const void* a_bf16, const void* b_bf16, int64_t M, int N,
   rc = make_mat_map_2d(&p.b_map, b_bf16, K, N, K, bn / p.cluster);
   if (rc != CS_OK) return rc;
   p.n_variants = 1;
+  p.ext_steps = nullptr;
   p.n_steps[0] = K / 64;
   for (int s = 0; s < K / 64; ++s) p.steps[0][s] = KStep::make(s * 64, s * 64, 0, 0, 0);
   p.a_mode = 0;

@@ -96,6 +96,52 @@ heat_to_gray_kernel(const float* __restrict__ heat, int64_t n, uint8_t* __restri
   }
 }
 
+// N3: heatmap rendering tail of heatmap() (utils/image_processing.py:164-166) in one pass:
+//   gray = 255 - uint8(255 * heat)                      (float64 product, truncation)
+//   cm   = applyColorMap(gray, JET)                      (256 x 3 LUT, channel order as cv2 returns)
+//   out  = addWeighted(img, 0.5, cm, 0.5, 0)             (a/2 + b/2 exact in fp32, cvRound =
+//                                                          round-half-to-even, no saturation needed)
+// 10 B/pixel (4 heat + 3 image in, 3 out); four pixels per thread with 128/96-bit accesses.
+__device__ __forceinline__ uint32_t blend_half_even(uint32_t a, uint32_t b) {
+  const uint32_t s = a + b, r = s >> 1;
+  return r + (s & r & 1u);
+}
+
+__global__ void __launch_bounds__(256)
+heat_blend_kernel(const float* __restrict__ heat, const uint8_t* __restrict__ img,
+                  const uint8_t* __restrict__ lut, int64_t n_px, uint8_t* __restrict__ out) {
+  __shared__ uint8_t lut_s[768];
+  for (int i = threadIdx.x; i < 768; i += blockDim.x) lut_s[i] = lut[i];
+  __syncthreads();
+  auto gray_of = [](float h) {
+    double v = 255.0 * (double)h;
+    return (uint32_t)(uint8_t)(255 - (int)(uint8_t)(int)v);
+  };
+  const int64_t n4 = n_px >> 2;
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t q = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; q < n4; q += stride) {
+    const float4 h = __ldcs(reinterpret_cast<const float4*>(heat) + q);
+    const uint32_t* ip = reinterpret_cast<const uint32_t*>(img) + 3 * q;
+    const uint32_t w[3] = {__ldcs(ip), __ldcs(ip + 1), __ldcs(ip + 2)};
+    const uint32_t g[4] = {gray_of(h.x), gray_of(h.y), gray_of(h.z), gray_of(h.w)};
+    uint32_t o[3] = {0, 0, 0};
+#pragma unroll
+    for (int b = 0; b < 12; ++b) {          // byte b = pixel b/3, channel b%3
+      const uint32_t a = (w[b >> 2] >> (8 * (b & 3))) & 0xffu;
+      const uint32_t c = lut_s[g[b / 3] * 3 + b % 3];
+      o[b >> 2] |= blend_half_even(a, c) << (8 * (b & 3));
+    }
+    uint32_t* op = reinterpret_cast<uint32_t*>(out) + 3 * q;
+    __stcs(op, o[0]); __stcs(op + 1, o[1]); __stcs(op + 2, o[2]);
+  }
+  if (blockIdx.x == 0 && threadIdx.x < (n_px & 3)) {   // tail pixels
+    const int64_t px = (n4 << 2) + threadIdx.x;
+    const uint32_t g = gray_of(heat[px]);
+    for (int c = 0; c < 3; ++c)
+      out[px * 3 + c] = (uint8_t)blend_half_even(img[px * 3 + c], lut_s[g * 3 + c]);
+  }
+}
+
 int make_grid(const char* fn, int H, int W, int tile, int interval, int bag_base, int n_bags,
               Grid* g) {
   int gh = cs::grid_count(H, tile, interval), gw = cs::grid_count(W, tile, interval);
@@ -180,6 +226,21 @@ int cs_heatmap_to_gray(const float* heat, int64_t n, uint8_t* gray_out, void* st
   int64_t want = cs::ceil_div<int64_t>(n, 256);
   int grid = (int)(want < 148 * 32 ? want : 148 * 32);
   heat_to_gray_kernel<<<grid, 256, 0, cs::as_stream(stream)>>>(heat, n, gray_out);
+  CS_LAUNCH_CHECK();
+  return CS_OK;
+}
+
+int cs_heatmap_blend(const float* heat, const uint8_t* img, const uint8_t* lut768, int64_t n_px,
+                     uint8_t* out, void* stream) {
+  CS_REQUIRE(heat && img && lut768 && out, "cs_heatmap_blend: NULL pointer");
+  CS_REQUIRE(n_px >= 0, "cs_heatmap_blend: n_px < 0");
+  CS_REQUIRE((reinterpret_cast<uintptr_t>(heat) & 15) == 0 && (reinterpret_cast<uintptr_t>(img) & 3) == 0 &&
+                 (reinterpret_cast<uintptr_t>(out) & 3) == 0,
+             "cs_heatmap_blend: heat must be 16-byte and img/out 4-byte aligned");
+  if (n_px == 0) return CS_OK;
+  int64_t want = cs::ceil_div<int64_t>(cs::ceil_div<int64_t>(n_px, 4), 256);
+  int grid = (int)(want < 148 * 16 ? (want > 0 ? want : 1) : 148 * 16);
+  heat_blend_kernel<<<grid, 256, 0, cs::as_stream(stream)>>>(heat, img, lut768, n_px, out);
   CS_LAUNCH_CHECK();
   return CS_OK;
 }

@@ -261,6 +261,7 @@ class LystoDataset(_TileSetBase):
         td = np.empty(len(keep), dtype=[("bag", np.int32), ("x", np.int32), ("y", np.int32), ("label", np.int64)])
         td["bag"], td["x"], td["y"], td["label"] = bag[keep], xy[keep, 0], xy[keep, 1], lab[keep]
         self.train_data = td
+        self.train_index = idxs[keep]      # dataset (tile) index of every train_data row
         return pos, neg
 
     def train_tensor(self, begin, count, device=None):

@@ -20,15 +20,17 @@ def _device_of(device):
     return torch.device("cuda", device.index if device.index is not None else torch.cuda.current_device())
 
 
-def inference_tiles_device(dataset, model, device):
-    """f32 CUDA tensor [N] of softmax(logits)[:,1] for every tile of `dataset`, dataset order."""
+def inference_tiles_device(dataset, model, device, want_features=False):
+    """f32 CUDA tensor [N] of softmax(logits)[:,1] for every tile of `dataset`, dataset order;
+    with want_features also the pooled encoder features f32 [N, F] (the input of fc_tile)."""
     device = _device_of(device)
     img = dataset.device_images(device)
     b0 = dataset.first_tile_bag
     n = dataset.num_tiles()
     clf = model.classifier(device)
     return clf.forward_tiles(img[b0:b0 + len(dataset._tile_bags)], dataset.tile_size, dataset.interval, 0, n,
-                             precision=model.precision, max_batch=model.max_batch)
+                             precision=model.precision, max_batch=model.max_batch,
+                             want_features=want_features)
 
 
 def inference_tiles(loader, model, device, epoch=None, total_epochs=None, mode='train'):

@@ -10,7 +10,7 @@ import torch.nn as nn
 
 from .resnet import MILResNet, Bottleneck
 
-__all__ = ["MILResNeXt", "MILresnext50_32x4d"]
+__all__ = ["MILResNeXt", "MILresnext50_32x4d", "MILresnext101_32x8d"]
 
 
 class MILResNeXt(MILResNet):
@@ -27,6 +27,18 @@ def MILresnext50_32x4d(pretrained=False, progress=True, **kwargs):
     kwargs["width_per_group"] = 4
     kwargs.setdefault("num_classes", 2)
     model = MILResNeXt("resnext50_32x4d", Bottleneck, [3, 4, 6, 3], **kwargs)
+    if model.fc_tile[1].out_features != 2:
+        model.fc_tile[1] = nn.Linear(model.fc_tile[1].in_features, 2)   # model/resnext.py:414
+    return model
+
+
+def MILresnext101_32x8d(pretrained=False, progress=True, **kwargs):
+    if pretrained:
+        raise RuntimeError("no network access: load weights with load_state_dict() instead")
+    kwargs["groups"] = 32
+    kwargs["width_per_group"] = 8
+    kwargs.setdefault("num_classes", 2)
+    model = MILResNeXt("resnext101_32x8d", Bottleneck, [3, 4, 23, 3], **kwargs)
     if model.fc_tile[1].out_features != 2:
         model.fc_tile[1] = nn.Linear(model.fc_tile[1].in_features, 2)   # model/resnext.py:414
     return model

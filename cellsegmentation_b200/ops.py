@@ -178,6 +178,21 @@ def heatmap_to_gray(heat):
     return out
 
 
+def heatmap_blend(heat, img, lut):
+    """heatmap() lines 164-166 fused: applyColorMap(255 - uint8(255*heat), JET) blended 0.5/0.5 with
+    img.  heat f32 [n,H,W], img u8 [n,H,W,3], lut u8 [256,3] (cv2's colormap table) -> u8 [n,H,W,3]."""
+    _req_cuda(heat, "heat", torch.float32)
+    _req_cuda(img, "img", torch.uint8)
+    _req_cuda(lut, "lut", torch.uint8)
+    if tuple(img.shape) != tuple(heat.shape) + (3,) or lut.numel() != 768:
+        raise ValueError("heatmap_blend: img %s / lut %s do not match heat %s"
+                         % (tuple(img.shape), tuple(lut.shape), tuple(heat.shape)))
+    out = torch.empty_like(img)
+    check(lib().cs_heatmap_blend(ptr(heat), ptr(img), ptr(lut), heat.numel(), ptr(out), cur_stream()),
+          "cs_heatmap_blend")
+    return out
+
+
 def hsv_refine(img, mask, v_thresh=170, out=None):
     """preprocess_masks lines 117-120: (mask != 0) & (max(R,G,B) <= v_thresh) as u8 0/1."""
     _req_cuda(img, "img", torch.uint8)

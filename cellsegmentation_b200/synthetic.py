@@ -32,8 +32,8 @@ def make_resnet_weights(arch="resnet34", seed=0):
     """Random-init BN-folded conv list + fc_tile for benchmarking: kaiming-normal convs
     (model/resnet.py:171-175), BN at init (gamma 1, beta 0, stats 0/1 -> identity fold up to eps)."""
     layers = {"resnet18": [2, 2, 2, 2], "resnet34": [3, 4, 6, 3], "resnet50": [3, 4, 6, 3],
-              "resnext50_32x4d": [3, 4, 6, 3]}[arch]
-    bottleneck = {"resnet50": (1, 64), "resnext50_32x4d": (32, 4)}.get(arch)   # (groups, width/group)
+              "resnext50_32x4d": [3, 4, 6, 3], "resnext101_32x8d": [3, 4, 23, 3]}[arch]
+    bottleneck = {"resnet50": (1, 64), "resnext50_32x4d": (32, 4), "resnext101_32x8d": (32, 8)}.get(arch)   # (groups, width/group)
     rng = np.random.default_rng(seed)
     s = np.float32(1.0 / np.sqrt(1.0 + 1e-5))
 

@@ -73,20 +73,34 @@ def generate_masks(dataset, tiles, groups, preprocess, save_masks=True, output_p
     return pseudo_masks
 
 
-def heatmap_arrays(testset, tiles, probs, groups):
-    """u8 [n,H,W,3] blended heatmaps of heatmap() without file output."""
-    import cv2
+_JET_LUT = None
+
+
+def _jet_lut(dev):
+    """cv2's COLORMAP_JET table (a constant of the third-party library, read once on the host)."""
+    global _JET_LUT
+    if _JET_LUT is None:
+        import cv2
+        _JET_LUT = cv2.applyColorMap(np.arange(256, dtype=np.uint8).reshape(256, 1), cv2.COLORMAP_JET)
+        _JET_LUT = np.ascontiguousarray(_JET_LUT.reshape(256, 3))
+    return torch.from_numpy(_JET_LUT).to(dev)
+
+
+def heatmap_arrays(testset, tiles, probs, groups, chunk=2048):
+    """u8 [n,H,W,3] blended heatmaps of heatmap() without file output: paint (per-pixel max),
+    gray, JET colour map and the 0.5/0.5 blend all run on the GPU (utils/image_processing.py:152-166)."""
     dev = _cuda_dev()
     n = len(testset.images)
     H, W = int(testset.image_size[0]), int(testset.image_size[1])
     g, x, y = _xy_tensors(tiles, groups, dev)
     p = torch.from_numpy(np.ascontiguousarray(np.asarray(probs, dtype=np.float32))).to(dev)
     heat = ops.paint_heatmap_xy(g, x, y, p, n, H, W, testset.tile_size)
-    gray = ops.heatmap_to_gray(heat).cpu().numpy()
+    lut = _jet_lut(dev)
     out = np.empty((n, H, W, 3), np.uint8)
-    for i, img in enumerate(testset.images):
-        cm = cv2.applyColorMap(gray[i], cv2.COLORMAP_JET)          # :165
-        out[i] = cv2.addWeighted(np.asarray(img), 0.5, cm, 0.5, 0)  # :166
+    for b0 in range(0, n, chunk):
+        b1 = min(n, b0 + chunk)
+        imgs = torch.from_numpy(np.ascontiguousarray(np.stack([np.asarray(im) for im in testset.images[b0:b1]]))).to(dev)
+        out[b0:b1] = ops.heatmap_blend(heat[b0:b1].contiguous(), imgs, lut).cpu().numpy()
     return out
 
 
@@ -97,5 +111,8 @@ def heatmap(testset, tiles, probs, groups, csv_file, output_path):
         grid = list(map(int, tiles[i]))
         w.writerow([g, '{}'.format(grid), probs[i]])
     imgs = heatmap_arrays(testset, tiles, probs, groups)
-    for i in range(len(testset.images)):
-        _imsave(os.path.join(output_path, "test_{:05}.png".format(i + 1)), imgs[i])
+    # PNG encoding releases the GIL inside cv2: write the files from a small thread pool
+    from concurrent.futures import ThreadPoolExecutor
+    with ThreadPoolExecutor(max_workers=min(16, os.cpu_count() or 1)) as pool:
+        list(pool.map(lambda i: _imsave(os.path.join(output_path, "test_{:05}.png".format(i + 1)), imgs[i]),
+                      range(len(testset.images))))

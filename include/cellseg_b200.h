@@ -48,7 +48,8 @@ typedef enum cs_arch {
   CS_ARCH_RESNET18 = 0,        /* model/resnet.py:336-343   BasicBlock [2,2,2,2] */
   CS_ARCH_RESNET34 = 1,        /* model/resnet.py:346-352   BasicBlock [3,4,6,3] */
   CS_ARCH_RESNET50 = 2,        /* model/resnet.py:355-361   Bottleneck [3,4,6,3] */
-  CS_ARCH_RESNEXT50_32X4D = 3  /* model/resnext.py:418-428  Bottleneck [3,4,6,3], groups 32 x 4 */
+  CS_ARCH_RESNEXT50_32X4D = 3, /* model/resnext.py:418-428  Bottleneck [3,4,6,3], groups 32 x 4 */
+  CS_ARCH_RESNEXT101_32X8D = 4 /* model/resnext.py:431-443  Bottleneck [3,4,23,3], groups 32 x 8 */
 } cs_arch;
 
 /* Library version: major*10000 + minor*100 + patch. */
@@ -106,7 +107,7 @@ int cs_gather_normalize(const uint8_t* img, int n_bags, int H, int W, int tile,
  *   fc_w [2][F], fc_b [2]  : fc_tile.1 (model/resnet.py:124-127), F = 512 (BasicBlock nets)
  *                            or 2048 (Bottleneck nets) = cs_model_feature_dim()
  * n_convs must equal the count implied by `arch` (resnet18: 20, resnet34: 36,
- * resnet50 / resnext50_32x4d: 53).
+ * resnet50 / resnext50_32x4d: 53, resnext101_32x8d: 104).
  * The library packs GEMM-ready bf16 copies and keeps the fp32 originals.
  * ------------------------------------------------------------------------- */
 typedef struct cs_model cs_model;
@@ -230,6 +231,14 @@ int cs_paint_heatmap_xy(const int32_t* bag, const int32_t* x, const int32_t* y,
 /* `255 - np.uint8(255 * masks[i])` (utils/image_processing.py:165) evaluated in
  * float64 exactly like numpy: gray_out u8 [n] = 255 - (uint8)(255.0 * (double)heat). */
 int cs_heatmap_to_gray(const float* heat, int64_t n, uint8_t* gray_out, void* stream);
+
+/* N3 -- heatmap() rendering tail, utils/image_processing.py:164-166, in one pass over the pixels:
+ * gray = 255 - uint8(255*heat); cm = applyColorMap(gray, COLORMAP_JET) through the 256x3 LUT
+ * `lut768` (device, entry g at lut768[3g..3g+2], channel order as cv2 returns it);
+ * out = addWeighted(img, 0.5, cm, 0.5, 0) (round half to even).  heat f32 [n_px], img / out
+ * u8 [n_px][3] (device).  heat 16-byte aligned, img / out 4-byte aligned. */
+int cs_heatmap_blend(const float* heat, const uint8_t* img, const uint8_t* lut768, int64_t n_px,
+                     uint8_t* out, void* stream);
 
 /* preprocess_masks() lines 117-120 (utils/image_processing.py:114-120):
  *   V = max(R,G,B) (cv2.cvtColor(BGR2HSV) + split()[2]; channel-order free)

@@ -13,9 +13,9 @@ import torch
 import torch.nn.functional as F
 
 LAYERS = {"resnet18": [2, 2, 2, 2], "resnet34": [3, 4, 6, 3], "resnet50": [3, 4, 6, 3],
-          "resnext50_32x4d": [3, 4, 6, 3]}
+          "resnext50_32x4d": [3, 4, 6, 3], "resnext101_32x8d": [3, 4, 23, 3]}
 # (groups, width_per_group) of the Bottleneck nets; model/resnet.py:355-361, model/resnext.py:418-428
-BOTTLENECK = {"resnet50": (1, 64), "resnext50_32x4d": (32, 4)}
+BOTTLENECK = {"resnet50": (1, 64), "resnext50_32x4d": (32, 4), "resnext101_32x8d": (32, 8)}
 PLANES = [64, 128, 256, 512]
 
 

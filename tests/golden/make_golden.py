@@ -102,7 +102,7 @@ def main():
          n=np.array(len(ds)))
 
     # 3. model forward through the reference classes + inference_tiles ----------------
-    for arch in ("resnet34", "resnet18", "resnet50", "resnext50_32x4d"):
+    for arch in ("resnet34", "resnet18", "resnet50", "resnext50_32x4d", "resnext101_32x8d"):
         gen_model(ref, ds, arch)
 
     # 4. sample(): capture the idxs handed to make_train_data -------------------------

@@ -16,8 +16,9 @@ def _model(arch, sd, cuda, precision):
     from cellsegmentation_b200.model import nets
     from cellsegmentation_b200.model.resnet import MILresnet18, MILresnet34, MILresnet50
     from cellsegmentation_b200.model.resnext import MILresnext50_32x4d
+    from cellsegmentation_b200.model.resnext import MILresnext101_32x8d
     net = {"resnet18": MILresnet18, "resnet34": MILresnet34, "resnet50": MILresnet50,
-           "resnext50_32x4d": MILresnext50_32x4d}[arch]()
+           "resnext50_32x4d": MILresnext50_32x4d, "resnext101_32x8d": MILresnext101_32x8d}[arch]()
     missing, unexpected = net.load_state_dict(sd, strict=False)
     assert not unexpected and not missing, (missing, unexpected)
     net.setmode("tile")
@@ -57,7 +58,7 @@ def test_inference_tiles_dataset_path_matches_reference_golden(cuda, precision, 
     assert lab == 0 or lab == ds.labels[ds.tileIDX[14]]
 
 
-@pytest.mark.parametrize("arch", ["resnet50", "resnext50_32x4d"])
+@pytest.mark.parametrize("arch", ["resnet50", "resnext50_32x4d", "resnext101_32x8d"])
 def test_bottleneck_nets_match_reference_golden(cuda, arch):
     """BASELINE config 4 (encoder swap): reference state_dict keys load, module call == golden."""
     from cellsegmentation_b200.inference import inference_tiles
@@ -241,5 +242,17 @@ def test_mil_epoch_single_process_equals_sample_plus_train_tile(cuda):
     gidx, glab = select_global(ds, net, cuda, 1, 30)
     assert np.array_equal(gidx, want_idx) and np.array_equal(glab, want_pl)
     opt = torch.optim.SGD(filter(lambda p: p.requires_grad, net.parameters()), lr=1e-6)
-    loss, pos, neg = mil_epoch(ds, net, cuda, torch.nn.CrossEntropyLoss(), opt, 1, 30, 0.5, 16, seed=3)
+    w0 = net.fc_tile[1].weight.detach().clone()
+    b0 = net.fc_tile[1].bias.detach().clone()
+    loss, pos, neg = mil_epoch(ds, net, cuda, torch.nn.CrossEntropyLoss(), opt, 1, 30, 0.5, 16, seed=3,
+                               cache_features=False)
     assert np.isfinite(loss) and pos + neg == len(ds.train_data)
+    w1 = net.fc_tile[1].weight.detach().clone()
+    # N2: the cached-feature epoch is the same computation without the second encoder pass
+    with torch.no_grad():
+        net.fc_tile[1].weight.copy_(w0); net.fc_tile[1].bias.copy_(b0)
+    loss_c, pos_c, neg_c = mil_epoch(ds, net, cuda, torch.nn.CrossEntropyLoss(), opt, 1, 30, 0.5, 16, seed=3,
+                                     cache_features=True)
+    assert (pos_c, neg_c) == (pos, neg)
+    assert abs(loss_c - loss) <= 1e-6 * max(1.0, abs(loss))
+    assert torch.allclose(net.fc_tile[1].weight.detach(), w1, rtol=0, atol=1e-9)

@@ -225,3 +225,29 @@ def test_remove_small_regions_bit_exact(cuda, H, W, density, seed):
         want = np.stack([omasks.remove_small_regions(x, mo, ha) for x in m]).astype(np.uint8)
         got = ops.remove_small_regions(torch.from_numpy(m.astype(np.uint8) * 3).to(cuda), mo, ha)
         assert int((got.cpu().numpy() != want).sum()) == 0, (mo, ha)
+
+
+def test_heatmap_blend_matches_cv2(cuda):
+    """N3: applyColorMap(JET) + addWeighted(.5,.5) fused on the GPU == cv2, every byte pair covered."""
+    import cv2
+    ops = _ops()
+    lut = cv2.applyColorMap(np.arange(256, dtype=np.uint8).reshape(256, 1), cv2.COLORMAP_JET).reshape(256, 3)
+    rng = np.random.default_rng(5)
+    # (a) all 256 x 256 (image byte, gray level) pairs: heat chosen so that 255 - uint8(255 h) = level
+    lv = np.repeat(np.arange(256), 256).reshape(1, 256, 256)
+    heat = ((255 - lv) / 255.0).astype(np.float32)
+    heat = np.where((255 - (255.0 * heat.astype(np.float64)).astype(np.uint8)) == lv, heat,
+                    np.nextafter(heat, np.float32(2))).astype(np.float32)
+    assert np.array_equal(255 - (255.0 * heat.astype(np.float64)).astype(np.uint8), lv)
+    img = np.tile(np.arange(256, dtype=np.uint8), 256).reshape(1, 256, 256, 1).repeat(3, axis=3)
+    # (b) random maps with an odd pixel count (tail path) and unaligned-looking shapes
+    heat2 = rng.random((3, 37, 41), dtype=np.float32)
+    heat2[rng.random(heat2.shape) < 0.5] = 0.0
+    img2 = rng.integers(0, 256, (3, 37, 41, 3), dtype=np.uint8)
+    for h, im in ((heat, img), (heat2, img2)):
+        got = ops.heatmap_blend(torch.from_numpy(h).to(cuda), torch.from_numpy(np.ascontiguousarray(im)).to(cuda),
+                                torch.from_numpy(np.ascontiguousarray(lut)).to(cuda)).cpu().numpy()
+        for i in range(h.shape[0]):
+            gray = (255 - np.uint8(255 * h[i].astype(np.float64)))
+            want = cv2.addWeighted(np.ascontiguousarray(im[i]), 0.5, cv2.applyColorMap(gray, cv2.COLORMAP_JET), 0.5, 0)
+            assert np.array_equal(got[i], want)

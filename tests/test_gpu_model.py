@@ -43,7 +43,9 @@ def test_tcgen05_gemm_matches_fp32_matmul(cuda, M, N, K, bn):
     # Bottleneck / ResNeXt shapes: pointwise, strided pointwise, grouped 3x3 in every form
     (8, 64, 256, 1, 1, 1), (4, 512, 128, 1, 1, 1), (8, 256, 512, 1, 2, 1), (2, 1024, 2048, 1, 2, 1),
     (1, 2048, 512, 1, 1, 1), (8, 128, 128, 3, 1, 32), (8, 256, 256, 3, 2, 32), (4, 256, 256, 3, 1, 32),
-    (4, 512, 512, 3, 2, 32), (2, 512, 512, 3, 1, 32), (2, 1024, 1024, 3, 2, 32), (1, 1024, 1024, 3, 1, 32)])
+    (4, 512, 512, 3, 2, 32), (2, 512, 512, 3, 1, 32), (2, 1024, 1024, 3, 2, 32), (1, 1024, 1024, 3, 1, 32),
+    # ResNeXt-101 32x8d widths: more step-list variants than fit the kernel parameters
+    (8, 256, 256, 3, 1, 32), (4, 1024, 1024, 3, 2, 32), (2, 2048, 2048, 3, 2, 32)])
 def test_tcgen05_conv_matches_conv2d(cuda, H, Cin, Cout, k, stride, groups):
     ops = _ops()
     g = torch.Generator().manual_seed(H * 1000 + Cin + Cout + stride + 7 * groups + k)
@@ -67,7 +69,7 @@ def _setup(arch, n_bags=2, interval=20, tile=32, seed=3):
     return bags, x, sd
 
 
-ARCHS = ["resnet34", "resnet18", "resnet50", "resnext50_32x4d"]
+ARCHS = ["resnet34", "resnet18", "resnet50", "resnext50_32x4d", "resnext101_32x8d"]
 
 
 @pytest.mark.parametrize("arch", ARCHS)

@@ -35,7 +35,7 @@ def test_transform_matches_reference_bit_exact():
     assert g["tileIDX"].min() == 1            # first bag has no tiles
 
 
-@pytest.mark.parametrize("arch", ["resnet34", "resnet18", "resnet50", "resnext50_32x4d"])
+@pytest.mark.parametrize("arch", ["resnet34", "resnet18", "resnet50", "resnext50_32x4d", "resnext101_32x8d"])
 def test_model_forward_matches_reference(arch):
     g = golden("model_%s.npz" % arch)
     _, x = _transform_dataset()
