@@ -87,6 +87,18 @@ def peaks():
         return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0}, "fallback"
 
 
+def measured_traffic(n_inst):
+    """DRAM bytes of the conv stage for n_inst instances, from the committed `ncu --set full`
+    capture of one forward batch (profiles/summarize_full.py); None when no capture is there."""
+    try:
+        t = json.load(open(os.path.join(ROOT, "profiles", "r01_h_traffic.json")))
+        return {"bytes": t["dram_bytes_per_instance"] * n_inst, "per_instance": t["dram_bytes_per_instance"],
+                "source": "profiles/r01_h_traffic.json (dram__bytes_read.sum + dram__bytes_write.sum over the "
+                          "%d launches of one %d-instance batch)" % (t["launches"], t["instances"])}
+    except Exception:
+        return None
+
+
 def cpu_reference_step(n_bags, sd, labels, seed):
     """The reference's CPU path restated (oracle port): unfold -> ResNet-34 fp32 forward ->
     lexsort + adaptive top-k predicate.  Returns (instances, seconds)."""
@@ -336,9 +348,11 @@ def main():
                     "d2h_bytes_per_step": int(m_sel * 5)},
             "gpu_launches": int(gpu_launches),
             "clocks": clocks,
-            "roofline": {"bound": "tensor", "kernel": "conv stage: stem + 32 conv_gemm_kernel launches + head per batch",
+            "roofline": {"bound": "tensor", "kernel": "conv stage: stem_win_kernel + 32 conv_halo/conv_gemm launches + head per batch",
                          "achieved": tflops, "peak": peak, "unit": "TFLOP/s", "frac": tflops / peak,
-                         "peak_kind": pk_kind + " bf16_tflops_sustained", "traffic": None,
+                         "peak_kind": pk_kind + " bf16_tflops_sustained",
+                         "traffic": (measured_traffic(n_inst) or {}).get("bytes"),
+                         "traffic_detail": measured_traffic(n_inst),
                          "flop_per_instance": FLOP_INBOUNDS,
                          "achieved_nominal": FLOP_NOMINAL * n_inst / (fwd_ms * 1e-3) / 1e12,
                          "fwd_ms_per_step": fwd_ms,
