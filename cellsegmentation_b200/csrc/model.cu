@@ -36,6 +36,11 @@ const bool g_snake = !env_is("CELLSEG_SNAKE", "0");          // alternate the ti
 const int g_cluster = env_is("CELLSEG_CLUSTER", "2") ? 2 : 1;  // 2-CTA B multicast (no gain measured)
 const bool g_disable_halo = env_is("CELLSEG_HALO", "0");     // diagnostics: generic kernel only
 const bool g_force_cuda_core_stem = env_is("CELLSEG_STEM", "cuda");
+// Residual stream: bf16 by default.  CELLSEG_RESIDUAL=hilo carries a second bf16 tensor
+// lo = value - bf16(value) between blocks (~16 mantissa bits); measured max|dp| moves by < 1.5e-3
+// (ResNet-34 0.0101 -> 0.0098) while the block epilogues move twice the bytes (-11 % throughput).
+const bool g_no_lo = !env_is("CELLSEG_RESIDUAL", "hilo");
+const int g_xbufs = g_no_lo ? 2 : 4;
 const bool g_im2col_stem = env_is("CELLSEG_STEM", "im2col");   // first tensor-core stem (stem_tc.cu)
 
 struct ConvW {
@@ -447,21 +452,22 @@ int build_tc_plan(cs_model* m, int tile, int64_t max_batch, void* ws, int64_t ws
   int64_t xe, me;
   act_sizes(m, tile, &xe, &me);
   const int64_t xb = round_up(plan->b_pad * xe * 2, 1024), mb = round_up(plan->b_pad * me * 2, 1024);
-  if (ws_bytes < 4 * xb + 2 * mb + 1024) {
+  if (ws_bytes < g_xbufs * xb + 2 * mb + 1024) {
     set_error("bf16 workspace too small: %lld < %lld", (long long)ws_bytes,
-              (long long)(4 * xb + 2 * mb + 1024));
+              (long long)(g_xbufs * xb + 2 * mb + 1024));
     return CS_ERR_WORKSPACE;
   }
   uintptr_t base = round_up((int64_t)(uintptr_t)ws, 1024);
   for (int i = 0; i < 2; ++i) {
     plan->x_hi[i] = reinterpret_cast<__nv_bfloat16*>(base + i * xb);
-    plan->x_lo[i] = reinterpret_cast<__nv_bfloat16*>(base + (2 + i) * xb);
-    plan->mid[i] = reinterpret_cast<__nv_bfloat16*>(base + 4 * xb + i * mb);
+    plan->x_lo[i] = g_no_lo ? nullptr : reinterpret_cast<__nv_bfloat16*>(base + (2 + i) * xb);
+    plan->mid[i] = reinterpret_cast<__nv_bfloat16*>(base + g_xbufs * xb + i * mb);
   }
   const int64_t bp = plan->b_pad;
   auto push = [&](PlannedConv& pc, const __nv_bfloat16* rh, const __nv_bfloat16* rl, __nv_bfloat16* oh,
                   __nv_bfloat16* ol, int relu) {
-    pc.p.res_hi = rh; pc.p.res_lo = rl; pc.p.out_hi = oh; pc.p.out_lo = ol; pc.p.relu = relu;
+    pc.p.res_hi = rh; pc.p.res_lo = g_no_lo ? nullptr : rl; pc.p.out_hi = oh;
+    pc.p.out_lo = g_no_lo ? nullptr : ol; pc.p.relu = relu;
     int rc = finalize_io_maps(pc, bp);
     if (rc != CS_OK) { free_planned(pc); return rc; }
     plan->layers.push_back(pc);
@@ -530,7 +536,7 @@ int build_tc_plan(cs_model* m, int tile, int64_t max_batch, void* ws, int64_t ws
     H = Ho; W = Wo; C = b.cout;
   }
   plan->x4_hi = plan->x_hi[xi];
-  plan->x4_lo = plan->x_lo[xi];
+  plan->x4_lo = g_no_lo ? nullptr : plan->x_lo[xi];
   plan->P4 = H * W;
   plan->C4 = C;
   if (tile == 32) {
@@ -792,7 +798,7 @@ int64_t cs_model_workspace_bytes(const cs_model* m, int tile, int64_t max_batch,
   int64_t xe, me;
   act_sizes(m, tile, &xe, &me);
   int64_t b_pad = round_up(max_batch, kGemmBM);
-  return 4 * round_up(b_pad * xe * 2, 1024) + 2 * round_up(b_pad * me * 2, 1024) + 4096;
+  return g_xbufs * round_up(b_pad * xe * 2, 1024) + 2 * round_up(b_pad * me * 2, 1024) + 4096;
 }
 
 int cs_model_forward_tiles(cs_model* m, const uint8_t* img, int n_bags, int H, int W, int tile,

@@ -132,3 +132,24 @@ def test_forward_tile16(cuda, arch):
     got16 = clf.forward_tiles(d_img, 16, 20, precision="bf16", max_batch=512).cpu().numpy()
     assert np.abs(got16 - want).max() < BF16_TOL
     clf.close()
+
+
+def test_hilo_residual_mode_subprocess(cuda):
+    """CELLSEG_RESIDUAL=hilo (read when the library loads) keeps the hi/lo residual stream: same gate."""
+    import os
+    import subprocess
+    import sys
+    code = (
+        "import sys, numpy as np, torch; sys.path.insert(0, %r); sys.path.insert(0, %r)\n"
+        "from test_gpu_model import _setup, _ops, BF16_TOL\n"
+        "from oracle import model as omodel\n"
+        "ops = _ops(); bags, x, sd = _setup('resnet34')\n"
+        "want = omodel.forward_probs(sd, x, 'resnet34')\n"
+        "clf = ops.TileClassifier('resnet34', omodel.fold_bn(sd, 'resnet34'), sd['fc_tile.1.weight'], sd['fc_tile.1.bias'])\n"
+        "got = clf.forward_tiles(torch.from_numpy(bags).cuda(), 32, 20, precision='bf16', max_batch=256).cpu().numpy()\n"
+        "d = float(np.abs(got - want).max()); print('hilo max|dp|', d); assert d < BF16_TOL\n"
+    ) % (os.path.dirname(os.path.dirname(os.path.abspath(__file__))), os.path.dirname(os.path.abspath(__file__)))
+    env = dict(os.environ, CELLSEG_RESIDUAL="hilo")
+    r = subprocess.run([sys.executable, "-c", code], env=env, capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stdout + r.stderr
+    assert "hilo max|dp|" in r.stdout
