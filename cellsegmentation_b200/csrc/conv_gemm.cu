@@ -14,11 +14,14 @@
 // Operands land in shared memory in the 128-byte-swizzled K-major layout UMMA expects;
 // accumulators live in TMEM (two stages: the epilogue of tile i overlaps the MMAs of tile i+1).
 //
-// Clusters (CL = 2): the launch list showed every layer pinned at the L2 -> SM bandwidth, and
-// the weight tile B is the larger operand.  Two CTAs of a cluster take neighbouring M tiles of
-// the same N tile and walk the K steps in lockstep; each loads half of B and multicasts it to
-// both, so a CTA pulls A + B/2 per step instead of A + B.  A stage is released by a multicast
-// tcgen05.commit to both CTAs' "empty" barriers (count = CL).
+// CTA pairs (CL = 2, tcgen05 cta_group::2): with both operands in shared memory a single-CTA
+// MMA is bound by operand reads (~66 B/clk measured: 40-60 % tensor-pipe utilisation).  Two CTAs
+// of a cluster take neighbouring M tiles of the same N tile; each loads its own A tile and HALF
+// of the B tile, the leader (rank 0) issues one M = 256 MMA per K slice for both, and every CTA
+// finds its 128 x N accumulator rows in its own TMEM.  Per CTA the B bytes read per MMA halve.
+// All operand loads complete on the leader's "full" barrier; a multicast commit releases the
+// stage in both CTAs and hands the accumulator to both epilogues; both epilogues return the
+// accumulator stage on the leader's "tempty" barrier.
 //
 // Warp roles (320 threads, one CTA per SM, persistent):
 //   warp 0 : TMA producer (one lane)          warp 1 : TMEM alloc + MMA issuer (one lane)
@@ -29,11 +32,11 @@
 namespace cs {
 namespace {
 
-template <int BN>
+template <int BN, int CL>
 struct GemmCfg {
   static constexpr int kMaxStages = 8;
   static constexpr uint32_t kABytes = kGemmBM * kGemmBK * 2;  // 16 KB
-  static constexpr uint32_t kBBytes = BN * kGemmBK * 2;
+  static constexpr uint32_t kBBytes = (BN / CL) * kGemmBK * 2;   // a pair member holds half of B
   static constexpr uint32_t kStageBytes = kABytes + kBBytes;
   static constexpr uint32_t kSmemLimit = 227 * 1024;
   // Shared memory: [stages x (A|B)] [staging: 2 sets of hi(+lo) tiles] [barriers]; the stage
@@ -54,7 +57,7 @@ constexpr int kGemmThreads = 352;  // TMA warp, MMA warp, 8 epilogue warps, epil
 template <int BN, int CL>
 __global__ void __launch_bounds__(kGemmThreads, 1)
 conv_gemm_kernel(const __grid_constant__ GemmParams p) {
-  using Cfg = GemmCfg<BN>;
+  using Cfg = GemmCfg<BN, CL>;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw = smem_u32(smem_raw);
   const uint32_t base = (raw + 1023u) & ~1023u;
@@ -84,18 +87,23 @@ conv_gemm_kernel(const __grid_constant__ GemmParams p) {
   if (warp == 0 && lane == 0) {
     for (int s = 0; s < n_stages; ++s) {
       mbar_init(full_bar(s), 1);
-      mbar_init(empty_bar(s), CL);
+      mbar_init(empty_bar(s), 1);
     }
     for (int a = 0; a < 2; ++a) {
       mbar_init(tfull_bar(a), 1);
-      mbar_init(tempty_bar(a), kEpiThreads);
+      // single CTA: every epilogue thread arrives; pair: one elected lane per epilogue warp of
+      // both CTAs arrives on the leader's barrier
+      mbar_init(tempty_bar(a), CL == 1 ? kEpiThreads : CL * kEpiWarps);
     }
     epi_bars_init(ebars);
     fence_barrier_init();
     prefetch_tmap(&p.b_map);
     prefetch_tmap(&p.a_map[0]);
   }
-  if (warp == 1) tmem_alloc(smem_u32((const void*)tmem_slot), Cfg::kTmemCols);
+  if (warp == 1) {
+    if (CL == 1) tmem_alloc(smem_u32((const void*)tmem_slot), Cfg::kTmemCols);
+    else tmem_alloc_pair(smem_u32((const void*)tmem_slot), Cfg::kTmemCols);
+  }
   tc_fence_before();
   __syncthreads();
   if (CL > 1) cluster_sync_all();   // peers' barriers are initialised before any remote arrive
@@ -127,28 +135,32 @@ conv_gemm_kernel(const __grid_constant__ GemmParams p) {
           mbar_wait(empty_bar(stage), phase ^ 1u);
           const uint32_t a_dst = base + stage * Cfg::kStageBytes;
           const uint32_t b_dst = a_dst + Cfg::kABytes;
-          mbar_expect_tx(full_bar(stage), Cfg::kStageBytes);
           const int mp = st.map();
-          if (((p.a_mode >> mp) & 1) == 0)
-            tma_load_2d(a_dst, &p.a_map[mp], full_bar(stage), st.a_c0(), m_tile * kGemmBM);
-          else
-            tma_load_4d(a_dst, &p.a_map[mp], full_bar(stage), st.a_c0(), st.dx(), st.dy(),
-                        m_tile * p.units_per_mtile);
           if (CL == 1) {
+            mbar_expect_tx(full_bar(stage), Cfg::kStageBytes);
+            if (((p.a_mode >> mp) & 1) == 0)
+              tma_load_2d(a_dst, &p.a_map[mp], full_bar(stage), st.a_c0(), m_tile * kGemmBM);
+            else
+              tma_load_4d(a_dst, &p.a_map[mp], full_bar(stage), st.a_c0(), st.dx(), st.dy(),
+                          m_tile * p.units_per_mtile);
             tma_load_2d(b_dst, &p.b_map, full_bar(stage), st.b_k(), n_tile * BN);
           } else {
-            // this CTA's slice of the B tile, delivered to every CTA of the cluster
-            constexpr int kSliceRows = BN / CL;
-            tma_load_2d_mcast(b_dst + rank * (kSliceRows * 128), &p.b_map, full_bar(stage), st.b_k(),
-                              n_tile * BN + rank * kSliceRows, kMask);
+            // both CTAs' boxes complete on the leader's barrier, which expects the pair's bytes
+            if (rank == 0) mbar_expect_tx(full_bar(stage), CL * Cfg::kStageBytes);
+            if (((p.a_mode >> mp) & 1) == 0)
+              tma_load_2d_pair(a_dst, &p.a_map[mp], full_bar(stage), st.a_c0(), m_tile * kGemmBM);
+            else
+              tma_load_4d_pair(a_dst, &p.a_map[mp], full_bar(stage), st.a_c0(), st.dx(), st.dy(),
+                               m_tile * p.units_per_mtile);
+            tma_load_2d_pair(b_dst, &p.b_map, full_bar(stage), st.b_k(), n_tile * BN + rank * (BN / CL));
           }
           if (++stage == n_stages) { stage = 0; phase ^= 1u; }
         }
       }
     }
   } else if (warp == 1) {
-    if (lane == 0) {
-      constexpr uint32_t idesc = umma_idesc_bf16(kGemmBM, BN);
+    if (lane == 0 && rank == 0) {
+      constexpr uint32_t idesc = umma_idesc_bf16(kGemmBM * CL, BN);
       int stage = 0;
       uint32_t phase = 0;
       int acc = 0;
@@ -170,15 +182,21 @@ conv_gemm_kernel(const __grid_constant__ GemmParams p) {
 #pragma unroll
           for (int k = 0; k < kGemmBK / 16; ++k) {
             // +32 B per K=16 slice inside the 128-byte swizzle row: +2 in (addr >> 4)
-            umma_bf16(d_tmem, a_desc + (uint64_t)(2 * k), b_desc + (uint64_t)(2 * k), idesc,
-                      (s > 0 || k > 0) ? 1u : 0u);
+            if (CL == 1)
+              umma_bf16(d_tmem, a_desc + (uint64_t)(2 * k), b_desc + (uint64_t)(2 * k), idesc,
+                        (s > 0 || k > 0) ? 1u : 0u);
+            else
+              umma_bf16_pair(d_tmem, a_desc + (uint64_t)(2 * k), b_desc + (uint64_t)(2 * k), idesc,
+                             (s > 0 || k > 0) ? 1u : 0u);
           }
-          // frees the stage when these MMAs retire -- in every CTA that wrote into it
+          // frees the stage when these MMAs retire -- in both CTAs of a pair
           if (CL == 1) umma_commit(empty_bar(stage));
-          else umma_commit_mcast(empty_bar(stage), kMask);
+          else umma_commit_pair(empty_bar(stage), kMask);
           if (++stage == n_stages) { stage = 0; phase ^= 1u; }
         }
-        umma_commit(tfull_bar(acc));  // accumulator complete -> epilogue
+        // accumulator complete -> epilogue(s)
+        if (CL == 1) umma_commit(tfull_bar(acc));
+        else umma_commit_pair(tfull_bar(acc), kMask);
         acc ^= 1;
         if (acc == 0) acc_phase ^= 1u;
       }
@@ -212,7 +230,12 @@ conv_gemm_kernel(const __grid_constant__ GemmParams p) {
         mbar_arrive(ebars.out_ready[s]);
       }
       tc_fence_before();
-      mbar_arrive(tempty_bar(acc));
+      if (CL == 1) {
+        mbar_arrive(tempty_bar(acc));
+      } else {
+        __syncwarp();
+        if (lane == 0) mbar_arrive_leader(tempty_bar(acc));
+      }
       acc ^= 1;
       if (acc == 0) acc_phase ^= 1u;
     }
@@ -252,13 +275,14 @@ conv_gemm_kernel(const __grid_constant__ GemmParams p) {
   if (CL > 1) cluster_sync_all();   // no CTA leaves while a peer may still write into it
   if (warp == 1) {
     tc_fence_after();
-    tmem_dealloc(tmem_base, Cfg::kTmemCols);
+    if (CL == 1) tmem_dealloc(tmem_base, Cfg::kTmemCols);
+    else tmem_dealloc_pair(tmem_base, Cfg::kTmemCols);
   }
 }
 
 template <int BN, int CL>
 int launch_gemm_bn(const GemmParams& p, cudaStream_t st) {
-  using Cfg = GemmCfg<BN>;
+  using Cfg = GemmCfg<BN, CL>;
   static bool attr_done[64] = {false};
   int dev = 0;
   CS_CUDA(cudaGetDevice(&dev));

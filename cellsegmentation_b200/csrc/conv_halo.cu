@@ -16,7 +16,11 @@
 // memory for the whole kernel.  M row r of the accumulator is pixel (oy = r / (W*IMG),
 // img = (r / W) % IMG, ox = r % W); the epilogue maps it back to [instance][y][x][c].
 //
-// Warp roles as in fwd_tc.cu: warp 0 TMA, warp 1 MMA issue, warps 2-9 epilogue.
+// CTA pairs (CL = 2, tcgen05 cta_group::2) as in conv_gemm.cu: neighbouring M tiles, each CTA
+// holds its own halo tile and HALF of every weight tile (the resident set shrinks to 36 KB),
+// the leader issues M = 256 MMAs for both.
+//
+// Warp roles as in conv_gemm.cu: warp 0 TMA, warp 1 MMA issue, warps 2-9 epilogue, warp 10 DMA.
 #include "fwd.cuh"
 #include "gemm_epilogue.cuh"
 
@@ -25,15 +29,15 @@ namespace {
 
 constexpr int kHaloThreads = 352;  // TMA warp, MMA warp, 8 epilogue warps, epilogue DMA warp
 
-template <int BN, int W, int CCH, bool BRES>
+template <int BN, int W, int CCH, bool BRES, int CL>
 struct HaloCfg {
   static constexpr int kImg = 128 / (W * W);            // instances per M tile
   static constexpr int kRowsY = W * kImg;               // accumulator rows per output y
   static constexpr int kHaloRows = kRowsY * (W + 2);
   static constexpr uint32_t kABytes = kHaloRows * 128;  // 20 KB (8x8) / 24 KB (4x4)
-  static constexpr uint32_t kBTile = BN * 128;
+  static constexpr uint32_t kBTile = (BN / CL) * 128;
   static constexpr uint32_t kStageBytes = kABytes + (BRES ? 0 : 3 * kBTile);
-  static constexpr int kStages = BRES ? 4 : 2;
+  static constexpr int kStages = BRES ? (CL == 2 ? 6 : 4) : (CL == 2 ? 3 : 2);   // what fits 227 KB
   static constexpr uint32_t kBResBytes = BRES ? 9 * CCH * kBTile : 0;
   static constexpr uint32_t kStagingOffset = kStages * kStageBytes + kBResBytes;
   static constexpr uint32_t kBarOffset = kStagingOffset + kEpiStagingBytes;
@@ -42,13 +46,14 @@ struct HaloCfg {
   static constexpr int kSteps = 3 * CCH;                // (dx, channel chunk)
   static constexpr uint32_t kTmemCols = 2 * BN;
   static_assert(kABytes % 1024 == 0 && kStageBytes % 1024 == 0, "stages must keep 1 KB alignment");
+  static_assert(kSmemBytes <= 227 * 1024, "shared memory budget");
   static_assert((kRowsY * 128) % 1024 == 0, "a dy shift must move whole swizzle atoms");
 };
 
-template <int BN, int W, int CCH, bool BRES>
+template <int BN, int W, int CCH, bool BRES, int CL>
 __global__ void __launch_bounds__(kHaloThreads, 1)
 conv_halo_kernel(const __grid_constant__ HaloParams p) {
-  using Cfg = HaloCfg<BN, W, CCH, BRES>;
+  using Cfg = HaloCfg<BN, W, CCH, BRES, CL>;
   constexpr int Cin = CCH * 64;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw = smem_u32(smem_raw);
@@ -71,58 +76,81 @@ conv_halo_kernel(const __grid_constant__ HaloParams p) {
   const uint32_t staging = base + Cfg::kStagingOffset;
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int rank = CL > 1 ? (int)cluster_ctarank() : 0;
+  constexpr uint16_t kMask = (uint16_t)((1u << CL) - 1u);
+  // a cluster walks groups of CL neighbouring M tiles; CTA `rank` owns tile group * CL + rank
+  const int m_groups = (p.num_m_tiles + CL - 1) / CL;
+  const int first = blockIdx.x / CL, step_g = gridDim.x / CL;
+  auto tile_of = [&](int gi) { return (p.reverse ? m_groups - 1 - gi : gi) * CL + rank; };
 
   if (warp == 0 && lane == 0) {
     for (int s = 0; s < Cfg::kStages; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
-    for (int a = 0; a < 2; ++a) { mbar_init(tfull_bar(a), 1); mbar_init(tempty_bar(a), kEpiThreads); }
+    for (int a = 0; a < 2; ++a) {
+      mbar_init(tfull_bar(a), 1);
+      mbar_init(tempty_bar(a), CL == 1 ? kEpiThreads : CL * kEpiWarps);
+    }
     mbar_init(bres_bar, 1);
     epi_bars_init(ebars);
     fence_barrier_init();
     prefetch_tmap(&p.a_map);
     prefetch_tmap(&p.b_map);
   }
-  if (warp == 1) tmem_alloc(smem_u32((const void*)tmem_slot), Cfg::kTmemCols);
+  if (warp == 1) {
+    if (CL == 1) tmem_alloc(smem_u32((const void*)tmem_slot), Cfg::kTmemCols);
+    else tmem_alloc_pair(smem_u32((const void*)tmem_slot), Cfg::kTmemCols);
+  }
   tc_fence_before();
   __syncthreads();
+  if (CL > 1) cluster_sync_all();   // the leader's barriers exist before the peer's loads signal them
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
   pdl_launch_dependents();
 
   if (warp == 0) {
     if (lane == 0) {
+      const int b_row = rank * (BN / CL);   // this CTA's rows of every weight tile
       if (BRES) {   // weights are constants: fetch them while the previous layer still drains
-        mbar_expect_tx(bres_bar, Cfg::kBResBytes);
-        for (int t = 0; t < 9 * CCH; ++t)   // tile index = tap * CCH + chunk = K column / 64
-          tma_load_2d(bres + t * Cfg::kBTile, &p.b_map, bres_bar, t * 64, 0);
+        if (rank == 0) mbar_expect_tx(bres_bar, CL * Cfg::kBResBytes);
+        for (int t = 0; t < 9 * CCH; ++t) {   // tile index = tap * CCH + chunk = K column / 64
+          if (CL == 1) tma_load_2d(bres + t * Cfg::kBTile, &p.b_map, bres_bar, t * 64, 0);
+          else tma_load_2d_pair(bres + t * Cfg::kBTile, &p.b_map, bres_bar, t * 64, b_row);
+        }
       }
       pdl_wait();
       int stage = 0;
       uint32_t phase = 0;
-      for (int mi = blockIdx.x; mi < p.num_m_tiles; mi += gridDim.x) {
-        const int m_tile = p.reverse ? p.num_m_tiles - 1 - mi : mi;
+      for (int gi = first; gi < m_groups; gi += step_g) {
+        const int m_tile = tile_of(gi);
         for (int s = 0; s < Cfg::kSteps; ++s) {
           const int dx = s / CCH, ch = s - dx * CCH;
           mbar_wait(empty_bar(stage), phase ^ 1u);
           const uint32_t a_dst = base + stage * Cfg::kStageBytes;
-          mbar_expect_tx(full_bar(stage), Cfg::kStageBytes);
-          tma_load_4d(a_dst, &p.a_map, full_bar(stage), ch * 64, dx - 1, m_tile * Cfg::kImg, -1);
+          if (rank == 0) mbar_expect_tx(full_bar(stage), CL * Cfg::kStageBytes);
+          if (CL == 1)
+            tma_load_4d(a_dst, &p.a_map, full_bar(stage), ch * 64, dx - 1, m_tile * Cfg::kImg, -1);
+          else
+            tma_load_4d_pair(a_dst, &p.a_map, full_bar(stage), ch * 64, dx - 1, m_tile * Cfg::kImg, -1);
           if (!BRES) {
-            for (int dy = 0; dy < 3; ++dy)
-              tma_load_2d(a_dst + Cfg::kABytes + dy * Cfg::kBTile, &p.b_map, full_bar(stage),
-                          (dy * 3 + dx) * Cin + ch * 64, 0);
+            for (int dy = 0; dy < 3; ++dy) {
+              if (CL == 1)
+                tma_load_2d(a_dst + Cfg::kABytes + dy * Cfg::kBTile, &p.b_map, full_bar(stage),
+                            (dy * 3 + dx) * Cin + ch * 64, 0);
+              else
+                tma_load_2d_pair(a_dst + Cfg::kABytes + dy * Cfg::kBTile, &p.b_map, full_bar(stage),
+                                 (dy * 3 + dx) * Cin + ch * 64, b_row);
+            }
           }
           if (++stage == Cfg::kStages) { stage = 0; phase ^= 1u; }
         }
       }
     }
   } else if (warp == 1) {
-    if (lane == 0) {
-      constexpr uint32_t idesc = umma_idesc_bf16(128, BN);
+    if (lane == 0 && rank == 0) {
+      constexpr uint32_t idesc = umma_idesc_bf16(128 * CL, BN);
       if (BRES) mbar_wait(bres_bar, 0);
       int stage = 0, acc = 0;
       uint32_t phase = 0, acc_phase = 0;
-      for (int mi = blockIdx.x; mi < p.num_m_tiles; mi += gridDim.x) {
-        const int m_tile = p.reverse ? p.num_m_tiles - 1 - mi : mi;
+      for (int gi = first; gi < m_groups; gi += step_g) {
         mbar_wait(tempty_bar(acc), acc_phase ^ 1u);
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + (uint32_t)(acc * BN);
@@ -138,14 +166,21 @@ conv_halo_kernel(const __grid_constant__ HaloParams p) {
                                         : a_src + Cfg::kABytes + dy * Cfg::kBTile;
             const uint64_t b_desc = umma_desc_sw128(b_src);
 #pragma unroll
-            for (int k = 0; k < 4; ++k)
-              umma_bf16(d_tmem, a_desc + (uint64_t)(2 * k), b_desc + (uint64_t)(2 * k), idesc,
-                        (s > 0 || dy > 0 || k > 0) ? 1u : 0u);
+            for (int k = 0; k < 4; ++k) {
+              if (CL == 1)
+                umma_bf16(d_tmem, a_desc + (uint64_t)(2 * k), b_desc + (uint64_t)(2 * k), idesc,
+                          (s > 0 || dy > 0 || k > 0) ? 1u : 0u);
+              else
+                umma_bf16_pair(d_tmem, a_desc + (uint64_t)(2 * k), b_desc + (uint64_t)(2 * k), idesc,
+                               (s > 0 || dy > 0 || k > 0) ? 1u : 0u);
+            }
           }
-          umma_commit(empty_bar(stage));
+          if (CL == 1) umma_commit(empty_bar(stage));
+          else umma_commit_pair(empty_bar(stage), kMask);
           if (++stage == Cfg::kStages) { stage = 0; phase ^= 1u; }
         }
-        umma_commit(tfull_bar(acc));
+        if (CL == 1) umma_commit(tfull_bar(acc));
+        else umma_commit_pair(tfull_bar(acc), kMask);
         acc ^= 1;
         if (acc == 0) acc_phase ^= 1u;
       }
@@ -161,8 +196,8 @@ conv_halo_kernel(const __grid_constant__ HaloParams p) {
     int acc = 0;
     uint32_t acc_phase = 0;
     int64_t q = 0;
-    for (int mi = blockIdx.x; mi < p.num_m_tiles; mi += gridDim.x) {
-      const int m_tile = p.reverse ? p.num_m_tiles - 1 - mi : mi;
+    for (int gi = first; gi < m_groups; gi += step_g) {
+      const int m_tile = tile_of(gi);
       const int64_t inst = (int64_t)m_tile * Cfg::kImg + img;
       const int64_t row = inst * (W * W) + oy * W + ox;
       mbar_wait(tfull_bar(acc), acc_phase);
@@ -179,7 +214,12 @@ conv_halo_kernel(const __grid_constant__ HaloParams p) {
         mbar_arrive(ebars.out_ready[s]);
       }
       tc_fence_before();
-      mbar_arrive(tempty_bar(acc));
+      if (CL == 1) {
+        mbar_arrive(tempty_bar(acc));
+      } else {
+        __syncwarp();
+        if (lane == 0) mbar_arrive_leader(tempty_bar(acc));
+      }
       acc ^= 1;
       if (acc == 0) acc_phase ^= 1u;
     }
@@ -188,11 +228,10 @@ conv_halo_kernel(const __grid_constant__ HaloParams p) {
     // epilogue DMA thread: tiles move as {64 ch, W, IMG, H} boxes of the {C, W, T, H} maps, i.e.
     // in accumulator row order
     int n_items = 0;
-    for (int mi = blockIdx.x; mi < p.num_m_tiles; mi += gridDim.x) ++n_items;
+    for (int gi = first; gi < m_groups; gi += step_g) ++n_items;
     auto coords = [&](int64_t q, int* c0, int* t0) {
       const int item = (int)(q / Cfg::kChunks), c = (int)(q % Cfg::kChunks);
-      const int mi = blockIdx.x + item * gridDim.x;
-      const int m_tile = p.reverse ? p.num_m_tiles - 1 - mi : mi;
+      const int m_tile = tile_of(first + item * step_g);
       *c0 = c * 64;
       *t0 = m_tile * Cfg::kImg;
     };
@@ -217,26 +256,29 @@ conv_halo_kernel(const __grid_constant__ HaloParams p) {
 
   tc_fence_before();
   __syncthreads();
+  if (CL > 1) cluster_sync_all();   // no CTA leaves while the pair's MMAs may still read its tiles
   if (warp == 1) {
     tc_fence_after();
-    tmem_dealloc(tmem_base, Cfg::kTmemCols);
+    if (CL == 1) tmem_dealloc(tmem_base, Cfg::kTmemCols);
+    else tmem_dealloc_pair(tmem_base, Cfg::kTmemCols);
   }
 }
 
-template <int BN, int W, int CCH, bool BRES>
+template <int BN, int W, int CCH, bool BRES, int CL>
 int launch_halo(const HaloParams& p, cudaStream_t st) {
-  using Cfg = HaloCfg<BN, W, CCH, BRES>;
+  using Cfg = HaloCfg<BN, W, CCH, BRES, CL>;
   static bool attr_done[64] = {false};
   int dev = 0;
   CS_CUDA(cudaGetDevice(&dev));
   if (dev >= 64 || !attr_done[dev]) {
-    CS_CUDA(cudaFuncSetAttribute(conv_halo_kernel<BN, W, CCH, BRES>,
+    CS_CUDA(cudaFuncSetAttribute(conv_halo_kernel<BN, W, CCH, BRES, CL>,
                                  cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg::kSmemBytes));
     if (dev < 64) attr_done[dev] = true;
   }
-  int grid = p.num_m_tiles < kNumSMs ? p.num_m_tiles : kNumSMs;
-  CS_CUDA(launch_pdl(conv_halo_kernel<BN, W, CCH, BRES>, dim3((unsigned)grid), dim3(kHaloThreads),
-                     Cfg::kSmemBytes, st, 1, p));
+  const int groups = (p.num_m_tiles + CL - 1) / CL;
+  const int clusters = groups < kNumSMs / CL ? groups : kNumSMs / CL;
+  CS_CUDA(launch_pdl(conv_halo_kernel<BN, W, CCH, BRES, CL>, dim3((unsigned)(clusters * CL)),
+                     dim3(kHaloThreads), Cfg::kSmemBytes, st, CL, p));
   return CS_OK;
 }
 
@@ -248,8 +290,13 @@ bool halo_supported(int W, int Cin, int Cout) {
 
 int launch_conv_halo(const HaloParams& p, int W, int Cin, cudaStream_t st) {
   if (p.num_m_tiles <= 0) return CS_OK;
-  if (W == 8 && Cin == 64) return launch_halo<64, 8, 1, true>(p, st);
-  if (W == 4 && Cin == 128) return launch_halo<128, 4, 2, false>(p, st);
+  if (p.cluster > 1) {
+    if (W == 8 && Cin == 64) return launch_halo<64, 8, 1, true, 2>(p, st);
+    if (W == 4 && Cin == 128) return launch_halo<128, 4, 2, false, 2>(p, st);
+  } else {
+    if (W == 8 && Cin == 64) return launch_halo<64, 8, 1, true, 1>(p, st);
+    if (W == 4 && Cin == 128) return launch_halo<128, 4, 2, false, 1>(p, st);
+  }
   set_error("launch_conv_halo: unsupported geometry W=%d Cin=%d", W, Cin);
   return CS_ERR_UNSUPPORTED;
 }

@@ -99,7 +99,8 @@ int make_mat_map_2d(CUtensorMap* map, const void* base, int64_t K, int64_t rows,
 // Stride-1 3x3 conv with y-halo tiles (conv_halo.cu): 8x8x64 and 4x4x128 stages.
 struct HaloParams {
   CUtensorMap a_map;  // make_act_map_halo
-  CUtensorMap b_map;  // [Cout][9*Cin] K-major, box {64, Cout}
+  CUtensorMap b_map;  // [Cout][9*Cin] K-major, box {64, Cout / cluster}
+  int cluster;        // 1, or 2: CTA pairs (tcgen05 cta_group::2), each CTA holds half of B
   int num_m_tiles;    // ceil(instances / (128 / (W*W)))
   int reverse;        // walk M tiles from the last to the first
   int64_t n_inst;     // instances that exist

@@ -33,7 +33,10 @@ bool env_is(const char* name, const char* value) {
   return e != nullptr && strcmp(e, value) == 0;
 }
 const bool g_snake = !env_is("CELLSEG_SNAKE", "0");          // alternate the tile walk per layer
-const int g_cluster = env_is("CELLSEG_CLUSTER", "2") ? 2 : 1;  // 2-CTA B multicast (no gain measured)
+// CTA pairs (tcgen05 cta_group::2, M = 256): on by default for the N >= 128 kernels
+// (layer-2 halo convs -10 %, dense / pointwise GEMMs -7 %); the N = 64 halo conv of layer 1 is
+// 14 % slower in pair mode and stays single-CTA.  CELLSEG_CLUSTER=1 turns pairs off.
+const int g_cluster = env_is("CELLSEG_CLUSTER", "1") ? 1 : 2;
 const bool g_disable_halo = env_is("CELLSEG_HALO", "0");     // diagnostics: generic kernel only
 const bool g_force_cuda_core_stem = env_is("CELLSEG_STEM", "cuda");
 // Residual stream: bf16 by default.  CELLSEG_RESIDUAL=hilo carries a second bf16 tensor
@@ -309,7 +312,7 @@ int plan_conv(const ConvGeom& g, const float* w_oihw, const float* bias, const C
   CS_CUDA(cudaMemcpy(pc.d_B, B.data(), B.size() * sizeof(uint16_t), cudaMemcpyHostToDevice));
   CS_CUDA(cudaMalloc(&pc.d_bias, bias_full.size() * sizeof(float)));
   CS_CUDA(cudaMemcpy(pc.d_bias, bias_full.data(), bias_full.size() * sizeof(float), cudaMemcpyHostToDevice));
-  pc.p.cluster = g_cluster;
+  pc.p.cluster = pc.BN >= 128 ? g_cluster : 1;   // pairs do not pay off at N = 64
   rc = make_mat_map_2d(&pc.p.b_map, pc.d_B, K_cat, pc.p.n_total, K_cat, pc.BN / pc.p.cluster);
   if (rc != CS_OK) { free_planned(pc); return rc; }
   pc.p.bias = pc.d_bias;
@@ -317,7 +320,8 @@ int plan_conv(const ConvGeom& g, const float* w_oihw, const float* bias, const C
       halo_supported(g.Wi, g.Cin, g.Cout) && !g_disable_halo) {
     rc = make_act_map_halo(&pc.hp.a_map, in_hi, g.Cin, g.Wi, g.Hi, b_pad, 1);
     if (rc != CS_OK) { free_planned(pc); return rc; }
-    rc = make_mat_map_2d(&pc.hp.b_map, pc.d_B, K_cat, pc.p.n_total, K_cat, pc.BN);
+    pc.hp.cluster = pc.BN >= 128 ? g_cluster : 1;
+    rc = make_mat_map_2d(&pc.hp.b_map, pc.d_B, K_cat, pc.p.n_total, K_cat, pc.BN / pc.hp.cluster);
     if (rc != CS_OK) { free_planned(pc); return rc; }
     pc.hp.bias = pc.d_bias;
     pc.halo = true;
