@@ -32,7 +32,12 @@ struct Kept {
 __device__ __forceinline__ Kept kept_ranges(int64_t s, int64_t T, int64_t N, int64_t k) {
   Kept r{0, 0, 0, 0};
   if (T <= 0 || N <= 0) return r;
-  int64_t kp = k % N;
+  int64_t kp = k < N ? k : k % N;   // (the 64-bit division is ~100 instructions; k < N almost always)
+  if (s + T + kp <= N) {            // no wrap-around reaches this bag: the top min(k', T) ranks
+    const int t = (int)T, c = kp < T ? (int)kp : t;
+    r.a1 = t - c; r.b1 = t; r.a2 = t; r.b2 = t;
+    return r;
+  }
   int64_t J0 = N - kp - s;
   int64_t a1 = T - kp > 0 ? T - kp : 0;
   int64_t b1 = T < J0 ? T : J0;

@@ -64,7 +64,7 @@ select_fast_kernel(Segs segs, const float* __restrict__ prob, EmitArgs ea, int m
   const int n1 = kr.b1 - kr.a1, n2 = kr.b2 - kr.a2, n = n1 + n2;
   if (n == 0) return;                                     // all conditions block-uniform
   auto decline = [&]() {
-    if (tid == 0) fb_list[atomicAdd(fb_count, 1)] = b;
+    if (tid == 0) fb_list[atomicAdd(fb_count, 1)] = b;   // (fb_count was zeroed two stream ops earlier)
   };
   const bool suffix = (n2 == 0 && kr.b1 == T) || (n1 == 0 && kr.b2 == T);
   if (!suffix || n > kThreads || T > max_T) {
@@ -155,7 +155,10 @@ select_fast_kernel(Segs segs, const float* __restrict__ prob, EmitArgs ea, int m
     return;
   }
 
-  // 3. rank by counting; the n largest go to slots o0 + (n-1-rank): ascending (prob, index)
+  // 3. rank by counting; the n largest go to slots o0 + (n-1-rank): ascending (prob, index).
+  // The offsets come from the scan kernel this one was launched behind (programmatic dependent
+  // launch): everything above overlapped with it.
+  asm volatile("griddepcontrol.wait;" ::: "memory");
   const int64_t o0 = ea.out_offsets[b];
   const uint8_t pl = ea.labels[b] == 0 ? 0 : 1;
   for (int j = tid; j < count; j += kThreads) {
@@ -190,8 +193,8 @@ int launch_select_fast(const Segs& segs, const float* prob, const EmitArgs& ea, 
                                  (40000 + 4) * 4));
     if (dev < 64) attr_done[dev] = true;
   }
-  select_fast_kernel<<<segs.n_bags, kThreads, smem, st>>>(segs, prob, ea, (int)max_T, fb_count, fb_list);
-  CS_LAUNCH_CHECK();
+  CS_CUDA(launch_pdl(select_fast_kernel, dim3((unsigned)segs.n_bags), dim3(kThreads), smem, st, 1, segs, prob,
+                     ea, (int)max_T, fb_count, fb_list));
   *handled = true;
   return CS_OK;
 }

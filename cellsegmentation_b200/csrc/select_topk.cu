@@ -67,24 +67,32 @@ rank_count_kernel(Segs segs, const float* __restrict__ prob, float thr,
 // scanned by warp 0 and added in a second coalesced pass.
 __global__ void __launch_bounds__(1024)
 exclusive_scan_kernel(int64_t* __restrict__ data, int n) {
+  // dependents (the emit kernels) only need the offsets for their final stores: let them start
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
   __shared__ int64_t warp_tot[32];
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const int per = ((n + 31) / 32 + 31) / 32 * 32;        // slice length, multiple of 32
-  const int lo = min(warp * per, n), hi = min(lo + per, n);
-  int64_t carry = 0;
-  for (int base = lo; base < hi; base += 32) {
-    const int i = base + lane;
-    const int64_t v = i < hi ? data[i] : 0;
-    int64_t x = v;
+  // thread t owns the contiguous entries [t*per, (t+1)*per): independent loads, one block scan of
+  // the 1024 partial sums, then the running prefixes are written back
+  const int per = (n + 1023) / 1024;
+  const int lo = min(tid * per, n), hi = min(lo + per, n);
+  constexpr int kRegs = 24;                               // entries kept in registers (n <= 24 576)
+  int64_t v[kRegs];
+  int64_t sum = 0;
+  if (per <= kRegs) {                                     // all loads in flight at once
 #pragma unroll
-    for (int o = 1; o < 32; o <<= 1) {
-      const int64_t y = __shfl_up_sync(0xffffffffu, x, o);
-      if (lane >= o) x += y;
-    }
-    if (i < hi) data[i] = carry + x - v;                  // exclusive within the slice
-    carry += __shfl_sync(0xffffffffu, x, 31);
+    for (int k = 0; k < kRegs; ++k) v[k] = lo + k < hi ? data[lo + k] : 0;
+#pragma unroll
+    for (int k = 0; k < kRegs; ++k) sum += v[k];
+  } else {
+    for (int i = lo; i < hi; ++i) sum += data[i];
   }
-  if (lane == 0) warp_tot[warp] = carry;
+  int64_t x = sum;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    const int64_t y = __shfl_up_sync(0xffffffffu, x, o);
+    if (lane >= o) x += y;
+  }
+  if (lane == 31) warp_tot[warp] = x;
   __syncthreads();
   if (warp == 0) {
     const int64_t w = warp_tot[lane];
@@ -94,13 +102,24 @@ exclusive_scan_kernel(int64_t* __restrict__ data, int n) {
       const int64_t y = __shfl_up_sync(0xffffffffu, xs, o);
       if (lane >= o) xs += y;
     }
-    warp_tot[lane] = xs - w;                              // exclusive prefix of the slice totals
+    warp_tot[lane] = xs - w;                              // exclusive prefix of the warp totals
     if (lane == 31) data[n] = xs;
   }
   __syncthreads();
-  const int64_t off = warp_tot[warp];
-  if (off != 0)
-    for (int i = lo + lane; i < hi; i += 32) data[i] += off;
+  int64_t run = warp_tot[warp] + x - sum;                 // exclusive prefix of this thread's entries
+  if (per <= kRegs) {
+#pragma unroll
+    for (int k = 0; k < kRegs; ++k) {
+      if (lo + k < hi) data[lo + k] = run;
+      run += v[k];
+    }
+  } else {
+    for (int i = lo; i < hi; ++i) {
+      const int64_t t = data[i];
+      data[i] = run;
+      run += t;
+    }
+  }
 }
 
 // ---- per-bag sort + emit ----------------------------------------------------
@@ -275,6 +294,9 @@ int cs_select_topk(const float* prob, const int64_t* seg_offsets, int64_t unifor
              "cs_select_topk: tiles_per_pos, topk_neg and capacity must be >= 0");
   cudaStream_t st = cs::as_stream(stream);
   Segs segs{seg_offsets, uniform_T, n_bags};
+  int32_t* fb_count = static_cast<int32_t*>(workspace);
+  int32_t* fb_list = fb_count + 64;
+  if (!g_disable_fast) CS_CUDA(cudaMemsetAsync(fb_count, 0, sizeof(int32_t), st));
   select_count_kernel<<<cs::ceil_div(n_bags, 256), 256, 0, st>>>(segs, labels, tiles_per_pos,
                                                                  topk_neg, sel_offsets_out);
   CS_LAUNCH_CHECK();
@@ -289,11 +311,8 @@ int cs_select_topk(const float* prob, const int64_t* seg_offsets, int64_t unifor
   ea.out_offsets = sel_offsets_out;
   ea.capacity = capacity;
   // register-resident warp-per-bag path first; bags it declines are flagged and ordered exactly
-  int32_t* fb_count = static_cast<int32_t*>(workspace);
-  int32_t* fb_list = fb_count + 64;
   bool handled = false;
   if (!g_disable_fast) {
-    CS_CUDA(cudaMemsetAsync(fb_count, 0, sizeof(int32_t), st));
     rc = launch_select_fast(segs, prob, ea, uniform_T, fb_count, fb_list, st, &handled);
     if (rc != CS_OK) return rc;
   }

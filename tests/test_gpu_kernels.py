@@ -150,6 +150,29 @@ def test_select_topk_random_uniform(cuda, T, n_bags):
         assert np.array_equal(pl.cpu().numpy(), oselect.pseudo_labels(tid, lab, want))
 
 
+@pytest.mark.parametrize("T,n_bags,misalign", [(3025, 2500, 0), (225, 6000, 0), (3025, 700, 3), (784, 1900, 1)])
+def test_select_topk_many_bags_ring_wraps(cuda, T, n_bags, misalign):
+    """Enough bags per SM for the streaming ring to wrap several times; LYSTO-like labels (30 % zeros,
+    geometric counts up to 300: n <= 32, 32 < n <= 128 and declined n > 128 all occur), ties, and a
+    probability array whose start / end are not 16-byte aligned (clipped copy spans)."""
+    ops = _ops()
+    rng = np.random.default_rng(T + n_bags)
+    p = rng.uniform(0, 1, T * n_bags).astype(np.float32)
+    p[rng.uniform(size=p.size) < 0.02] = np.float32(1.0)
+    p[:T] = np.float32(0.5)                                        # one all-tied bag -> heavy-tie decline
+    lab = np.minimum(rng.geometric(1.0 / 8.0, n_bags), 300).astype(np.int32)
+    lab[rng.uniform(size=n_bags) < 0.3] = 0
+    lab[5] = 200
+    tid = np.repeat(np.arange(n_bags), T)
+    want = oselect.sample_indices(tid, lab, p, 1, 30)
+    buf = torch.zeros(p.size + 8, dtype=torch.float32, device=cuda)
+    view = buf[misalign:misalign + p.size]
+    view.copy_(torch.from_numpy(p))
+    idx, pl, _ = ops.select_topk(view, torch.from_numpy(lab).to(cuda), n_bags, T, 1, 30)
+    assert np.array_equal(idx.cpu().numpy().astype(np.int64), want)
+    assert np.array_equal(pl.cpu().numpy(), oselect.pseudo_labels(tid, lab, want))
+
+
 def test_select_topk_ragged_with_empty_bags(cuda):
     ops = _ops()
     rng = np.random.default_rng(9)
