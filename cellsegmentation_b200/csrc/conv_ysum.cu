@@ -1,0 +1,305 @@
+// K2c: the 8x8 x 64-channel stride-1 3x3 convolutions of layer 1 with the vertical taps summed
+// in the epilogue ("y-sum" form).
+//
+// Reference: BasicBlock conv1 / conv2 of layer1 (model/resnet.py:19-23, 28-43).
+//
+// With 64 output channels an MMA is N = 64 wide and the stage is bound by operand reads from
+// shared memory (~66 B/clk measured): every 128 x 16 A slice (4 KB) is fetched for 2 KB of B,
+// once per tap -- 36 MMAs and 216 KB of operand reads per M tile in the halo kernel.  Here the
+// three vertical taps of a kernel column share ONE MMA: the B tile of column dx stacks
+// W[dy = 0..2][dx] along N (N = 192), so an A slice is read once for three taps:
+//     D_dy[r][co] = sum_dx sum_ci  x[r shifted by dx][ci] * W[co][ci][dy][dx]      (12 MMAs, 120 KB)
+//     out[y][x]   = D_0[y-1][x] + D_1[y][x] + D_2[y+1][x]                          (epilogue)
+// The horizontal shift is still a TMA box fetched at x + dx - 1 (zero fill = padding).  Rows are
+// in natural order r = 64*img + 8*y + x, so tcgen05.ld.16x256b hands a thread the four image
+// rows of its TMEM lane quarter at one x: the vertical sum is register arithmetic, and only the
+// rows y = 3 | 4 between the two lane quarters of an image are exchanged through shared memory
+// (8 KB per tile).  Bias, residual, ReLU and the bf16 (hi / lo) split follow in place in the
+// swizzled staging tile that the DMA warp moves with TMA, as in gemm_epilogue.cuh.
+//
+// Warp roles (352 threads, one CTA per SM, persistent over M tiles of two instances):
+//   warp 0 TMA producer   warp 1 TMEM alloc + MMA issue   warps 2-9 epilogue (TMEM lane quarter
+//   = warp % 4, channel half = (warp - 2) / 4)   warp 10 epilogue DMA
+#include "fwd.cuh"
+#include "gemm_epilogue.cuh"
+
+namespace cs {
+namespace {
+
+constexpr int kThreads = 352;
+constexpr int kMaxStages = 6;                      // 6 when only bf16 tiles are staged, else 4
+constexpr uint32_t kABytes = 128 * 128;            // one shifted box: 128 rows x 64 ch bf16
+constexpr uint32_t kBTile = 192 * 128;             // [dy*64 + co][64 ci] of one dx
+constexpr uint32_t kBBytes = 3 * kBTile;           // 72 KB resident
+constexpr uint32_t kXchBytes = 2 * 8 * 1024;       // 2 tile parities x 8 warps x 1 KB
+// layout: [stages x A][B resident][2 staging sets][exchange][barriers]; stages * 16 KB + 2 sets
+// is 128 KB either way (4 + 2 x 32 KB with hi/lo tiles, 6 + 2 x 16 KB with bf16 only)
+constexpr uint32_t kOffB = 4 * kABytes + kEpiStagingBytes;        // start of the resident weights
+constexpr uint32_t kOffXch = kOffB + kBBytes;
+constexpr uint32_t kOffBars = kOffXch + kXchBytes;
+constexpr uint32_t kSmemBytes = kOffBars + 256 + 1024;
+constexpr uint32_t kAccCols = 256;                 // accumulator stage pitch in TMEM columns
+static_assert(kSmemBytes <= 227 * 1024, "shared memory budget");
+
+__device__ __forceinline__ void named_bar(int id, int n) {
+  asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(n) : "memory");
+}
+__device__ __forceinline__ uint32_t lds32(uint32_t addr) {
+  uint32_t v;
+  asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(addr));
+  return v;
+}
+__device__ __forceinline__ void sts32(uint32_t addr, uint32_t v) {
+  asm volatile("st.shared.u32 [%0], %1;" ::"r"(addr), "r"(v) : "memory");
+}
+
+__global__ void __launch_bounds__(kThreads, 1)
+conv_ysum_kernel(const __grid_constant__ YsumParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t raw = smem_u32(smem_raw);
+  const uint32_t base = (raw + 1023u) & ~1023u;
+  uint8_t* base_ptr = smem_raw + (base - raw);
+  const bool lo_tiles = p.res_lo != nullptr || p.out_lo != nullptr;
+  const int kStages = lo_tiles ? 4 : kMaxStages;
+  const uint32_t set_bytes = lo_tiles ? kEpiSetBytes : kEpiTileBytes;
+  const uint32_t bres = base + kOffB;
+  const uint32_t staging = base + kStages * kABytes;
+  const uint32_t bar_base = base + kOffBars;
+  auto full_bar = [&](int s) { return bar_base + 8u * s; };
+  auto empty_bar = [&](int s) { return bar_base + 8u * (kMaxStages + s); };
+  auto tfull_bar = [&](int a) { return bar_base + 8u * (2 * kMaxStages + a); };
+  auto tempty_bar = [&](int a) { return bar_base + 8u * (2 * kMaxStages + 2 + a); };
+  const uint32_t bres_bar = bar_base + 8u * (2 * kMaxStages + 4);
+  EpiBars ebars;
+  for (int s = 0; s < 2; ++s) {
+    ebars.res_full[s] = bar_base + 8u * (2 * kMaxStages + 5 + s);
+    ebars.out_ready[s] = bar_base + 8u * (2 * kMaxStages + 7 + s);
+  }
+  volatile uint32_t* tmem_slot =
+      reinterpret_cast<volatile uint32_t*>(base_ptr + kOffBars + 8 * (2 * kMaxStages + 9));
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+  if (warp == 0 && lane == 0) {
+    for (int s = 0; s < kStages; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
+    for (int a = 0; a < 2; ++a) { mbar_init(tfull_bar(a), 1); mbar_init(tempty_bar(a), kEpiThreads); }
+    mbar_init(bres_bar, 1);
+    epi_bars_init(ebars);
+    fence_barrier_init();
+    prefetch_tmap(&p.a_map);
+    prefetch_tmap(&p.b_map);
+  }
+  if (warp == 1) tmem_alloc(smem_u32((const void*)tmem_slot), 512);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  pdl_launch_dependents();
+
+  if (warp == 0) {
+    if (lane == 0) {
+      // weights are constants: fetch them while the previous layer still drains
+      mbar_expect_tx(bres_bar, kBBytes);
+      for (int dx = 0; dx < 3; ++dx) tma_load_2d(bres + dx * kBTile, &p.b_map, bres_bar, 0, dx * 192);
+      pdl_wait();
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int mi = blockIdx.x; mi < p.num_m_tiles; mi += gridDim.x) {
+        const int m_tile = p.reverse ? p.num_m_tiles - 1 - mi : mi;
+        for (int dx = 0; dx < 3; ++dx) {
+          mbar_wait(empty_bar(stage), phase ^ 1u);
+          mbar_expect_tx(full_bar(stage), kABytes);
+          tma_load_4d(base + stage * kABytes, &p.a_map, full_bar(stage), 0, dx - 1, 0, m_tile * 2);
+          if (++stage == kStages) { stage = 0; phase ^= 1u; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      constexpr uint32_t idesc = umma_idesc_bf16(128, 192);
+      mbar_wait(bres_bar, 0);
+      int stage = 0, acc = 0;
+      uint32_t phase = 0, acc_phase = 0;
+      for (int mi = blockIdx.x; mi < p.num_m_tiles; mi += gridDim.x) {
+        mbar_wait(tempty_bar(acc), acc_phase ^ 1u);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + (uint32_t)(acc * kAccCols);
+        for (int dx = 0; dx < 3; ++dx) {
+          mbar_wait(full_bar(stage), phase);
+          tc_fence_after();
+          const uint64_t a_desc = umma_desc_sw128(base + stage * kABytes);
+          const uint64_t b_desc = umma_desc_sw128(bres + dx * kBTile);
+#pragma unroll
+          for (int k = 0; k < 4; ++k)
+            umma_bf16(d_tmem, a_desc + (uint64_t)(2 * k), b_desc + (uint64_t)(2 * k), idesc,
+                      (dx > 0 || k > 0) ? 1u : 0u);
+          umma_commit(empty_bar(stage));
+          if (++stage == kStages) { stage = 0; phase ^= 1u; }
+        }
+        umma_commit(tfull_bar(acc));
+        acc ^= 1;
+        if (acc == 0) acc_phase ^= 1u;
+      }
+    }
+  } else if (warp < 2 + kEpiWarps) {
+    pdl_wait();
+    const int quad = warp & 3;                 // TMEM lanes 32*quad ..: image quad/2, rows y0 .. y0+3
+    const int half = (warp - 2) >> 2;          // channels 32*half .. 32*half+31
+    const int g = lane >> 2, t = lane & 3;     // x, channel-pair slot
+    const bool upper = (quad & 1) == 0;        // owns image rows 0..3 (else 4..7)
+    const int pair_bar = 1 + (quad >> 1) * 2 + half;          // named barrier of the two quarters
+    const int partner = (warp - 2) ^ 1;                        // same image, same channel half
+    float bias_r[4][2];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      bias_r[i][0] = p.bias[half * 32 + 8 * i + 2 * t];
+      bias_r[i][1] = p.bias[half * 32 + 8 * i + 2 * t + 1];
+    }
+    const bool rh = p.res_hi != nullptr, rl = p.res_lo != nullptr;
+    const bool oh = p.out_hi != nullptr, ol = p.out_lo != nullptr;
+    int acc = 0;
+    uint32_t acc_phase = 0;
+    int64_t q = 0;
+    for (int mi = blockIdx.x; mi < p.num_m_tiles; mi += gridDim.x, ++q) {
+      const int m_tile = p.reverse ? p.num_m_tiles - 1 - mi : mi;
+      mbar_wait(tfull_bar(acc), acc_phase);
+      tc_fence_after();
+      // R[dy][w][4i + 2h + e]: image row y0 + 2w + h, column x = g, channel 32*half + 8i + 2t + e
+      uint32_t R[3][2][16];
+#pragma unroll
+      for (int dy = 0; dy < 3; ++dy)
+#pragma unroll
+        for (int w = 0; w < 2; ++w)
+          tmem_ld_16x256b_x4(tmem_base + ((uint32_t)(quad * 32 + w * 16) << 16) +
+                                 (uint32_t)(acc * kAccCols + dy * 64 + half * 32),
+                             R[dy][w]);
+      tmem_ld_wait();
+      tc_fence_before();
+      mbar_arrive(tempty_bar(acc));
+      acc ^= 1;
+      if (acc == 0) acc_phase ^= 1u;
+      auto D = [&](int dy, int yy, int i, int e) -> float {
+        return __uint_as_float(R[dy][yy >> 1][4 * i + 2 * (yy & 1) + e]);
+      };
+      // rows 3 | 4 of an image live in different lane quarters: exchange them (fp32, 8 per thread)
+      float* xw = reinterpret_cast<float*>(base_ptr + kOffXch) + ((q & 1) * 8 + (warp - 2)) * 256 + lane * 8;
+      const float* xr = reinterpret_cast<const float*>(base_ptr + kOffXch) + ((q & 1) * 8 + partner) * 256 + lane * 8;
+      {
+        float4 e0, e1;
+        if (upper) {   // D_0 of row 3 feeds row 4 of the lower quarter
+          e0 = make_float4(D(0, 3, 0, 0), D(0, 3, 0, 1), D(0, 3, 1, 0), D(0, 3, 1, 1));
+          e1 = make_float4(D(0, 3, 2, 0), D(0, 3, 2, 1), D(0, 3, 3, 0), D(0, 3, 3, 1));
+        } else {       // D_2 of row 4 feeds row 3 of the upper quarter
+          e0 = make_float4(D(2, 0, 0, 0), D(2, 0, 0, 1), D(2, 0, 1, 0), D(2, 0, 1, 1));
+          e1 = make_float4(D(2, 0, 2, 0), D(2, 0, 2, 1), D(2, 0, 3, 0), D(2, 0, 3, 1));
+        }
+        reinterpret_cast<float4*>(xw)[0] = e0;
+        reinterpret_cast<float4*>(xw)[1] = e1;
+      }
+      named_bar(pair_bar, 64);
+      const float4 i0 = reinterpret_cast<const float4*>(xr)[0], i1 = reinterpret_cast<const float4*>(xr)[1];
+      const float imp[8] = {i0.x, i0.y, i0.z, i0.w, i1.x, i1.y, i1.z, i1.w};
+
+      const int s = (int)(q & 1);
+      mbar_wait(ebars.res_full[s], (uint32_t)((q >> 1) & 1));
+      const uint32_t stg = staging + s * set_bytes;
+#pragma unroll
+      for (int yy = 0; yy < 4; ++yy) {
+        const int row = quad * 32 + yy * 8 + g;          // row of the 128-row tile; row & 7 == g
+        const uint32_t row_addr = stg + (uint32_t)row * 128u + 4u * t;
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          float v[2];
+#pragma unroll
+          for (int e = 0; e < 2; ++e) {
+            float above, below;                           // D_0 of row y-1, D_2 of row y+1
+            if (yy > 0) above = D(0, yy - 1, i, e);
+            else above = upper ? 0.f : imp[2 * i + e];
+            if (yy < 3) below = D(2, yy + 1, i, e);
+            else below = upper ? imp[2 * i + e] : 0.f;
+            v[e] = above + D(1, yy, i, e) + below + bias_r[i][e];
+          }
+          const uint32_t addr = row_addr + ((((uint32_t)(half * 4 + i)) ^ (uint32_t)g) << 4);
+          if (rh) { const uint32_t r2 = lds32(addr); v[0] += bf16_lo_f(r2); v[1] += bf16_hi_f(r2); }
+          if (rl) { const uint32_t r2 = lds32(addr + kEpiTileBytes); v[0] += bf16_lo_f(r2); v[1] += bf16_hi_f(r2); }
+          if (p.relu) { v[0] = fmaxf(v[0], 0.f); v[1] = fmaxf(v[1], 0.f); }
+          if (p.out_f32 != nullptr) {
+            const int64_t grow = (int64_t)m_tile * 128 + row;
+            if (grow < p.n_inst * 64)
+              *reinterpret_cast<float2*>(p.out_f32 + grow * 64 + half * 32 + 8 * i + 2 * t) = make_float2(v[0], v[1]);
+          }
+          const uint32_t hi = pack_bf16x2(v[0], v[1]);
+          if (oh) sts32(addr, hi);
+          if (ol) sts32(addr + kEpiTileBytes, pack_bf16x2(v[0] - bf16_lo_f(hi), v[1] - bf16_hi_f(hi)));
+        }
+      }
+      fence_async_shared();
+      mbar_arrive(ebars.out_ready[s]);
+    }
+  } else if (lane == 0) {
+    pdl_wait();
+    int n_items = 0;
+    for (int mi = blockIdx.x; mi < p.num_m_tiles; mi += gridDim.x) ++n_items;
+    auto row_of = [&](int64_t q) {
+      const int mi = blockIdx.x + (int)q * gridDim.x;
+      return (p.reverse ? p.num_m_tiles - 1 - mi : mi) * 128;
+    };
+    const bool rh = p.res_hi != nullptr, rl = p.res_lo != nullptr;
+    const bool oh = p.out_hi != nullptr, ol = p.out_lo != nullptr;
+    epi_dma_loop(
+        (int64_t)n_items, staging, set_bytes, ebars,
+        (rh ? kEpiTileBytes : 0u) + (rl ? kEpiTileBytes : 0u), oh || ol,
+        [&](int64_t q, uint32_t set, uint32_t bar) {
+          if (rh) tma_load_2d(set, &p.res_hi_map, bar, 0, row_of(q));
+          if (rl) tma_load_2d(set + kEpiTileBytes, &p.res_lo_map, bar, 0, row_of(q));
+        },
+        [&](int64_t q, uint32_t set) {
+          if (oh) tma_store_2d(&p.out_hi_map, set, 0, row_of(q));
+          if (ol) tma_store_2d(&p.out_lo_map, set + kEpiTileBytes, 0, row_of(q));
+        });
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, 512);
+  }
+}
+
+}  // namespace
+
+bool ysum_supported(int W, int Cin, int Cout) { return W == 8 && Cin == 64 && Cout == 64; }
+
+// Host: [dx*192 + dy*64 + co][ci] bf16 from folded OIHW fp32 weights [64][64][3][3].
+void pack_ysum_weights(const float* w_oihw, uint16_t* out) {
+  auto rn = [](float f) {
+    uint32_t u;
+    memcpy(&u, &f, 4);
+    uint32_t lsb = (u >> 16) & 1u;
+    u += 0x7fffu + lsb;
+    return (uint16_t)(u >> 16);
+  };
+  for (int dx = 0; dx < 3; ++dx)
+    for (int dy = 0; dy < 3; ++dy)
+      for (int co = 0; co < 64; ++co)
+        for (int ci = 0; ci < 64; ++ci)
+          out[((dx * 192) + dy * 64 + co) * 64 + ci] = rn(w_oihw[((co * 64 + ci) * 3 + dy) * 3 + dx]);
+}
+
+int launch_conv_ysum(const YsumParams& p, cudaStream_t st) {
+  if (p.num_m_tiles <= 0) return CS_OK;
+  static bool attr_done[64] = {false};
+  int dev = 0;
+  CS_CUDA(cudaGetDevice(&dev));
+  if (dev >= 64 || !attr_done[dev]) {
+    CS_CUDA(cudaFuncSetAttribute(conv_ysum_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                 (int)kSmemBytes));
+    if (dev < 64) attr_done[dev] = true;
+  }
+  const int grid = p.num_m_tiles < kNumSMs ? p.num_m_tiles : kNumSMs;
+  CS_CUDA(launch_pdl(conv_ysum_kernel, dim3((unsigned)grid), dim3(kThreads), kSmemBytes, st, 1, p));
+  return CS_OK;
+}
+
+}  // namespace cs

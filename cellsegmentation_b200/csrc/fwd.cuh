@@ -119,6 +119,26 @@ int launch_conv_halo(const HaloParams& p, int W, int Cin, cudaStream_t st);
 int make_act_map_halo(CUtensorMap* map, const void* base, int C, int W, int H, int64_t T,
                       int halo /* 1: box H+2 rows for the A operand, 0: H rows for epilogue tiles */);
 
+// Layer-1 convs in y-sum form (conv_ysum.cu): 8x8 images, 64 -> 64 channels, stride 1.
+struct YsumParams {
+  CUtensorMap a_map;  // make_act_map_4d {C, W, H, T}, box {64, 8, 8, 2}
+  CUtensorMap b_map;  // [3*192][64] from pack_ysum_weights, box {64, 192}
+  int num_m_tiles;    // ceil(instances / 2)
+  int reverse;
+  int64_t n_inst;
+  const float* bias;
+  const __nv_bfloat16* res_hi;
+  const __nv_bfloat16* res_lo;
+  __nv_bfloat16* out_hi;
+  __nv_bfloat16* out_lo;
+  float* out_f32;
+  int relu;
+  CUtensorMap res_hi_map, res_lo_map, out_hi_map, out_lo_map;   // [rows][64], box {64, 128}
+};
+bool ysum_supported(int W, int Cin, int Cout);
+void pack_ysum_weights(const float* w_oihw, uint16_t* out /* [576 * 64] */);
+int launch_conv_ysum(const YsumParams& p, cudaStream_t st);
+
 struct StemArgs {
   // source A: u8 images + uniform grid
   const uint8_t* img;

@@ -44,6 +44,11 @@ const bool g_force_cuda_core_stem = env_is("CELLSEG_STEM", "cuda");
 // (ResNet-34 0.0101 -> 0.0098) while the block epilogues move twice the bytes (-11 % throughput).
 const bool g_no_lo = !env_is("CELLSEG_RESIDUAL", "hilo");
 const int g_xbufs = g_no_lo ? 2 : 4;
+// Layer 1 in y-sum form (conv_ysum.cu: three vertical taps per N = 192 MMA, summed in the
+// epilogue).  Halves the operand reads of the MMAs at the price of a three times larger
+// accumulator read-out: 102 vs 108 us per 18 944 instances against the halo kernel and +2 %
+// sustained throughput (less power).  CELLSEG_YSUM=0 puts layer 1 back on the halo kernel.
+const bool g_disable_ysum = env_is("CELLSEG_YSUM", "0");
 const bool g_im2col_stem = env_is("CELLSEG_STEM", "im2col");   // first tensor-core stem (stem_tc.cu)
 
 struct ConvW {
@@ -72,6 +77,9 @@ struct PlannedConv {
   bool halo = false;   // stride-1 3x3 on 8x8x64 / 4x4x128: y-halo kernel (conv_halo.cu)
   HaloParams hp;
   int halo_W = 0, halo_Cin = 0;
+  bool ysum = false;   // layer-1 y-sum kernel (conv_ysum.cu)
+  YsumParams yp;
+  uint16_t* d_B2 = nullptr;
   __nv_bfloat16* d_B = nullptr;
   float* d_bias = nullptr;
   uint32_t* d_ext_steps = nullptr;
@@ -81,6 +89,8 @@ void free_planned(PlannedConv& pc) {
   if (pc.d_B) cudaFree(pc.d_B);
   if (pc.d_bias) cudaFree(pc.d_bias);
   if (pc.d_ext_steps) cudaFree(pc.d_ext_steps);
+  if (pc.d_B2) cudaFree(pc.d_B2);
+  pc.d_B2 = nullptr;
   pc.d_B = nullptr;
   pc.d_bias = nullptr;
   pc.d_ext_steps = nullptr;
@@ -317,6 +327,18 @@ int plan_conv(const ConvGeom& g, const float* w_oihw, const float* bias, const C
   if (rc != CS_OK) { free_planned(pc); return rc; }
   pc.p.bias = pc.d_bias;
   if (!pc.dense && !gds && g.k == 3 && g.groups == 1 && g.stride == 1 && g.Hi == g.Wi &&
+      ysum_supported(g.Wi, g.Cin, g.Cout) && !g_disable_ysum) {
+    // layer 1: the shifted-box A map of this plan + weights regrouped per kernel column
+    std::vector<uint16_t> B2(576 * 64);
+    pack_ysum_weights(w_oihw, B2.data());
+    CS_CUDA(cudaMalloc(&pc.d_B2, B2.size() * sizeof(uint16_t)));
+    CS_CUDA(cudaMemcpy(pc.d_B2, B2.data(), B2.size() * sizeof(uint16_t), cudaMemcpyHostToDevice));
+    pc.yp.a_map = pc.p.a_map[0];
+    rc = make_mat_map_2d(&pc.yp.b_map, pc.d_B2, 64, 576, 64, 192);
+    if (rc != CS_OK) { free_planned(pc); return rc; }
+    pc.yp.bias = pc.d_bias;
+    pc.ysum = true;
+  } else if (!pc.dense && !gds && g.k == 3 && g.groups == 1 && g.stride == 1 && g.Hi == g.Wi &&
       halo_supported(g.Wi, g.Cin, g.Cout) && !g_disable_halo) {
     rc = make_act_map_halo(&pc.hp.a_map, in_hi, g.Cin, g.Wi, g.Hi, b_pad, 1);
     if (rc != CS_OK) { free_planned(pc); return rc; }
@@ -355,6 +377,19 @@ int finalize_io_maps(PlannedConv& pc, int64_t b_pad) {
 // Launches one planned convolution for `count` instances (pointers / relu taken from pc.p).
 int launch_planned(const PlannedConv& pc, int64_t count, float* out_f32, cudaStream_t st,
                    int reverse = 0) {
+  if (pc.ysum) {
+    YsumParams yp = pc.yp;
+    yp.res_hi = pc.p.res_hi; yp.res_lo = pc.p.res_lo;
+    yp.out_hi = pc.p.out_hi; yp.out_lo = pc.p.out_lo;
+    yp.res_hi_map = pc.p.res_hi_map; yp.res_lo_map = pc.p.res_lo_map;
+    yp.out_hi_map = pc.p.out_hi_map; yp.out_lo_map = pc.p.out_lo_map;
+    yp.out_f32 = out_f32;
+    yp.relu = pc.p.relu;
+    yp.n_inst = count;
+    yp.reverse = reverse;
+    yp.num_m_tiles = (int)ceil_div<int64_t>(count, 2);
+    return launch_conv_ysum(yp, st);
+  }
   if (pc.halo) {
     HaloParams hp = pc.hp;
     hp.res_hi = pc.p.res_hi; hp.res_lo = pc.p.res_lo;
