@@ -29,8 +29,8 @@ namespace {
 constexpr int kThreads = 352;
 constexpr int kMaxStages = 6;                      // 6 when only bf16 tiles are staged, else 4
 constexpr uint32_t kABytes = 128 * 128;            // one shifted box: 128 rows x 64 ch bf16
-constexpr uint32_t kBTile = 192 * 128;             // [dy*64 + co][64 ci] of one dx
-constexpr uint32_t kBBytes = 3 * kBTile;           // 72 KB resident
+constexpr uint32_t kBTileFull = 192 * 128;         // [dy*64 + co][64 ci] of one dx
+constexpr uint32_t kBBytes = 3 * kBTileFull;       // 72 KB resident (36 KB used by a pair member)
 constexpr uint32_t kXchBytes = 2 * 8 * 1024;       // 2 tile parities x 8 warps x 1 KB
 // layout: [stages x A][B resident][2 staging sets][exchange][barriers]; stages * 16 KB + 2 sets
 // is 128 KB either way (4 + 2 x 32 KB with hi/lo tiles, 6 + 2 x 16 KB with bf16 only)
@@ -53,8 +53,13 @@ __device__ __forceinline__ void sts32(uint32_t addr, uint32_t v) {
   asm volatile("st.shared.u32 [%0], %1;" ::"r"(addr), "r"(v) : "memory");
 }
 
+// CL = 2: CTA pairs (tcgen05 cta_group::2) as in conv_gemm.cu -- neighbouring M tiles, each CTA
+// holds its own A boxes and 96 of the 192 rows of every weight tile, the leader issues M = 256
+// MMAs for both.
+template <int CL>
 __global__ void __launch_bounds__(kThreads, 1)
 conv_ysum_kernel(const __grid_constant__ YsumParams p) {
+  constexpr uint32_t kBTile = kBTileFull / CL;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw = smem_u32(smem_raw);
   const uint32_t base = (raw + 1023u) & ~1023u;
@@ -79,19 +84,32 @@ conv_ysum_kernel(const __grid_constant__ YsumParams p) {
       reinterpret_cast<volatile uint32_t*>(base_ptr + kOffBars + 8 * (2 * kMaxStages + 9));
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int rank = CL > 1 ? (int)cluster_ctarank() : 0;
+  constexpr uint16_t kMask = (uint16_t)((1u << CL) - 1u);
+  // a cluster walks groups of CL neighbouring M tiles; CTA `rank` owns tile group * CL + rank
+  const int m_groups = (p.num_m_tiles + CL - 1) / CL;
+  const int first = blockIdx.x / CL, step_g = gridDim.x / CL;
+  auto tile_of = [&](int gi) { return (p.reverse ? m_groups - 1 - gi : gi) * CL + rank; };
 
   if (warp == 0 && lane == 0) {
     for (int s = 0; s < kStages; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
-    for (int a = 0; a < 2; ++a) { mbar_init(tfull_bar(a), 1); mbar_init(tempty_bar(a), kEpiThreads); }
+    for (int a = 0; a < 2; ++a) {
+      mbar_init(tfull_bar(a), 1);
+      mbar_init(tempty_bar(a), CL == 1 ? kEpiThreads : CL * kEpiWarps);
+    }
     mbar_init(bres_bar, 1);
     epi_bars_init(ebars);
     fence_barrier_init();
     prefetch_tmap(&p.a_map);
     prefetch_tmap(&p.b_map);
   }
-  if (warp == 1) tmem_alloc(smem_u32((const void*)tmem_slot), 512);
+  if (warp == 1) {
+    if (CL == 1) tmem_alloc(smem_u32((const void*)tmem_slot), 512);
+    else tmem_alloc_pair(smem_u32((const void*)tmem_slot), 512);
+  }
   tc_fence_before();
   __syncthreads();
+  if (CL > 1) cluster_sync_all();   // the leader's barriers exist before the peer's loads signal them
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
   pdl_launch_dependents();
@@ -99,28 +117,34 @@ conv_ysum_kernel(const __grid_constant__ YsumParams p) {
   if (warp == 0) {
     if (lane == 0) {
       // weights are constants: fetch them while the previous layer still drains
-      mbar_expect_tx(bres_bar, kBBytes);
-      for (int dx = 0; dx < 3; ++dx) tma_load_2d(bres + dx * kBTile, &p.b_map, bres_bar, 0, dx * 192);
+      if (rank == 0) mbar_expect_tx(bres_bar, CL * 3 * kBTile);
+      for (int dx = 0; dx < 3; ++dx) {
+        if (CL == 1) tma_load_2d(bres + dx * kBTile, &p.b_map, bres_bar, 0, dx * 192);
+        else tma_load_2d_pair(bres + dx * kBTile, &p.b_map, bres_bar, 0, dx * 192 + rank * (192 / CL));
+      }
       pdl_wait();
       int stage = 0;
       uint32_t phase = 0;
-      for (int mi = blockIdx.x; mi < p.num_m_tiles; mi += gridDim.x) {
-        const int m_tile = p.reverse ? p.num_m_tiles - 1 - mi : mi;
+      for (int gi = first; gi < m_groups; gi += step_g) {
+        const int m_tile = tile_of(gi);
         for (int dx = 0; dx < 3; ++dx) {
           mbar_wait(empty_bar(stage), phase ^ 1u);
-          mbar_expect_tx(full_bar(stage), kABytes);
-          tma_load_4d(base + stage * kABytes, &p.a_map, full_bar(stage), 0, dx - 1, 0, m_tile * 2);
+          if (rank == 0) mbar_expect_tx(full_bar(stage), CL * kABytes);
+          if (CL == 1)
+            tma_load_4d(base + stage * kABytes, &p.a_map, full_bar(stage), 0, dx - 1, 0, m_tile * 2);
+          else
+            tma_load_4d_pair(base + stage * kABytes, &p.a_map, full_bar(stage), 0, dx - 1, 0, m_tile * 2);
           if (++stage == kStages) { stage = 0; phase ^= 1u; }
         }
       }
     }
   } else if (warp == 1) {
-    if (lane == 0) {
-      constexpr uint32_t idesc = umma_idesc_bf16(128, 192);
+    if (lane == 0 && rank == 0) {
+      constexpr uint32_t idesc = umma_idesc_bf16(128 * CL, 192);
       mbar_wait(bres_bar, 0);
       int stage = 0, acc = 0;
       uint32_t phase = 0, acc_phase = 0;
-      for (int mi = blockIdx.x; mi < p.num_m_tiles; mi += gridDim.x) {
+      for (int gi = first; gi < m_groups; gi += step_g) {
         mbar_wait(tempty_bar(acc), acc_phase ^ 1u);
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + (uint32_t)(acc * kAccCols);
@@ -130,13 +154,20 @@ conv_ysum_kernel(const __grid_constant__ YsumParams p) {
           const uint64_t a_desc = umma_desc_sw128(base + stage * kABytes);
           const uint64_t b_desc = umma_desc_sw128(bres + dx * kBTile);
 #pragma unroll
-          for (int k = 0; k < 4; ++k)
-            umma_bf16(d_tmem, a_desc + (uint64_t)(2 * k), b_desc + (uint64_t)(2 * k), idesc,
-                      (dx > 0 || k > 0) ? 1u : 0u);
-          umma_commit(empty_bar(stage));
+          for (int k = 0; k < 4; ++k) {
+            if (CL == 1)
+              umma_bf16(d_tmem, a_desc + (uint64_t)(2 * k), b_desc + (uint64_t)(2 * k), idesc,
+                        (dx > 0 || k > 0) ? 1u : 0u);
+            else
+              umma_bf16_pair(d_tmem, a_desc + (uint64_t)(2 * k), b_desc + (uint64_t)(2 * k), idesc,
+                             (dx > 0 || k > 0) ? 1u : 0u);
+          }
+          if (CL == 1) umma_commit(empty_bar(stage));
+          else umma_commit_pair(empty_bar(stage), kMask);
           if (++stage == kStages) { stage = 0; phase ^= 1u; }
         }
-        umma_commit(tfull_bar(acc));
+        if (CL == 1) umma_commit(tfull_bar(acc));
+        else umma_commit_pair(tfull_bar(acc), kMask);
         acc ^= 1;
         if (acc == 0) acc_phase ^= 1u;
       }
@@ -160,8 +191,8 @@ conv_ysum_kernel(const __grid_constant__ YsumParams p) {
     int acc = 0;
     uint32_t acc_phase = 0;
     int64_t q = 0;
-    for (int mi = blockIdx.x; mi < p.num_m_tiles; mi += gridDim.x, ++q) {
-      const int m_tile = p.reverse ? p.num_m_tiles - 1 - mi : mi;
+    for (int gi = first; gi < m_groups; gi += step_g, ++q) {
+      const int m_tile = tile_of(gi);
       mbar_wait(tfull_bar(acc), acc_phase);
       tc_fence_after();
       // R[dy][w][4i + 2h + e]: image row y0 + 2w + h, column x = g, channel 32*half + 8i + 2t + e
@@ -175,7 +206,12 @@ conv_ysum_kernel(const __grid_constant__ YsumParams p) {
                              R[dy][w]);
       tmem_ld_wait();
       tc_fence_before();
-      mbar_arrive(tempty_bar(acc));
+      if (CL == 1) {
+        mbar_arrive(tempty_bar(acc));
+      } else {
+        __syncwarp();
+        if (lane == 0) mbar_arrive_leader(tempty_bar(acc));
+      }
       acc ^= 1;
       if (acc == 0) acc_phase ^= 1u;
       auto D = [&](int dy, int yy, int i, int e) -> float {
@@ -239,11 +275,8 @@ conv_ysum_kernel(const __grid_constant__ YsumParams p) {
   } else if (lane == 0) {
     pdl_wait();
     int n_items = 0;
-    for (int mi = blockIdx.x; mi < p.num_m_tiles; mi += gridDim.x) ++n_items;
-    auto row_of = [&](int64_t q) {
-      const int mi = blockIdx.x + (int)q * gridDim.x;
-      return (p.reverse ? p.num_m_tiles - 1 - mi : mi) * 128;
-    };
+    for (int gi = first; gi < m_groups; gi += step_g) ++n_items;
+    auto row_of = [&](int64_t q) { return tile_of(first + (int)q * step_g) * 128; };
     const bool rh = p.res_hi != nullptr, rl = p.res_lo != nullptr;
     const bool oh = p.out_hi != nullptr, ol = p.out_lo != nullptr;
     epi_dma_loop(
@@ -261,9 +294,11 @@ conv_ysum_kernel(const __grid_constant__ YsumParams p) {
 
   tc_fence_before();
   __syncthreads();
+  if (CL > 1) cluster_sync_all();   // no CTA leaves while the pair's MMAs may still read its tiles
   if (warp == 1) {
     tc_fence_after();
-    tmem_dealloc(tmem_base, 512);
+    if (CL == 1) tmem_dealloc(tmem_base, 512);
+    else tmem_dealloc_pair(tmem_base, 512);
   }
 }
 
@@ -287,19 +322,26 @@ void pack_ysum_weights(const float* w_oihw, uint16_t* out) {
           out[((dx * 192) + dy * 64 + co) * 64 + ci] = rn(w_oihw[((co * 64 + ci) * 3 + dy) * 3 + dx]);
 }
 
-int launch_conv_ysum(const YsumParams& p, cudaStream_t st) {
-  if (p.num_m_tiles <= 0) return CS_OK;
+template <int CL>
+int launch_ysum(const YsumParams& p, cudaStream_t st) {
   static bool attr_done[64] = {false};
   int dev = 0;
   CS_CUDA(cudaGetDevice(&dev));
   if (dev >= 64 || !attr_done[dev]) {
-    CS_CUDA(cudaFuncSetAttribute(conv_ysum_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    CS_CUDA(cudaFuncSetAttribute(conv_ysum_kernel<CL>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                  (int)kSmemBytes));
     if (dev < 64) attr_done[dev] = true;
   }
-  const int grid = p.num_m_tiles < kNumSMs ? p.num_m_tiles : kNumSMs;
-  CS_CUDA(launch_pdl(conv_ysum_kernel, dim3((unsigned)grid), dim3(kThreads), kSmemBytes, st, 1, p));
+  const int groups = (p.num_m_tiles + CL - 1) / CL;
+  const int clusters = groups < kNumSMs / CL ? groups : kNumSMs / CL;
+  CS_CUDA(launch_pdl(conv_ysum_kernel<CL>, dim3((unsigned)(clusters * CL)), dim3(kThreads), kSmemBytes, st,
+                     CL, p));
   return CS_OK;
+}
+
+int launch_conv_ysum(const YsumParams& p, cudaStream_t st) {
+  if (p.num_m_tiles <= 0) return CS_OK;
+  return p.cluster > 1 ? launch_ysum<2>(p, st) : launch_ysum<1>(p, st);
 }
 
 }  // namespace cs

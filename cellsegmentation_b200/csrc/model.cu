@@ -49,6 +49,7 @@ const int g_xbufs = g_no_lo ? 2 : 4;
 // accumulator read-out: 102 vs 108 us per 18 944 instances against the halo kernel and +2 %
 // sustained throughput (less power).  CELLSEG_YSUM=0 puts layer 1 back on the halo kernel.
 const bool g_disable_ysum = env_is("CELLSEG_YSUM", "0");
+const bool g_ysum_pairs = env_is("CELLSEG_YSUM_PAIRS", "1");   // experiment
 const bool g_im2col_stem = env_is("CELLSEG_STEM", "im2col");   // first tensor-core stem (stem_tc.cu)
 
 struct ConvW {
@@ -334,7 +335,8 @@ int plan_conv(const ConvGeom& g, const float* w_oihw, const float* bias, const C
     CS_CUDA(cudaMalloc(&pc.d_B2, B2.size() * sizeof(uint16_t)));
     CS_CUDA(cudaMemcpy(pc.d_B2, B2.data(), B2.size() * sizeof(uint16_t), cudaMemcpyHostToDevice));
     pc.yp.a_map = pc.p.a_map[0];
-    rc = make_mat_map_2d(&pc.yp.b_map, pc.d_B2, 64, 576, 64, 192);
+    pc.yp.cluster = g_ysum_pairs ? g_cluster : 1;
+    rc = make_mat_map_2d(&pc.yp.b_map, pc.d_B2, 64, 576, 64, 192 / pc.yp.cluster);
     if (rc != CS_OK) { free_planned(pc); return rc; }
     pc.yp.bias = pc.d_bias;
     pc.ysum = true;

@@ -153,3 +153,20 @@ def test_hilo_residual_mode_subprocess(cuda):
     r = subprocess.run([sys.executable, "-c", code], env=env, capture_output=True, text=True, timeout=600)
     assert r.returncode == 0, r.stdout + r.stderr
     assert "hilo max|dp|" in r.stdout
+
+
+@pytest.mark.parametrize("env", [{"CELLSEG_YSUM": "0"}, {"CELLSEG_YSUM_PAIRS": "1"}, {"CELLSEG_CLUSTER": "1"},
+                                 {"CELLSEG_STEM": "im2col"}, {"CELLSEG_RESIDUAL": "hilo", "CELLSEG_YSUM": "0"}],
+                         ids=lambda e: ",".join("%s=%s" % kv for kv in e.items()))
+def test_alternative_kernel_paths_subprocess(cuda, env):
+    """The switches are read when the library loads: run the conv-form and ResNet-34 parity tests in a
+    child process for every alternative kernel path (halo layer 1, y-sum CTA pairs, single-CTA MMAs,
+    im2col stem, hi/lo residual stream)."""
+    import os
+    import subprocess
+    import sys
+    here = os.path.abspath(__file__)
+    r = subprocess.run([sys.executable, "-m", "pytest", here, "-x", "-q", "-p", "no:cacheprovider", "-k",
+                        "conv_matches or (within_2e2 and resnet34) or tile16"],
+                       env=dict(os.environ, **env), capture_output=True, text=True, timeout=900)
+    assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-2000:]
