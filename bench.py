@@ -91,9 +91,9 @@ def measured_traffic(n_inst):
     """DRAM bytes of the conv stage for n_inst instances, from the committed `ncu --set full`
     capture of one forward batch (profiles/summarize_full.py); None when no capture is there."""
     try:
-        t = json.load(open(os.path.join(ROOT, "profiles", "r01_h_traffic.json")))
+        t = json.load(open(os.path.join(ROOT, "profiles", "r01_n_traffic.json")))
         return {"bytes": t["dram_bytes_per_instance"] * n_inst, "per_instance": t["dram_bytes_per_instance"],
-                "source": "profiles/r01_h_traffic.json (dram__bytes_read.sum + dram__bytes_write.sum over the "
+                "source": "profiles/r01_n_traffic.json (dram__bytes_read.sum + dram__bytes_write.sum over the "
                           "%d launches of one %d-instance batch)" % (t["launches"], t["instances"])}
     except Exception:
         return None
