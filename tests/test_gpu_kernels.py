@@ -250,6 +250,24 @@ def test_remove_small_regions_bit_exact(cuda, H, W, density, seed):
         assert int((got.cpu().numpy() != want).sum()) == 0, (mo, ha)
 
 
+def test_remove_small_regions_noise_batch(cuda):
+    """Per-pixel noise at every density (thousands of runs per image, one giant component on one side),
+    more images than resident CTAs, and shapes that take the pixel-level fallback (wider than the
+    bit-image limit / more runs than the run table)."""
+    ops = _ops()
+    rng = np.random.default_rng(11)
+    dens = np.linspace(0.05, 0.95, 160)
+    m = rng.uniform(size=(160, 299, 299)) < dens[:, None, None]
+    want = np.stack([omasks.remove_small_regions(x, 400, 120) for x in m]).astype(np.uint8)
+    got = ops.remove_small_regions(torch.from_numpy(m.astype(np.uint8)).to(cuda), 400, 120)
+    assert int((got.cpu().numpy() != want).sum()) == 0
+    for shape in [(40, 400), (330, 331)]:
+        m2 = rng.uniform(size=(3,) + shape) < 0.5
+        want2 = np.stack([omasks.remove_small_regions(x, 30, 9) for x in m2]).astype(np.uint8)
+        got2 = ops.remove_small_regions(torch.from_numpy(m2.astype(np.uint8)).to(cuda), 30, 9)
+        assert int((got2.cpu().numpy() != want2).sum()) == 0, shape
+
+
 def test_heatmap_blend_matches_cv2(cuda):
     """N3: applyColorMap(JET) + addWeighted(.5,.5) fused on the GPU == cv2, every byte pair covered."""
     import cv2
