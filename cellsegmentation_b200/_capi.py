@@ -48,6 +48,9 @@ _PROTOS = {
     "cs_lexsort_segments": (c_int, [c_void_p, c_void_p, c_int64, c_int, c_void_p, c_void_p]),
     "cs_select_topk": (c_int, [c_void_p, c_void_p, c_int64, c_int, c_void_p, c_int32, c_int32,
                                c_void_p, c_void_p, c_void_p, c_int64, c_void_p, c_int64, c_void_p]),
+    "cs_select_topk_shard": (c_int, [c_void_p, c_void_p, c_int64, c_int, c_void_p, c_int32, c_int32, c_int64,
+                                     c_int64, c_void_p, c_void_p, c_void_p, c_int64, c_void_p, c_int64,
+                                     c_void_p]),
     "cs_select_workspace_bytes": (c_int64, [c_int]),
     "cs_rank_threshold": (c_int, [c_void_p, c_void_p, c_int64, c_int, c_float, c_void_p, c_void_p,
                                   c_void_p, c_int64, c_void_p]),

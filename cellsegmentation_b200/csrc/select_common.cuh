@@ -9,6 +9,12 @@ struct Segs {
   const int64_t* offsets;  // nullptr -> uniform
   int64_t uniform_T;
   int n_bags;
+  // The literal predicate groups[i] != groups[(i + k) % N] looks at GLOBAL positions.  When the
+  // bags are one shard of a larger set, g_off is the global index of this shard's first tile and
+  // g_total the global tile count N (0: the shard is the whole set).
+  int64_t g_off, g_total;
+  __device__ __forceinline__ int64_t gstart(int b) const { return start(b) + g_off; }
+  __device__ __forceinline__ int64_t gtotal() const { return g_total > 0 ? g_total : total(); }
   __device__ __forceinline__ int64_t start(int b) const {
     return offsets ? offsets[b] : (int64_t)b * uniform_T;
   }

@@ -59,8 +59,8 @@ select_fast_kernel(Segs segs, const float* __restrict__ prob, EmitArgs ea, int m
   const int64_t s = segs.start(b);
   const int T = (int)(segs.start(b + 1) - s);
   if (T <= 0) return;
-  const int64_t N = segs.total();
-  const Kept kr = kept_ranges(s, T, N, bag_k(ea.labels, b, ea.tiles_per_pos, ea.topk_neg));
+  const Kept kr = kept_ranges(segs.gstart(b), T, segs.gtotal(),
+                              bag_k(ea.labels, b, ea.tiles_per_pos, ea.topk_neg));
   const int n1 = kr.b1 - kr.a1, n2 = kr.b2 - kr.a2, n = n1 + n2;
   if (n == 0) return;                                     // all conditions block-uniform
   auto decline = [&]() {

@@ -39,8 +39,8 @@ __global__ void select_count_kernel(Segs segs, const int32_t* __restrict__ label
                                     int64_t* __restrict__ counts) {
   int b = blockIdx.x * blockDim.x + threadIdx.x;
   if (b >= segs.n_bags) return;
-  int64_t s = segs.start(b), e = segs.start(b + 1), N = segs.total();
-  counts[b] = kept_ranges(s, e - s, N, bag_k(labels, b, tiles_per_pos, topk_neg)).count();
+  int64_t s = segs.start(b), e = segs.start(b + 1);
+  counts[b] = kept_ranges(segs.gstart(b), e - s, segs.gtotal(), bag_k(labels, b, tiles_per_pos, topk_neg)).count();
 }
 
 __global__ void __launch_bounds__(256)
@@ -169,8 +169,8 @@ seg_sort_kernel(Segs segs, const float* __restrict__ prob, EmitArgs ea) {
   if (kMode == kLexsort) {
     for (int r = threadIdx.x; r < T; r += kThreads) ea.idx_out[s + r] = (int32_t)(s + idx[r]);
   } else if (kMode == kSelect) {
-    const int64_t N = segs.total();
-    const Kept kr = kept_ranges(s, T, N, bag_k(ea.labels, b, ea.tiles_per_pos, ea.topk_neg));
+    const Kept kr = kept_ranges(segs.gstart(b), T, segs.gtotal(),
+                                bag_k(ea.labels, b, ea.tiles_per_pos, ea.topk_neg));
     const int64_t o0 = ea.out_offsets[b];
     const uint8_t pl = ea.labels[b] == 0 ? 0 : 1;
     const int n1 = kr.b1 - kr.a1, n = kr.count();
@@ -273,7 +273,7 @@ int cs_lexsort_segments(const float* prob, const int64_t* seg_offsets, int64_t u
   int rc = check_segs("cs_lexsort_segments", prob, seg_offsets, uniform_T, n_bags);
   if (rc != CS_OK) return rc;
   CS_REQUIRE(order_out != nullptr, "cs_lexsort_segments: order_out is NULL");
-  Segs segs{seg_offsets, uniform_T, n_bags};
+  Segs segs{seg_offsets, uniform_T, n_bags, 0, 0};
   EmitArgs ea{};
   ea.idx_out = order_out;
   return launch_sort<kLexsort>(segs, prob, ea, uniform_T, cs::as_stream(stream));
@@ -283,7 +283,19 @@ int cs_select_topk(const float* prob, const int64_t* seg_offsets, int64_t unifor
                    const int32_t* labels, int32_t tiles_per_pos, int32_t topk_neg,
                    int32_t* sel_idx_out, uint8_t* sel_label_out, int64_t* sel_offsets_out,
                    int64_t capacity, void* workspace, int64_t workspace_bytes, void* stream) {
+  return cs_select_topk_shard(prob, seg_offsets, uniform_T, n_bags, labels, tiles_per_pos, topk_neg, 0, 0,
+                              sel_idx_out, sel_label_out, sel_offsets_out, capacity, workspace,
+                              workspace_bytes, stream);
+}
+
+int cs_select_topk_shard(const float* prob, const int64_t* seg_offsets, int64_t uniform_T, int n_bags,
+                         const int32_t* labels, int32_t tiles_per_pos, int32_t topk_neg,
+                         int64_t global_tile_offset, int64_t global_total_tiles,
+                         int32_t* sel_idx_out, uint8_t* sel_label_out, int64_t* sel_offsets_out,
+                         int64_t capacity, void* workspace, int64_t workspace_bytes, void* stream) {
   int rc = check_segs("cs_select_topk", prob, seg_offsets, uniform_T, n_bags);
+  CS_REQUIRE(global_tile_offset >= 0 && global_total_tiles >= 0,
+             "cs_select_topk_shard: global offset / total must be >= 0");
   CS_REQUIRE(workspace != nullptr && workspace_bytes >= cs_select_workspace_bytes(n_bags),
              "cs_select_topk: workspace too small (need %lld bytes)",
              (long long)cs_select_workspace_bytes(n_bags));
@@ -293,7 +305,7 @@ int cs_select_topk(const float* prob, const int64_t* seg_offsets, int64_t unifor
   CS_REQUIRE(tiles_per_pos >= 0 && topk_neg >= 0 && capacity >= 0,
              "cs_select_topk: tiles_per_pos, topk_neg and capacity must be >= 0");
   cudaStream_t st = cs::as_stream(stream);
-  Segs segs{seg_offsets, uniform_T, n_bags};
+  Segs segs{seg_offsets, uniform_T, n_bags, global_tile_offset, global_total_tiles};
   int32_t* fb_count = static_cast<int32_t*>(workspace);
   int32_t* fb_list = fb_count + 64;
   if (!g_disable_fast) CS_CUDA(cudaMemsetAsync(fb_count, 0, sizeof(int32_t), st));
@@ -333,7 +345,7 @@ int cs_rank_threshold(const float* prob, const int64_t* seg_offsets, int64_t uni
   CS_REQUIRE(sel_idx_out && sel_offsets_out, "cs_rank_threshold: NULL pointer");
   CS_REQUIRE(capacity >= 0, "cs_rank_threshold: capacity < 0");
   cudaStream_t st = cs::as_stream(stream);
-  Segs segs{seg_offsets, uniform_T, n_bags};
+  Segs segs{seg_offsets, uniform_T, n_bags, 0, 0};
   rank_count_kernel<<<n_bags, 256, 0, st>>>(segs, prob, threshold, sel_offsets_out);
   CS_LAUNCH_CHECK();
   exclusive_scan_kernel<<<1, 1024, 0, st>>>(sel_offsets_out, n_bags);

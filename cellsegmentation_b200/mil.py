@@ -49,8 +49,11 @@ def select_global(trainset, model, device, tiles_per_pos, topk_neg, cache_featur
                 probs, feat = probs
             labels = torch.as_tensor(np.asarray(shard.labels, dtype=np.int32)).to(device)
             off = torch.from_numpy(shard.seg_offsets()).to(device)
+            # the predicate of sample() wraps around the GLOBAL tile array (inference.py:37-40): a shard
+            # evaluates it at its global position, or a one-bag shard would compare a bag with itself
             idx, pl, _ = ops.select_topk(probs, labels, len(shard.images), max(shard.tiles_per_bag, 1),
-                                         tiles_per_pos, topk_neg, seg_offsets=off)
+                                         tiles_per_pos, topk_neg, seg_offsets=off,
+                                         global_offset=tile_off, global_total=trainset.num_tiles())
         else:
             idx = torch.zeros(0, dtype=torch.int32, device=device)
             pl = torch.zeros(0, dtype=torch.uint8, device=device)

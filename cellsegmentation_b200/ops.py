@@ -86,8 +86,10 @@ def lexsort_segments(prob, n_bags, uniform_T, seg_offsets=None):
 
 
 def select_topk(prob, labels, n_bags, uniform_T, tiles_per_pos, topk_neg, seg_offsets=None,
-                capacity=None):
-    """Adaptive top-k (inference.py:31-42). Returns (idx i32 [M], pseudo-label u8 [M], offsets i64)."""
+                capacity=None, global_offset=0, global_total=0):
+    """Adaptive top-k (inference.py:31-42). Returns (idx i32 [M], pseudo-label u8 [M], offsets i64).
+    For one shard of a larger set pass the global index of its first tile and the global tile count
+    (the predicate wraps around the GLOBAL array); indices stay relative to the shard."""
     _req_cuda(prob, "prob", torch.float32)
     _req_cuda(labels, "labels", torch.int32)
     so, T = _segs(seg_offsets, uniform_T, n_bags)
@@ -98,10 +100,10 @@ def select_topk(prob, labels, n_bags, uniform_T, tiles_per_pos, topk_neg, seg_of
     off = torch.empty(n_bags + 1, dtype=torch.int64, device=prob.device)
     ws = torch.empty(max(int(lib().cs_select_workspace_bytes(n_bags)), 1), dtype=torch.uint8,
                      device=prob.device)
-    check(lib().cs_select_topk(ptr(prob), so, T, n_bags, ptr(labels), int(tiles_per_pos),
-                               int(topk_neg), ptr(idx), ptr(lab), ptr(off), capacity, ptr(ws),
-                               ws.numel(), cur_stream()),
-          "cs_select_topk")
+    check(lib().cs_select_topk_shard(ptr(prob), so, T, n_bags, ptr(labels), int(tiles_per_pos),
+                                     int(topk_neg), int(global_offset), int(global_total), ptr(idx),
+                                     ptr(lab), ptr(off), capacity, ptr(ws), ws.numel(), cur_stream()),
+          "cs_select_topk_shard")
     M = int(off[-1].item())
     if M > capacity:
         raise _capi.CellSegError("select_topk: %d kept instances exceed capacity %d" % (M, capacity))

@@ -185,6 +185,17 @@ int cs_select_topk(const float* prob, const int64_t* seg_offsets, int64_t unifor
                    int32_t topk_neg, int32_t* sel_idx_out, uint8_t* sel_label_out,
                    int64_t* sel_offsets_out, int64_t capacity, void* workspace,
                    int64_t workspace_bytes, void* stream);
+
+/* Same for ONE SHARD of a larger bag set (bags partitioned across GPUs): the literal predicate
+ * groups[i] != groups[(i + k) % N] of inference.py:37-40 is evaluated at GLOBAL positions, so the
+ * shard passes the global index of its first tile and the global tile count N.  Inputs and the
+ * returned indices are relative to the shard (index 0 = first tile of the shard).  With
+ * global_total_tiles == 0 the shard is the whole set (= cs_select_topk). */
+int cs_select_topk_shard(const float* prob, const int64_t* seg_offsets, int64_t uniform_T, int n_bags,
+                         const int32_t* labels, int32_t tiles_per_pos, int32_t topk_neg,
+                         int64_t global_tile_offset, int64_t global_total_tiles,
+                         int32_t* sel_idx_out, uint8_t* sel_label_out, int64_t* sel_offsets_out,
+                         int64_t capacity, void* workspace, int64_t workspace_bytes, void* stream);
 /* Bytes of device workspace cs_select_topk needs (the list of bags the register-resident
  * fast path hands to the exact per-bag sort). */
 int64_t cs_select_workspace_bytes(int n_bags);

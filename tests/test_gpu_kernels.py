@@ -173,6 +173,36 @@ def test_select_topk_many_bags_ring_wraps(cuda, T, n_bags, misalign):
     assert np.array_equal(pl.cpu().numpy(), oselect.pseudo_labels(tid, lab, want))
 
 
+@pytest.mark.parametrize("T,sizes", [(225, [2, 1, 1, 3, 1]), (64, [1, 1, 1, 1]), (300, [3, 0, 2, 1])])
+def test_select_topk_shards_equal_global(cuda, T, sizes):
+    """Bags partitioned over ranks: every shard evaluates the wrap-around predicate at its GLOBAL
+    position (cs_select_topk_shard), so one-bag shards, empty shards and counts beyond the shard
+    size (k >= shard tiles) reproduce the single-process selection."""
+    ops = _ops()
+    n_bags = sum(sizes)
+    rng = np.random.default_rng(T + n_bags)
+    p = rng.uniform(0, 1, T * n_bags).astype(np.float32)
+    lab = rng.integers(0, 12, n_bags).astype(np.int32)
+    lab[0] = 0
+    lab[-1] = 2 * T + 7                      # k wraps around the global array
+    lab[1 % n_bags] = T + 3                  # k larger than a one-bag shard
+    tid = np.repeat(np.arange(n_bags), T)
+    for tpp, tk in [(1, 30), (3, 5)]:
+        want = oselect.sample_indices(tid, lab, p, tpp, tk)
+        got_idx, got_pl, b0 = [], [], 0
+        for nb in sizes:
+            if nb > 0:
+                sl = slice(b0 * T, (b0 + nb) * T)
+                idx, pl, _ = ops.select_topk(torch.from_numpy(p[sl]).to(cuda),
+                                             torch.from_numpy(lab[b0:b0 + nb]).to(cuda), nb, T, tpp, tk,
+                                             global_offset=b0 * T, global_total=n_bags * T)
+                got_idx.append(idx.cpu().numpy().astype(np.int64) + b0 * T)
+                got_pl.append(pl.cpu().numpy())
+            b0 += nb
+        assert np.array_equal(np.concatenate(got_idx), want)
+        assert np.array_equal(np.concatenate(got_pl), oselect.pseudo_labels(tid, lab, want))
+
+
 def test_select_topk_ragged_with_empty_bags(cuda):
     ops = _ops()
     rng = np.random.default_rng(9)
