@@ -256,3 +256,18 @@ def test_mil_epoch_single_process_equals_sample_plus_train_tile(cuda):
     assert (pos_c, neg_c) == (pos, neg)
     assert abs(loss_c - loss) <= 1e-6 * max(1.0, abs(loss))
     assert torch.allclose(net.fc_tile[1].weight.detach(), w1, rtol=0, atol=1e-9)
+
+
+def test_distributed_mil_epoch_torchrun(cuda):
+    """tests/dist_mil_epoch.py under torchrun on every visible GPU (needs >= 2): rank-identical global
+    selection (sharded scoring + shard-aware top-k + NCCL all-gather) and identical fc_tile weights."""
+    import subprocess
+    import sys
+    n = torch.cuda.device_count()
+    if n < 2:
+        pytest.skip("needs at least 2 GPUs")
+    here = os.path.dirname(os.path.abspath(__file__))
+    r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", str(n),
+                        "--master-addr", "127.0.0.1", "--master-port", "29541",
+                        os.path.join(here, "dist_mil_epoch.py")], capture_output=True, text=True, timeout=900)
+    assert r.returncode == 0 and "PASS" in r.stdout, r.stdout[-2000:] + r.stderr[-2000:]
