@@ -156,7 +156,8 @@ def test_hilo_residual_mode_subprocess(cuda):
 
 
 @pytest.mark.parametrize("env", [{"CELLSEG_YSUM": "0"}, {"CELLSEG_YSUM_PAIRS": "1"}, {"CELLSEG_CLUSTER": "1"},
-                                 {"CELLSEG_STEM": "im2col"}, {"CELLSEG_RESIDUAL": "hilo", "CELLSEG_YSUM": "0"}],
+                                 {"CELLSEG_STEM": "im2col"}, {"CELLSEG_RESIDUAL": "hilo", "CELLSEG_YSUM": "0"},
+                                 {"CELLSEG_RESIDUAL": "hilo"}],
                          ids=lambda e: ",".join("%s=%s" % kv for kv in e.items()))
 def test_alternative_kernel_paths_subprocess(cuda, env):
     """The switches are read when the library loads: run the conv-form and ResNet-34 parity tests in a
