@@ -136,6 +136,9 @@ seg_sort_kernel(Segs segs, const float* __restrict__ prob, EmitArgs ea) {
   const int64_t s = segs.start(b);
   const int T = (int)(segs.start(b + 1) - s);
   if (T <= 0) continue;
+  if (kMode == kRank && ea.rank_fast_cap > 0 &&
+      ea.out_offsets[b + 1] - ea.out_offsets[b] <= ea.rank_fast_cap)
+    continue;                                   // emitted by rank_fast_kernel
   const int P = pow2_ceil(T);
   uint32_t* key = reinterpret_cast<uint32_t*>(smem_raw);
   uint16_t* idx = reinterpret_cast<uint16_t*>(smem_raw + (size_t)P * 4);
@@ -204,6 +207,54 @@ seg_sort_kernel(Segs segs, const float* __restrict__ prob, EmitArgs ea) {
     }
   }
   __syncthreads();   // shared memory is reused by the next item
+  }
+}
+
+// rank() fast path: with a threshold like 0.95 a bag keeps a few per cent of its instances, so
+// instead of ordering the whole bag the CTA streams it once, appends the instances > thr to a
+// shared list (their number is already known from the offsets) and ranks those by counting:
+// ascending (prob, index), exactly the suffix of the lexsort order the exact kernel would emit.
+// Bags that keep more than kRankCap entries are left to the exact kernel.
+constexpr int kRankCap = 512;
+
+__global__ void __launch_bounds__(128)
+rank_fast_kernel(Segs segs, const float* __restrict__ prob, EmitArgs ea) {
+  __shared__ unsigned long long cand[kRankCap];
+  __shared__ int s_count;
+  const int b = blockIdx.x, tid = threadIdx.x, lane = tid & 31;
+  const int64_t o0 = ea.out_offsets[b];
+  const int n = (int)(ea.out_offsets[b + 1] - o0);
+  if (n <= 0 || n > kRankCap) return;
+  const int64_t s = segs.start(b);
+  const int T = (int)(segs.start(b + 1) - s);
+  if (tid == 0) s_count = 0;
+  __syncthreads();
+  for (int j0 = 0; j0 < T; j0 += 128) {
+    const int j = j0 + tid;
+    const float p = j < T ? prob[s + j] : 0.f;
+    const bool in = j < T && p > ea.thr;           // NaN compares false, like the reference
+    const unsigned mask = __ballot_sync(0xffffffffu, in);
+    int base = 0;
+    if (lane == 0 && mask) base = atomicAdd(&s_count, __popc(mask));
+    base = __shfl_sync(0xffffffffu, base, 0);
+    if (in) {
+      const int pos = base + __popc(mask & ((1u << lane) - 1u));
+      if (pos < kRankCap) cand[pos] = ((unsigned long long)cs::float_sort_key(p) << 32) | (unsigned)j;
+    }
+  }
+  __syncthreads();
+  const int count = s_count < kRankCap ? s_count : kRankCap;     // == n
+  for (int j = tid; j < count; j += 128) {
+    const unsigned long long me = cand[j];
+    int below = 0;
+#pragma unroll 4
+    for (int i = 0; i < count; ++i) below += cand[i] < me ? 1 : 0;
+    const int64_t pos = o0 + below;
+    if (pos < ea.capacity) {
+      const int64_t gi = s + (int64_t)(unsigned)(me & 0xffffffffull);
+      ea.idx_out[pos] = (int32_t)gi;
+      if (ea.prob_out) ea.prob_out[pos] = prob[gi];
+    }
   }
 }
 
@@ -356,6 +407,11 @@ int cs_rank_threshold(const float* prob, const int64_t* seg_offsets, int64_t uni
   ea.prob_out = sel_prob_out;
   ea.out_offsets = sel_offsets_out;
   ea.capacity = capacity;
+  if (!g_disable_fast) {
+    rank_fast_kernel<<<n_bags, 128, 0, st>>>(segs, prob, ea);
+    CS_LAUNCH_CHECK();
+    ea.rank_fast_cap = kRankCap;
+  }
   return launch_sort<kRank>(segs, prob, ea, uniform_T, st);
 }
 

@@ -232,6 +232,27 @@ def test_rank_threshold_golden(cuda):
     assert np.array_equal(tid[idx], g["groups"])
 
 
+@pytest.mark.parametrize("thr", [0.95, 0.5, 0.999, -1.0])
+def test_rank_threshold_random_fast_and_exact_paths(cuda, thr):
+    """rank(): bags keeping <= 512 entries take the compact + rank-by-counting kernel, the others the
+    exact per-bag sort; both must give lexsort order restricted to prob > thr (ties, NaN, -0.0)."""
+    ops = _ops()
+    rng = np.random.default_rng(17)
+    n_bags, T = 300, 3025
+    p = rng.uniform(0, 1, n_bags * T).astype(np.float32)
+    p[rng.uniform(size=p.size) < 0.01] = np.float32(0.97)          # ties above the usual threshold
+    p[rng.uniform(size=p.size) < 0.001] = np.float32(np.nan)
+    p[5 * T:6 * T] = np.float32(0.99)                              # one bag keeps everything
+    p[7 * T:8 * T] = np.float32(0.1)                               # one keeps nothing (thr > 0.1)
+    tid = np.repeat(np.arange(n_bags), T)
+    order = np.lexsort((p, tid))
+    want = order[p[order] > np.float32(thr)]
+    idx, kp, off = ops.rank_threshold(torch.from_numpy(p).to(cuda), n_bags, T, thr)
+    assert np.array_equal(idx.cpu().numpy().astype(np.int64), want)
+    assert np.array_equal(kp.cpu().numpy().view(np.uint32), p[want].view(np.uint32))
+    assert np.array_equal(np.diff(off.cpu().numpy()), np.bincount(tid[want], minlength=n_bags))
+
+
 # ----------------------------------------------------------------------------- K4a
 def test_paint_mask_and_heatmap_golden(cuda):
     import cv2
