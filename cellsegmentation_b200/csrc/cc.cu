@@ -24,7 +24,7 @@
 
 namespace {
 
-constexpr int kThreads = 512;
+constexpr int kThreads = 1024;
 constexpr int kMaxRuns = 16384;         // pure per-pixel noise at 299 x 299 has ~9 000 runs; 196 KB
 constexpr int kMaxW = 320;              // 10 words per row
 constexpr int kMaxH = 320;
