@@ -23,9 +23,10 @@
 // stage in both CTAs and hands the accumulator to both epilogues; both epilogues return the
 // accumulator stage on the leader's "tempty" barrier.
 //
-// Warp roles (320 threads, one CTA per SM, persistent):
+// Warp roles (352 threads, one CTA per SM, persistent):
 //   warp 0 : TMA producer (one lane)          warp 1 : TMEM alloc + MMA issuer (one lane)
 //   warps 2-9 : epilogue; warp % 4 = TMEM lane quadrant, (warp-2)/4 = column half.
+//   warp 10 : epilogue DMA (residual tiles in, result tiles out by TMA; gemm_epilogue.cuh)
 #include "fwd.cuh"
 #include "gemm_epilogue.cuh"
 

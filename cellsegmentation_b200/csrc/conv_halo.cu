@@ -2,7 +2,7 @@
 //
 // Reference: BasicBlock conv1 / conv2 of layer1 and layer2 (model/resnet.py:19-23, 28-43).
 //
-// The generic kernel (fwd_tc.cu) fetches one shifted 128-row box per tap: 9 L2 reads of the
+// The generic kernel (conv_gemm.cu) fetches one shifted 128-row box per tap: 9 L2 reads of the
 // same activations and 9 reads of the weights per M tile, and the launch list shows those
 // layers pinned at the L2->SM bandwidth.  Here a K step fetches ONE box per horizontal shift
 // dx that also carries a one-pixel halo in y:

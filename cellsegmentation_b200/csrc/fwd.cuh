@@ -29,7 +29,7 @@ int launch_head_fp32(const float* x4, int64_t n, int P, int C, const float* fc_w
                      cudaStream_t st);
 
 // ---------------------------------------------------------------------------
-// bf16 tcgen05 path (fwd_tc.cu)
+// bf16 tcgen05 path (stem_win.cu, conv_ysum.cu, conv_halo.cu, conv_gemm.cu, fwd_tc.cu)
 // ---------------------------------------------------------------------------
 constexpr int kGemmBM = 128;       // UMMA M (rows per CTA tile)
 constexpr int kGemmBK = 64;        // bf16 elements per K step = one 128-byte swizzle row

@@ -1,5 +1,6 @@
 // K2 (bf16 mode) support code: CUDA-core stem (tile 16), tile head, TMA descriptor builders.
-// The tensor-core kernels live in conv_gemm.cu, conv_halo.cu and stem_tc.cu.
+// The tensor-core kernels live in stem_win.cu (stem_tc.cu: im2col predecessor), conv_ysum.cu,
+// conv_halo.cu and conv_gemm.cu.
 #include "fwd.cuh"
 #include "gemm_epilogue.cuh"
 

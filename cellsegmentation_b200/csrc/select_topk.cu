@@ -373,7 +373,7 @@ int cs_select_topk_shard(const float* prob, const int64_t* seg_offsets, int64_t 
   ea.label_out = sel_label_out;
   ea.out_offsets = sel_offsets_out;
   ea.capacity = capacity;
-  // register-resident warp-per-bag path first; bags it declines are flagged and ordered exactly
+  // CTA-per-bag fast path first (select_fast.cu); bags it declines are listed and ordered exactly
   bool handled = false;
   if (!g_disable_fast) {
     rc = launch_select_fast(segs, prob, ea, uniform_T, fb_count, fb_list, st, &handled);

@@ -10,7 +10,7 @@
 // (bit-exact against torchvision; checked in tests/).
 //
 // Algorithmic bytes per instance: 3*S*S read (L2-resident: tiles of one bag
-// overlap) + 12*S*S written.  The fused bf16 forward (fwd_tc.cu) never
+// overlap) + 12*S*S written.  The fused bf16 forward (stem_win.cu) never
 // materialises this tensor; this kernel is the drop-in for __getitem__ batches and
 // the input of the fp32 parity path.
 #include "common.cuh"
