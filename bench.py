@@ -356,7 +356,10 @@ def main():
                          "flop_per_instance": FLOP_INBOUNDS,
                          "achieved_nominal": FLOP_NOMINAL * n_inst / (fwd_ms * 1e-3) / 1e12,
                          "fwd_ms_per_step": fwd_ms,
-                         "select": {"bound": "hbm", "ms_per_step": sel_ms,
+                         "select_in_step": {"bound": "hbm", "ms_per_step": sel_ms,
+                                            "note": "the step's own selection over %d bags: four small launches + "
+                                                    "the .item() sync, launch-latency bound; select_20k is the "
+                                                    "kernel at the config's full size" % B,
                                     "achieved": SELECT_BYTES_PER_INST * n_inst / (sel_ms * 1e-3) / 1e9,
                                     "peak": pk["hbm_gbs"], "unit": "GB/s",
                                     "frac": SELECT_BYTES_PER_INST * n_inst / (sel_ms * 1e-3) / 1e9 / pk["hbm_gbs"]}},
