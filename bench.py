@@ -2,12 +2,24 @@
 """Headline benchmark: instances/sec of (score + adaptive top-k) — BASELINE.json configs[1].
 
   python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+                  [--workload score_select|mil_epoch]
 
-Workload: ResNet-34 tile-instance inference (tile 32, interval 5 -> 3025 instances per 299x299
-bag, bf16 tcgen05 path) followed by the count-driven adaptive top-k selection, on synthetic
-LYSTO-shaped bags with random-init weights.  A step scores and selects one slice of
-`--bags-per-step` bags of the HBM-resident bag array (the slice advances every step, so both
-the u8 inputs and the activation workspace exceed L2).  One JSON line on rank 0.
+score_select (default): ResNet-34 tile-instance inference (tile 32, interval 5 -> 3025 instances
+per 299x299 bag, bf16 tcgen05 path) followed by the count-driven adaptive top-k selection, on
+synthetic LYSTO-shaped bags with random-init weights.  A step scores and selects one slice of
+`--bags-per-step` bags of the HBM-resident bag array (the slice advances every step, so both the
+u8 inputs and the activation workspace exceed L2).  After warm-up and outside the timed region
+the step's output is VERIFIED: 4096 sampled probabilities against the fp32 CUDA-core path
+(<= 2e-2) and the whole selection against the oracle's sample() on the same probabilities
+(bit-exact).  Side legs (rank 0, timed alone): select over 20 000 bags, HSV refine, connected
+components with their CPU baselines, configs[3] (ResNeXt-50, interval 3) and -- on EVERY rank,
+because it is the one leg with collectives -- configs[2], the MIL epoch.
+
+mil_epoch: configs[2] as the headline: one train_tile.py epoch (score 18 000 bags at interval
+20 -> adaptive top-k -> one packed all-gather -> make_train_data -> fc_tile training with one
+all-reduce per step), bags sharded over the ranks (strong scaling).
+
+One JSON line on rank 0.
 """
 import argparse
 import json
@@ -23,9 +35,10 @@ sys.path.insert(0, ROOT)
 
 TILE, INTERVAL, H = 32, 5, 299
 T_PER_BAG = 3025
-FLOP_INBOUNDS = 82.18e6      # in-bounds FLOP per 32x32 instance, ResNet-34
-FLOP_NOMINAL = 149.52e6      # nominal (zero-padding taps included)
-SELECT_BYTES_PER_INST = 4.0  # SURVEY 8(d)
+FLOP_INBOUNDS = 82.18e6        # in-bounds FLOP per 32x32 instance, ResNet-34
+FLOP_INBOUNDS_RX50 = 167.98e6  # ResNeXt-50 32x4d
+SELECT_BYTES_PER_INST = 4.0    # SURVEY 8(d)
+METRIC = "instances/sec (score+adaptive top-k)"
 
 
 def parse():
@@ -34,11 +47,15 @@ def parse():
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="score_select", choices=["score_select", "mil_epoch"])
     ap.add_argument("--bags-per-step", type=int, default=1024, help="bags scored per step per GPU")
     ap.add_argument("--resident-bags", type=int, default=0, help="bags resident in HBM per GPU (0: auto)")
     ap.add_argument("--max-batch", type=int, default=37888, help="instances per forward batch")
-    ap.add_argument("--ref-bags", type=int, default=2, help="bags per step of the CPU reference arm")
+    ap.add_argument("--ref-bags", type=int, default=8, help="bags per step of the CPU reference arm (configs[0]: 8)")
+    ap.add_argument("--mil-bags", type=int, default=18000, help="training bags of the MIL epoch (all ranks together)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-side-legs", action="store_true")
+    ap.add_argument("--no-verify", action="store_true")
     return ap.parse_args()
 
 
@@ -88,20 +105,27 @@ def peaks():
 
 
 def measured_traffic(n_inst):
-    """DRAM bytes of the conv stage for n_inst instances, from the committed `ncu --set full`
-    capture of one forward batch (profiles/summarize_full.py); None when no capture is there."""
-    try:
-        t = json.load(open(os.path.join(ROOT, "profiles", "r01_n_traffic.json")))
-        return {"bytes": t["dram_bytes_per_instance"] * n_inst, "per_instance": t["dram_bytes_per_instance"],
-                "source": "profiles/r01_n_traffic.json (dram__bytes_read.sum + dram__bytes_write.sum over the "
-                          "%d launches of one %d-instance batch)" % (t["launches"], t["instances"])}
-    except Exception:
-        return None
+    """DRAM bytes of the conv stage for n_inst instances, from the newest committed `ncu --set
+    full` capture of one forward batch (profiles/summarize_full.py); None when there is none."""
+    for name in ("r02_traffic.json", "r01_n_traffic.json"):
+        try:
+            t = json.load(open(os.path.join(ROOT, "profiles", name)))
+            return {"bytes": t["dram_bytes_per_instance"] * n_inst, "per_instance": t["dram_bytes_per_instance"],
+                    "source": "profiles/%s (dram__bytes_read.sum + dram__bytes_write.sum over the %d launches of "
+                              "one %d-instance batch)" % (name, t["launches"], t["instances"])}
+        except Exception:
+            continue
+    return None
 
 
+# ------------------------------------------------------------------------------------------------
+# CPU reference arm: the oracle port of the reference's own CPU path (no GPU, no product code)
+# ------------------------------------------------------------------------------------------------
 def cpu_reference_step(n_bags, sd, labels, seed):
-    """The reference's CPU path restated (oracle port): unfold -> ResNet-34 fp32 forward ->
-    lexsort + adaptive top-k predicate.  Returns (instances, seconds)."""
+    """inference_tiles + sample on the host, restated (oracle port): per-tile crop / ToTensor /
+    Normalize in a Python loop -- it mirrors the reference's LystoTestset.__getitem__, 94 us per
+    tile -- then the ResNet-34 fp32 forward on all host cores and np.lexsort + the
+    literal per-position top-k loop of sample().  Returns (instances, seconds)."""
     import numpy as np
     import torch
     from oracle import model as omodel, select as oselect, synth, tiles as otiles
@@ -114,6 +138,51 @@ def cpu_reference_step(n_bags, sd, labels, seed):
     return x.shape[0], time.perf_counter() - t0
 
 
+def cpu_mil_epoch(n_bags, sd, labels, seed):
+    """One MIL epoch on the host (oracle port): unfold at interval 20, forward, sample(),
+    make_train_data, train_tile (fc_tile only).  Returns (scored instances, seconds)."""
+    import numpy as np
+    import torch
+    from oracle import model as omodel, select as oselect, synth, tiles as otiles, train as otrain
+    bags = synth.make_bags(n_bags, seed=seed)
+    t0 = time.perf_counter()
+    x = torch.from_numpy(otiles.unfold(list(bags), 20, TILE))
+    probs = omodel.forward_probs(sd, x, "resnet34", batch=4096)
+    T = x.shape[0] // n_bags
+    tid = np.repeat(np.arange(n_bags), T)
+    idx = oselect.sample_indices_loop(tid, labels[:n_bags], probs, 1, 30)
+    grid = otiles.get_tiles((H, H, 3), 20, TILE)
+    np.random.seed(seed)
+    td, _, _ = oselect.make_train_data(tid, [grid[i % T] for i in range(len(tid))], labels[:n_bags], idx, 0.5)
+    rows = [int(r[0]) * T + grid.index(tuple(r[1])) for r in td]
+    y = torch.tensor([int(r[2]) for r in td], dtype=torch.int64)
+    if len(rows):
+        otrain.train_tile_epoch(sd, x[rows], y, 40960, 5e-4)
+    return x.shape[0], time.perf_counter() - t0
+
+
+def cpu_masks_baseline(n=48):
+    """preprocess_masks on the host as the reference runs it (utils/image_processing.py:114-124):
+    cv2 cvtColor/split/threshold/AND (lines 117-120) and the connected-component clean-up (scipy
+    restatement of skimage's remove_small_objects/holes), single thread, masks/s each."""
+    import numpy as np
+    from oracle import masks as omasks, synth
+    bags = synth.make_bags(n, seed=77)
+    rng = np.random.default_rng(5)
+    blob = rng.random((n, H // 13 + 1, H // 13 + 1)) < 0.45
+    raw = np.repeat(np.repeat(blob, 13, 1), 13, 2)[:, :H, :H].astype(np.uint8)
+    t0 = time.perf_counter()
+    ref = [omasks.hsv_refine_cv2(bags[i], raw[i]) for i in range(n)]
+    t1 = time.perf_counter()
+    for i in range(n):
+        omasks.remove_small_regions(ref[i] != 0, 400, 120)
+    t2 = time.perf_counter()
+    return {"hsv_masks_per_s": n / (t1 - t0), "cc_masks_per_s": n / (t2 - t1),
+            "chain_masks_per_s": n / (t2 - t0), "cores": 1, "kind": "port",
+            "sample": "%d synthetic 299x299 bags: cv2 BGR2HSV+split+threshold+AND, then scipy.ndimage.label "
+                      "clean-up (min object 400, hole 120), one host thread" % n}
+
+
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
@@ -123,26 +192,150 @@ def run_reference(args):
     from oracle import model as omodel
     torch.set_num_threads(os.cpu_count())
     sd = omodel.make_state_dict("resnet34", seed=0, random_bn=False)
-    labels = np.array([3, 0, 7, 1, 12, 0, 40, 5] * 8, np.int32)
+    labels = np.array([0, 3, 0, 7, 1, 300, 12, 40] * 8, np.int32)
+    mil = args.workload == "mil_epoch"
+    step = cpu_mil_epoch if mil else cpu_reference_step
+    nb = args.ref_bags * (12 if mil else 1)
     for i in range(args.warmup):
-        cpu_reference_step(1 if i else 1, sd, labels, 100 + i)
+        step(1, sd, labels, 100 + i)
     inst, secs = 0, 0.0
     for i in range(args.steps):
-        n, s = cpu_reference_step(args.ref_bags, sd, labels, i)
+        n, s = step(nb, sd, labels, i)
         inst += n; secs += s
     val = inst / secs
-    sample = "%d bags x 3025 instances per step (unfold + fp32 forward + lexsort/top-k loop)" % args.ref_bags
+    if mil:
+        sample = ("%d bags x 225 instances per step: unfold + fp32 forward + lexsort/top-k loop + make_train_data + "
+                  "fc_tile training (oracle port of one train_tile.py epoch)" % nb)
+        workload = ("configs[2] MIL epoch (score -> adaptive top-k -> pseudo-label -> fc_tile training), tile 32 "
+                    "interval 20; CPU reference path (oracle port) on a bounded sample")
+        metric = "instances/sec (MIL epoch: score+select+train)"
+    else:
+        sample = ("%d bags x 3025 instances per step (configs[0] batch of 8): per-tile unfold loop as in the reference's "
+                  "__getitem__ + fp32 forward on all cores + lexsort/top-k loop" % nb)
+        workload = ("configs[1] ResNet-34 tile inference + adaptive top-k, tile 32 interval 5; CPU reference path "
+                    "(oracle port of inference_tiles + sample) on a bounded sample of the same per-instance work")
+        metric = METRIC
     print(json.dumps({
-        "impl": "reference", "metric": "instances/sec (score+adaptive top-k)", "value": val,
+        "impl": "reference", "metric": metric, "value": val,
         "unit": "instances/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
-        "ms_per_step": 1e3 * secs / args.steps, "higher_is_better": True, "scaling": "weak",
+        "ms_per_step": 1e3 * secs / args.steps, "higher_is_better": True,
+        "scaling": "strong" if mil else "weak",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": "configs[1] ResNet-34 tile inference + adaptive top-k, tile 32 interval 5; "
-                               "CPU reference path (oracle port of inference_tiles + sample) on a bounded sample"},
+        "config": {"workload": workload},
         "cpu_baseline": {"value": val, "unit": "instances/s", "cores": os.cpu_count(), "kind": "port",
                          "sample": sample},
         "e2e": {"value": val, "unit": "instances/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }))
+
+
+# ------------------------------------------------------------------------------------------------
+# configs[2]: the MIL epoch (all ranks; the one leg with collectives)
+# ------------------------------------------------------------------------------------------------
+def run_mil_epoch_leg(dev, rank, world, n_bags, batch_size=40960, reps=2, cache_modes=(True, False)):
+    """One train_tile.py epoch per measurement: score the rank's shard of `n_bags` bags (tile 32,
+    interval 20 -> 225 instances per bag) -> adaptive top-k -> packed all-gather -> make_train_data
+    -> fc_tile training (Adam lr 5e-4 wd 1e-4, batch 40 960, CE) with one all-reduce per step.
+    Timed with CUDA events around the whole epoch (host work included), max over ranks."""
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+    from cellsegmentation_b200 import synthetic
+    from cellsegmentation_b200.dataset import LystoDataset
+    from cellsegmentation_b200.distributed import shard_range
+    from cellsegmentation_b200.mil import mil_epoch
+    from cellsegmentation_b200.model.resnet import MILresnet34
+
+    labels = synthetic.make_labels(n_bags + 1, seed=11)
+    # every rank materialises only its own shard of the global bag array
+    lo, hi = shard_range(n_bags, rank, world)                    # in units of tile-owning bags
+    first_img = 0 if lo == 0 else lo + 1
+    last_img = hi + 1
+    mine = synthetic.make_bags_device(last_img - first_img, dev, seed=1000 + rank)
+    # global view: a LystoDataset whose `images` exposes len() and slicing of the local range only
+    ds = LystoDataset.from_device_tensor(mine if world == 1 else _ShardedBags(mine, first_img, n_bags + 1),
+                                         labels, TILE, 20)
+    torch.manual_seed(0)
+    net = MILresnet34()
+    net.setmode("tile")
+    net.to(dev)
+    crit = torch.nn.CrossEntropyLoss()
+    out = {}
+    T = ds.tiles_per_bag
+    n_inst = n_bags * T
+    for cache in cache_modes:
+        best = None
+        for rep in range(reps + 1):                              # first repetition is warm-up
+            opt = torch.optim.Adam(filter(lambda p: p.requires_grad, net.parameters()), lr=5e-4, weight_decay=1e-4)
+            timing = {}
+            torch.cuda.synchronize()
+            if world > 1:
+                dist.barrier()
+                torch.cuda.synchronize()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            loss, pos, neg = mil_epoch(ds, net, dev, crit, opt, 1, 30, 0.5, batch_size, seed=rep,
+                                       cache_features=cache, timing=timing)
+            e1.record()
+            torch.cuda.synchronize()
+            ms = e0.elapsed_time(e1)
+
+            def span(key):
+                evs = timing.get(key)
+                if not evs:
+                    return 0.0
+                if isinstance(evs, tuple):
+                    return evs[0].elapsed_time(evs[1])
+                return sum(a.elapsed_time(b) for a, b in evs)
+            row = [ms, span("score_events"), span("select_events"), span("allgather_events"), span("allreduce_events")]
+            t = torch.tensor(row, dtype=torch.float64, device=dev)
+            if world > 1:
+                dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            row = t.tolist()
+            if rep > 0 and (best is None or row[0] < best[0]):
+                best = row + [len(timing.get("allreduce_events", [])), pos, neg, loss,
+                              timing.get("allgather_bytes", 0), timing.get("allreduce_bytes", 0)]
+        steps = -(-(best[6] + best[7]) // batch_size)
+        out["cache_features" if cache else "recompute"] = {
+            "epoch_ms": best[0], "instances_per_s": n_inst / (best[0] * 1e-3),
+            "score_ms": best[1], "select_ms": best[2],
+            "allgather_ms": best[3], "allgather_bytes_per_rank": best[9],
+            "allreduce_ms_total": best[4], "allreduce_calls": best[5], "allreduce_bytes_per_call": best[10],
+            "host_and_train_ms": best[0] - best[1] - best[2] - best[3],
+            "train_steps": steps, "selected_pos": best[6], "selected_neg": best[7], "loss": best[8]}
+    out["workload"] = ("configs[2]: one MIL epoch, %d bags (+1 tile-less bag 0) sharded over %d rank(s), tile 32 "
+                       "interval 20 (%d instances/bag, %d scored), batch %d, Adam, CE; strong scaling"
+                       % (n_bags, world, T, n_inst, batch_size))
+    out["instances"] = n_inst
+    out["collectives"] = ("1 all_gather_into_tensor of (1 + capacity) int64 per rank + 1 all_reduce of 1027 fp32 "
+                          "per training step; none at world 1")
+    if net._clf is not None:
+        net._clf.close()
+    return out
+
+
+class _ShardedBags:
+    """Global bag array of which only this rank's contiguous range is materialised: supports
+    len() and the contiguous slicing shard_dataset() performs -- all the MIL epoch asks of
+    `trainset.images` -- so an 8-GPU epoch holds 1/8 of the bags per GPU."""
+
+    def __init__(self, local, first, total):
+        self.local, self.first, self.total = local, first, total
+        self.is_cuda, self.dtype, self.device = True, local.dtype, local.device
+        self.shape = (total,) + tuple(local.shape[1:])
+
+    def __len__(self):
+        return self.total
+
+    def __getitem__(self, sl):
+        if not isinstance(sl, slice):
+            raise TypeError("only contiguous slices of the sharded bag array are available")
+        a, b, _ = sl.indices(self.total)
+        if a >= b:
+            return self.local[0:0]
+        if a < self.first or b > self.first + self.local.shape[0]:
+            raise IndexError("bags [%d,%d) are not resident on this rank (has [%d,%d))"
+                             % (a, b, self.first, self.first + self.local.shape[0]))
+        return self.local[a - self.first:b - self.first]
 
 
 def main():
@@ -163,6 +356,37 @@ def main():
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
 
+    def sync_all():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+            torch.cuda.synchronize()
+
+    pk, pk_kind = peaks()
+
+    if args.workload == "mil_epoch":
+        sampler = ClockSampler(local)
+        if rank == 0:
+            sampler.start()
+        leg = run_mil_epoch_leg(dev, rank, world, args.mil_bags, reps=max(args.steps, 1))
+        clocks = sampler.stop() if rank == 0 else None
+        if rank == 0:
+            c = leg["cache_features"]
+            out = {"metric": "instances/sec (MIL epoch: score+select+train)", "value": c["instances_per_s"],
+                   "unit": "instances/s", "n_gpus": world, "steps": max(args.steps, 1), "warmup": 1,
+                   "ms_per_step": c["epoch_ms"], "higher_is_better": True, "scaling": "strong",
+                   "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
+                   "config": {"workload": leg["workload"], "feature_cache": True},
+                   "e2e": {"value": c["instances_per_s"], "unit": "instances/s",
+                           "h2d_bytes_per_step": 0, "d2h_bytes_per_step": int(c["allgather_bytes_per_rank"] * world),
+                           "note": "bags are HBM resident across epochs as in train_tile.py (the dataset is loaded "
+                                   "once); the epoch's D2H is the gathered selection"},
+                   "gpu_launches": None, "clocks": clocks, "mil_epoch": leg}
+            print(json.dumps(out))
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
     B = args.bags_per_step
     resident = args.resident_bags or max(B * (args.steps + args.warmup + 1), B)
     resident = min(resident, 20000 // max(world, 1)) if args.resident_bags == 0 else resident
@@ -175,6 +399,7 @@ def main():
     n_inst = B * T_PER_BAG
     prob = torch.empty(n_inst, dtype=torch.float32, device=dev)
     cap = int(B * 330)
+    sel_buf = ops.select_buffers(B, cap, dev)
     launches = [0]
 
     def step_device(i, ev=None):
@@ -185,21 +410,45 @@ def main():
         clf.forward_tiles(view, TILE, INTERVAL, precision="bf16", max_batch=args.max_batch, prob_out=prob)
         if ev:
             ev[1].record()
-        idx, pl, off = ops.select_topk(prob, labels[b0:b0 + B], B, T_PER_BAG, 1, 30, capacity=cap)
+        # no host round trip: outputs pre-allocated, the kept count stays on the device (offsets[-1])
+        ops.select_topk(prob, labels[b0:b0 + B], B, T_PER_BAG, 1, 30, sync=False, out=sel_buf)
         if ev:
             ev[2].record()
         launches[0] += clf.last_launch_count + 4   # + count, scan, fast select, exact fallback
-        return idx
-
-    def sync_all():
-        torch.cuda.synchronize()
-        if world > 1:
-            dist.barrier()
-            torch.cuda.synchronize()
+        return b0
 
     for i in range(args.warmup):
-        step_device(i)
+        b0 = step_device(i)
     sync_all()
+
+    # ---- verification of the step's output (outside the timed region) ----------------------------
+    verify = None
+    if not args.no_verify and rank == 0:
+        from oracle import select as oselect
+        clf32 = ops.TileClassifier("resnet34", convs, fc_w, fc_b, device=dev)
+        view = bags[b0:b0 + B]
+        rng = np.random.default_rng(0)
+        worst = 0.0
+        for s0 in sorted(rng.integers(0, n_inst - 512, 8).tolist()) + [0, n_inst - 512]:
+            p32 = clf32.forward_tiles(view, TILE, INTERVAL, inst_begin=int(s0), inst_count=512, precision="fp32",
+                                      max_batch=512)
+            worst = max(worst, float((p32 - prob[s0:s0 + 512]).abs().max()))
+        clf32.close()
+        p_h = prob.cpu().numpy()
+        lab_h = labels_h[b0:b0 + B]
+        want = oselect.sample_indices(np.repeat(np.arange(B), T_PER_BAG), lab_h, p_h, 1, 30)
+        m = int(sel_buf[2][-1].item())
+        got = sel_buf[0][:m].cpu().numpy().astype(np.int64)
+        got_pl = sel_buf[1][:m].cpu().numpy()
+        sel_ok = bool(np.array_equal(got, want)) and \
+            bool(np.array_equal(got_pl, (lab_h[want // T_PER_BAG] != 0).astype(np.uint8)))
+        verify = {"probs_checked": 5120, "max_abs_dp_vs_fp32_cuda": worst, "tol": 2e-2,
+                  "selection_equals_oracle": sel_ok, "selected": m, "finite": bool(np.isfinite(p_h).all())}
+        if not (worst <= 2e-2 and sel_ok and verify["finite"]):
+            print(json.dumps({"error": "verification of the timed step failed", "verify": verify}))
+            sys.exit(3)
+    sync_all()
+
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
@@ -230,23 +479,20 @@ def main():
         return min(a.elapsed_time(b) for a, b in ev)
 
     side = {}
-    if rank == 0:
+    if rank == 0 and not args.no_side_legs:
         nb_sel = 20000
         g = torch.Generator(device=dev); g.manual_seed(7)
         p_all = torch.rand(nb_sel * T_PER_BAG, device=dev, generator=g)
         lab_all = torch.from_numpy(synthetic.make_labels(nb_sel, seed=3)).to(dev)
-        sel_out = {}
-
-        def run_sel():
-            sel_out["r"] = ops.select_topk(p_all, lab_all, nb_sel, T_PER_BAG, 1, 30, capacity=nb_sel * 330)
-        ms = time_alone(run_sel)
-        m_kept = int(sel_out["r"][0].numel())
+        buf20 = ops.select_buffers(nb_sel, nb_sel * 330, dev)
+        ms = time_alone(lambda: ops.select_topk(p_all, lab_all, nb_sel, T_PER_BAG, 1, 30, sync=False, out=buf20))
+        m_kept = int(buf20[2][-1].item())
         sel_bytes = 4.0 * p_all.numel() + 5.0 * m_kept + 4.0 * nb_sel
         side["select_20k"] = {"bound": "hbm", "bags": nb_sel, "instances": int(p_all.numel()), "kept": m_kept,
                               "ms": ms, "instances_per_s": p_all.numel() / (ms * 1e-3),
                               "achieved": sel_bytes / (ms * 1e-3) / 1e9, "unit": "GB/s",
-                              "note": "4 launches (count, scan, fast select, exact fallback) + one .item() sync inside the timing"}
-        del p_all, sel_out
+                              "note": "whole cs_select_topk call (all its launches), pre-allocated outputs, no host sync"}
+        del p_all, buf20
         # K4b at the config-5 size class: 8000 bags (3.6 GB of traffic per launch, >> L2)
         nb_m = max(resident, 8000)
         imgs_m = bags if nb_m == resident else synthetic.make_bags_device(nb_m, dev, seed=99)
@@ -270,25 +516,46 @@ def main():
         side["remove_small_regions"] = {"bags": nb_c, "ms": ms_cc, "masks_per_s": nb_c / (ms_cc * 1e-3),
                                         "note": "includes a device copy of the 2000 input masks"}
         side["preprocess_masks_chain"] = {"masks_per_s": 1.0 / (ms / nb_m * 1e-3 + ms_cc / nb_c * 1e-3)}
+        if not args.no_cpu_baseline:
+            cpu_m = cpu_masks_baseline()
+            side["hsv_refine"]["cpu_baseline"] = {"value": cpu_m["hsv_masks_per_s"], "unit": "masks/s", "cores": 1,
+                                                  "kind": "port", "sample": cpu_m["sample"]}
+            side["remove_small_regions"]["cpu_baseline"] = {"value": cpu_m["cc_masks_per_s"], "unit": "masks/s",
+                                                            "cores": 1, "kind": "port", "sample": cpu_m["sample"]}
+            side["preprocess_masks_chain"]["cpu_baseline"] = {"value": cpu_m["chain_masks_per_s"], "unit": "masks/s",
+                                                              "cores": 1, "kind": "port", "sample": cpu_m["sample"]}
         del masks, out_m, cc_in, work
         # configs[3]: ResNeXt-50 32x4d backbone at a denser tile stride (interval 3 -> 8100
-        # instances per bag), score + select, timed alone on a 64-bag slice
-        nb_x, iv_x = 64, 3
+        # instances per bag), score + select over 256 bags = 2.07 M instances (55 forward batches)
+        nb_x, iv_x = min(256, resident), 3
         t_x = ((H - TILE + iv_x - 1) // iv_x + 1) ** 2
         cx, fwx, fbx = synthetic.make_resnet_weights("resnext50_32x4d", seed=0)
         clf_x = ops.TileClassifier("resnext50_32x4d", cx, fwx, fbx, device=dev)
         prob_x = torch.empty(nb_x * t_x, dtype=torch.float32, device=dev)
+        buf_x = ops.select_buffers(nb_x, nb_x * 330, dev)
+        fwd_x = {}
 
         def run_x():
-            clf_x.forward_tiles(bags[:nb_x], TILE, iv_x, precision="bf16", max_batch=args.max_batch // 2,
-                                prob_out=prob_x)
-            ops.select_topk(prob_x, labels[:nb_x], nb_x, t_x, 1, 30, capacity=nb_x * 330)
-        ms_x = time_alone(run_x, reps=3)
+            a, b, c = (torch.cuda.Event(enable_timing=True) for _ in range(3))
+            a.record()
+            clf_x.forward_tiles(bags[:nb_x], TILE, iv_x, precision="bf16", max_batch=args.max_batch, prob_out=prob_x)
+            b.record()
+            ops.select_topk(prob_x, labels[:nb_x], nb_x, t_x, 1, 30, sync=False, out=buf_x)
+            c.record()
+            fwd_x["ev"] = (a, b)
+        ms_x = time_alone(run_x, reps=2)
+        fwd_ms_x = fwd_x["ev"][0].elapsed_time(fwd_x["ev"][1])
+        tf_x = FLOP_INBOUNDS_RX50 * nb_x * t_x / (fwd_ms_x * 1e-3) / 1e12
+        peak_t = pk.get("bf16_tflops_sustained", pk.get("bf16_tflops"))
         side["resnext50_32x4d_dense_stride"] = {
-            "workload": "configs[3]: ResNeXt-50 32x4d, tile 32 interval 3 (%d instances/bag), %d bags" % (t_x, nb_x),
-            "ms": ms_x, "instances_per_s": nb_x * t_x / (ms_x * 1e-3), "launches": clf_x.last_launch_count + 4}
+            "bound": "tensor",
+            "workload": "configs[3]: ResNeXt-50 32x4d, tile 32 interval 3 (%d instances/bag), %d bags = %d instances"
+                        % (t_x, nb_x, nb_x * t_x),
+            "ms": ms_x, "fwd_ms": fwd_ms_x, "instances_per_s": nb_x * t_x / (ms_x * 1e-3),
+            "achieved": tf_x, "unit": "TFLOP/s", "peak": peak_t, "frac": tf_x / peak_t,
+            "flop_per_instance": FLOP_INBOUNDS_RX50, "launches": clf_x.last_launch_count + 4}
         clf_x.close()
-        del prob_x
+        del prob_x, buf_x
 
     # ---- end to end: host (pinned) bags -> H2D -> score + select -> D2H of the selection
     host = torch.empty((B, H, H, 3), dtype=torch.uint8).pin_memory()
@@ -298,17 +565,19 @@ def main():
     d_lab = torch.empty(B, dtype=torch.int32, device=dev)
     out_idx = torch.empty(cap, dtype=torch.int32).pin_memory()
     out_lab = torch.empty(cap, dtype=torch.uint8).pin_memory()
+    out_off = torch.empty(B + 1, dtype=torch.int64).pin_memory()
 
     def step_e2e():
         stage.copy_(host, non_blocking=True)
         d_lab.copy_(host_labels, non_blocking=True)
         clf.forward_tiles(stage, TILE, INTERVAL, precision="bf16", max_batch=args.max_batch, prob_out=prob)
-        idx, pl, off = ops.select_topk(prob, d_lab, B, T_PER_BAG, 1, 30, capacity=cap)
-        m = idx.numel()
-        out_idx[:m].copy_(idx, non_blocking=True)
-        out_lab[:m].copy_(pl, non_blocking=True)
+        ops.select_topk(prob, d_lab, B, T_PER_BAG, 1, 30, sync=False, out=sel_buf)
+        # the selection leaves in its capacity-sized buffers with the per-bag offsets: one sync per step
+        out_idx.copy_(sel_buf[0], non_blocking=True)
+        out_lab.copy_(sel_buf[1], non_blocking=True)
+        out_off.copy_(sel_buf[2], non_blocking=True)
         torch.cuda.current_stream().synchronize()
-        return m
+        return int(out_off[-1])
 
     for _ in range(2):
         m_sel = step_e2e()
@@ -326,14 +595,25 @@ def main():
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     ms_total, ms_e2e, fwd_ms, sel_ms = t.tolist()
 
+    # free the headline workload before the MIL-epoch leg (18 000 bags + 8 GB of cached features at N = 1)
+    del host, stage, bags, prob
+    clf.close()
+    torch.cuda.empty_cache()
+    mil_leg = None
+    if not args.no_side_legs:
+        try:
+            mil_leg = run_mil_epoch_leg(dev, rank, world, args.mil_bags, reps=1)
+        except Exception as e:  # the headline must not be lost to a side leg
+            mil_leg = {"error": "%s: %s" % (type(e).__name__, e)}
+
     if rank == 0:
-        pk, pk_kind = peaks()
         value = world * n_inst * args.steps / (ms_total * 1e-3)
         e2e_v = world * n_inst * args.steps / (ms_e2e * 1e-3)
         tflops = FLOP_INBOUNDS * n_inst / (fwd_ms * 1e-3) / 1e12
         peak = pk.get("bf16_tflops_sustained", pk.get("bf16_tflops"))
+        traffic = measured_traffic(n_inst)
         out = {
-            "metric": "instances/sec (score+adaptive top-k)", "value": value, "unit": "instances/s",
+            "metric": METRIC, "value": value, "unit": "instances/s",
             "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms_total / args.steps, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
@@ -343,41 +623,45 @@ def main():
                        "bags_per_step_per_gpu": B, "instances_per_step_per_gpu": n_inst,
                        "max_batch": args.max_batch, "tiles_per_pos": 1, "topk_neg": 30,
                        "l2": "inputs (u8 slice %.0f MB + activation workspace) larger than L2; no flush" % (B * 268203 / 1e6),
-                       "weights": "random-init ResNet-34, BN folded"},
+                       "weights": "random-init ResNet-34, BN folded",
+                       "reference_arm_sample": "the CPU arm times the same per-instance work on %d bags per step "
+                                               "(configs[0]); rates are per instance and comparable" % args.ref_bags},
             "e2e": {"value": e2e_v, "unit": "instances/s", "h2d_bytes_per_step": int(B * 268203 + 4 * B),
-                    "d2h_bytes_per_step": int(m_sel * 5)},
+                    "d2h_bytes_per_step": int(cap * 5 + 8 * (B + 1)), "selected_per_step": m_sel},
             "gpu_launches": int(gpu_launches),
             "clocks": clocks,
-            "roofline": {"bound": "tensor", "kernel": "conv stage: stem_win_kernel + 32 conv_halo/conv_gemm launches + head per batch",
+            "verify": verify,
+            "roofline": {"bound": "tensor", "kernel": "conv stage: stem + conv launches + head per forward batch",
                          "achieved": tflops, "peak": peak, "unit": "TFLOP/s", "frac": tflops / peak,
                          "peak_kind": pk_kind + " bf16_tflops_sustained",
-                         "traffic": (measured_traffic(n_inst) or {}).get("bytes"),
-                         "traffic_detail": measured_traffic(n_inst),
+                         "traffic": (traffic or {}).get("bytes"),
+                         "traffic_detail": traffic,
                          "flop_per_instance": FLOP_INBOUNDS,
-                         "achieved_nominal": FLOP_NOMINAL * n_inst / (fwd_ms * 1e-3) / 1e12,
                          "fwd_ms_per_step": fwd_ms,
                          "select_in_step": {"bound": "hbm", "ms_per_step": sel_ms,
-                                            "note": "the step's own selection over %d bags: four small launches + "
-                                                    "the .item() sync, launch-latency bound; select_20k is the "
-                                                    "kernel at the config's full size" % B,
-                                    "achieved": SELECT_BYTES_PER_INST * n_inst / (sel_ms * 1e-3) / 1e9,
-                                    "peak": pk["hbm_gbs"], "unit": "GB/s",
-                                    "frac": SELECT_BYTES_PER_INST * n_inst / (sel_ms * 1e-3) / 1e9 / pk["hbm_gbs"]}},
+                                            "note": "the step's own selection over %d bags (launch-latency bound at "
+                                                    "this size; select_20k is the kernel at the config's full size)" % B,
+                                            "achieved": SELECT_BYTES_PER_INST * n_inst / (sel_ms * 1e-3) / 1e9,
+                                            "peak": pk["hbm_gbs"], "unit": "GB/s",
+                                            "frac": SELECT_BYTES_PER_INST * n_inst / (sel_ms * 1e-3) / 1e9 / pk["hbm_gbs"]}},
         }
         for k, v in side.items():
-            if "achieved" in v:
+            if v.get("bound") == "hbm" and "achieved" in v:
                 v["peak"] = pk["hbm_gbs"]
                 v["frac"] = v["achieved"] / pk["hbm_gbs"]
             out["roofline"][k] = v
+        if mil_leg is not None:
+            out["mil_epoch"] = mil_leg
         if not args.no_cpu_baseline:
             from oracle import model as omodel
             torch.set_num_threads(os.cpu_count())
             sd = omodel.make_state_dict("resnet34", seed=0, random_bn=False)
-            lab8 = np.array([3, 0, 7, 1, 12, 0, 40, 5], np.int32)
+            lab8 = np.array([0, 3, 0, 7, 1, 300, 12, 40], np.int32)
             cpu_reference_step(1, sd, lab8, 99)
-            n, s = cpu_reference_step(3, sd, lab8, 0)
+            n, s = cpu_reference_step(4, sd, lab8, 0)
             out["cpu_baseline"] = {"value": n / s, "unit": "instances/s", "cores": os.cpu_count(), "kind": "port",
-                                   "sample": "3 bags x 3025 instances: unfold + fp32 forward + lexsort/top-k loop (oracle port)"}
+                                   "sample": "4 bags x 3025 instances: per-tile unfold loop (as the reference's "
+                                             "__getitem__) + fp32 forward on all cores + lexsort/top-k loop (oracle port)"}
         print(json.dumps(out))
     if world > 1:
         dist.destroy_process_group()

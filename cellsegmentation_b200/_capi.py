@@ -72,7 +72,7 @@ _PROTOS = {
     "cs_debug_gemm_bf16": (c_int, [c_void_p, c_void_p, c_int64, c_int, c_int, c_void_p, c_int,
                                    c_void_p, c_void_p]),
     "cs_debug_conv_bf16": (c_int, [c_void_p, c_int64, c_int, c_int, c_int, c_int, c_int, c_int, c_int,
-                                   c_void_p, c_void_p, c_void_p, c_void_p]),
+                                   c_void_p, c_void_p, c_int, c_void_p, c_void_p]),
 }
 
 EXPORTED = tuple(_PROTOS)

@@ -319,7 +319,7 @@ remove_small_regions_kernel(uint8_t* mask, int n_bags, int H, int W, int min_obj
 }
 
 int cc_grid(int n_bags) {
-  int g = cs::kNumSMs;      // the run tables take most of an SM's shared memory: one CTA per SM
+  int g = cs::num_sms();      // the run tables take most of an SM's shared memory: one CTA per SM
   return n_bags < g ? n_bags : g;
 }
 

@@ -13,7 +13,8 @@ namespace cs {
 void set_error(const char* fmt, ...);
 const char* last_error();
 
-constexpr int kNumSMs = 148;  // B200: 2 dies x 74 SMs
+// SM count of the current device, cached per device (B200: 2 dies x 74 SMs = 148).
+int num_sms();
 
 inline cudaStream_t as_stream(void* s) { return reinterpret_cast<cudaStream_t>(s); }
 

@@ -298,7 +298,7 @@ int launch_gemm_bn(const GemmParams& p, cudaStream_t st) {
   const uint32_t smem = Cfg::smem_bytes(q.stages, q.epi_set_bytes);
   const int m_groups = (p.num_m_tiles + CL - 1) / CL;
   const int work = m_groups * p.num_n_tiles;
-  int clusters = work < kNumSMs / CL ? work : kNumSMs / CL;
+  int clusters = work < num_sms() / CL ? work : num_sms() / CL;
   CS_CUDA(launch_pdl(conv_gemm_kernel<BN, CL>, dim3((unsigned)(clusters * CL)), dim3(kGemmThreads), smem, st,
                      CL, q));
   return CS_OK;

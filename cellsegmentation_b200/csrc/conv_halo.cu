@@ -276,7 +276,7 @@ int launch_halo(const HaloParams& p, cudaStream_t st) {
     if (dev < 64) attr_done[dev] = true;
   }
   const int groups = (p.num_m_tiles + CL - 1) / CL;
-  const int clusters = groups < kNumSMs / CL ? groups : kNumSMs / CL;
+  const int clusters = groups < num_sms() / CL ? groups : num_sms() / CL;
   CS_CUDA(launch_pdl(conv_halo_kernel<BN, W, CCH, BRES, CL>, dim3((unsigned)(clusters * CL)),
                      dim3(kHaloThreads), Cfg::kSmemBytes, st, CL, p));
   return CS_OK;

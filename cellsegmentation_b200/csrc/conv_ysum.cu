@@ -17,16 +17,21 @@
 // (8 KB per tile).  Bias, residual, ReLU and the bf16 (hi / lo) split follow in place in the
 // swizzled staging tile that the DMA warp moves with TMA, as in gemm_epilogue.cuh.
 //
-// Warp roles (352 threads, one CTA per SM, persistent over M tiles of two instances):
-//   warp 0 TMA producer   warp 1 TMEM alloc + MMA issue   warps 2-9 epilogue (TMEM lane quarter
-//   = warp % 4, channel half = (warp - 2) / 4)   warp 10 epilogue DMA
+// Warp roles (one CTA per SM, persistent over M tiles of two instances):
+//   warp 0 TMA producer   warp 1 TMEM alloc + MMA issue   warps 2 .. 2+EW-1 epilogue (TMEM lane
+//   quarter = warp % 4, channel group = (warp - 2) / 4)   last warp: epilogue DMA
+// EW = 16 epilogue warps (four per scheduler, 16 channels each) is the default: with EW = 8 a
+// tile's epilogue (~450 dependent instructions per thread, two warps per scheduler) took ~2 400
+// cycles against 1 152 cycles of MMA and bounded the kernel (46-48 % tensor pipe, ncu r01_n).
+#include <stdlib.h>
+#include <string.h>
+
 #include "fwd.cuh"
 #include "gemm_epilogue.cuh"
 
 namespace cs {
 namespace {
 
-constexpr int kThreads = 352;
 constexpr int kMaxStages = 6;                      // 6 when only bf16 tiles are staged, else 4
 constexpr uint32_t kABytes = 128 * 128;            // one shifted box: 128 rows x 64 ch bf16
 constexpr uint32_t kBTileFull = 192 * 128;         // [dy*64 + co][64 ci] of one dx
@@ -53,12 +58,28 @@ __device__ __forceinline__ void sts32(uint32_t addr, uint32_t v) {
   asm volatile("st.shared.u32 [%0], %1;" ::"r"(addr), "r"(v) : "memory");
 }
 
+template <int NI>
+__device__ __forceinline__ void tmem_ld_16x256b(uint32_t taddr, uint32_t (&r)[4 * NI]);
+template <>
+__device__ __forceinline__ void tmem_ld_16x256b<4>(uint32_t taddr, uint32_t (&r)[16]) {
+  tmem_ld_16x256b_x4(taddr, r);
+}
+template <>
+__device__ __forceinline__ void tmem_ld_16x256b<2>(uint32_t taddr, uint32_t (&r)[8]) {
+  asm volatile("tcgen05.ld.sync.aligned.16x256b.x2.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]),
+                 "=r"(r[7])
+               : "r"(taddr));
+}
+
 // CL = 2: CTA pairs (tcgen05 cta_group::2) as in conv_gemm.cu -- neighbouring M tiles, each CTA
 // holds its own A boxes and 96 of the 192 rows of every weight tile, the leader issues M = 256
 // MMAs for both.
-template <int CL>
-__global__ void __launch_bounds__(kThreads, 1)
+template <int CL, int EW>
+__global__ void __launch_bounds__((EW + 3) * 32, 1)
 conv_ysum_kernel(const __grid_constant__ YsumParams p) {
+  constexpr int NI = 32 / EW;                     // 8-channel groups per epilogue thread: 4 | 2
+  constexpr int CW = 8 * NI;                      // channels per epilogue warp: 32 | 16
   constexpr uint32_t kBTile = kBTileFull / CL;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw = smem_u32(smem_raw);
@@ -95,10 +116,10 @@ conv_ysum_kernel(const __grid_constant__ YsumParams p) {
     for (int s = 0; s < kStages; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
     for (int a = 0; a < 2; ++a) {
       mbar_init(tfull_bar(a), 1);
-      mbar_init(tempty_bar(a), CL == 1 ? kEpiThreads : CL * kEpiWarps);
+      mbar_init(tempty_bar(a), CL == 1 ? EW * 32 : CL * EW);
     }
     mbar_init(bres_bar, 1);
-    epi_bars_init(ebars);
+    epi_bars_init(ebars, EW * 32);
     fence_barrier_init();
     prefetch_tmap(&p.a_map);
     prefetch_tmap(&p.b_map);
@@ -172,19 +193,19 @@ conv_ysum_kernel(const __grid_constant__ YsumParams p) {
         if (acc == 0) acc_phase ^= 1u;
       }
     }
-  } else if (warp < 2 + kEpiWarps) {
+  } else if (warp < 2 + EW) {
     pdl_wait();
     const int quad = warp & 3;                 // TMEM lanes 32*quad ..: image quad/2, rows y0 .. y0+3
-    const int half = (warp - 2) >> 2;          // channels 32*half .. 32*half+31
+    const int cg = (warp - 2) >> 2;            // channels CW*cg .. CW*cg + CW-1
     const int g = lane >> 2, t = lane & 3;     // x, channel-pair slot
     const bool upper = (quad & 1) == 0;        // owns image rows 0..3 (else 4..7)
-    const int pair_bar = 1 + (quad >> 1) * 2 + half;          // named barrier of the two quarters
-    const int partner = (warp - 2) ^ 1;                        // same image, same channel half
-    float bias_r[4][2];
+    const int pair_bar = 1 + (quad >> 1) * (EW / 4) + cg;     // named barrier of the two quarters
+    const int partner = (warp - 2) ^ 1;                        // same image, same channel group
+    float bias_r[NI][2];
 #pragma unroll
-    for (int i = 0; i < 4; ++i) {
-      bias_r[i][0] = p.bias[half * 32 + 8 * i + 2 * t];
-      bias_r[i][1] = p.bias[half * 32 + 8 * i + 2 * t + 1];
+    for (int i = 0; i < NI; ++i) {
+      bias_r[i][0] = p.bias[cg * CW + 8 * i + 2 * t];
+      bias_r[i][1] = p.bias[cg * CW + 8 * i + 2 * t + 1];
     }
     const bool rh = p.res_hi != nullptr, rl = p.res_lo != nullptr;
     const bool oh = p.out_hi != nullptr, ol = p.out_lo != nullptr;
@@ -195,15 +216,15 @@ conv_ysum_kernel(const __grid_constant__ YsumParams p) {
       const int m_tile = tile_of(gi);
       mbar_wait(tfull_bar(acc), acc_phase);
       tc_fence_after();
-      // R[dy][w][4i + 2h + e]: image row y0 + 2w + h, column x = g, channel 32*half + 8i + 2t + e
-      uint32_t R[3][2][16];
+      // R[dy][w][4i + 2h + e]: image row y0 + 2w + h, column x = g, channel CW*cg + 8i + 2t + e
+      uint32_t R[3][2][4 * NI];
 #pragma unroll
       for (int dy = 0; dy < 3; ++dy)
 #pragma unroll
         for (int w = 0; w < 2; ++w)
-          tmem_ld_16x256b_x4(tmem_base + ((uint32_t)(quad * 32 + w * 16) << 16) +
-                                 (uint32_t)(acc * kAccCols + dy * 64 + half * 32),
-                             R[dy][w]);
+          tmem_ld_16x256b<NI>(tmem_base + ((uint32_t)(quad * 32 + w * 16) << 16) +
+                                  (uint32_t)(acc * kAccCols + dy * 64 + cg * CW),
+                              R[dy][w]);
       tmem_ld_wait();
       tc_fence_before();
       if (CL == 1) {
@@ -217,24 +238,24 @@ conv_ysum_kernel(const __grid_constant__ YsumParams p) {
       auto D = [&](int dy, int yy, int i, int e) -> float {
         return __uint_as_float(R[dy][yy >> 1][4 * i + 2 * (yy & 1) + e]);
       };
-      // rows 3 | 4 of an image live in different lane quarters: exchange them (fp32, 8 per thread)
-      float* xw = reinterpret_cast<float*>(base_ptr + kOffXch) + ((q & 1) * 8 + (warp - 2)) * 256 + lane * 8;
-      const float* xr = reinterpret_cast<const float*>(base_ptr + kOffXch) + ((q & 1) * 8 + partner) * 256 + lane * 8;
-      {
-        float4 e0, e1;
-        if (upper) {   // D_0 of row 3 feeds row 4 of the lower quarter
-          e0 = make_float4(D(0, 3, 0, 0), D(0, 3, 0, 1), D(0, 3, 1, 0), D(0, 3, 1, 1));
-          e1 = make_float4(D(0, 3, 2, 0), D(0, 3, 2, 1), D(0, 3, 3, 0), D(0, 3, 3, 1));
-        } else {       // D_2 of row 4 feeds row 3 of the upper quarter
-          e0 = make_float4(D(2, 0, 0, 0), D(2, 0, 0, 1), D(2, 0, 1, 0), D(2, 0, 1, 1));
-          e1 = make_float4(D(2, 0, 2, 0), D(2, 0, 2, 1), D(2, 0, 3, 0), D(2, 0, 3, 1));
-        }
-        reinterpret_cast<float4*>(xw)[0] = e0;
-        reinterpret_cast<float4*>(xw)[1] = e1;
+      // rows 3 | 4 of an image live in different lane quarters: exchange them (fp32, 2*NI per thread)
+      constexpr int kXw = 64 * NI;               // floats per warp slot (kXchBytes covers 2 x EW slots)
+      float* xw = reinterpret_cast<float*>(base_ptr + kOffXch) + ((q & 1) * EW + (warp - 2)) * kXw + lane * 2 * NI;
+      const float* xr = reinterpret_cast<const float*>(base_ptr + kOffXch) + ((q & 1) * EW + partner) * kXw + lane * 2 * NI;
+#pragma unroll
+      for (int i = 0; i < NI; i += 2) {
+        // D_0 of row 3 feeds row 4 of the lower quarter; D_2 of row 4 feeds row 3 of the upper one
+        reinterpret_cast<float4*>(xw)[i >> 1] =
+            upper ? make_float4(D(0, 3, i, 0), D(0, 3, i, 1), D(0, 3, i + 1, 0), D(0, 3, i + 1, 1))
+                  : make_float4(D(2, 0, i, 0), D(2, 0, i, 1), D(2, 0, i + 1, 0), D(2, 0, i + 1, 1));
       }
       named_bar(pair_bar, 64);
-      const float4 i0 = reinterpret_cast<const float4*>(xr)[0], i1 = reinterpret_cast<const float4*>(xr)[1];
-      const float imp[8] = {i0.x, i0.y, i0.z, i0.w, i1.x, i1.y, i1.z, i1.w};
+      float imp[2 * NI];
+#pragma unroll
+      for (int i = 0; i < NI; i += 2) {
+        const float4 v4 = reinterpret_cast<const float4*>(xr)[i >> 1];
+        imp[2 * i] = v4.x; imp[2 * i + 1] = v4.y; imp[2 * i + 2] = v4.z; imp[2 * i + 3] = v4.w;
+      }
 
       const int s = (int)(q & 1);
       mbar_wait(ebars.res_full[s], (uint32_t)((q >> 1) & 1));
@@ -244,7 +265,7 @@ conv_ysum_kernel(const __grid_constant__ YsumParams p) {
         const int row = quad * 32 + yy * 8 + g;          // row of the 128-row tile; row & 7 == g
         const uint32_t row_addr = stg + (uint32_t)row * 128u + 4u * t;
 #pragma unroll
-        for (int i = 0; i < 4; ++i) {
+        for (int i = 0; i < NI; ++i) {
           float v[2];
 #pragma unroll
           for (int e = 0; e < 2; ++e) {
@@ -255,14 +276,14 @@ conv_ysum_kernel(const __grid_constant__ YsumParams p) {
             else below = upper ? imp[2 * i + e] : 0.f;
             v[e] = above + D(1, yy, i, e) + below + bias_r[i][e];
           }
-          const uint32_t addr = row_addr + ((((uint32_t)(half * 4 + i)) ^ (uint32_t)g) << 4);
+          const uint32_t addr = row_addr + ((((uint32_t)(cg * NI + i)) ^ (uint32_t)g) << 4);
           if (rh) { const uint32_t r2 = lds32(addr); v[0] += bf16_lo_f(r2); v[1] += bf16_hi_f(r2); }
           if (rl) { const uint32_t r2 = lds32(addr + kEpiTileBytes); v[0] += bf16_lo_f(r2); v[1] += bf16_hi_f(r2); }
           if (p.relu) { v[0] = fmaxf(v[0], 0.f); v[1] = fmaxf(v[1], 0.f); }
           if (p.out_f32 != nullptr) {
             const int64_t grow = (int64_t)m_tile * 128 + row;
             if (grow < p.n_inst * 64)
-              *reinterpret_cast<float2*>(p.out_f32 + grow * 64 + half * 32 + 8 * i + 2 * t) = make_float2(v[0], v[1]);
+              *reinterpret_cast<float2*>(p.out_f32 + grow * 64 + cg * CW + 8 * i + 2 * t) = make_float2(v[0], v[1]);
           }
           const uint32_t hi = pack_bf16x2(v[0], v[1]);
           if (oh) sts32(addr, hi);
@@ -322,26 +343,34 @@ void pack_ysum_weights(const float* w_oihw, uint16_t* out) {
           out[((dx * 192) + dy * 64 + co) * 64 + ci] = rn(w_oihw[((co * 64 + ci) * 3 + dy) * 3 + dx]);
 }
 
-template <int CL>
+template <int CL, int EW>
 int launch_ysum(const YsumParams& p, cudaStream_t st) {
   static bool attr_done[64] = {false};
   int dev = 0;
   CS_CUDA(cudaGetDevice(&dev));
   if (dev >= 64 || !attr_done[dev]) {
-    CS_CUDA(cudaFuncSetAttribute(conv_ysum_kernel<CL>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    CS_CUDA(cudaFuncSetAttribute(conv_ysum_kernel<CL, EW>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                  (int)kSmemBytes));
     if (dev < 64) attr_done[dev] = true;
   }
+  const int sms = num_sms();
   const int groups = (p.num_m_tiles + CL - 1) / CL;
-  const int clusters = groups < kNumSMs / CL ? groups : kNumSMs / CL;
-  CS_CUDA(launch_pdl(conv_ysum_kernel<CL>, dim3((unsigned)(clusters * CL)), dim3(kThreads), kSmemBytes, st,
-                     CL, p));
+  const int clusters = groups < sms / CL ? groups : sms / CL;
+  CS_CUDA(launch_pdl(conv_ysum_kernel<CL, EW>, dim3((unsigned)(clusters * CL)), dim3((EW + 3) * 32), kSmemBytes,
+                     st, CL, p));
   return CS_OK;
 }
 
+// CELLSEG_YSUM_EPI=8 restores the two-warps-per-scheduler epilogue of round 1.
+const bool g_epi8 = []() {
+  const char* e = getenv("CELLSEG_YSUM_EPI");
+  return e != nullptr && strcmp(e, "8") == 0;
+}();
+
 int launch_conv_ysum(const YsumParams& p, cudaStream_t st) {
   if (p.num_m_tiles <= 0) return CS_OK;
-  return p.cluster > 1 ? launch_ysum<2>(p, st) : launch_ysum<1>(p, st);
+  if (g_epi8) return p.cluster > 1 ? launch_ysum<2, 8>(p, st) : launch_ysum<1, 8>(p, st);
+  return p.cluster > 1 ? launch_ysum<2, 16>(p, st) : launch_ysum<1, 16>(p, st);
 }
 
 }  // namespace cs

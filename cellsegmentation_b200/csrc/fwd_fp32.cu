@@ -199,7 +199,7 @@ int launch_maxpool_fp32(const float* in, float* out, int64_t n, int Hi, int Wi, 
   int Ho = (Hi + 2 - 3) / 2 + 1, Wo = (Wi + 2 - 3) / 2 + 1;
   int64_t total = n * Ho * Wo * C;
   int64_t want = ceil_div<int64_t>(total, 256);
-  int grid = (int)(want < (int64_t)kNumSMs * 32 ? want : (int64_t)kNumSMs * 32);
+  int grid = (int)(want < (int64_t)num_sms() * 32 ? want : (int64_t)num_sms() * 32);
   maxpool3x3s2_kernel<<<grid, 256, 0, st>>>(in, out, n, Hi, Wi, Ho, Wo, C);
   CS_LAUNCH_CHECK();
   return CS_OK;

@@ -145,7 +145,14 @@ stem_bf16_kernel(StemArgs a) {
 }
 
 // Tile head on the hi/lo stream: avgpool+maxpool -> Linear(C,2) -> softmax[:,1].
-// Reference: model/resnet.py:266-267, inference.py:24-27.  One warp per instance.
+// Reference: model/resnet.py:266-267, inference.py:24-27.  One warp per instance; a lane owns
+// groups of 8 consecutive channels (one 16-byte load per pixel, C % 256 == 0), so a 512-channel
+// 1x1 map is two independent 16-byte loads per lane and the launch streams x4 at HBM speed.
+__device__ __forceinline__ void unpack8(const uint4& u, float (&v)[8]) {
+  v[0] = bf16_lo_f(u.x); v[1] = bf16_hi_f(u.x); v[2] = bf16_lo_f(u.y); v[3] = bf16_hi_f(u.y);
+  v[4] = bf16_lo_f(u.z); v[5] = bf16_hi_f(u.z); v[6] = bf16_lo_f(u.w); v[7] = bf16_hi_f(u.w);
+}
+
 __global__ void __launch_bounds__(256)
 head_bf16_kernel(const __nv_bfloat16* __restrict__ x_hi, const __nv_bfloat16* __restrict__ x_lo,
                  int64_t n, int P, int C, const float* __restrict__ fc_w,
@@ -158,19 +165,39 @@ head_bf16_kernel(const __nv_bfloat16* __restrict__ x_hi, const __nv_bfloat16* __
   if (warp >= n) return;
   const __nv_bfloat16* xh = x_hi + warp * (int64_t)P * C;
   const __nv_bfloat16* xl = x_lo ? x_lo + warp * (int64_t)P * C : nullptr;
+  const float fp = (float)P;
   float z0 = 0.f, z1 = 0.f;
-  for (int c = lane; c < C; c += 32) {
-    float s = 0.f, mx = -INFINITY;
+#pragma unroll 2
+  for (int c = lane * 8; c < C; c += 256) {
+    float s[8], mx[8];
+#pragma unroll
+    for (int e = 0; e < 8; ++e) { s[e] = 0.f; mx[e] = -INFINITY; }
     for (int q = 0; q < P; ++q) {
-      float v = __bfloat162float(xh[(int64_t)q * C + c]);
-      if (xl) v += __bfloat162float(xl[(int64_t)q * C + c]);
-      s += v;
-      mx = fmaxf(mx, v);
+      float v[8];
+      unpack8(__ldg(reinterpret_cast<const uint4*>(xh + (int64_t)q * C + c)), v);
+      if (xl) {
+        float w[8];
+        unpack8(__ldg(reinterpret_cast<const uint4*>(xl + (int64_t)q * C + c)), w);
+#pragma unroll
+        for (int e = 0; e < 8; ++e) v[e] += w[e];
+      }
+#pragma unroll
+      for (int e = 0; e < 8; ++e) { s[e] += v[e]; mx[e] = fmaxf(mx[e], v[e]); }
     }
-    float f = s / (float)P + mx;
-    if (feat_out) feat_out[warp * C + c] = f;
-    z0 = fmaf(f, fc_w[c], z0);
-    z1 = fmaf(f, fc_w[C + c], z1);
+    float f[8];
+#pragma unroll
+    for (int e = 0; e < 8; ++e) f[e] = s[e] / fp + mx[e];
+    if (feat_out) {
+      float4* fo = reinterpret_cast<float4*>(feat_out + warp * C + c);
+      fo[0] = make_float4(f[0], f[1], f[2], f[3]);
+      fo[1] = make_float4(f[4], f[5], f[6], f[7]);
+    }
+    const float4 a0 = __ldg(reinterpret_cast<const float4*>(fc_w + c)), a1 = __ldg(reinterpret_cast<const float4*>(fc_w + c + 4));
+    const float4 b0 = __ldg(reinterpret_cast<const float4*>(fc_w + C + c)), b1 = __ldg(reinterpret_cast<const float4*>(fc_w + C + c + 4));
+    z0 = fmaf(f[0], a0.x, z0); z0 = fmaf(f[1], a0.y, z0); z0 = fmaf(f[2], a0.z, z0); z0 = fmaf(f[3], a0.w, z0);
+    z0 = fmaf(f[4], a1.x, z0); z0 = fmaf(f[5], a1.y, z0); z0 = fmaf(f[6], a1.z, z0); z0 = fmaf(f[7], a1.w, z0);
+    z1 = fmaf(f[0], b0.x, z1); z1 = fmaf(f[1], b0.y, z1); z1 = fmaf(f[2], b0.z, z1); z1 = fmaf(f[3], b0.w, z1);
+    z1 = fmaf(f[4], b1.x, z1); z1 = fmaf(f[5], b1.y, z1); z1 = fmaf(f[6], b1.z, z1); z1 = fmaf(f[7], b1.w, z1);
   }
   for (int o = 16; o > 0; o >>= 1) {
     z0 += __shfl_xor_sync(0xffffffffu, z0, o);
@@ -272,9 +299,9 @@ int launch_stem_bf16(const StemArgs& a, cudaStream_t st) {
     if (dev < 64) lut_done[dev] = true;
   }
   if (a.count <= 0) return CS_OK;
-  int grid = (int)(a.count < (int64_t)kNumSMs * 4 ? a.count : (int64_t)kNumSMs * 4);
+  int grid = (int)(a.count < (int64_t)num_sms() * 4 ? a.count : (int64_t)num_sms() * 4);
   if (a.tile == 32) {
-    grid = (int)(a.count < kNumSMs ? a.count : kNumSMs);
+    grid = (int)(a.count < num_sms() ? a.count : num_sms());
     stem_bf16_kernel<32><<<grid, 256, StemGeom<32>::kSmem, st>>>(a);
   } else if (a.tile == 16) {
     stem_bf16_kernel<16><<<grid, 256, StemGeom<16>::kSmem, st>>>(a);
@@ -290,6 +317,7 @@ int launch_head_bf16(const __nv_bfloat16* x_hi, const __nv_bfloat16* x_lo, int64
                      const float* fc_w, const float* fc_b, float* prob_out, float* logits_out,
                      float* feat_out, cudaStream_t st) {
   if (n <= 0) return CS_OK;
+  CS_REQUIRE(C % 256 == 0, "launch_head_bf16: feature width %d must be a multiple of 256", C);
   int64_t blocks = ceil_div<int64_t>(n * 32, 256);
   CS_CUDA(launch_pdl(head_bf16_kernel, dim3((unsigned)blocks), dim3(256), 0, st, 1, x_hi, x_lo, n, P, C,
                      fc_w, fc_b, prob_out, logits_out, feat_out));

@@ -119,10 +119,10 @@ struct EpiBars {
   uint32_t out_ready[2];
 };
 
-__device__ __forceinline__ void epi_bars_init(const EpiBars& b) {
+__device__ __forceinline__ void epi_bars_init(const EpiBars& b, uint32_t epi_threads = kEpiThreads) {
   for (int s = 0; s < 2; ++s) {
     mbar_init(b.res_full[s], 1);
-    mbar_init(b.out_ready[s], kEpiThreads);
+    mbar_init(b.out_ready[s], epi_threads);
   }
 }
 

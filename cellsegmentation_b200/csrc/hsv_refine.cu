@@ -181,7 +181,7 @@ int cs_hsv_refine(const uint8_t* img, const uint8_t* mask, int64_t n_px, int v_t
       int v = e ? atoi(e) : 0;
       return v > 0 ? v : 32;
     }();
-    int64_t cap = (int64_t)cs::kNumSMs * ctas_per_sm;
+    int64_t cap = (int64_t)cs::num_sms() * ctas_per_sm;
     int grid = (int)(want < cap ? want : cap);
     hsv_refine_vec_kernel<<<grid, 256, 0, st>>>((const u32x8*)img, (const u32x8*)mask,
                                                (u32x8*)out, n_vec, thr4);
@@ -190,8 +190,8 @@ int cs_hsv_refine(const uint8_t* img, const uint8_t* mask, int64_t n_px, int v_t
   int64_t done = n_vec * kPxPerWarp;
   if (done < n_px) {
     int64_t rem = n_px - done;
-    int grid = (int)(cs::ceil_div<int64_t>(rem, 256) < 148 * 16 ? cs::ceil_div<int64_t>(rem, 256)
-                                                                 : 148 * 16);
+    int grid = (int)(cs::ceil_div<int64_t>(rem, 256) < cs::num_sms() * 16 ? cs::ceil_div<int64_t>(rem, 256)
+                                                                 : cs::num_sms() * 16);
     hsv_refine_scalar_kernel<<<grid, 256, 0, st>>>(img, mask, out, done, n_px, v_thresh);
     CS_LAUNCH_CHECK();
   }
@@ -205,7 +205,7 @@ int cs_bgr2hsv_u8(const uint8_t* img, int64_t n_px, uint8_t* hsv_out, void* stre
   int rc = ensure_hsv_tables();
   if (rc != CS_OK) return rc;
   int64_t want = cs::ceil_div<int64_t>(n_px, 256);
-  int grid = (int)(want < 148 * 32 ? want : 148 * 32);
+  int grid = (int)(want < cs::num_sms() * 32 ? want : cs::num_sms() * 32);
   bgr2hsv_kernel<<<grid, 256, 0, cs::as_stream(stream)>>>(img, hsv_out, n_px);
   CS_LAUNCH_CHECK();
   return CS_OK;

@@ -968,9 +968,10 @@ int cs_debug_gemm_bf16(const void* a_bf16, const void* b_bf16, int64_t M, int N,
 // One k x k conv (k = 3: pad 1; k = 1: pad 0; stride 1|2; `groups` groups with the torch weight
 // layout [Cout][Cin/groups][k][k]) through plan_conv: in_hi bf16 [n][Hi*Wi][Cin] (device),
 // w_host / bias_host fp32 (host) -> out_f32 [n][Ho*Wo][Cout] (device), no ReLU.  n % 128 == 0.
+// reverse: walk the work items backwards (the snake order of odd layers).
 int cs_debug_conv_bf16(const void* in_hi, int64_t n, int Hi, int Wi, int Cin, int Cout, int k,
                        int stride, int groups, const float* w_host, const float* bias_host,
-                       float* out_f32, void* stream) {
+                       int reverse, float* out_f32, void* stream) {
   CS_REQUIRE(in_hi && w_host && bias_host && out_f32, "cs_debug_conv_bf16: NULL pointer");
   CS_REQUIRE(n > 0 && n % kGemmBM == 0, "cs_debug_conv_bf16: n must be a positive multiple of 128");
   CS_REQUIRE((k == 1 || k == 3) && groups >= 1 && Cin % groups == 0 && Cout % groups == 0,
@@ -991,7 +992,7 @@ int cs_debug_conv_bf16(const void* in_hi, int64_t n, int Hi, int Wi, int Cin, in
                  reinterpret_cast<const __nv_bfloat16*>(in_hi), nullptr, n, &pc);
   if (rc != CS_OK) return rc;
   pc.p.relu = 0;
-  rc = launch_planned(pc, n, out_f32, as_stream(stream));
+  rc = launch_planned(pc, n, out_f32, as_stream(stream), reverse != 0);
   cudaError_t e = cudaStreamSynchronize(as_stream(stream));
   free_planned(pc);
   if (rc != CS_OK) return rc;

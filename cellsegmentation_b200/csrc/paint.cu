@@ -154,7 +154,7 @@ int make_grid(const char* fn, int H, int W, int tile, int interval, int bag_base
 
 int warp_grid(int64_t n_items) {
   int64_t want = cs::ceil_div<int64_t>(n_items * 32, 256);
-  int64_t cap = (int64_t)cs::kNumSMs * 8 * 4;
+  int64_t cap = (int64_t)cs::num_sms() * 8 * 4;
   return (int)(want < cap ? (want > 0 ? want : 1) : cap);
 }
 
@@ -224,7 +224,7 @@ int cs_heatmap_to_gray(const float* heat, int64_t n, uint8_t* gray_out, void* st
   CS_REQUIRE(n >= 0, "cs_heatmap_to_gray: n < 0");
   if (n == 0) return CS_OK;
   int64_t want = cs::ceil_div<int64_t>(n, 256);
-  int grid = (int)(want < 148 * 32 ? want : 148 * 32);
+  int grid = (int)(want < cs::num_sms() * 32 ? want : cs::num_sms() * 32);
   heat_to_gray_kernel<<<grid, 256, 0, cs::as_stream(stream)>>>(heat, n, gray_out);
   CS_LAUNCH_CHECK();
   return CS_OK;
@@ -239,7 +239,7 @@ int cs_heatmap_blend(const float* heat, const uint8_t* img, const uint8_t* lut76
              "cs_heatmap_blend: heat must be 16-byte and img/out 4-byte aligned");
   if (n_px == 0) return CS_OK;
   int64_t want = cs::ceil_div<int64_t>(cs::ceil_div<int64_t>(n_px, 4), 256);
-  int grid = (int)(want < 148 * 16 ? (want > 0 ? want : 1) : 148 * 16);
+  int grid = (int)(want < cs::num_sms() * 16 ? (want > 0 ? want : 1) : cs::num_sms() * 16);
   heat_blend_kernel<<<grid, 256, 0, cs::as_stream(stream)>>>(heat, img, lut768, n_px, out);
   CS_LAUNCH_CHECK();
   return CS_OK;

@@ -295,7 +295,7 @@ int launch_sort(const Segs& segs, const float* prob, const EmitArgs& ea, int64_t
                                  cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSegPow2 * 6));
     if (dev < 64) attr_set[dev][kMode] = true;
   }
-  const int grid = ea.fb_list != nullptr ? (segs.n_bags < 148 * 4 ? segs.n_bags : 148 * 4) : segs.n_bags;
+  const int grid = ea.fb_list != nullptr ? (segs.n_bags < cs::num_sms() * 4 ? segs.n_bags : cs::num_sms() * 4) : segs.n_bags;
   seg_sort_kernel<kMode><<<grid, kThreads, smem, st>>>(segs, prob, ea);
   CS_LAUNCH_CHECK();
   return CS_OK;

@@ -341,7 +341,7 @@ int launch_stem_tc(const StemArgs& a, const void* w_bf16_dev, const uint16_t* lu
   if (rc != CS_OK) return rc;
   p.a = a;
   p.lut_bf16 = lut_bf16_dev;
-  int grid = (int)(a.count < kNumSMs ? a.count : kNumSMs);
+  int grid = (int)(a.count < num_sms() ? a.count : num_sms());
   CS_CUDA(launch_pdl(stem_tc_kernel, dim3((unsigned)grid), dim3(kThreads), Smem::total + 1024, st, 1, p));
   return CS_OK;
 }

@@ -422,7 +422,7 @@ int launch_stem_win(const StemArgs& a, const void* w_packed_dev, const uint16_t*
     }
     for (int c = 0; c < 3; ++c) { p.norm_a[c] = nc.a[c]; p.norm_b[c] = nc.b[c]; }
   }
-  int grid = (int)(a.count < kNumSMs ? a.count : kNumSMs);
+  int grid = (int)(a.count < num_sms() ? a.count : num_sms());
   CS_CUDA(launch_pdl(stem_win_kernel, dim3((unsigned)grid), dim3(kThreads), Smem::total + 1024, st, 1, p));
   return CS_OK;
 }

@@ -101,7 +101,7 @@ int ensure_lut() {
 
 int launch_cfg(int64_t total) {
   int64_t want = cs::ceil_div<int64_t>(total, 256);
-  int64_t cap = (int64_t)cs::kNumSMs * 8 * 8;
+  int64_t cap = (int64_t)cs::num_sms() * 8 * 8;
   return (int)(want < cap ? want : cap);
 }
 

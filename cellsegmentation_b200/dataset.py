@@ -308,6 +308,23 @@ class LystoDataset(_TileSetBase):
         return ds
 
 
+    @classmethod
+    def from_device_tensor(cls, images, labels, tile_size, interval):
+        """Bags that already live in HBM as one u8 [Nb,H,W,3] CUDA tensor (synthetic benchmarks):
+        same bag / tile bookkeeping as from_arrays without a host copy of the images."""
+        if not (getattr(images, "is_cuda", False) and images.dtype == torch.uint8):
+            raise TypeError("images must be a CUDA uint8 tensor [Nb,H,W,3] (or a sliceable view of one)")
+        ds = cls(tile_size=tile_size, interval=interval, kfold=None, _ensemble_init=True)
+        n = int(images.shape[0])
+        ds.images = images
+        ds.organs = ["synthetic"] * n
+        ds.labels = [int(v) for v in labels]
+        ds.cls_labels = [categorize(v) for v in ds.labels]
+        ds.transformIDX = [0] * n
+        ds._tile_bags = list(range(1, n))        # add_data(tileidx=0) owns no tiles
+        return ds
+
+
 class LystoTestset(_TileSetBase):
     """Test set; mode "tile" (dataset/dataset.py:346-435).  Every bag owns tiles."""
 

@@ -159,8 +159,11 @@ class MILResNet(nn.Module):
     def _fc_version(self):
         return tuple((t._version, t.data_ptr()) for t in self.fc_tile.parameters())
 
-    def classifier(self, device=None):
-        """The libcellseg_b200 model for the current weights (rebuilt when they change)."""
+    def classifier(self, device=None, need_fc=True):
+        """The libcellseg_b200 model for the current weights (rebuilt when they change).
+        need_fc=False leaves a stale device copy of fc_tile alone: callers that only want the
+        pooled features (training, where fc_tile runs under autograd) then pay no host sync
+        after every optimizer step."""
         if device is None:
             device = self.conv1.weight.device
         if device.type != "cuda":
@@ -178,7 +181,7 @@ class MILResNet(nn.Module):
                                            device=device)
             self._clf_key = key
             self._fc_key = self._fc_version()
-        elif self._fc_key != self._fc_version():
+        elif need_fc and self._fc_key != self._fc_version():
             self._clf.set_fc(fc.weight, fc.bias)
             self._fc_key = self._fc_version()
         return self._clf
@@ -186,9 +189,9 @@ class MILResNet(nn.Module):
     def encode(self, x):
         """Pooled 512*expansion-d features avgpool(x4)+maxpool(x4) (model/resnet.py:266), no grad."""
         with torch.no_grad():
-            _, feat = self.classifier(x.device).forward_tensor(
+            feat = self.classifier(x.device, need_fc=False).forward_tensor(
                 x.contiguous().float(), precision=self.precision, max_batch=self.max_batch,
-                want_features=True)
+                want_features=True, want_logits=False)
         return feat
 
     def forward(self, x, freeze_bn=False):

@@ -85,25 +85,42 @@ def lexsort_segments(prob, n_bags, uniform_T, seg_offsets=None):
     return order
 
 
+def select_buffers(n_bags, capacity, device):
+    """Pre-allocated outputs + workspace of select_topk: (idx i32 [capacity], pseudo-label u8
+    [capacity], offsets i64 [n_bags+1], workspace u8)."""
+    return (torch.empty(capacity, dtype=torch.int32, device=device),
+            torch.empty(capacity, dtype=torch.uint8, device=device),
+            torch.empty(n_bags + 1, dtype=torch.int64, device=device),
+            torch.empty(max(int(lib().cs_select_workspace_bytes(n_bags)), 1), dtype=torch.uint8, device=device))
+
+
 def select_topk(prob, labels, n_bags, uniform_T, tiles_per_pos, topk_neg, seg_offsets=None,
-                capacity=None, global_offset=0, global_total=0):
+                capacity=None, global_offset=0, global_total=0, sync=True, out=None):
     """Adaptive top-k (inference.py:31-42). Returns (idx i32 [M], pseudo-label u8 [M], offsets i64).
     For one shard of a larger set pass the global index of its first tile and the global tile count
-    (the predicate wraps around the GLOBAL array); indices stay relative to the shard."""
+    (the predicate wraps around the GLOBAL array); indices stay relative to the shard.
+
+    sync=False: no host round trip at all -- the full-capacity buffers are returned and the kept
+    count M stays on the device as offsets[-1] (entries at and beyond M are unspecified; the
+    kernels never write past `capacity`).  out: buffers from select_buffers() to write into."""
     _req_cuda(prob, "prob", torch.float32)
     _req_cuda(labels, "labels", torch.int32)
     so, T = _segs(seg_offsets, uniform_T, n_bags)
-    if capacity is None:
-        capacity = prob.numel()
-    idx = torch.empty(capacity, dtype=torch.int32, device=prob.device)
-    lab = torch.empty(capacity, dtype=torch.uint8, device=prob.device)
-    off = torch.empty(n_bags + 1, dtype=torch.int64, device=prob.device)
-    ws = torch.empty(max(int(lib().cs_select_workspace_bytes(n_bags)), 1), dtype=torch.uint8,
-                     device=prob.device)
+    if out is not None:
+        idx, lab, off, ws = out
+        capacity = idx.numel()
+        if lab.numel() < capacity or off.numel() != n_bags + 1:
+            raise ValueError("select_topk: out buffers do not match capacity / n_bags")
+    else:
+        if capacity is None:
+            capacity = prob.numel()
+        idx, lab, off, ws = select_buffers(n_bags, capacity, prob.device)
     check(lib().cs_select_topk_shard(ptr(prob), so, T, n_bags, ptr(labels), int(tiles_per_pos),
                                      int(topk_neg), int(global_offset), int(global_total), ptr(idx),
                                      ptr(lab), ptr(off), capacity, ptr(ws), ws.numel(), cur_stream()),
           "cs_select_topk_shard")
+    if not sync:
+        return idx, lab, off
     M = int(off[-1].item())
     if M > capacity:
         raise _capi.CellSegError("select_topk: %d kept instances exceed capacity %d" % (M, capacity))
@@ -307,18 +324,22 @@ class TileClassifier:
               "cs_model_forward_tiles")
         return (prob_out, feat) if want_features else prob_out
 
-    def forward_tensor(self, x, precision="bf16", max_batch=37888, want_features=False):
-        """Drop-in for model(x): x f32 [n,3,S,S] normalised tiles -> logits f32 [n,2]."""
+    def forward_tensor(self, x, precision="bf16", max_batch=37888, want_features=False, want_logits=True):
+        """Drop-in for model(x): x f32 [n,3,S,S] normalised tiles -> logits f32 [n,2] (and / or the
+        pooled features f32 [n,F]; want_logits=False skips the device fc, e.g. when fc_tile runs
+        under autograd in torch)."""
         _req_cuda(x, "x", torch.float32)
         n, _, S, _ = x.shape
         prec = PRECISIONS[precision]
         ws = self._workspace(S, max_batch, prec)
-        logits = torch.empty((n, 2), dtype=torch.float32, device=x.device)
+        logits = torch.empty((n, 2), dtype=torch.float32, device=x.device) if want_logits else None
         feat = torch.empty((n, self.feature_dim), dtype=torch.float32, device=x.device) if want_features else None
         check(lib().cs_model_forward_tensor(self._h, ptr(x), n, S, prec, ptr(logits), ptr(feat),
                                             ptr(ws), ws.numel(), max_batch, cur_stream()),
               "cs_model_forward_tensor")
-        return (logits, feat) if want_features else logits
+        if want_features and want_logits:
+            return logits, feat
+        return feat if want_features else logits
 
     @property
     def last_launch_count(self):
@@ -338,7 +359,7 @@ def debug_gemm_bf16(a, b, bias, bn):
     return out
 
 
-def debug_conv_bf16(x_hi, w, bias, stride, groups=1):
+def debug_conv_bf16(x_hi, w, bias, stride, groups=1, reverse=False):
     """x_hi bf16 [n,H,W,Cin] (cuda), w f32 [Cout,Cin/groups,k,k] (cpu), bias f32 [Cout] (cpu)
     -> f32 [n,Ho,Wo,Cout] through the production planner + tcgen05 kernels (k = 1 or 3)."""
     _req_cuda(x_hi, "x_hi", torch.bfloat16)
@@ -350,6 +371,6 @@ def debug_conv_bf16(x_hi, w, bias, stride, groups=1):
     bn_ = np.ascontiguousarray(bias.detach().cpu().numpy(), dtype=np.float32)
     out = torch.zeros((n, Ho, Wo, Cout), dtype=torch.float32, device=x_hi.device)
     check(lib().cs_debug_conv_bf16(ptr(x_hi), n, H, W, Cin, Cout, k, stride, groups, wn.ctypes.data,
-                                   bn_.ctypes.data, ptr(out), cur_stream()),
+                                   bn_.ctypes.data, int(bool(reverse)), ptr(out), cur_stream()),
           "cs_debug_conv_bf16")
     return out

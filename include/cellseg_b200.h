@@ -286,10 +286,11 @@ int cs_debug_gemm_bf16(const void* a_bf16, const void* b_bf16, int64_t M, int N,
 /* One k x k convolution (k = 3: pad 1, k = 1: pad 0; stride 1|2; `groups` groups, torch weight
  * layout [Cout][Cin/groups][k][k]) through the production planner:
  * in_hi bf16 [n][Hi*Wi][Cin] (device), w_host / bias_host fp32 (host)
- * -> out_f32 [n][Ho*Wo][Cout] (device), no ReLU.  n % 128 == 0.  Synchronises. */
+ * -> out_f32 [n][Ho*Wo][Cout] (device), no ReLU.  n % 128 == 0.  reverse != 0 walks the work
+ * items from the last to the first, as odd layers of the forward do.  Synchronises. */
 int cs_debug_conv_bf16(const void* in_hi, int64_t n, int Hi, int Wi, int Cin, int Cout, int k,
                        int stride, int groups, const float* w_host, const float* bias_host,
-                       float* out_f32, void* stream);
+                       int reverse, float* out_f32, void* stream);
 
 #ifdef __cplusplus
 }

@@ -23,6 +23,28 @@ def _stub(name, **attrs):
     return m
 
 
+class _LegacyNumpy:
+    """numpy as dataset/dataset.py:168 expects it (requirements.txt pins numpy 1.22): np.array()
+    of ragged rows `(bag, (x, y), label)` yields an object[M,3] array (with a deprecation warning)
+    instead of raising as numpy >= 1.24 does.  Everything else is the installed numpy."""
+
+    def __init__(self, real):
+        self._real = real
+
+    def __getattr__(self, name):
+        return getattr(self._real, name)
+
+    def array(self, obj, *args, **kwargs):
+        try:
+            return self._real.array(obj, *args, **kwargs)
+        except ValueError:
+            rows = list(obj)
+            out = self._real.empty((len(rows), 3), dtype=object)
+            for r, row in enumerate(rows):
+                out[r, 0], out[r, 1], out[r, 2] = row
+            return out
+
+
 _imported = None
 
 
@@ -63,8 +85,13 @@ def import_reference():
         import utils as ref_utils
         import inference as ref_inference
         import evaluate as ref_evaluate
+        import train as ref_train
+    import numpy
+    # make_train_data (dataset/dataset.py:166-201) runs unmodified once its module sees the numpy
+    # it was written for (ragged rows -> object array)
+    sys.modules[ref_dataset.LystoDataset.__module__].np = _LegacyNumpy(numpy)
     ns = types.SimpleNamespace(dataset=ref_dataset, utils=ref_utils, inference=ref_inference,
-                               evaluate=ref_evaluate, captured=captured)
+                               evaluate=ref_evaluate, train=ref_train, captured=captured)
     _imported = ns
     return ns
 

@@ -74,8 +74,75 @@ def gen_model(ref, ds, arch):
          x3_sum=x3.double().sum(dim=(1, 2, 3)).numpy(), x4=x4.numpy().reshape(16, -1))
 
 
+def td_rows(train_data):
+    """object[M,3] rows (bag, (x, y), label) -> int64 [M,4]."""
+    return np.array([[int(r[0]), int(r[1][0]), int(r[1][1]), int(r[2])] for r in train_data], np.int64).reshape(-1, 4)
+
+
+def gen_train(ref):
+    """make_train_data (dataset/dataset.py:166-201) and train_tile (train/train.py:12-48) executed
+    unmodified: the reference's own LystoDataset, MILresnet34, DataLoader and training loop on CPU."""
+    import contextlib
+    out = {}
+    bags = synth.make_bags(5, seed=41)
+    labels = [9, 3, 0, 7, 0]
+    ds = ref_dataset(ref, bags, labels, 32, 20)
+    n = len(ds.tileIDX)
+    idxs = np.arange(3, n, 5)
+    out["idxs"] = idxs.astype(np.int64)
+    for name, ratio, seed in (("r05", 0.5, 7), ("r20", 2.0, 8), ("rnone", None, 9), ("r01", 0.1, 10)):
+        np.random.seed(seed)
+        with contextlib.redirect_stdout(io.StringIO()):
+            pos, neg = ds.make_train_data(list(idxs), ratio)
+        out["td_" + name] = td_rows(ds.train_data)
+        out["pn_" + name] = np.array([pos, neg, seed], np.int64)
+        out["ratio_" + name] = np.array(np.nan if ratio is None else ratio)
+    # all-positive / all-negative selections (one class is pruned to nothing or kept whole)
+    pos_only = np.array([i for i in range(n) if labels[ds.tileIDX[i]] != 0][::7], np.int64)
+    np.random.seed(11)
+    with contextlib.redirect_stdout(io.StringIO()):
+        pos, neg = ds.make_train_data(list(pos_only), 0.5)
+    out["idxs_posonly"], out["td_posonly"], out["pn_posonly"] = pos_only, td_rows(ds.train_data), np.array([pos, neg, 11])
+
+    # train_tile on the r05 train_data, shuffle=False, plain SGD: loss + updated fc_tile
+    np.random.seed(7)
+    with contextlib.redirect_stdout(io.StringIO()):
+        ds.make_train_data(list(idxs), 0.5)
+    net = ref_shim.load_reference_module("resnet").MILresnet34()
+    sd = omodel.make_state_dict("resnet34", seed=3)
+    ds.setmode(1)
+    calib = torch.stack([ds[i][0] for i in range(0, len(ds), 3)])
+    sd = omodel.calibrate_head(sd, calib, "resnet34")
+    net.load_state_dict(sd, strict=False)
+    net.setmode("tile")
+    ds.setmode(3)
+    loader = torch.utils.data.DataLoader(ds, batch_size=16, shuffle=False, num_workers=0)
+    opt = torch.optim.SGD(filter(lambda p: p.requires_grad, net.parameters()), lr=0.05, weight_decay=1e-4)
+    crit = torch.nn.CrossEntropyLoss()
+    losses = []
+    with contextlib.redirect_stderr(io.StringIO()):
+        for epoch in (1, 2):
+            losses.append(ref.train.train_tile(loader, epoch, 2, net, torch.device("cpu"), crit, opt, None, 1.0))
+    trained = [n_ for n_, p in net.named_parameters() if p.requires_grad]
+    # (the decoder's upconv* also stay requires_grad in tile mode, model/resnet.py:315-319, but are
+    # not part of the tile graph: no gradient ever reaches them)
+    assert trained[:2] == ["fc_tile.1.weight", "fc_tile.1.bias"] and \
+        all(t.startswith(("upconv", "seg_out_conv")) for t in trained[2:]), trained
+    assert all(p.grad is None for n_, p in net.named_parameters() if n_.startswith(("upconv", "seg_out_conv")))
+    out["train_losses"] = np.array(losses, np.float64)
+    out["train_fc_w"] = net.fc_tile[1].weight.detach().numpy().copy()
+    out["train_fc_b"] = net.fc_tile[1].bias.detach().numpy().copy()
+    out["train_hparams"] = np.array([16, 0.05, 1e-4, 1.0])          # batch, lr, weight decay, gamma
+    enc_same = all(torch.equal(net.state_dict()[k], sd[k]) for k in sd if not k.startswith("fc_tile") and
+                   k in net.state_dict() and not k.endswith("num_batches_tracked"))
+    assert enc_same, "train_tile changed encoder weights or BN statistics"
+    save("train.npz", **out)
+
+
 def main():
     ref = ref_shim.import_reference()
+    if sys.argv[1:] == ["train"]:
+        return gen_train(ref)
     if len(sys.argv) > 1:          # python make_golden.py resnet50 ...: only those model fixtures
         ds = ref_dataset(ref, synth.make_bags(3, seed=11), [4, 0, 9], 32, 20)
         for arch in sys.argv[1:]:
@@ -205,6 +272,9 @@ def main():
             ip.remove_small_regions = keep_fn
     save("masks.npz", kept=keep.astype(np.int64), probs=ph, heat_imgs=heat_imgs,
          csv=np.frombuffer(csv_text.encode(), np.uint8), raw=raw, pre_cc=pre_cc, full=full)
+
+    # 8. make_train_data + train_tile, executed unmodified ---------------------------------
+    gen_train(ref)
 
 
 if __name__ == "__main__":

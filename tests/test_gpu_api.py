@@ -1,4 +1,5 @@
 """GPU tests of the reference-facing Python surfaces (drop-in API) against the oracle / goldens."""
+import contextlib
 import io
 import os
 
@@ -271,3 +272,31 @@ def test_distributed_mil_epoch_torchrun(cuda):
                         "--master-addr", "127.0.0.1", "--master-port", "29541",
                         os.path.join(here, "dist_mil_epoch.py")], capture_output=True, text=True, timeout=900)
     assert r.returncode == 0 and "PASS" in r.stdout, r.stdout[-2000:] + r.stderr[-2000:]
+
+
+def test_train_tile_matches_reference_golden_fp32(cuda):
+    """The product's train_tile + LystoDataset (mode 3) against train/train.py:12-48 executed
+    unmodified on the reference's own MILresnet34 / DataLoader (tests/golden/train.npz): two
+    epochs of SGD, mean losses and the updated fc_tile."""
+    from cellsegmentation_b200.dataset import LystoDataset
+    from cellsegmentation_b200.train import train_tile
+    g = golden("train.npz")
+    bags = synth.make_bags(5, seed=41)
+    ds = LystoDataset.from_arrays(list(bags), [9, 3, 0, 7, 0], 32, 20)
+    x = torch.from_numpy(otiles.unfold(list(bags[1:]), 20, 32))
+    sd = omodel.calibrate_head(omodel.make_state_dict("resnet34", seed=3), x[::3], "resnet34")
+    net = _model("resnet34", sd, cuda, "fp32")
+    np.random.seed(7)
+    with contextlib.redirect_stdout(io.StringIO()):
+        ds.make_train_data(g["idxs"], 0.5)
+    td = ds.train_data
+    assert np.array_equal(np.stack([td["bag"], td["x"], td["y"], td["label"]], 1).astype(np.int64), g["td_r05"])
+    ds.setmode(3)
+    bs, lr, wd, gamma = g["train_hparams"]
+    loader = torch.utils.data.DataLoader(ds, batch_size=int(bs), shuffle=False)
+    opt = torch.optim.SGD(filter(lambda p: p.requires_grad, net.parameters()), lr=float(lr), weight_decay=float(wd))
+    losses = [train_tile(loader, e, 2, net, cuda, torch.nn.CrossEntropyLoss(), opt, None, float(gamma))
+              for e in (1, 2)]
+    assert np.allclose(losses, g["train_losses"], rtol=0, atol=2e-5), (losses, g["train_losses"])
+    assert np.abs(net.fc_tile[1].weight.detach().cpu().numpy() - g["train_fc_w"]).max() < 2e-5
+    assert np.abs(net.fc_tile[1].bias.detach().cpu().numpy() - g["train_fc_b"]).max() < 2e-5

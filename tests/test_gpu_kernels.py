@@ -343,3 +343,25 @@ def test_heatmap_blend_matches_cv2(cuda):
             gray = (255 - np.uint8(255 * h[i].astype(np.float64)))
             want = cv2.addWeighted(np.ascontiguousarray(im[i]), 0.5, cv2.applyColorMap(gray, cv2.COLORMAP_JET), 0.5, 0)
             assert np.array_equal(got[i], want)
+
+
+def test_remove_small_regions_known_answers(cuda):
+    """Hand-derivable masks (sizes 399/400/401, holes 119/120/121, diagonal contact, border pocket,
+    objects-before-holes order): the GPU clean-up against answers that do not come from the scipy
+    restatement (skimage itself cannot be executed in this environment)."""
+    from test_oracle_golden import _kat_masks
+    ops = _ops()
+    cases = _kat_masks()
+    m = np.stack([c[1] for c in cases]).astype(np.uint8)
+    want = np.stack([c[2] for c in cases]).astype(np.uint8)
+    got = ops.remove_small_regions(torch.from_numpy(m).to(cuda), 400, 120).cpu().numpy()
+    for i, c in enumerate(cases):
+        assert np.array_equal(got[i], want[i]), c[0]
+    # the same masks embedded in 299 x 299 images (the production shape)
+    big = np.zeros((len(cases), 299, 299), np.uint8)
+    big[:, 100:196, 150:246] = m
+    wbig = np.zeros_like(big)
+    for i, c in enumerate(cases):
+        wbig[i] = omasks.remove_small_regions(big[i] != 0, 400, 120)
+    got = ops.remove_small_regions(torch.from_numpy(big).to(cuda), 400, 120).cpu().numpy()
+    assert np.array_equal(got, wbig)

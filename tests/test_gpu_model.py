@@ -61,6 +61,45 @@ def test_tcgen05_conv_matches_conv2d(cuda, H, Cin, Cout, k, stride, groups):
     assert err < 2e-3, err
 
 
+# ---- the benchmarked regime: every persistent kernel loops many times per CTA ------------------
+# bench.py runs forward batches of 37 888 instances (~128 work items per CTA in layer 1): ring
+# and accumulator phases wrap dozens of times and odd layers walk their tiles backwards.  The
+# small-n cases above are checked against F.conv2d; here the same inputs go through ONE large
+# launch (>= 8 iterations per CTA, forwards and backwards) and must reproduce, bit for bit, the
+# result of 128..256-instance launches of the same kernel.
+@pytest.mark.parametrize("H,Cin,Cout,k,stride,groups,n", [
+    (8, 64, 64, 3, 1, 1, 8192),          # layer 1: y-sum kernel, 27 M tiles per CTA
+    (8, 64, 128, 3, 2, 1, 16384),        # layer-2 entry: shifted boxes over four parity maps
+    (4, 128, 128, 3, 1, 1, 16384),       # layer 2: halo kernel, CTA pairs
+    (4, 128, 256, 3, 2, 1, 32768),       # layer-3 entry: dense form
+    (2, 256, 256, 3, 1, 1, 65536),       # layer 3: dense form, 4 N tiles
+    (1, 512, 512, 3, 1, 1, 81920),       # layer 4: centre tap only
+    (8, 64, 256, 1, 1, 1, 8192),         # Bottleneck pointwise
+    (8, 256, 256, 3, 2, 32, 8192),       # ResNeXt grouped 3x3, per-tile step lists
+])
+@pytest.mark.parametrize("reverse", [False, True], ids=["fwd", "rev"])
+def test_tcgen05_conv_many_iterations_per_cta(cuda, H, Cin, Cout, k, stride, groups, n, reverse):
+    ops = _ops()
+    g = torch.Generator().manual_seed(H * 1000 + Cin + Cout + stride + 7 * groups + k + 99)
+    x = torch.randn(n, H, H, Cin, generator=g).to(torch.bfloat16).to(cuda)
+    w = _bf16_round(torch.randn(Cout, Cin // groups, k, k, generator=g) / (k * (Cin // groups) ** 0.5))
+    b = torch.randn(Cout, generator=g)
+    got = ops.debug_conv_bf16(x, w, b, stride, groups, reverse=reverse)
+    chunk = 256
+    # spot-check chunks at the beginning, middle and end (first / last work items of many CTAs)
+    for c0 in (0, chunk, n // 2 - chunk, n // 2 + 3 * chunk, n - 2 * chunk, n - chunk):
+        ref = ops.debug_conv_bf16(x[c0:c0 + chunk].contiguous(), w, b, stride, groups)
+        assert torch.equal(got[c0:c0 + chunk], ref), (c0, (got[c0:c0 + chunk] - ref).abs().max().item())
+    # ... and the whole tensor against a second pass in the opposite direction
+    other = ops.debug_conv_bf16(x, w, b, stride, groups, reverse=not reverse)
+    assert torch.equal(got, other)
+    # numerics of a sample against fp64 conv2d
+    xs = x[n - 64:].float().cpu()
+    want = F.conv2d(xs.permute(0, 3, 1, 2).double(), w.double(), b.double(), stride=stride,
+                    padding=1 if k == 3 else 0, groups=groups).permute(0, 2, 3, 1)
+    assert (got[n - 64:].cpu().double() - want).abs().max().item() < 2e-3
+
+
 def _setup(arch, n_bags=2, interval=20, tile=32, seed=3):
     bags = synth.make_bags(n_bags + 1, seed=11)[1:]
     x = torch.from_numpy(otiles.unfold(list(bags), interval, tile))
@@ -118,6 +157,38 @@ def test_forward_bf16_within_2e2(cuda, arch):
     clf.close()
 
 
+@pytest.mark.parametrize("arch,interval,n_bags", [("resnet34", 5, 14), ("resnext50_32x4d", 3, 5)])
+def test_forward_bf16_at_bench_scale(cuda, arch, interval, n_bags):
+    """The benchmarked configuration: max_batch 37 888 (bench.py default), test-time interval
+    (3025 / 8100 instances per bag), more instances than one batch with a ragged last batch that
+    is not a multiple of 128.  (i) every probability within 2e-2 of the CPU oracle, (ii) the same
+    call in 256-instance batches (the regime of the small tests) agrees to 1e-6."""
+    ops = _ops()
+    bags = synth.make_bags(n_bags, seed=31)
+    x = torch.from_numpy(otiles.unfold(list(bags), interval, 32))
+    n = x.shape[0]
+    assert n > 37888 and (n - 37888) % 128 != 0
+    sd = omodel.calibrate_head(omodel.make_state_dict(arch, seed=3), x[::97], arch)
+    want = omodel.forward_probs(sd, x, arch, batch=4096)
+    clf = ops.TileClassifier(arch, omodel.fold_bn(sd, arch), sd["fc_tile.1.weight"], sd["fc_tile.1.bias"])
+    d_img = torch.from_numpy(bags).to(cuda)
+    got = clf.forward_tiles(d_img, 32, interval, precision="bf16", max_batch=37888)
+    launches_big = clf.last_launch_count
+    diff = np.abs(got.cpu().numpy() - want)
+    print("bf16 %s at scale: n %d max|dp| %.4g mean %.4g" % (arch, n, diff.max(), diff.mean()))
+    assert diff.max() < BF16_TOL, diff.max()
+    small = clf.forward_tiles(d_img, 32, interval, precision="bf16", max_batch=256)
+    assert launches_big < clf.last_launch_count
+    assert (got - small).abs().max().item() <= 1e-6
+    # pooled features of the big batches (the MIL feature cache) against the small ones too
+    _, f_big = clf.forward_tiles(d_img, 32, interval, inst_begin=5, inst_count=40001, precision="bf16",
+                                 max_batch=37888, want_features=True)
+    _, f_small = clf.forward_tiles(d_img, 32, interval, inst_begin=5, inst_count=40001, precision="bf16",
+                                   max_batch=512, want_features=True)
+    assert torch.equal(f_big, f_small)
+    clf.close()
+
+
 @pytest.mark.parametrize("arch", ["resnet34", "resnext50_32x4d"])
 def test_forward_tile16(cuda, arch):
     ops = _ops()
@@ -168,6 +239,7 @@ def test_alternative_kernel_paths_subprocess(cuda, env):
     import sys
     here = os.path.abspath(__file__)
     r = subprocess.run([sys.executable, "-m", "pytest", here, "-x", "-q", "-p", "no:cacheprovider", "-k",
-                        "conv_matches or (within_2e2 and resnet34) or tile16"],
+                        "conv_matches or (within_2e2 and resnet34) or tile16 or many_iterations or "
+                        "(bench_scale and resnet34)"],
                        env=dict(os.environ, **env), capture_output=True, text=True, timeout=900)
     assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-2000:]

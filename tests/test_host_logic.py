@@ -70,34 +70,114 @@ def test_shard_range_and_dataset_shards():
     assert tot == ds.num_tiles() and seen == [2, 3, 4, 5, 6, 7]
 
 
+def _spawn(target, world, *args):
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 29500 + (os.getpid() % 2000) + _spawn.calls * 7
+    _spawn.calls += 1
+    procs = [ctx.Process(target=target, args=(r, world, port, q) + args) for r in range(world)]
+    [p.start() for p in procs]
+    res = sorted((q.get(timeout=180) for _ in range(world)), key=lambda t: t[0])
+    [p.join(60) for p in procs]
+    return res
+
+
+_spawn.calls = 0
+
+
 def _worker(rank, world, port, q):
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
     dist.init_process_group("gloo", rank=rank, world_size=world)
-    from cellsegmentation_b200.distributed import allgather_selection, allreduce_mean_grads
-    # each rank "selected" a different number of tiles of its own shard
-    n = 3 + 2 * rank
-    idx = torch.arange(n, dtype=torch.int32) * 2
-    lab = torch.full((n,), rank, dtype=torch.uint8)
-    gi, gl = allgather_selection(idx, lab, tile_offset=1000 * rank)
-    lin = torch.nn.Linear(4, 2)
-    with torch.no_grad():
-        lin.weight.fill_(0.5); lin.bias.zero_()
-    lin(torch.full((1, 4), float(rank + 1))).sum().backward()
-    allreduce_mean_grads(list(lin.parameters()))
-    q.put((rank, gi.tolist(), gl.tolist(), lin.weight.grad[0].tolist()))
+    from cellsegmentation_b200.distributed import allgather_selection, allreduce_flat, broadcast_seed
+    # each rank "selected" a different number of tiles of its own shard; the buffers are
+    # capacity-sized and the count lives in a tensor (on the GPU path it never visits the host)
+    n, cap = 3 + 2 * rank, 6
+    idx = torch.full((cap,), -7, dtype=torch.int32)
+    idx[:n] = torch.arange(n, dtype=torch.int32) * 2
+    lab = torch.full((cap,), rank, dtype=torch.uint8)
+    gi, gl = allgather_selection(idx, lab, torch.tensor([n]), tile_offset=1000 * rank, capacity=cap)
+    g1, g2 = torch.full((2, 4), float(rank + 1)), torch.tensor([10.0 * (rank + 1)])
+    flat = allreduce_flat([g1, g2])
+    np.random.seed(100 + rank)                     # different states: only rank 0's draw may count
+    seed_none = broadcast_seed(None, torch.device("cpu"))
+    seed_given = broadcast_seed(41 + rank, torch.device("cpu"))
+    q.put((rank, gi.tolist(), gl.tolist(), flat.tolist(), seed_none, seed_given))
     dist.destroy_process_group()
 
 
 def test_gloo_world2_allgather_and_grad_allreduce():
-    ctx = mp.get_context("spawn")
-    q = ctx.Queue()
-    port = 29500 + (os.getpid() % 2000)
-    procs = [ctx.Process(target=_worker, args=(r, 2, port, q)) for r in range(2)]
-    [p.start() for p in procs]
-    res = sorted(q.get(timeout=120) for _ in range(2))
-    [p.join(60) for p in procs]
+    res = _spawn(_worker, 2)
     want_idx = [0, 2, 4] + [1000, 1002, 1004, 1006, 1008]
-    for rank, gi, gl, g in res:
+    np.random.seed(100)
+    want_seed = int(np.random.randint(0, 2 ** 31 - 1))
+    for rank, gi, gl, flat, seed_none, seed_given in res:
         assert gi == want_idx
         assert gl == [0, 0, 0, 1, 1, 1, 1, 1]
-        assert g == [1.5] * 4                      # mean of grads 1.0 and 2.0
+        assert flat == [3.0] * 8 + [30.0]          # one bucket: sum over ranks
+        assert seed_none == want_seed and seed_given == 41
+
+
+def test_selection_capacity_is_the_closed_form_bound():
+    from cellsegmentation_b200.distributed import kept_upper_bound, selection_capacity
+    labels = [3, 0, 7, 1, 300, 0]
+    assert kept_upper_bound(labels, 225, 1, 30).tolist() == [3, 30, 7, 1, 225, 30]
+    assert selection_capacity(labels, 225, 1, 30, 1) == 296
+    assert selection_capacity(labels, 225, 1, 30, 2) == 256      # shards [3,0,7] and [1,300,0]
+    assert selection_capacity(labels, 225, 2, 30, 4) == 255      # shards of 2 bags; [300, 0] -> 225 + 30
+    # the bound holds for the literal predicate on a toy set, wrap-around included
+    tid = np.repeat(np.arange(6), 225)
+    rng = np.random.default_rng(0)
+    kept = oselect.sample_indices(tid, np.array(labels), rng.random(len(tid)).astype(np.float32), 1, 30)
+    per_bag = np.bincount(tid[kept], minlength=6)
+    assert (per_bag <= kept_upper_bound(labels, 225, 1, 30)).all()
+
+
+class _FakeModel(torch.nn.Module):
+    def __init__(self):
+        super().__init__()
+        self.fc_tile = torch.nn.Sequential(torch.nn.Flatten(), torch.nn.Linear(8, 2))
+
+
+def _train_worker(rank, world, port, q, crit_kind):
+    """train_selected with a feature cache is torch-only: run it on CPU tensors under gloo."""
+    if world > 1:
+        os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+        dist.init_process_group("gloo", rank=rank, world_size=world)
+    from cellsegmentation_b200 import mil
+    from cellsegmentation_b200.distributed import shard_dataset
+    ds = _ds(7, (2, 0, 5, 1, 0, 9, 3))
+    T = ds.tiles_per_bag
+    g = torch.Generator().manual_seed(5)
+    feat_all = torch.randn(ds.num_tiles(), 8, generator=g)
+    idxs = np.sort(np.random.default_rng(1).choice(ds.num_tiles(), 300, replace=False))
+    np.random.seed(11)
+    ds.make_train_data(idxs, 0.5)
+    shard, off = shard_dataset(ds, rank, world)
+    cache = {"feat": feat_all[off:off + shard.num_tiles()], "begin": off, "end": off + shard.num_tiles()}
+    torch.manual_seed(3)
+    net = _FakeModel()
+    crit = {"ce": torch.nn.CrossEntropyLoss(),
+            "ce_weighted": torch.nn.CrossEntropyLoss(weight=torch.tensor([0.3, 1.7]), label_smoothing=0.1),
+            "nll_like": lambda o, l: torch.nn.functional.nll_loss(torch.log_softmax(o, 1), l)}[crit_kind]
+    opt = torch.optim.SGD(net.parameters(), lr=0.1)
+    sched = torch.optim.lr_scheduler.OneCycleLR(opt, max_lr=0.2, total_steps=50)
+    loss = mil.train_selected(ds, net, torch.device("cpu"), crit, opt, 64, gamma=1.0, shuffle_seed=2,
+                              feature_cache=cache, scheduler=sched)
+    q.put((rank, loss, net.fc_tile[1].weight.detach().numpy().copy(), net.fc_tile[1].bias.detach().numpy().copy(),
+           sched.last_epoch))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("crit_kind", ["ce", "ce_weighted", "nll_like"])
+def test_gloo_world2_train_selected_equals_single_process(crit_kind):
+    """the data-parallel step must reproduce single-process training (loss and weights),
+    including class-weighted / label-smoothed CE and criteria that are plain per-row means."""
+    (_, loss1, w1, b1, steps1), = _spawn(_train_worker, 1, crit_kind)
+    res = _spawn(_train_worker, 2, crit_kind)
+    for rank, loss, w, b, steps in res:
+        assert steps == steps1 > 0
+        assert abs(loss - loss1) < 1e-5, (loss, loss1)
+        np.testing.assert_allclose(w, w1, rtol=0, atol=2e-6)
+        np.testing.assert_allclose(b, b1, rtol=0, atol=2e-6)
+    assert np.array_equal(res[0][2], res[1][2])

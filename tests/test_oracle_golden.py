@@ -177,3 +177,115 @@ def test_make_train_data_shuffle_is_index_shuffle():
     assert [tuple(r[1]) for r in td2] == [tuple(tiles_grid[i]) for i in idxs[perm]]
     assert pos + neg == len(td) and pos == int(neg * 0.5) or neg == int(pos / 0.5)
     assert lab.sum() >= pos
+
+
+# ---- make_train_data / train_tile: pinned to the reference's own methods (train.npz) -------------
+def _train_golden_dataset():
+    bags = synth.make_bags(5, seed=41)
+    labels = [9, 3, 0, 7, 0]
+    grid = otiles.get_tiles((299, 299, 3), 20, 32)
+    tid = np.repeat(np.arange(1, 5), 225)            # bag 0 owns no tiles
+    tiles_grid = [grid[i % 225] for i in range(len(tid))]
+    return bags, labels, tid, tiles_grid
+
+
+@pytest.mark.parametrize("case", ["r05", "r20", "rnone", "r01", "posonly"])
+def test_make_train_data_matches_reference_method(case):
+    """dataset/dataset.py:166-201 executed unmodified (under the numpy it was written for) vs the
+    oracle restatement AND the product's LystoDataset.make_train_data, same np.random seed."""
+    g = golden("train.npz")
+    _, labels, tid, tiles_grid = _train_golden_dataset()
+    idxs = g["idxs_posonly"] if case == "posonly" else g["idxs"]
+    pos_w, neg_w, seed = (int(v) for v in g["pn_" + case])
+    ratio = 0.5 if case == "posonly" else (None if np.isnan(g["ratio_" + case]) else float(g["ratio_" + case]))
+    np.random.seed(seed)
+    td, pos, neg = oselect.make_train_data(tid, tiles_grid, labels, idxs, ratio)
+    rows = np.array([[int(r[0]), int(r[1][0]), int(r[1][1]), int(r[2])] for r in td], np.int64).reshape(-1, 4)
+    assert (pos, neg) == (pos_w, neg_w)
+    assert np.array_equal(rows, g["td_" + case])
+    from cellsegmentation_b200.dataset import LystoDataset
+    ds = LystoDataset.from_arrays([np.zeros((299, 299, 3), np.uint8)] * 5, labels, 32, 20)
+    np.random.seed(seed)
+    import contextlib
+    import io
+    with contextlib.redirect_stdout(io.StringIO()):
+        pos_p, neg_p = ds.make_train_data(idxs, ratio)
+    got = ds.train_data
+    assert (pos_p, neg_p) == (pos_w, neg_w)
+    assert np.array_equal(np.stack([got["bag"], got["x"], got["y"], got["label"]], 1).astype(np.int64).reshape(-1, 4),
+                          g["td_" + case])
+
+
+def test_train_tile_oracle_matches_reference_loop():
+    """train/train.py:12-48 executed unmodified (reference MILresnet34, DataLoader, SGD) vs the
+    oracle restatement: two epochs' mean losses and the updated fc_tile."""
+    from oracle import train as otrain
+    g = golden("train.npz")
+    bags, labels, tid, tiles_grid = _train_golden_dataset()
+    x = torch.from_numpy(otiles.unfold(list(bags[1:]), 20, 32))
+    sd = omodel.calibrate_head(omodel.make_state_dict("resnet34", seed=3), x[::3], "resnet34")
+    td = g["td_r05"]
+    tiles = torch.stack([torch.from_numpy(otiles.normalize_tile(bags[b][r:r + 32, c:c + 32])) for b, r, c, _ in td])
+    y = torch.from_numpy(td[:, 3].copy())
+    bs, lr, wd, gamma = g["train_hparams"]
+    losses = []
+    for _ in range(2):
+        loss, w, b = otrain.train_tile_epoch(sd, tiles, y, int(bs), lr=float(lr), gamma=float(gamma),
+                                             weight_decay=float(wd))
+        sd = dict(sd)
+        sd["fc_tile.1.weight"], sd["fc_tile.1.bias"] = w, b
+        losses.append(loss)
+    assert np.allclose(losses, g["train_losses"], rtol=0, atol=2e-6), (losses, g["train_losses"])
+    assert np.abs(w.numpy() - g["train_fc_w"]).max() < 2e-6
+    assert np.abs(b.numpy() - g["train_fc_b"]).max() < 2e-6
+
+
+# ---- remove_small_regions: known-answer masks (skimage itself cannot be run here) ----------------
+def _kat_masks():
+    """Masks whose clean-up is derivable by hand from skimage 0.19's definition: objects with
+    size < min_size are removed, holes with area < area_threshold are filled, connectivity 1
+    (4-neighbours; diagonal contact does not join), background touching the border is one
+    big component (never a small hole unless it is small)."""
+    H = W = 96
+    cases = []
+    # objects of 399 / 400 / 401 pixels: only the first disappears (min_size 400)
+    m = np.zeros((H, W), bool)
+    m[2:21, 2:23] = True           # 19 x 21 = 399
+    m[30:50, 2:22] = True          # 20 x 20 = 400
+    m[60:80, 2:22] = True; m[80, 2] = True     # 401
+    w = m.copy(); w[2:21, 2:23] = False
+    cases.append(("sizes_399_400_401", m, w))
+    # holes of 119 / 120 / 121 pixels inside one big object: the 119-hole is filled (threshold 120)
+    m = np.ones((H, W), bool)
+    m[5:12, 5:22] = False          # 7 x 17 = 119
+    m[20:30, 5:17] = False         # 10 x 12 = 120
+    m[40:51, 5:16] = False         # 11 x 11 = 121
+    w = m.copy(); w[5:12, 5:22] = True
+    cases.append(("holes_119_120_121", m, w))
+    # two 15 x 15 blobs touching only diagonally: 225 + 225 pixels, NOT joined under connectivity 1
+    m = np.zeros((H, W), bool)
+    m[10:25, 10:25] = True; m[25:40, 25:40] = True
+    cases.append(("diagonal_blobs_removed", m, np.zeros((H, W), bool)))
+    # the same blobs joined by one edge-adjacent pixel: one 451-pixel object, kept
+    m2 = m.copy(); m2[24, 25] = True
+    cases.append(("edge_joined_blobs_kept", m2, m2.copy()))
+    # a small background pocket on the border is a hole like any other (area 30 < 120): filled;
+    # a diagonal-only leak does not connect it to the outside background
+    m = np.ones((H, W), bool)
+    m[0:5, 0:6] = False            # 30-pixel pocket in the corner
+    m[40:96, 60:96] = False        # large background region (2016): stays
+    w = m.copy(); w[0:5, 0:6] = True
+    cases.append(("border_pocket_filled", m, w))
+    # object removal happens BEFORE hole filling: a 380-pixel ring (20x20 minus a 20-px hole) is removed
+    # as an object (380 < 400) even though filling its hole first would have made it 400
+    m = np.zeros((H, W), bool)
+    m[10:30, 10:30] = True; m[15:19, 15:20] = False     # 400 - 20 = 380
+    cases.append(("order_objects_then_holes", m, np.zeros((H, W), bool)))
+    return cases
+
+
+@pytest.mark.parametrize("idx", range(6))
+def test_remove_small_regions_known_answers_oracle(idx):
+    name, m, want = _kat_masks()[idx]
+    got = omasks.remove_small_regions(m, 400, 120)
+    assert np.array_equal(got, want), name
