@@ -45,6 +45,12 @@ _PROTOS = {
     "cs_model_forward_tensor": (c_int, [c_void_p, c_void_p, c_int64, c_int, c_int, c_void_p,
                                         c_void_p, c_void_p, c_int64, c_int64, c_void_p]),
     "cs_model_last_launch_count": (c_int64, [c_void_p]),
+    "cs_model_forward_image": (c_int, [c_void_p, c_void_p, c_int64, c_int, c_void_p, c_void_p, c_void_p,
+                                       c_void_p, c_void_p, c_void_p, c_int64, c_int64, c_void_p]),
+    "cs_conv2d_nhwc_f32": (c_int, [c_void_p, c_int64, c_int, c_int, c_int, c_void_p, c_void_p, c_int, c_int,
+                                   c_int, c_int, c_int, c_void_p, c_void_p]),
+    "cs_resize_bilinear_nhwc_f32": (c_int, [c_void_p, c_int64, c_int, c_int, c_int, c_int, c_int, c_void_p,
+                                            c_void_p]),
     "cs_lexsort_segments": (c_int, [c_void_p, c_void_p, c_int64, c_int, c_void_p, c_void_p]),
     "cs_select_topk": (c_int, [c_void_p, c_void_p, c_int64, c_int, c_void_p, c_int32, c_int32,
                                c_void_p, c_void_p, c_void_p, c_int64, c_void_p, c_int64, c_void_p]),

@@ -20,6 +20,7 @@ SOURCES = [
     "unfold.cu",
     "select_topk.cu",
     "select_fast.cu",
+    "select_reg.cu",
     "paint.cu",
     "cc.cu",
     "fwd_fp32.cu",

@@ -24,6 +24,8 @@ struct ConvF32Args {
 int launch_conv_fp32(const ConvF32Args& a, cudaStream_t st);
 int launch_maxpool_fp32(const float* in, float* out, int64_t n, int Hi, int Wi, int C,
                         cudaStream_t st);
+int launch_bilinear_fp32(const float* in, float* out, int64_t n, int Hi, int Wi, int Ho, int Wo, int C,
+                         cudaStream_t st);
 int launch_head_fp32(const float* x4, int64_t n, int P, int C, const float* fc_w,
                      const float* fc_b, float* prob_out, float* logits_out, float* feat_out,
                      cudaStream_t st);

@@ -181,7 +181,49 @@ head_fp32_kernel(const float* __restrict__ x4, int64_t n, int P, int C,
   }
 }
 
+// F.interpolate(mode="bilinear", align_corners=True) on NHWC fp32 (model/resnet.py:282-300):
+// source coordinate = dst * (in - 1) / (out - 1), the two-tap lerp ATen performs in fp32
+// (upsample_bilinear2d: h1lambda = src - floor(src), out = h0l*(w0l*a + w1l*b) + h1l*(...)).
+__global__ void __launch_bounds__(256)
+bilinear_ac_kernel(const float* __restrict__ in, float* __restrict__ out, int64_t n, int Hi, int Wi,
+                   int Ho, int Wo, int C, float sh, float sw) {
+  const int64_t total = n * Ho * Wo * C;
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += stride) {
+    const int c = (int)(e % C);
+    int64_t r = e / C;
+    const int ox = (int)(r % Wo); r /= Wo;
+    const int oy = (int)(r % Ho);
+    const int64_t img = r / Ho;
+    const float fy = sh * (float)oy, fx = sw * (float)ox;
+    int y0 = (int)fy, x0 = (int)fx;
+    y0 = y0 < Hi - 1 ? y0 : Hi - 1;
+    x0 = x0 < Wi - 1 ? x0 : Wi - 1;
+    const int y1 = y0 < Hi - 1 ? y0 + 1 : y0, x1 = x0 < Wi - 1 ? x0 + 1 : x0;
+    const float ly = fy - (float)y0, lx = fx - (float)x0;
+    const float hy = 1.f - ly, hx = 1.f - lx;
+    const float* base = in + img * (int64_t)Hi * Wi * C + c;
+    const float a = base[((int64_t)y0 * Wi + x0) * C], b = base[((int64_t)y0 * Wi + x1) * C];
+    const float cc = base[((int64_t)y1 * Wi + x0) * C], d = base[((int64_t)y1 * Wi + x1) * C];
+    out[e] = hy * (hx * a + lx * b) + ly * (hx * cc + lx * d);
+  }
+}
+
 }  // namespace
+
+int launch_bilinear_fp32(const float* in, float* out, int64_t n, int Hi, int Wi, int Ho, int Wo, int C,
+                         cudaStream_t st) {
+  const int64_t total = n * Ho * Wo * C;
+  if (total <= 0) return CS_OK;
+  // area_pixel_compute_scale(align_corners=True): (in - 1) / (out - 1), 0 when out == 1
+  const float sh = Ho > 1 ? (float)(Hi - 1) / (float)(Ho - 1) : 0.f;
+  const float sw = Wo > 1 ? (float)(Wi - 1) / (float)(Wo - 1) : 0.f;
+  const int64_t want = ceil_div<int64_t>(total, 256);
+  const int grid = (int)(want < (int64_t)num_sms() * 32 ? want : (int64_t)num_sms() * 32);
+  bilinear_ac_kernel<<<grid, 256, 0, st>>>(in, out, n, Hi, Wi, Ho, Wo, C, sh, sw);
+  CS_LAUNCH_CHECK();
+  return CS_OK;
+}
 
 int launch_conv_fp32(const ConvF32Args& a, cudaStream_t st) {
   if (a.Cout % 4 != 0) {

@@ -459,8 +459,13 @@ namespace {
 
 // Largest block-level activation (elements per instance) at this tile size: x buffers hold
 // block inputs / outputs, mid buffers the conv1 / conv2 outputs.
+// Output size of the stem conv (7x7, stride 2, pad 3) and of the 3x3 / 2 max pool behind it
+// (model/resnet.py:236-239): 32 -> 16 -> 8 for tiles, 299 -> 150 -> 75 for whole images.
+int stem_conv_size(int S) { return (S + 6 - 7) / 2 + 1; }
+int stem_pool_size(int S) { return (stem_conv_size(S) + 2 - 3) / 2 + 1; }
+
 void act_sizes(const cs_model* m, int tile, int64_t* x_elems, int64_t* mid_elems) {
-  int H = tile / 4;
+  int H = stem_pool_size(tile);
   int64_t xe = (int64_t)H * H * 64, me = 0;
   for (const BlockDesc& b : m->blocks) {
     const int Ho = (H + 2 - 3) / b.stride + 1;
@@ -481,7 +486,8 @@ int64_t fp32_floats_per_inst(const cs_model* m, int tile) {
   int64_t xe, me;
   act_sizes(m, tile, &xe, &me);
   // input tile + stem conv output + x, y, ds + two mids
-  return (int64_t)3 * tile * tile + (int64_t)(tile / 2) * (tile / 2) * 64 + 3 * xe + 2 * me;
+  const int64_t hc = stem_conv_size(tile);
+  return (int64_t)3 * tile * tile + hc * hc * 64 + 3 * xe + 2 * me;
 }
 
 int build_tc_plan(cs_model* m, int tile, int64_t max_batch, void* ws, int64_t ws_bytes) {
@@ -632,10 +638,13 @@ int run_tc_batch(cs_model* m, const StemArgs& stem_in, int64_t count, float* pro
 }
 
 // fp32 path for `count` instances whose normalised NCHW tiles are at x_in.
+// maps_out (nullable): four device pointers receiving the NHWC fp32 outputs of layer1..layer4
+// (x1..x4 of resnet_forward(return_intermediate=True), model/resnet.py:240-246).
 int run_fp32_batch(cs_model* m, const float* x_in, int tile, int64_t count, float* ws_f,
-                   float* prob_out, float* logits_out, float* feat_out, cudaStream_t st) {
+                   float* prob_out, float* logits_out, float* feat_out, cudaStream_t st,
+                   float* const* maps_out = nullptr) {
   const int S = tile;
-  const int Hc = S / 2, Hp = S / 4;
+  const int Hc = stem_conv_size(S), Hp = stem_pool_size(S);
   int64_t xe, me;
   act_sizes(m, tile, &xe, &me);
   float* c1 = ws_f;
@@ -666,7 +675,16 @@ int run_fp32_batch(cs_model* m, const float* x_in, int tile, int64_t count, floa
     return launch_conv_fp32(c, st);
   };
   int xi = 0, H = Hp, W = Hp, C = 64;
+  size_t bi = 0;
+  int layer = 0;
   for (const BlockDesc& b : m->blocks) {
+    if (maps_out && bi > 0 && b.stride == 2) {   // a stride-2 block opens the next layer: x is x_{layer+1}
+      if (maps_out[layer])
+        CS_CUDA(cudaMemcpyAsync(maps_out[layer], xb[xi], sizeof(float) * count * H * W * C,
+                                cudaMemcpyDeviceToDevice, st));
+      ++layer;
+    }
+    ++bi;
     const int Ho = (H + 2 - 3) / b.stride + 1, Wo = (W + 2 - 3) / b.stride + 1;
     float* x = xb[xi];
     float* y = xb[1 - xi];
@@ -685,6 +703,9 @@ int run_fp32_batch(cs_model* m, const float* x_in, int tile, int64_t count, floa
     }
     xi = 1 - xi; H = Ho; W = Wo; C = b.cout;
   }
+  if (maps_out && maps_out[3])
+    CS_CUDA(cudaMemcpyAsync(maps_out[3], xb[xi], sizeof(float) * count * H * W * C,
+                            cudaMemcpyDeviceToDevice, st));
   rc = launch_head_fp32(xb[xi], count, H * W, C, m->d_fc_w, m->d_fc_b, prob_out, logits_out,
                         feat_out, st);
   if (rc != CS_OK) return rc;
@@ -695,8 +716,9 @@ int run_fp32_batch(cs_model* m, const float* x_in, int tile, int64_t count, floa
 int check_forward_args(const char* fn, const cs_model* m, int tile, int precision, void* ws,
                        int64_t ws_bytes, int64_t max_batch) {
   CS_REQUIRE(m != nullptr, "%s: model is NULL", fn);
-  CS_REQUIRE(tile == 16 || tile == 32, "%s: tile %d unsupported (16 or 32)", fn, tile);
   CS_REQUIRE(precision == CS_PREC_FP32 || precision == CS_PREC_BF16, "%s: bad precision %d", fn, precision);
+  CS_REQUIRE(tile == 16 || tile == 32 || (precision == CS_PREC_FP32 && tile >= 16 && tile <= 2048),
+             "%s: tile %d unsupported (bf16: 16 or 32; fp32: 16 .. 2048)", fn, tile);
   CS_REQUIRE(ws != nullptr && max_batch > 0, "%s: workspace is NULL or max_batch <= 0", fn);
   int64_t need = cs_model_workspace_bytes(m, tile, max_batch, precision);
   if (ws_bytes < need) {
@@ -831,7 +853,9 @@ int cs_model_set_fc(cs_model* m, const float* fc_w_host, const float* fc_b_host)
 }
 
 int64_t cs_model_workspace_bytes(const cs_model* m, int tile, int64_t max_batch, int precision) {
-  if (!m || max_batch <= 0 || (tile != 16 && tile != 32)) return 0;
+  if (!m || max_batch <= 0) return 0;
+  if (precision != CS_PREC_FP32 && tile != 16 && tile != 32) return 0;
+  if (tile < 16 || tile > 2048) return 0;
   if (precision == CS_PREC_FP32) {
     int64_t chunk = max_batch < kFp32Chunk ? max_batch : kFp32Chunk;
     return chunk * fp32_floats_per_inst(m, tile) * 4 + 4096;
@@ -925,6 +949,74 @@ int cs_model_forward_tensor(cs_model* m, const float* x, int64_t n, int tile, in
     }
   }
   return CS_OK;
+}
+
+// N4: the encoder on whole images (Stage-1 "image" mode, model/resnet.py:271-278, and the
+// encoder half of "segment" mode, :259-260).  fp32 CUDA-core path, any square size.
+int cs_model_forward_image(cs_model* m, const float* x, int64_t n, int size, float* feat_out,
+                           float* x1_out, float* x2_out, float* x3_out, float* x4_out,
+                           void* workspace, int64_t workspace_bytes, int64_t max_batch, void* stream) {
+  int rc = check_forward_args("cs_model_forward_image", m, size, CS_PREC_FP32, workspace, workspace_bytes,
+                              max_batch);
+  if (rc != CS_OK) return rc;
+  CS_REQUIRE(x && n >= 0, "cs_model_forward_image: NULL input or n < 0");
+  CS_REQUIRE(feat_out || x1_out || x2_out || x3_out || x4_out, "cs_model_forward_image: no output requested");
+  cudaStream_t st = as_stream(stream);
+  m->last_launches = 0;
+  const int64_t per = (int64_t)3 * size * size;
+  const int64_t chunk = max_batch < kFp32Chunk ? max_batch : kFp32Chunk;
+  float* x_unused = reinterpret_cast<float*>(round_up((int64_t)(uintptr_t)workspace, 256));
+  float* rest = x_unused + chunk * per;
+  // per-instance element counts of x1..x4 (layer outputs)
+  int64_t map_elems[4];
+  {
+    int H = stem_pool_size(size), li = -1;
+    size_t bi = 0;
+    for (const BlockDesc& b : m->blocks) {
+      if (bi == 0 || b.stride == 2) ++li;
+      H = (H + 2 - 3) / b.stride + 1;
+      map_elems[li] = (int64_t)H * H * b.cout;
+      ++bi;
+    }
+  }
+  float* outs[4] = {x1_out, x2_out, x3_out, x4_out};
+  for (int64_t done = 0; done < n; done += chunk) {
+    const int64_t cnt = n - done < chunk ? n - done : chunk;
+    float* maps[4];
+    for (int i = 0; i < 4; ++i) maps[i] = outs[i] ? outs[i] + done * map_elems[i] : nullptr;
+    rc = run_fp32_batch(m, x + done * per, size, cnt, rest, nullptr, nullptr,
+                        feat_out ? feat_out + done * m->feat_dim : nullptr, st, maps);
+    if (rc != CS_OK) return rc;
+  }
+  return CS_OK;
+}
+
+// N4: one conv2d on NHWC fp32 maps (Stage-3 decoder layers upconv1..8 / seg_out_conv with their
+// BatchNorm folded by the caller, model/resnet.py:194-199, 280-303): w_dev is [k*k*Cin][Cout]
+// (row index (dy*k+dx)*Cin + ci), bias_dev [Cout]; Cout % 4 == 0.
+int cs_conv2d_nhwc_f32(const float* in, int64_t n, int H, int W, int Cin, const float* w_dev,
+                       const float* bias_dev, int Cout, int k, int stride, int pad, int relu,
+                       float* out, void* stream) {
+  CS_REQUIRE(in && w_dev && bias_dev && out, "cs_conv2d_nhwc_f32: NULL pointer");
+  CS_REQUIRE(n >= 0 && H > 0 && W > 0 && Cin > 0 && Cout > 0 && k > 0 && stride > 0 && pad >= 0,
+             "cs_conv2d_nhwc_f32: bad geometry");
+  if (n == 0) return CS_OK;
+  ConvF32Args c{};
+  c.in = in; c.in_sn = (int64_t)H * W * Cin; c.in_sc = 1; c.in_sy = (int64_t)W * Cin; c.in_sx = Cin;
+  c.Hi = H; c.Wi = W; c.Cin = Cin;
+  c.Ho = (H + 2 * pad - k) / stride + 1; c.Wo = (W + 2 * pad - k) / stride + 1;
+  c.Cout = Cout; c.k = k; c.stride = stride; c.pad = pad;
+  c.w = w_dev; c.bias = bias_dev; c.residual = nullptr; c.out = out;
+  c.M = n * c.Ho * c.Wo; c.relu = relu;
+  return launch_conv_fp32(c, as_stream(stream));
+}
+
+// F.interpolate(x, size, mode="bilinear", align_corners=True) on NHWC fp32 maps.
+int cs_resize_bilinear_nhwc_f32(const float* in, int64_t n, int Hi, int Wi, int C, int Ho, int Wo,
+                                float* out, void* stream) {
+  CS_REQUIRE(in && out, "cs_resize_bilinear_nhwc_f32: NULL pointer");
+  CS_REQUIRE(n >= 0 && Hi > 0 && Wi > 0 && Ho > 0 && Wo > 0 && C > 0, "cs_resize_bilinear_nhwc_f32: bad geometry");
+  return launch_bilinear_fp32(in, out, n, Hi, Wi, Ho, Wo, C, as_stream(stream));
 }
 
 int64_t cs_model_last_launch_count(const cs_model* m) { return m ? m->last_launches : 0; }

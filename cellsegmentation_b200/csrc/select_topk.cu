@@ -33,16 +33,6 @@ namespace {
 constexpr int kThreads = 512;
 constexpr int kMaxSegPow2 = 32768;  // 6 B * 32768 = 192 KB of shared memory
 
-// ---- per-bag kept counts ----------------------------------------------------
-__global__ void select_count_kernel(Segs segs, const int32_t* __restrict__ labels,
-                                    int32_t tiles_per_pos, int32_t topk_neg,
-                                    int64_t* __restrict__ counts) {
-  int b = blockIdx.x * blockDim.x + threadIdx.x;
-  if (b >= segs.n_bags) return;
-  int64_t s = segs.start(b), e = segs.start(b + 1);
-  counts[b] = kept_ranges(segs.gstart(b), e - s, segs.gtotal(), bag_k(labels, b, tiles_per_pos, topk_neg)).count();
-}
-
 __global__ void __launch_bounds__(256)
 rank_count_kernel(Segs segs, const float* __restrict__ prob, float thr,
                   int64_t* __restrict__ counts) {
@@ -119,6 +109,51 @@ exclusive_scan_kernel(int64_t* __restrict__ data, int n) {
       data[i] = run;
       run += t;
     }
+  }
+}
+
+// Per-bag kept counts AND their exclusive scan in one launch (the counts are closed-form in the
+// count labels): offsets[b] = sum of kept(b') for b' < b, offsets[n] = total.  Same structure as
+// exclusive_scan_kernel with the loads replaced by the count formula.
+__global__ void __launch_bounds__(1024)
+select_offsets_kernel(Segs segs, const int32_t* __restrict__ labels, int32_t tiles_per_pos,
+                      int32_t topk_neg, int64_t* __restrict__ offsets) {
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+  __shared__ int64_t warp_tot[32];
+  const int n = segs.n_bags;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int per = (n + 1023) / 1024;
+  const int lo = min(tid * per, n), hi = min(lo + per, n);
+  auto kept = [&](int b) -> int64_t {
+    const int64_t s = segs.start(b), e = segs.start(b + 1);
+    return kept_ranges(segs.gstart(b), e - s, segs.gtotal(), bag_k(labels, b, tiles_per_pos, topk_neg)).count();
+  };
+  int64_t sum = 0;
+  for (int i = lo; i < hi; ++i) sum += kept(i);
+  int64_t x = sum;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    const int64_t y = __shfl_up_sync(0xffffffffu, x, o);
+    if (lane >= o) x += y;
+  }
+  if (lane == 31) warp_tot[warp] = x;
+  __syncthreads();
+  if (warp == 0) {
+    const int64_t w = warp_tot[lane];
+    int64_t xs = w;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const int64_t y = __shfl_up_sync(0xffffffffu, xs, o);
+      if (lane >= o) xs += y;
+    }
+    warp_tot[lane] = xs - w;
+    if (lane == 31) offsets[n] = xs;
+  }
+  __syncthreads();
+  int64_t run = warp_tot[warp] + x - sum;
+  for (int i = lo; i < hi; ++i) {
+    offsets[i] = run;
+    run += kept(i);
   }
 }
 
@@ -264,6 +299,12 @@ const bool g_disable_fast = []() {
   return e != nullptr && e[0] == '0';
 }();
 
+// CELLSEG_SELECT_FAST=staged keeps the round-1 shared-memory fast path for every bag size.
+const bool g_staged_fast = []() {
+  const char* e = getenv("CELLSEG_SELECT_FAST");
+  return e != nullptr && e[0] == 's';
+}();
+
 struct SegHostInfo {
   int max_pow2;
 };
@@ -360,10 +401,7 @@ int cs_select_topk_shard(const float* prob, const int64_t* seg_offsets, int64_t 
   int32_t* fb_count = static_cast<int32_t*>(workspace);
   int32_t* fb_list = fb_count + 64;
   if (!g_disable_fast) CS_CUDA(cudaMemsetAsync(fb_count, 0, sizeof(int32_t), st));
-  select_count_kernel<<<cs::ceil_div(n_bags, 256), 256, 0, st>>>(segs, labels, tiles_per_pos,
-                                                                 topk_neg, sel_offsets_out);
-  CS_LAUNCH_CHECK();
-  exclusive_scan_kernel<<<1, 1024, 0, st>>>(sel_offsets_out, n_bags);
+  select_offsets_kernel<<<1, 1024, 0, st>>>(segs, labels, tiles_per_pos, topk_neg, sel_offsets_out);
   CS_LAUNCH_CHECK();
   EmitArgs ea{};
   ea.labels = labels;
@@ -373,11 +411,19 @@ int cs_select_topk_shard(const float* prob, const int64_t* seg_offsets, int64_t 
   ea.label_out = sel_label_out;
   ea.out_offsets = sel_offsets_out;
   ea.capacity = capacity;
-  // CTA-per-bag fast path first (select_fast.cu); bags it declines are listed and ordered exactly
+  // CTA-per-bag fast paths first: register-resident (select_reg.cu) for bags of up to 4093
+  // instances, shared-memory staged (select_fast.cu) beyond; bags they decline are listed and
+  // ordered exactly
   bool handled = false;
   if (!g_disable_fast) {
-    rc = launch_select_fast(segs, prob, ea, uniform_T, fb_count, fb_list, st, &handled);
-    if (rc != CS_OK) return rc;
+    if (!g_staged_fast) {
+      rc = launch_select_reg(segs, prob, ea, uniform_T, fb_count, fb_list, st, &handled);
+      if (rc != CS_OK) return rc;
+    }
+    if (!handled) {
+      rc = launch_select_fast(segs, prob, ea, uniform_T, fb_count, fb_list, st, &handled);
+      if (rc != CS_OK) return rc;
+    }
   }
   if (handled) {
     ea.fb_count = fb_count;

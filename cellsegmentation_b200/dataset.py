@@ -165,6 +165,15 @@ class _TileSetBase(Dataset):
                 self._dev = host.pin_memory().to(device, non_blocking=True)
         return self._dev
 
+    def image_tensor(self, idx_begin, count, device=None):
+        """Normalised whole images [count,3,H,W] (the per-image transform of the "image" modes,
+        dataset/dataset.py:424-428): the bag is its own single tile."""
+        img = self.device_images(device)
+        H, W = int(img.shape[1]), int(img.shape[2])
+        if H != W:
+            raise ValueError("image modes need square bags")
+        return ops.unfold_normalize(img, H, H, idx_begin, count)
+
     def tile_tensor(self, idx_begin, count, device=None):
         """Normalised tiles [count,3,S,S] of dataset indices idx_begin.. (mode 1 / 'tile')."""
         img = self.device_images(device)
@@ -365,8 +374,8 @@ class LystoTestset(_TileSetBase):
         if self.mode == "tile":
             assert self.num_tiles() > 0, "Dataset tile size and interval have to be settled for tile mode. "
             return self.tile_tensor(idx, 1)[0].cpu()
-        elif self.mode == "image":
-            raise NotImplementedError("image mode belongs to Stage-1 counting (out of scope)")
+        elif self.mode == "image":                     # dataset/dataset.py:424-428
+            return self.id[idx], self.image_tensor(idx, 1)[0].cpu()
         raise Exception("Something wrong in setmode.")
 
     def __len__(self):

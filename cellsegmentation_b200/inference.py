@@ -53,6 +53,52 @@ def inference_tiles(loader, model, device, epoch=None, total_epochs=None, mode='
     return probs.numpy()
 
 
+def inference_image(loader, model, device, epoch=None, total_epochs=None, mode='train', cls_limit=False,
+                    return_id=False):
+    """Forward inference to obtain image-level categories and cell counts (inference.py:46-95).
+    With this package's LystoTestset in mode "image" the whole images are normalised on the
+    device; the model must be in mode "image" (fp32 encoder at 299 x 299 + fc_image heads)."""
+    from .dataset import categorize, de_categorize
+    model.eval()
+    ds = loader.dataset
+    ids, categories, counts = np.array(()), np.array(()), np.array(())
+
+    def consume(output, batch_ids):
+        nonlocal ids, categories, counts
+        if batch_ids is not None:
+            ids = np.concatenate((ids, batch_ids))
+        output_cls = F.softmax(output[0], dim=1).detach().clone().cpu()
+        output_reg = output[1].detach()[:, 0].clone().cpu()
+        output_reg = np.round(output_reg.numpy()).astype(int)
+        cat_labels = np.argmax(output_cls, axis=1)
+        if cls_limit:
+            for i, x in enumerate(output_reg):
+                if categorize(x) > cat_labels[i]:
+                    output_reg[i] = de_categorize(cat_labels[i])[1]
+                elif categorize(x) < cat_labels[i]:
+                    output_reg[i] = de_categorize(cat_labels[i])[0]
+        categories = np.concatenate((categories, cat_labels))
+        counts = np.concatenate((counts, output_reg))
+
+    with torch.no_grad():
+        if isinstance(ds, _TileSetBase) and ds.mode == "image":
+            dev = _device_of(device)
+            bs = loader.batch_size or 1
+            with torch.cuda.device(dev):
+                for b in range(0, len(ds.images), bs):
+                    cnt = min(bs, len(ds.images) - b)
+                    consume(model(ds.image_tensor(b, cnt, dev)), None if mode == 'train' else np.asarray(ds.id[b:b + cnt]))
+        else:
+            for data in loader:
+                if mode == 'train':
+                    consume(model(data[0].to(device)), None)
+                else:
+                    consume(model(data[1].to(device)), data[0])
+    if return_id:
+        return ids, categories, counts
+    return categories, counts
+
+
 def _probs_on_device(dataset, probs, device):
     last = getattr(dataset, "_last_probs", None)
     if last is not None and probs is last[1]:

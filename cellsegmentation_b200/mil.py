@@ -130,7 +130,11 @@ def train_selected(trainset, model, device, criterion, optimizer, batch_size, ga
     else:
         begin, end = int(tile_off), int(tile_off) + shard.num_tiles()
     first_img = getattr(shard, "_first_img", 0)
-    params = [p for p in model.parameters() if p.requires_grad]
+    # tile mode trains fc_tile alone (model/resnet.py:315-319); the decoder's upconv5..8 also keep
+    # requires_grad there but never receive a gradient -- they must not enter the all-reduce, or
+    # zero gradients + weight decay would move them where the reference's optimizer skips them
+    params = [p for p in model.fc_tile.parameters() if p.requires_grad] if hasattr(model, "fc_tile") else \
+        [p for p in model.parameters() if p.requires_grad]
     dev = params[0].device
     loss_acc = torch.zeros((), dtype=torch.float64, device=dev)
     tile_num = 0

@@ -10,7 +10,11 @@ Tile mode: the encoder is frozen (setmode("tile") sets requires_grad False, :315
 evaluated with running BN statistics both under model.eval() (inference.py:12) and under
 freeze_bn=True (train/train.py:33, model/resnet.py:254-258), so the forward is
     features = CUDA encoder(x)  [no grad]      ->  logits = fc_tile(features)  [autograd]
-Image and segment modes (Stage 1 / Stage 3 networks) are out of scope and raise.
+Image and segment modes run forward-only (model.eval()): the encoder at
+299 x 299 and the Stage-3 decoder on the fp32 CUDA-core kernels (cs_model_forward_image,
+cs_conv2d_nhwc_f32, cs_resize_bilinear_nhwc_f32), the small fc_image heads in torch.  That is
+what test_tile.py --reg_limit (:88-105), train_seg.py's mask generation (:255-269) and
+test_seg.py call; TRAINING the Stage-1 heads or the decoder stays out of scope and raises.
 """
 import torch
 import torch.nn as nn
@@ -95,9 +99,34 @@ class MILResNet(nn.Module):
         self.avgpool_tile = nn.AdaptiveAvgPool2d((1, 1))
         self.maxpool_tile = nn.AdaptiveMaxPool2d((1, 1))
         self.fc_tile = nn.Sequential(nn.Flatten(), nn.Linear(512 * block.expansion, num_classes))
+        # Stage-1 heads (model/resnet.py:129-153, map_size = 1) and Stage-3 decoder (:155-165)
+        feat = 512 * block.expansion
+        self.avgpool_image = nn.AdaptiveAvgPool2d((1, 1))
+        self.maxpool_image = nn.AdaptiveMaxPool2d((1, 1))
+        self.fc_image_cls = nn.Sequential(nn.Flatten(), nn.BatchNorm1d(feat), nn.Dropout(p=0.25), nn.ReLU(inplace=True),
+                                          nn.Linear(feat, 64), nn.BatchNorm1d(64), nn.Dropout(), nn.Linear(64, 7))
+        self.fc_image_reg = nn.Sequential(nn.Flatten(), nn.BatchNorm1d(feat), nn.Dropout(p=0.25), nn.ReLU(inplace=True),
+                                          nn.Linear(feat, 64), nn.BatchNorm1d(64), nn.Dropout(), nn.Linear(64, 1),
+                                          nn.ReLU(inplace=True))
+        e = expansion
+        self.expansion = expansion
+        self.upconv1 = self.upsample_conv(512 * e, 256 * e)
+        self.upconv2 = self.upsample_conv(512 * e, 256 * e)
+        self.upconv3 = self.upsample_conv(256 * e, 128 * e)
+        self.upconv4 = self.upsample_conv(256 * e, 128 * e)
+        self.upconv5 = self.upsample_conv(128 * e, 64 * e)
+        self.upconv6 = self.upsample_conv(128 * e, 64 * e)
+        self.upconv7 = self.upsample_conv(64 * e, 64 if e == 1 else 32 * e)
+        self.upconv8 = self.upsample_conv(64 if e == 1 else 32 * e, 64)
+        self.seg_out_conv = nn.Conv2d(64, 2, kernel_size=1)
+        self.image_max_batch = 4       # images per fp32 encoder chunk (299 x 299: ~15 MB of maps each)
+        self._dec_key = None
+        self._dec = None
         for m in self.modules():                       # model/resnet.py:171-178
             if isinstance(m, nn.Conv2d):
                 nn.init.kaiming_normal_(m.weight)
+                if m.bias is not None:
+                    nn.init.constant_(m.bias, 0)
             elif isinstance(m, nn.BatchNorm2d):
                 nn.init.constant_(m.weight, 1)
                 nn.init.constant_(m.bias, 0)
@@ -117,6 +146,11 @@ class MILResNet(nn.Module):
             layers.append(block(self.inplanes, planes, groups=self.groups, base_width=self.base_width))
         return nn.Sequential(*layers)
 
+    @staticmethod
+    def upsample_conv(in_channels, out_channels):      # model/resnet.py:194-199
+        return nn.Sequential(nn.Conv2d(in_channels, out_channels, kernel_size=3, padding=1),
+                             nn.BatchNorm2d(out_channels), nn.ReLU(inplace=True))
+
     # ---- requires_grad groups (model/resnet.py:196-232, 308-333) ----------------------------
     def set_encoder_grads(self, requires_grad):
         for m in (self.conv1, self.bn1, self.layer1, self.layer2, self.layer3, self.layer4):
@@ -125,15 +159,21 @@ class MILResNet(nn.Module):
     def set_tile_module_grads(self, requires_grad):
         self.fc_tile.requires_grad_(requires_grad)
 
+    def set_image_module_grads(self, requires_grad):
+        self.fc_image_cls.requires_grad_(requires_grad)
+        self.fc_image_reg.requires_grad_(requires_grad)
+
+    def set_seg_module_grads(self, requires_grad):     # upconv5..8 keep their state, as in the reference (:228-232)
+        for m in (self.upconv1, self.upconv2, self.upconv3, self.upconv4, self.seg_out_conv):
+            m.requires_grad_(requires_grad)
+
     def setmode(self, mode):
-        if mode == "tile":
-            self.set_encoder_grads(False)
-            self.set_tile_module_grads(True)
-        elif mode in ("image", "segment"):
-            self.set_encoder_grads(mode == "image")
-            self.set_tile_module_grads(False)
-        else:
+        if mode not in ("tile", "image", "segment"):
             raise Exception("Invalid mode: {}.".format(mode))
+        self.set_encoder_grads(mode == "image")
+        self.set_tile_module_grads(mode == "tile")
+        self.set_image_module_grads(mode == "image")
+        self.set_seg_module_grads(mode == "segment")
         self.mode = mode
 
     # ---- device classifier ------------------------------------------------------------------
@@ -153,7 +193,7 @@ class MILResNet(nn.Module):
 
     def _encoder_version(self):
         enc = [t for n, t in list(self.named_parameters()) + list(self.named_buffers())
-               if not n.startswith("fc_tile")]
+               if n.startswith(("conv1", "bn1", "layer"))]
         return tuple((t._version, t.data_ptr()) for t in enc)
 
     def _fc_version(self):
@@ -194,11 +234,66 @@ class MILResNet(nn.Module):
                 want_features=True, want_logits=False)
         return feat
 
+    # ---- N4: whole-image encoder, Stage-1 heads, Stage-3 decoder (forward only) --------------
+    def _decoder(self, device):
+        """BN-folded decoder weights on the device, packed [k*k*Cin, Cout] for cs_conv2d_nhwc_f32."""
+        mods = [self.upconv1, self.upconv2, self.upconv3, self.upconv4, self.upconv5, self.upconv6,
+                self.upconv7, self.upconv8]
+        tensors = [t for m in mods + [self.seg_out_conv] for t in list(m.parameters()) + list(m.buffers())]
+        key = (str(device), tuple((t._version, t.data_ptr()) for t in tensors))
+        if self._dec_key != key:
+            dec = []
+            with torch.no_grad():
+                for m in mods:
+                    conv, bn = m[0], m[1]
+                    s = bn.weight.float() / torch.sqrt(bn.running_var.float() + bn.eps)
+                    w = conv.weight.float() * s[:, None, None, None]
+                    b = (conv.bias.float() - bn.running_mean.float()) * s + bn.bias.float()
+                    dec.append((w.permute(2, 3, 1, 0).reshape(-1, w.shape[0]).contiguous().to(device),
+                                b.contiguous().to(device)))
+                w = torch.zeros((4, 64, 1, 1), dtype=torch.float32, device=self.seg_out_conv.weight.device)
+                b = torch.zeros(4, dtype=torch.float32, device=w.device)
+                w[:2] = self.seg_out_conv.weight.float()       # Cout padded 2 -> 4 for the float4 epilogue
+                b[:2] = self.seg_out_conv.bias.float()
+                dec.append((w.permute(2, 3, 1, 0).reshape(-1, 4).contiguous().to(device), b.to(device)))
+            self._dec, self._dec_key = dec, key
+        return self._dec
+
+    def _forward_whole_image(self, x):
+        if self.training:
+            raise NotImplementedError("mode %r runs forward-only on the B200 stack (call model.eval()): training "
+                                      "the Stage-1 heads / Stage-3 decoder is out of scope" % self.mode)
+        if x.device.type != "cuda":
+            raise ops._capi.CellSegError("the encoder runs on sm_100a only; move the input to a CUDA device")
+        clf = self.classifier(x.device, need_fc=False)
+        x = x.contiguous().float()
+        with torch.no_grad():
+            if self.mode == "image":                           # model/resnet.py:271-278
+                feat = clf.forward_image(x, max_batch=self.image_max_batch)
+                out = feat.view(feat.shape[0], -1, 1, 1)       # avgpool_image(x4) + maxpool_image(x4), map size 1
+                return self.fc_image_cls(out), self.fc_image_reg(out)
+            if self.encoder_name.startswith("resnext"):
+                raise NotImplementedError("segment mode of MILResNeXt: the reference's decoder (512-channel upconv1, "
+                                          "model/resnext.py:209) does not fit its own 2048-channel x4 either")
+            x1, x2, x3, x4 = clf.forward_image(x, max_batch=self.image_max_batch, want_features=False, want_maps=True)
+            d = self._decoder(x.device)
+            up = lambda t, i: ops.conv2d_nhwc(t, d[i][0], d[i][1], 3, 1, 1, relu=True)     # noqa: E731
+            o = up(ops.resize_bilinear_nhwc(x4, x3.shape[1]), 0)                            # :282-283
+            o = up(torch.cat([o, x3], dim=3), 1)                                            # :284-285
+            o = up(ops.resize_bilinear_nhwc(o, x2.shape[1]), 2)                             # :287-288
+            o = up(torch.cat([o, x2], dim=3), 3)                                            # :289-290
+            o = up(ops.resize_bilinear_nhwc(o, x1.shape[1]), 4)                             # :292-293
+            o = up(torch.cat([o, x1], dim=3), 5)                                            # :294-295
+            o = up(ops.resize_bilinear_nhwc(o, (x.shape[2] - 1) // 2 + 1), 6)               # :297-298 (150)
+            o = up(o, 7)                                                                    # :299
+            o = ops.resize_bilinear_nhwc(o, x.shape[2])                                     # :300
+            o = ops.conv2d_nhwc(o, d[8][0], d[8][1], 1, 1, 0, relu=False)[..., :2]          # :301
+            return o.permute(0, 3, 1, 2).contiguous()
+
     def forward(self, x, freeze_bn=False):
         if self.mode != "tile":
             if self.mode in ("image", "segment"):
-                raise NotImplementedError("mode %r (Stage 1 / Stage 3 heads) is out of scope of the "
-                                          "B200 hot path" % self.mode)
+                return self._forward_whole_image(x)
             raise Exception("Something wrong in setmode.")
         if self.training and not freeze_bn:
             raise NotImplementedError("tile mode with batch-statistics BN: the hot path always runs the "

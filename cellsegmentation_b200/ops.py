@@ -341,9 +341,67 @@ class TileClassifier:
             return logits, feat
         return feat if want_features else logits
 
+    def map_shapes(self, size):
+        """[(H, C)] of x1..x4 for square inputs of `size` pixels (75/38/19/10 at 299)."""
+        h = ((size - 1) // 2 + 1 - 1) // 2 + 1                   # conv 7x7/2 pad 3, max pool 3x3/2 pad 1
+        exp = self.feature_dim // 512
+        out = []
+        for li in range(4):
+            if li > 0:
+                h = (h - 1) // 2 + 1
+            out.append((h, 64 * exp << li))
+        return out
+
+    def forward_image(self, x, max_batch=4, want_features=True, want_maps=False):
+        """N4: the encoder on whole normalised images x f32 [n,3,S,S] (fp32 CUDA-core path).
+        Returns the pooled feature avgpool(x4)+maxpool(x4) f32 [n,F] and / or the NHWC maps
+        [x1, x2, x3, x4] (model/resnet.py:234-248 with return_intermediate=True)."""
+        _req_cuda(x, "x", torch.float32)
+        n, _, S, S2 = x.shape
+        if S != S2:
+            raise ValueError("forward_image needs square images")
+        ws = self._workspace(S, max_batch, CS_PREC_FP32)
+        feat = torch.empty((n, self.feature_dim), dtype=torch.float32, device=x.device) if want_features else None
+        maps = [torch.empty((n, h, h, c), dtype=torch.float32, device=x.device) for h, c in self.map_shapes(S)] \
+            if want_maps else [None] * 4
+        check(lib().cs_model_forward_image(self._h, ptr(x), n, S, ptr(feat), ptr(maps[0]), ptr(maps[1]),
+                                           ptr(maps[2]), ptr(maps[3]), ptr(ws), ws.numel(), max_batch,
+                                           cur_stream()), "cs_model_forward_image")
+        if want_features and want_maps:
+            return feat, maps
+        return maps if want_maps else feat
+
     @property
     def last_launch_count(self):
         return int(lib().cs_model_last_launch_count(self._h))
+
+
+def conv2d_nhwc(x, w_packed, bias, k, stride=1, pad=0, relu=False):
+    """conv2d on NHWC f32 maps: x [n,H,W,Cin], w_packed [k*k*Cin, Cout] (row (dy*k+dx)*Cin+ci),
+    bias [Cout] (BatchNorm folded by the caller) -> [n,Ho,Wo,Cout].  Decoder layers of N4."""
+    _req_cuda(x, "x", torch.float32)
+    _req_cuda(w_packed, "w_packed", torch.float32)
+    _req_cuda(bias, "bias", torch.float32)
+    n, H, W, Cin = x.shape
+    Cout = w_packed.shape[1]
+    if w_packed.shape[0] != k * k * Cin or bias.numel() != Cout or Cout % 4:
+        raise ValueError("conv2d_nhwc: weight %s / bias %s do not match Cin %d, k %d (Cout %% 4 == 0)"
+                         % (tuple(w_packed.shape), tuple(bias.shape), Cin, k))
+    Ho, Wo = (H + 2 * pad - k) // stride + 1, (W + 2 * pad - k) // stride + 1
+    out = torch.empty((n, Ho, Wo, Cout), dtype=torch.float32, device=x.device)
+    check(lib().cs_conv2d_nhwc_f32(ptr(x), n, H, W, Cin, ptr(w_packed), ptr(bias), Cout, k, stride, pad,
+                                   int(bool(relu)), ptr(out), cur_stream()), "cs_conv2d_nhwc_f32")
+    return out
+
+
+def resize_bilinear_nhwc(x, size):
+    """F.interpolate(x, size=size, mode="bilinear", align_corners=True) on an NHWC f32 map."""
+    _req_cuda(x, "x", torch.float32)
+    n, H, W, C = x.shape
+    out = torch.empty((n, size, size, C), dtype=torch.float32, device=x.device)
+    check(lib().cs_resize_bilinear_nhwc_f32(ptr(x), n, H, W, C, size, size, ptr(out), cur_stream()),
+          "cs_resize_bilinear_nhwc_f32")
+    return out
 
 
 def debug_gemm_bf16(a, b, bias, bn):

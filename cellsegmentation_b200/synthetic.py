@@ -67,3 +67,23 @@ def make_resnet_weights(arch="resnet34", seed=0):
     fc_w = torch.from_numpy(rng.uniform(-bound, bound, (2, fd)).astype(np.float32)) * 0.05
     fc_b = torch.zeros(2)
     return convs, fc_w, fc_b
+
+
+def calibrate_head(clf, bags, tile, interval, n_calib=4096, sigma=2.0, max_batch=512):
+    """fc_tile for a random-init encoder whose probabilities spread over (0, 1) instead of
+    saturating (SURVEY 3.5-12 / 7 "Precision gates" recipe, the one the parity tests use): the
+    head is aligned with the first principal component of the pooled features of `n_calib`
+    instances and scaled so the logit difference has standard deviation `sigma`.  Features come
+    from the classifier's own fp32 CUDA path.  Returns (fc_w [2,F], fc_b [2]) and installs them."""
+    n_calib = min(n_calib, bags.shape[0] * 3025 if interval == 5 else n_calib)
+    _, feat = clf.forward_tiles(bags, tile, interval, inst_begin=0, inst_count=n_calib, precision="fp32",
+                                max_batch=max_batch, want_features=True)
+    f = feat.double().cpu().numpy()
+    mu = f.mean(0)
+    _, _, vt = np.linalg.svd(f - mu, full_matrices=False)
+    w = vt[0]
+    s = sigma / ((f - mu) @ w).std()
+    fc_w = torch.from_numpy(np.stack([-w * s / 2, w * s / 2]).astype(np.float32))
+    fc_b = torch.from_numpy(np.array([(mu @ w) * s / 2, -(mu @ w) * s / 2], np.float32))
+    clf.set_fc(fc_w, fc_b)
+    return fc_w, fc_b

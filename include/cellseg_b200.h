@@ -274,6 +274,35 @@ int cs_remove_small_regions(uint8_t* mask, int n_bags, int H, int W, int min_obj
                             void* stream);
 
 /* ---------------------------------------------------------------------------
+ * N4 — whole-image encoder and Stage-3 decoder building blocks (fp32 CUDA-core
+ * path; standard-shape convs outside the tile hot path).
+ * ------------------------------------------------------------------------- */
+
+/* The encoder on whole square images (reference: MILResNet.forward modes "image" and
+ * "segment", model/resnet.py:250-278; callers test_tile.py:88-105 --reg_limit,
+ * train_seg.py:255-269, inference.py:46-95).  x: f32 [n][3][size][size] normalised (device).
+ * feat_out (nullable): f32 [n][F] = avgpool_image(x4) + maxpool_image(x4) at map size 1.
+ * x1_out..x4_out (nullable): NHWC f32 outputs of layer1..layer4 (resnet_forward(x, True)),
+ * e.g. 75x75x64, 38x38x128, 19x19x256, 10x10x512 for ResNet-34 at 299.
+ * Workspace: cs_model_workspace_bytes(m, size, max_batch, CS_PREC_FP32). */
+int cs_model_forward_image(cs_model* m, const float* x, int64_t n, int size, float* feat_out,
+                           float* x1_out, float* x2_out, float* x3_out, float* x4_out,
+                           void* workspace, int64_t workspace_bytes, int64_t max_batch,
+                           void* stream);
+
+/* conv2d on NHWC f32 maps with BatchNorm folded by the caller (decoder layers upconv1..8 and
+ * seg_out_conv, model/resnet.py:194-199, 280-303).  w_dev: [k*k*Cin][Cout], row index
+ * (dy*k + dx)*Cin + ci; bias_dev [Cout]; Cout % 4 == 0.  out: [n][Ho][Wo][Cout]. */
+int cs_conv2d_nhwc_f32(const float* in, int64_t n, int H, int W, int Cin, const float* w_dev,
+                       const float* bias_dev, int Cout, int k, int stride, int pad, int relu,
+                       float* out, void* stream);
+
+/* F.interpolate(x, size=(Ho, Wo), mode="bilinear", align_corners=True) on NHWC f32 maps
+ * (model/resnet.py:282, 287, 292, 297, 300). */
+int cs_resize_bilinear_nhwc_f32(const float* in, int64_t n, int Hi, int Wi, int C, int Ho, int Wo,
+                                float* out, void* stream);
+
+/* ---------------------------------------------------------------------------
  * Diagnostics — used by tests/ to exercise the tcgen05 GEMM kernel and the
  * production conv planner in isolation.  Not part of the reference surface.
  * ------------------------------------------------------------------------- */

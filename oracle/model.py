@@ -142,6 +142,43 @@ def make_state_dict(arch="resnet34", seed=0, random_bn=True):
     return sd
 
 
+def make_image_seg_state(arch="resnet34", seed=0):
+    """Deterministic weights for the Stage-1 heads (fc_image_cls / fc_image_reg, model/resnet.py:129-153)
+    and the Stage-3 decoder (upconv1..8, seg_out_conv, :155-165): same keys and shapes as the
+    reference modules, loaded with load_state_dict(strict=False) into the reference (golden
+    generation) and into the mirror (tests)."""
+    rng = np.random.default_rng([seed, 4242])
+    e = 4 if arch in BOTTLENECK else 1
+    feat = 512 * e
+    sd = {}
+
+    def t(a):
+        return torch.from_numpy(np.ascontiguousarray(a, dtype=np.float32))
+
+    def bn(name, c):
+        sd[name + ".weight"] = t(rng.uniform(0.8, 1.2, c))
+        sd[name + ".bias"] = t(rng.standard_normal(c) * 0.1)
+        sd[name + ".running_mean"] = t(rng.standard_normal(c) * 0.1)
+        sd[name + ".running_var"] = t(rng.uniform(0.8, 1.2, c))
+
+    for head, n_out in (("fc_image_cls", 7), ("fc_image_reg", 1)):
+        bn(head + ".1", feat)
+        sd[head + ".4.weight"] = t(rng.standard_normal((64, feat)) / np.sqrt(feat))
+        sd[head + ".4.bias"] = t(rng.standard_normal(64) * 0.1)
+        bn(head + ".5", 64)
+        sd[head + ".7.weight"] = t(rng.standard_normal((n_out, 64)) / 8.0)
+        sd[head + ".7.bias"] = t(rng.standard_normal(n_out) * 0.1 + (1.0 if n_out == 1 else 0.0))
+    chans = [(512 * e, 256 * e), (512 * e, 256 * e), (256 * e, 128 * e), (256 * e, 128 * e), (128 * e, 64 * e),
+             (128 * e, 64 * e), (64 * e, 64 if e == 1 else 32 * e), (64 if e == 1 else 32 * e, 64)]
+    for i, (ci, co) in enumerate(chans, start=1):
+        sd["upconv%d.0.weight" % i] = t(rng.standard_normal((co, ci, 3, 3)) * np.sqrt(2.0 / (ci * 9)))
+        sd["upconv%d.0.bias" % i] = t(rng.standard_normal(co) * 0.05)
+        bn("upconv%d.1" % i, co)
+    sd["seg_out_conv.weight"] = t(rng.standard_normal((2, 64, 1, 1)) * np.sqrt(2.0 / 64))
+    sd["seg_out_conv.bias"] = t(rng.standard_normal(2) * 0.05)
+    return sd
+
+
 def calibrate_head(sd, calib_x, arch="resnet34", sigma=2.0):
     """PC-1-aligned, zero-centred fc_tile so probabilities spread over (0,1) instead of
     saturating (SURVEY 3.5-12 / 7 'Precision gates' recipe)."""

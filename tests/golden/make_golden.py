@@ -117,7 +117,7 @@ def gen_train(ref):
     net.setmode("tile")
     ds.setmode(3)
     loader = torch.utils.data.DataLoader(ds, batch_size=16, shuffle=False, num_workers=0)
-    opt = torch.optim.SGD(filter(lambda p: p.requires_grad, net.parameters()), lr=0.05, weight_decay=1e-4)
+    opt = torch.optim.SGD(filter(lambda p: p.requires_grad, net.parameters()), lr=2e-5, weight_decay=1e-4)
     crit = torch.nn.CrossEntropyLoss()
     losses = []
     with contextlib.redirect_stderr(io.StringIO()):
@@ -132,17 +132,54 @@ def gen_train(ref):
     out["train_losses"] = np.array(losses, np.float64)
     out["train_fc_w"] = net.fc_tile[1].weight.detach().numpy().copy()
     out["train_fc_b"] = net.fc_tile[1].bias.detach().numpy().copy()
-    out["train_hparams"] = np.array([16, 0.05, 1e-4, 1.0])          # batch, lr, weight decay, gamma
+    out["train_hparams"] = np.array([16, 2e-5, 1e-4, 1.0])          # batch, lr, weight decay, gamma
     enc_same = all(torch.equal(net.state_dict()[k], sd[k]) for k in sd if not k.startswith("fc_tile") and
                    k in net.state_dict() and not k.endswith("num_batches_tracked"))
     assert enc_same, "train_tile changed encoder weights or BN statistics"
     save("train.npz", **out)
 
 
+def gen_image_seg(ref):
+    """N4: MILResNet.forward in modes "image" and "segment" (model/resnet.py:271-303) on whole
+    299 x 299 images, through the reference class + inference_image (inference.py:46-95)."""
+    import contextlib
+    from oracle import tiles as otiles
+    out = {}
+    bags = synth.make_bags(3, seed=51)
+    x = torch.from_numpy(np.stack([otiles.normalize_tile(b) for b in bags]))
+    for arch in ("resnet34", "resnet18"):
+        net = getattr(ref_shim.load_reference_module("resnet"), "MIL" + arch)()
+        sd = omodel.make_state_dict(arch, seed=3)
+        sd.update(omodel.make_image_seg_state(arch, seed=5))
+        missing, unexpected = net.load_state_dict(sd, strict=False)
+        assert not unexpected and all("num_batches_tracked" in k for k in missing), (missing, unexpected)
+        net.eval()
+        with torch.no_grad():
+            net.setmode("image")
+            cls, reg = net(x)
+            net.setmode("segment")
+            seg = net(x[:2])
+        out[arch + "_cls"], out[arch + "_reg"] = cls.numpy(), reg.numpy()
+        out[arch + "_seg_sample"] = seg.numpy()[:, :, ::5, ::5].copy()
+        out[arch + "_seg_sum"] = seg.double().sum(dim=(2, 3)).numpy()
+        out[arch + "_seg_absmax"] = np.array(float(seg.abs().max()))
+        if arch == "resnet34":      # inference_image over a (ids, image) loader, with and without cls_limit
+            net.setmode("image")
+            loader = [(np.array([7, 8]), x[:2]), (np.array([9]), x[2:])]
+            for lim in (False, True):
+                with contextlib.redirect_stderr(io.StringIO()):
+                    ids, cats, counts = ref.inference.inference_image(loader, net, torch.device("cpu"), mode="test",
+                                                                      cls_limit=lim, return_id=True)
+                out["inf_ids"], out["inf_cats_%d" % lim], out["inf_counts_%d" % lim] = ids, cats, counts
+    save("image_seg.npz", **out)
+
+
 def main():
     ref = ref_shim.import_reference()
     if sys.argv[1:] == ["train"]:
         return gen_train(ref)
+    if sys.argv[1:] == ["image_seg"]:
+        return gen_image_seg(ref)
     if len(sys.argv) > 1:          # python make_golden.py resnet50 ...: only those model fixtures
         ds = ref_dataset(ref, synth.make_bags(3, seed=11), [4, 0, 9], 32, 20)
         for arch in sys.argv[1:]:
@@ -275,6 +312,9 @@ def main():
 
     # 8. make_train_data + train_tile, executed unmodified ---------------------------------
     gen_train(ref)
+
+    # 9. N4: image / segment modes on whole images -----------------------------------------
+    gen_image_seg(ref)
 
 
 if __name__ == "__main__":

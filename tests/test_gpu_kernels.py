@@ -130,7 +130,8 @@ def test_select_topk_golden(cuda, case):
     assert np.array_equal(order, np.lexsort((p, tid)))
 
 
-@pytest.mark.parametrize("T,n_bags", [(1, 5), (2, 3), (33, 7), (225, 16), (3025, 9), (4097, 3), (8100, 2)])
+@pytest.mark.parametrize("T,n_bags", [(1, 5), (2, 3), (33, 7), (225, 16), (1021, 5), (3025, 9), (3069, 4), (3364, 6),
+                                       (4093, 3), (4094, 3), (4097, 3), (8100, 2)])
 def test_select_topk_random_uniform(cuda, T, n_bags):
     ops = _ops()
     rng = np.random.default_rng(T * 31 + n_bags)
@@ -201,6 +202,21 @@ def test_select_topk_shards_equal_global(cuda, T, sizes):
             b0 += nb
         assert np.array_equal(np.concatenate(got_idx), want)
         assert np.array_equal(np.concatenate(got_pl), oselect.pseudo_labels(tid, lab, want))
+
+
+@pytest.mark.parametrize("mode", ["staged", "0"])
+def test_select_topk_other_paths_subprocess(cuda, mode):
+    """CELLSEG_SELECT_FAST is read when the library loads: =staged routes every bag through the
+    shared-memory fast path of round 1 (still used for bags longer than 4093 instances), =0 through
+    the exact bitonic kernel alone."""
+    import os
+    import subprocess
+    import sys
+    here = os.path.abspath(__file__)
+    r = subprocess.run([sys.executable, "-m", "pytest", here, "-x", "-q", "-p", "no:cacheprovider", "-k",
+                        "select_topk and not subprocess"],
+                       env=dict(os.environ, CELLSEG_SELECT_FAST=mode), capture_output=True, text=True, timeout=900)
+    assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-2000:]
 
 
 def test_select_topk_ragged_with_empty_bags(cuda):

@@ -235,7 +235,7 @@ def test_train_tile_oracle_matches_reference_loop():
         sd = dict(sd)
         sd["fc_tile.1.weight"], sd["fc_tile.1.bias"] = w, b
         losses.append(loss)
-    assert np.allclose(losses, g["train_losses"], rtol=0, atol=2e-6), (losses, g["train_losses"])
+    assert np.allclose(losses, g["train_losses"], rtol=1e-5, atol=2e-6), (losses, g["train_losses"])
     assert np.abs(w.numpy() - g["train_fc_w"]).max() < 2e-6
     assert np.abs(b.numpy() - g["train_fc_b"]).max() < 2e-6
 

@@ -2,10 +2,15 @@
 # round-2 call 1: full GPU tests, default bench, A/B of the y-sum epilogue, launch list
 cd "$GRAFT_REPO_ROOT" || exit 1
 mkdir -p gpurun_out
-timeout 1200 python -m pytest tests -m gpu -x -q > gpurun_out/r2a_tests.log 2>&1; echo "tests rc=$?" | tee -a gpurun_out/r2a_tests.log
-tail -5 gpurun_out/r2a_tests.log
-timeout 600 python bench.py > gpurun_out/r2a_bench.json 2> gpurun_out/r2a_bench.err; echo "bench rc=$?"
+timeout 1500 python -m pytest tests -m gpu -q > gpurun_out/r2a_tests.log 2>&1; echo "tests rc=$?" | tee -a gpurun_out/r2a_tests.log
+tail -15 gpurun_out/r2a_tests.log
+timeout 600 python bench.py > gpurun_out/r2a_bench.json 2> gpurun_out/r2a_bench.err; rc=$?; echo "bench rc=$rc"
 tail -c 600 gpurun_out/r2a_bench.err
+if [ $rc -ne 0 ]; then
+  tail -c 600 gpurun_out/r2a_bench.json
+  CELLSEG_SELECT_FAST=staged timeout 600 python bench.py > gpurun_out/r2a_bench_staged.json 2> gpurun_out/r2a_bench_staged.err; echo "bench(staged select) rc=$?"
+  tail -c 1500 gpurun_out/r2a_bench_staged.json
+fi
 CELLSEG_YSUM_EPI=8 timeout 300 python bench.py --no-side-legs --no-cpu-baseline --no-verify > gpurun_out/r2a_bench_epi8.json 2>&1
 CELLSEG_YSUM_PAIRS=1 timeout 300 python bench.py --no-side-legs --no-cpu-baseline --no-verify > gpurun_out/r2a_bench_pairs.json 2>&1
 python - <<'PY'
