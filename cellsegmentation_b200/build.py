@@ -26,7 +26,7 @@ SOURCES = [
     "fwd_fp32.cu",
     "fwd_tc.cu",
     "conv_gemm.cu",
-    "stem_tc.cu", "stem_win.cu",
+    "stem_win.cu",
     "conv_halo.cu", "conv_ysum.cu",
     "model.cu",
 ]

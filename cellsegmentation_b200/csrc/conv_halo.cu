@@ -20,6 +20,12 @@
 // holds its own halo tile and HALF of every weight tile (the resident set shrinks to 36 KB),
 // the leader issues M = 256 MMAs for both.
 //
+// DS = true adds the BasicBlock's 1x1 stride-2 downsample of the block input as one more K step
+// (layer-2 entry, model/resnet.py:36-40 with downsample): a {64 ch, W, IMG, H} box of the
+// block input's even pixels, already in accumulator row order, meets the weight columns behind
+// the nine taps.  That convolution ran in the generic shifted-box kernel before (nine boxes per
+// M tile): 220 us against 138 us for the same 3x3 without the shortcut (ncu r2a).
+//
 // Warp roles as in conv_gemm.cu: warp 0 TMA, warp 1 MMA issue, warps 2-9 epilogue, warp 10 DMA.
 #include "fwd.cuh"
 #include "gemm_epilogue.cuh"
@@ -50,11 +56,13 @@ struct HaloCfg {
   static_assert((kRowsY * 128) % 1024 == 0, "a dy shift must move whole swizzle atoms");
 };
 
-template <int BN, int W, int CCH, bool BRES, int CL>
+template <int BN, int W, int CCH, bool BRES, int CL, bool DS>
 __global__ void __launch_bounds__(kHaloThreads, 1)
 conv_halo_kernel(const __grid_constant__ HaloParams p) {
   using Cfg = HaloCfg<BN, W, CCH, BRES, CL>;
   constexpr int Cin = CCH * 64;
+  static_assert(!DS || !BRES, "the downsample step loads its weight tile with the stage");
+  constexpr uint32_t kDsBytes = 128 * 128 + Cfg::kBTile;   // one 128-row box + one weight tile
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw = smem_u32(smem_raw);
   const uint32_t base = (raw + 1023u) & ~1023u;
@@ -94,6 +102,7 @@ conv_halo_kernel(const __grid_constant__ HaloParams p) {
     fence_barrier_init();
     prefetch_tmap(&p.a_map);
     prefetch_tmap(&p.b_map);
+    if (DS) prefetch_tmap(&p.ds_map);
   }
   if (warp == 1) {
     if (CL == 1) tmem_alloc(smem_u32((const void*)tmem_slot), Cfg::kTmemCols);
@@ -142,6 +151,19 @@ conv_halo_kernel(const __grid_constant__ HaloParams p) {
           }
           if (++stage == Cfg::kStages) { stage = 0; phase ^= 1u; }
         }
+        if (DS) {   // shortcut: even pixels of the block input + the weight columns behind the taps
+          mbar_wait(empty_bar(stage), phase ^ 1u);
+          const uint32_t a_dst = base + stage * Cfg::kStageBytes;
+          if (rank == 0) mbar_expect_tx(full_bar(stage), CL * kDsBytes);
+          if (CL == 1) {
+            tma_load_4d(a_dst, &p.ds_map, full_bar(stage), 0, 0, m_tile * Cfg::kImg, 0);
+            tma_load_2d(a_dst + Cfg::kABytes, &p.b_map, full_bar(stage), 9 * Cin, 0);
+          } else {
+            tma_load_4d_pair(a_dst, &p.ds_map, full_bar(stage), 0, 0, m_tile * Cfg::kImg, 0);
+            tma_load_2d_pair(a_dst + Cfg::kABytes, &p.b_map, full_bar(stage), 9 * Cin, b_row);
+          }
+          if (++stage == Cfg::kStages) { stage = 0; phase ^= 1u; }
+        }
       }
     }
   } else if (warp == 1) {
@@ -174,6 +196,21 @@ conv_halo_kernel(const __grid_constant__ HaloParams p) {
                 umma_bf16_pair(d_tmem, a_desc + (uint64_t)(2 * k), b_desc + (uint64_t)(2 * k), idesc,
                                (s > 0 || dy > 0 || k > 0) ? 1u : 0u);
             }
+          }
+          if (CL == 1) umma_commit(empty_bar(stage));
+          else umma_commit_pair(empty_bar(stage), kMask);
+          if (++stage == Cfg::kStages) { stage = 0; phase ^= 1u; }
+        }
+        if (DS) {
+          mbar_wait(full_bar(stage), phase);
+          tc_fence_after();
+          const uint32_t a_src = base + stage * Cfg::kStageBytes;
+          const uint64_t a_desc = umma_desc_sw128(a_src);
+          const uint64_t b_desc = umma_desc_sw128(a_src + Cfg::kABytes);
+#pragma unroll
+          for (int k = 0; k < 4; ++k) {
+            if (CL == 1) umma_bf16(d_tmem, a_desc + (uint64_t)(2 * k), b_desc + (uint64_t)(2 * k), idesc, 1u);
+            else umma_bf16_pair(d_tmem, a_desc + (uint64_t)(2 * k), b_desc + (uint64_t)(2 * k), idesc, 1u);
           }
           if (CL == 1) umma_commit(empty_bar(stage));
           else umma_commit_pair(empty_bar(stage), kMask);
@@ -264,20 +301,20 @@ conv_halo_kernel(const __grid_constant__ HaloParams p) {
   }
 }
 
-template <int BN, int W, int CCH, bool BRES, int CL>
+template <int BN, int W, int CCH, bool BRES, int CL, bool DS = false>
 int launch_halo(const HaloParams& p, cudaStream_t st) {
   using Cfg = HaloCfg<BN, W, CCH, BRES, CL>;
   static bool attr_done[64] = {false};
   int dev = 0;
   CS_CUDA(cudaGetDevice(&dev));
   if (dev >= 64 || !attr_done[dev]) {
-    CS_CUDA(cudaFuncSetAttribute(conv_halo_kernel<BN, W, CCH, BRES, CL>,
+    CS_CUDA(cudaFuncSetAttribute(conv_halo_kernel<BN, W, CCH, BRES, CL, DS>,
                                  cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg::kSmemBytes));
     if (dev < 64) attr_done[dev] = true;
   }
   const int groups = (p.num_m_tiles + CL - 1) / CL;
   const int clusters = groups < num_sms() / CL ? groups : num_sms() / CL;
-  CS_CUDA(launch_pdl(conv_halo_kernel<BN, W, CCH, BRES, CL>, dim3((unsigned)(clusters * CL)),
+  CS_CUDA(launch_pdl(conv_halo_kernel<BN, W, CCH, BRES, CL, DS>, dim3((unsigned)(clusters * CL)),
                      dim3(kHaloThreads), Cfg::kSmemBytes, st, CL, p));
   return CS_OK;
 }
@@ -290,6 +327,12 @@ bool halo_supported(int W, int Cin, int Cout) {
 
 int launch_conv_halo(const HaloParams& p, int W, int Cin, cudaStream_t st) {
   if (p.num_m_tiles <= 0) return CS_OK;
+  if (p.has_ds) {
+    if (W == 4 && Cin == 128)
+      return p.cluster > 1 ? launch_halo<128, 4, 2, false, 2, true>(p, st) : launch_halo<128, 4, 2, false, 1, true>(p, st);
+    set_error("launch_conv_halo: fused downsample only for the 4x4 x 128 stage");
+    return CS_ERR_UNSUPPORTED;
+  }
   if (p.cluster > 1) {
     if (W == 8 && Cin == 64) return launch_halo<64, 8, 1, true, 2>(p, st);
     if (W == 4 && Cin == 128) return launch_halo<128, 4, 2, false, 2>(p, st);
@@ -299,6 +342,38 @@ int launch_conv_halo(const HaloParams& p, int W, int Cin, cudaStream_t st) {
   }
   set_error("launch_conv_halo: unsupported geometry W=%d Cin=%d", W, Cin);
   return CS_ERR_UNSUPPORTED;
+}
+
+// View of the even pixels of a [T][2H][2W][C] tensor as {C, W, T, H} with a {64, W, IMG, H} box:
+// the input of a 1x1 stride-2 downsample in accumulator row order.
+int make_act_map_halo_ds(CUtensorMap* map, const void* base, int C, int W, int H, int64_t T) {
+  // same encoder call as make_act_map_halo; pixel strides doubled, no halo
+  typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*,
+                                    const cuuint64_t*, const cuuint64_t*, const cuuint32_t*,
+                                    const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                    CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+  void* ptr = nullptr;
+  cudaDriverEntryPointQueryResult qres;
+  CS_CUDA(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &ptr, cudaEnableDefault, &qres));
+  if (qres != cudaDriverEntryPointSuccess || !ptr) {
+    set_error("cuTensorMapEncodeTiled is not available from this driver");
+    return CS_ERR_CUDA;
+  }
+  EncodeTiledFn enc = reinterpret_cast<EncodeTiledFn>(ptr);
+  const int img = 128 / (W * H);
+  cuuint64_t dims[4] = {(cuuint64_t)C, (cuuint64_t)W, (cuuint64_t)T, (cuuint64_t)H};
+  // byte strides of dims 1..3: x (2 pixels), instance, y (2 rows of 2W pixels)
+  cuuint64_t strides[3] = {(cuuint64_t)2 * C * 2, (cuuint64_t)(2 * H) * (2 * W) * C * 2, (cuuint64_t)2 * (2 * W) * C * 2};
+  cuuint32_t box[4] = {64, (cuuint32_t)W, (cuuint32_t)img, (cuuint32_t)H};
+  cuuint32_t estr[4] = {1, 1, 1, 1};
+  CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(base), dims, strides,
+                   box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                   CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    set_error("cuTensorMapEncodeTiled(halo ds C=%d W=%d H=%d T=%lld) failed: %d", C, W, H, (long long)T, (int)r);
+    return CS_ERR_CUDA;
+  }
+  return CS_OK;
 }
 
 // {C, W, T, H} map with a {64, W, IMG, H + 2} box: instances sit between x and y in the box

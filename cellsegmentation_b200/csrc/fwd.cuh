@@ -115,8 +115,13 @@ struct HaloParams {
   int relu;
   // TMA views {C, W, T, H}, box {64, W, IMG, H} (make_act_map_halo with halo = 0)
   CUtensorMap res_hi_map, res_lo_map, out_hi_map, out_lo_map;
+  // fused 1x1 stride-2 downsample of the block input (layer-2 entry): one extra K step whose A
+  // box comes from ds_map (make_act_map_halo_ds) and whose weights are B columns [9*Cin, +64)
+  CUtensorMap ds_map;
+  int has_ds;
 };
 bool halo_supported(int W, int Cin, int Cout);
+int make_act_map_halo_ds(CUtensorMap* map, const void* base, int C, int W, int H, int64_t T);
 int launch_conv_halo(const HaloParams& p, int W, int Cin, cudaStream_t st);
 int make_act_map_halo(CUtensorMap* map, const void* base, int C, int W, int H, int64_t T,
                       int halo /* 1: box H+2 rows for the A operand, 0: H rows for epilogue tiles */);
@@ -157,12 +162,6 @@ struct StemArgs {
   __nv_bfloat16* out_lo;
 };
 int launch_stem_bf16(const StemArgs& a, cudaStream_t st);
-
-// Tensor-core stem (stem_tc.cu), tile 32 only: w_bf16_dev is [64][192] packed by
-// pack_stem_weights_bf16, lut_bf16_dev the bf16 rounding of the 3x256 normalisation LUT.
-void pack_stem_weights_bf16(const float* w_oihw, uint16_t* out /* [64*192] */);
-int launch_stem_tc(const StemArgs& a, const void* w_bf16_dev, const uint16_t* lut_bf16_dev,
-                   cudaStream_t st);
 
 // Window-form tensor-core stem (stem_win.cu), tile 32 only: no im2col, the padded bf16 image is
 // the UMMA operand.  w_packed_dev holds stem_win_weight_bytes() bytes from pack_stem_weights_win.

@@ -1,5 +1,5 @@
 // K2 (bf16 mode) support code: CUDA-core stem (tile 16), tile head, TMA descriptor builders.
-// The tensor-core kernels live in stem_win.cu (stem_tc.cu: im2col predecessor), conv_ysum.cu,
+// The tensor-core kernels live in stem_win.cu, conv_ysum.cu,
 // conv_halo.cu and conv_gemm.cu.
 #include "fwd.cuh"
 #include "gemm_epilogue.cuh"
@@ -292,21 +292,16 @@ int launch_stem_bf16(const StemArgs& a, cudaStream_t st) {
     float lut[768];
     get_norm_lut_host(lut);
     CS_CUDA(cudaMemcpyToSymbol(c_stem_lut, lut, sizeof(lut)));
-    CS_CUDA(cudaFuncSetAttribute(stem_bf16_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                 (int)StemGeom<32>::kSmem));
     CS_CUDA(cudaFuncSetAttribute(stem_bf16_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                  (int)StemGeom<16>::kSmem));
     if (dev < 64) lut_done[dev] = true;
   }
   if (a.count <= 0) return CS_OK;
   int grid = (int)(a.count < (int64_t)num_sms() * 4 ? a.count : (int64_t)num_sms() * 4);
-  if (a.tile == 32) {
-    grid = (int)(a.count < num_sms() ? a.count : num_sms());
-    stem_bf16_kernel<32><<<grid, 256, StemGeom<32>::kSmem, st>>>(a);
-  } else if (a.tile == 16) {
+  if (a.tile == 16) {   // tile 32 runs the window-form tensor-core stem (stem_win.cu)
     stem_bf16_kernel<16><<<grid, 256, StemGeom<16>::kSmem, st>>>(a);
   } else {
-    set_error("bf16 stem: tile %d unsupported (16 or 32)", a.tile);
+    set_error("CUDA-core bf16 stem: tile %d unsupported (16 only)", a.tile);
     return CS_ERR_UNSUPPORTED;
   }
   CS_LAUNCH_CHECK();

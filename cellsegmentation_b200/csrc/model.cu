@@ -38,7 +38,7 @@ const bool g_snake = !env_is("CELLSEG_SNAKE", "0");          // alternate the ti
 // 14 % slower in pair mode and stays single-CTA.  CELLSEG_CLUSTER=1 turns pairs off.
 const int g_cluster = env_is("CELLSEG_CLUSTER", "1") ? 1 : 2;
 const bool g_disable_halo = env_is("CELLSEG_HALO", "0");     // diagnostics: generic kernel only
-const bool g_force_cuda_core_stem = env_is("CELLSEG_STEM", "cuda");
+const bool g_disable_halo_ds = env_is("CELLSEG_HALO_DS", "0");   // layer-2 entry conv2 in the generic kernel
 // Residual stream: bf16 by default.  CELLSEG_RESIDUAL=hilo carries a second bf16 tensor
 // lo = value - bf16(value) between blocks (~16 mantissa bits); measured max|dp| moves by < 1.5e-3
 // (ResNet-34 0.0101 -> 0.0098) while the block epilogues move twice the bytes (-11 % throughput).
@@ -49,8 +49,10 @@ const int g_xbufs = g_no_lo ? 2 : 4;
 // accumulator read-out: 102 vs 108 us per 18 944 instances against the halo kernel and +2 %
 // sustained throughput (less power).  CELLSEG_YSUM=0 puts layer 1 back on the halo kernel.
 const bool g_disable_ysum = env_is("CELLSEG_YSUM", "0");
-const bool g_ysum_pairs = env_is("CELLSEG_YSUM_PAIRS", "1");   // experiment
-const bool g_im2col_stem = env_is("CELLSEG_STEM", "im2col");   // first tensor-core stem (stem_tc.cu)
+// y-sum in CTA pairs (M = 256 MMAs, each CTA holds half of every weight tile): with the 16-warp
+// epilogue the kernel is no longer epilogue-bound and the halved B-operand reads pay, +1.5..2 %
+// on the whole step.  CELLSEG_YSUM_PAIRS=0 keeps single-CTA MMAs.
+const bool g_ysum_pairs = !env_is("CELLSEG_YSUM_PAIRS", "0");
 
 struct ConvW {
   int cin = 0, cout = 0, k = 0, stride = 1, pad = 0, groups = 1;
@@ -340,10 +342,17 @@ int plan_conv(const ConvGeom& g, const float* w_oihw, const float* bias, const C
     if (rc != CS_OK) { free_planned(pc); return rc; }
     pc.yp.bias = pc.d_bias;
     pc.ysum = true;
-  } else if (!pc.dense && !gds && g.k == 3 && g.groups == 1 && g.stride == 1 && g.Hi == g.Wi &&
-      halo_supported(g.Wi, g.Cin, g.Cout) && !g_disable_halo) {
+  } else if (!pc.dense && g.k == 3 && g.groups == 1 && g.stride == 1 && g.Hi == g.Wi &&
+      halo_supported(g.Wi, g.Cin, g.Cout) && !g_disable_halo &&
+      (!gds || (!g_disable_halo_ds && g.Wi == 4 && gds->Cin == 64 && gds->stride == 2 && gds->Hi == 8 && gds->Wi == 8))) {
     rc = make_act_map_halo(&pc.hp.a_map, in_hi, g.Cin, g.Wi, g.Hi, b_pad, 1);
     if (rc != CS_OK) { free_planned(pc); return rc; }
+    pc.hp.has_ds = 0;
+    if (gds) {   // BasicBlock shortcut of the layer-2 entry as one more K step of the halo kernel
+      rc = make_act_map_halo_ds(&pc.hp.ds_map, ds_in_hi, gds->Cin, g.Wi, g.Hi, b_pad);
+      if (rc != CS_OK) { free_planned(pc); return rc; }
+      pc.hp.has_ds = 1;
+    }
     pc.hp.cluster = pc.BN >= 128 ? g_cluster : 1;
     rc = make_mat_map_2d(&pc.hp.b_map, pc.d_B, K_cat, pc.p.n_total, K_cat, pc.BN / pc.hp.cluster);
     if (rc != CS_OK) { free_planned(pc); return rc; }
@@ -423,12 +432,10 @@ struct TcPlan {
   const __nv_bfloat16* x4_hi = nullptr;
   const __nv_bfloat16* x4_lo = nullptr;
   int P4 = 1, C4 = 512;
-  uint16_t* d_stem_w = nullptr;  // [64][192] bf16 for the tensor-core stem (tile 32)
   uint16_t* d_stem_w2 = nullptr; // window-form stem weights (stem_win.cu)
   uint16_t* d_lut = nullptr;     // [3][256] bf16 normalisation LUT
   ~TcPlan() {
     for (auto& l : layers) free_planned(l);
-    if (d_stem_w) cudaFree(d_stem_w);
     if (d_stem_w2) cudaFree(d_stem_w2);
     if (d_lut) cudaFree(d_lut);
   }
@@ -587,13 +594,10 @@ int build_tc_plan(cs_model* m, int tile, int64_t max_batch, void* ws, int64_t ws
   plan->P4 = H * W;
   plan->C4 = C;
   if (tile == 32) {
-    std::vector<uint16_t> sw(64 * 192), lut(768);
-    pack_stem_weights_bf16(m->convs[0].w.data(), sw.data());
+    std::vector<uint16_t> lut(768);
     float lut_f[768];
     get_norm_lut_host(lut_f);
     for (int i = 0; i < 768; ++i) lut[i] = f32_to_bf16_rn(lut_f[i]);
-    CS_CUDA(cudaMalloc(&plan->d_stem_w, sw.size() * 2));
-    CS_CUDA(cudaMemcpy(plan->d_stem_w, sw.data(), sw.size() * 2, cudaMemcpyHostToDevice));
     std::vector<uint16_t> sw2(stem_win_weight_bytes() / 2);
     pack_stem_weights_win(m->convs[0].w.data(), sw2.data());
     CS_CUDA(cudaMalloc(&plan->d_stem_w2, sw2.size() * 2));
@@ -615,9 +619,8 @@ int run_tc_batch(cs_model* m, const StemArgs& stem_in, int64_t count, float* pro
   sa.out_hi = pl.x_hi[0];
   sa.out_lo = nullptr;   // bf16 stream only; the first block's residual add reads x_hi alone
   int rc;
-  if (pl.tile == 32 && !g_force_cuda_core_stem)
-    rc = g_im2col_stem ? launch_stem_tc(sa, pl.d_stem_w, pl.d_lut, st)
-                       : launch_stem_win(sa, pl.d_stem_w2, pl.d_lut, st);
+  if (pl.tile == 32)
+    rc = launch_stem_win(sa, pl.d_stem_w2, pl.d_lut, st);
   else
     rc = launch_stem_bf16(sa, st);
   if (rc != CS_OK) return rc;

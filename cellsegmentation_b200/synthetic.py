@@ -8,15 +8,27 @@ import torch
 IMAGE_SIZE = 299
 
 
-def make_bags_device(n_bags, device, seed=0, chunk=512):
-    """u8 [n_bags,299,299,3] resident in HBM; uniform noise (compute is data independent)."""
+def make_bags_device(n_bags, device, seed=0, chunk=512, kind="blobs"):
+    """u8 [n_bags,299,299,3] resident in HBM, generated on the device.
+    kind="blobs" (default): smooth 23-pixel blobs of brightness 60..250 plus N(0, 12) pixel noise,
+    the recipe of the parity tests' bags (oracle/synth.py; SURVEY 8d: "smooth blobs + noise so
+    that V straddles 170") -- tiles of one bag differ from each other as LYSTO tiles do, so a
+    calibrated head separates them and the bf16-vs-fp32 check of bench.py means something.
+    kind="noise": iid uniform bytes (every tile statistically the same)."""
     g = torch.Generator(device=device)
     g.manual_seed(1234567 + seed)
     out = torch.empty((n_bags, IMAGE_SIZE, IMAGE_SIZE, 3), dtype=torch.uint8, device=device)
+    cells = IMAGE_SIZE // 23 + 2
     for b in range(0, n_bags, chunk):
         e = min(n_bags, b + chunk)
-        out[b:e] = torch.randint(0, 256, (e - b, IMAGE_SIZE, IMAGE_SIZE, 3), dtype=torch.uint8,
-                                 device=device, generator=g)
+        if kind == "noise":
+            out[b:e] = torch.randint(0, 256, (e - b, IMAGE_SIZE, IMAGE_SIZE, 3), dtype=torch.uint8,
+                                     device=device, generator=g)
+            continue
+        coarse = torch.rand((e - b, cells, cells, 3), device=device, generator=g) * 190.0 + 60.0
+        up = coarse.repeat_interleave(23, 1).repeat_interleave(23, 2)[:, :IMAGE_SIZE, :IMAGE_SIZE]
+        up = up + torch.randn(up.shape, device=device, generator=g) * 12.0
+        out[b:e] = up.clamp_(0, 255).to(torch.uint8)
     return out
 
 

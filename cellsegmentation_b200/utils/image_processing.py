@@ -1,9 +1,10 @@
 """Heatmaps, pseudo-masks and HSV refinement (mirror of utils/image_processing.py).
 
 heatmap / generate_masks / preprocess_masks / remove_small_regions keep the reference
-signatures (utils/image_processing.py:146, 79, 114, 14).  Painting, the HSV-threshold AND and the
-connected-component clean-up of remove_small_regions run on the GPU (paint.cu, hsv_refine.cu,
-cc.cu); the JET colour map / blend (cv2) and PNG/CSV writing stay on the host.
+signatures (utils/image_processing.py:146, 79, 114, 14).  Painting, the gray map + JET colour
+map + 0.5/0.5 blend, the HSV-threshold AND and the connected-component clean-up of
+remove_small_regions all run on the GPU (paint.cu, hsv_refine.cu, cc.cu); only the PNG encode
+(a host thread pool) and the CSV writing stay on the host.
 """
 import csv
 import os
@@ -43,7 +44,7 @@ def hsv_refine_batch(images_dev, masks_dev, v_thresh=170):
 
 
 def preprocess_masks(img, mask):
-    """utils/image_processing.py:114-124 for one image: GPU HSV-threshold AND, host CC clean-up."""
+    """utils/image_processing.py:114-124 for one image: HSV-threshold AND and connected-component clean-up, both on the GPU."""
     dev = _cuda_dev()
     d_img = torch.from_numpy(np.ascontiguousarray(img, dtype=np.uint8)).to(dev)
     d_mask = torch.from_numpy(np.ascontiguousarray(np.asarray(mask) != 0).astype(np.uint8)).to(dev)

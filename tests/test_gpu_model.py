@@ -226,14 +226,15 @@ def test_hilo_residual_mode_subprocess(cuda):
     assert "hilo max|dp|" in r.stdout
 
 
-@pytest.mark.parametrize("env", [{"CELLSEG_YSUM": "0"}, {"CELLSEG_YSUM_PAIRS": "1"}, {"CELLSEG_CLUSTER": "1"},
-                                 {"CELLSEG_STEM": "im2col"}, {"CELLSEG_RESIDUAL": "hilo", "CELLSEG_YSUM": "0"},
+@pytest.mark.parametrize("env", [{"CELLSEG_YSUM": "0"}, {"CELLSEG_YSUM_PAIRS": "0"}, {"CELLSEG_CLUSTER": "1"},
+                                 {"CELLSEG_YSUM_EPI": "8"}, {"CELLSEG_HALO_DS": "0"},
+                                 {"CELLSEG_RESIDUAL": "hilo", "CELLSEG_YSUM": "0"},
                                  {"CELLSEG_RESIDUAL": "hilo"}],
                          ids=lambda e: ",".join("%s=%s" % kv for kv in e.items()))
 def test_alternative_kernel_paths_subprocess(cuda, env):
     """The switches are read when the library loads: run the conv-form and ResNet-34 parity tests in a
     child process for every alternative kernel path (halo layer 1, y-sum CTA pairs, single-CTA MMAs,
-    im2col stem, hi/lo residual stream)."""
+    8-warp y-sum epilogue, unfused layer-2 shortcut, hi/lo residual stream)."""
     import os
     import subprocess
     import sys
