@@ -24,13 +24,20 @@
 
 namespace {
 
-constexpr int kThreads = 1024;
-constexpr int kMaxRuns = 16384;         // pure per-pixel noise at 299 x 299 has ~9 000 runs; 196 KB
+// Two table sizes.  LYSTO-like masks have ~2 000 runs: the first launch gives every image a
+// 4 096-run table (63 KB of shared memory, 512 threads: three CTAs per SM); the few images that
+// overflow it (pure per-pixel noise at 299 x 299 has ~9 000 runs) are listed and redone by a
+// second launch with 16 384-run tables (196 KB, one CTA per SM), which also owns the
+// pixel-level fallback.  With one table size for all (round 1) every image paid for the noise
+// case: one CTA per SM, 1.3 M masks/s.
+constexpr int kSmallRuns = 4096, kSmallThreads = 512;
+constexpr int kBigRuns = 16384, kBigThreads = 1024;
 constexpr int kMaxW = 320;              // 10 words per row
 constexpr int kMaxH = 320;
 constexpr int kWords = kMaxW / 32;
 
-struct Smem {
+template <int kMaxRuns, int kThreads>
+struct SmemT {
   uint32_t bits[kMaxH * kWords];        // row-major bit image
   uint32_t row_first[kMaxH + 1];        // first run id of every row (exclusive scan of counts)
   uint16_t run_s[kMaxRuns], run_e[kMaxRuns];   // inclusive x range of a run
@@ -72,6 +79,7 @@ __device__ __forceinline__ void unite_s(uint32_t* parent, uint32_t a, uint32_t b
 }
 
 // word j of row r of the (optionally inverted) image; bits >= W are always 0
+template <class Smem>
 __device__ __forceinline__ uint32_t row_word(const Smem& sm, int r, int j, int W, bool invert) {
   if (j < 0 || j >= kWords) return 0u;
   uint32_t w = sm.bits[r * kWords + j];
@@ -86,7 +94,8 @@ __device__ __forceinline__ uint32_t row_word(const Smem& sm, int r, int j, int W
 
 // Removes (flips) the 4-connected components of set bits (of cleared bits when invert) whose
 // size is < thresh.  Returns false (nothing changed) if the image has too many runs.
-__device__ bool prune_runs(Smem& sm, int H, int W, bool invert, uint32_t thresh) {
+template <int kMaxRuns, int kThreads>
+__device__ bool prune_runs(SmemT<kMaxRuns, kThreads>& sm, int H, int W, bool invert, uint32_t thresh) {
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   // 1a. runs per row
   for (int r0 = 0; r0 < H; r0 += kThreads) {
@@ -245,7 +254,8 @@ __device__ void prune_components(uint8_t* img, int H, int W, int target, int thr
   __syncthreads();
 }
 
-__device__ void load_bits(Smem& sm, const uint8_t* img, int H, int W) {
+template <int kMaxRuns, int kThreads>
+__device__ void load_bits(SmemT<kMaxRuns, kThreads>& sm, const uint8_t* img, int H, int W) {
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   constexpr int kRowsPerIter = 4;   // 40 byte loads in flight per lane hide the L2 latency
   for (int r0 = warp * kRowsPerIter; r0 < H; r0 += (kThreads / 32) * kRowsPerIter) {
@@ -273,7 +283,8 @@ __device__ void load_bits(Smem& sm, const uint8_t* img, int H, int W) {
   __syncthreads();
 }
 
-__device__ void store_bits(const Smem& sm, uint8_t* img, int H, int W) {
+template <int kMaxRuns, int kThreads>
+__device__ void store_bits(const SmemT<kMaxRuns, kThreads>& sm, uint8_t* img, int H, int W) {
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   for (int r = warp; r < H; r += kThreads / 32) {
     uint8_t* row = img + (size_t)r * W;
@@ -286,16 +297,24 @@ __device__ void store_bits(const Smem& sm, uint8_t* img, int H, int W) {
   __syncthreads();
 }
 
+// FIRST = true: every image, small tables; images that overflow them (or do not fit the bit
+// image at all) are appended to ovf_list.  FIRST = false: the listed images only, big tables,
+// then the pixel-level path in global memory.
+template <int kMaxRuns, int kThreads, bool FIRST>
 __global__ void __launch_bounds__(kThreads)
 remove_small_regions_kernel(uint8_t* mask, int n_bags, int H, int W, int min_object,
-                            int hole_area, int* __restrict__ ws) {
+                            int hole_area, int* __restrict__ ovf_count, int* __restrict__ ovf_list,
+                            int* __restrict__ ws) {
   extern __shared__ __align__(16) uint8_t smem_raw[];
+  using Smem = SmemT<kMaxRuns, kThreads>;
   Smem& sm = *reinterpret_cast<Smem*>(smem_raw);
   const int P = H * W;
-  int* parent = ws + (size_t)blockIdx.x * 2 * P;
-  int* size = parent + P;
+  int* parent = FIRST ? nullptr : ws + (size_t)blockIdx.x * 2 * P;
+  int* size = FIRST ? nullptr : parent + P;
   const bool fits = W <= kMaxW && H <= kMaxH;
-  for (int b = blockIdx.x; b < n_bags; b += gridDim.x) {
+  const int n_items = FIRST ? n_bags : *ovf_count;
+  for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
+    const int b = FIRST ? item : ovf_list[item];
     uint8_t* img = mask + (size_t)b * P;
     bool done = false;
     if (fits) {
@@ -309,7 +328,10 @@ remove_small_regions_kernel(uint8_t* mask, int n_bags, int H, int W, int min_obj
       }
       __syncthreads();
     }
-    if (!done) {   // pixel-level path on the untouched bytes
+    if (done) continue;
+    if (FIRST) {   // the bytes are untouched: the second launch redoes this image
+      if (threadIdx.x == 0) ovf_list[atomicAdd(ovf_count, 1)] = b;
+    } else {       // pixel-level path on the untouched bytes
       for (int p = threadIdx.x; p < P; p += blockDim.x) img[p] = img[p] != 0 ? 1 : 0;
       __syncthreads();
       if (min_object > 0) prune_components(img, H, W, 1, min_object, parent, size);
@@ -319,7 +341,7 @@ remove_small_regions_kernel(uint8_t* mask, int n_bags, int H, int W, int min_obj
 }
 
 int cc_grid(int n_bags) {
-  int g = cs::num_sms();      // the run tables take most of an SM's shared memory: one CTA per SM
+  int g = cs::num_sms();      // second launch: the big run tables take an SM's shared memory
   return n_bags < g ? n_bags : g;
 }
 
@@ -329,7 +351,8 @@ extern "C" {
 
 int64_t cs_cc_workspace_bytes(int n_bags, int H, int W) {
   if (n_bags <= 0 || H <= 0 || W <= 0) return 0;
-  return (int64_t)cc_grid(n_bags) * 2 * H * W * (int64_t)sizeof(int) + 256;
+  // overflow counter + list, then two int32 per pixel per CTA of the second launch
+  return 256 + 4 * (int64_t)n_bags + 256 + (int64_t)cc_grid(n_bags) * 2 * H * W * (int64_t)sizeof(int) + 256;
 }
 
 int cs_remove_small_regions(uint8_t* mask, int n_bags, int H, int W, int min_object_size,
@@ -345,17 +368,31 @@ int cs_remove_small_regions(uint8_t* mask, int n_bags, int H, int W, int min_obj
                   (long long)workspace_bytes, (long long)cs_cc_workspace_bytes(n_bags, H, W));
     return CS_ERR_WORKSPACE;
   }
+  using SmallSmem = SmemT<kSmallRuns, kSmallThreads>;
+  using BigSmem = SmemT<kBigRuns, kBigThreads>;
+  auto small_k = remove_small_regions_kernel<kSmallRuns, kSmallThreads, true>;
+  auto big_k = remove_small_regions_kernel<kBigRuns, kBigThreads, false>;
   static bool attr_done[64] = {false};
   int dev = 0;
   CS_CUDA(cudaGetDevice(&dev));
   if (dev >= 64 || !attr_done[dev]) {
-    CS_CUDA(cudaFuncSetAttribute(remove_small_regions_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                 (int)sizeof(Smem)));
+    CS_CUDA(cudaFuncSetAttribute(small_k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(SmallSmem)));
+    CS_CUDA(cudaFuncSetAttribute(big_k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(BigSmem)));
     if (dev < 64) attr_done[dev] = true;
   }
-  int* ws = reinterpret_cast<int*>((reinterpret_cast<uintptr_t>(workspace) + 255) & ~(uintptr_t)255);
-  remove_small_regions_kernel<<<cc_grid(n_bags), kThreads, sizeof(Smem), cs::as_stream(stream)>>>(
-      mask, n_bags, H, W, min_object_size, hole_area_threshold, ws);
+  cudaStream_t st = cs::as_stream(stream);
+  int* base = reinterpret_cast<int*>((reinterpret_cast<uintptr_t>(workspace) + 255) & ~(uintptr_t)255);
+  int* ovf_count = base;
+  int* ovf_list = base + 64;
+  int* ws = reinterpret_cast<int*>((reinterpret_cast<uintptr_t>(ovf_list + n_bags) + 255) & ~(uintptr_t)255);
+  CS_CUDA(cudaMemsetAsync(ovf_count, 0, sizeof(int), st));
+  const int per_sm = (int)((227 * 1024) / (sizeof(SmallSmem) + 1024));
+  const int small_grid = n_bags < cs::num_sms() * per_sm ? n_bags : cs::num_sms() * per_sm;
+  small_k<<<small_grid, kSmallThreads, sizeof(SmallSmem), st>>>(mask, n_bags, H, W, min_object_size,
+                                                               hole_area_threshold, ovf_count, ovf_list, nullptr);
+  CS_LAUNCH_CHECK();
+  big_k<<<cc_grid(n_bags), kBigThreads, sizeof(BigSmem), st>>>(mask, n_bags, H, W, min_object_size,
+                                                              hole_area_threshold, ovf_count, ovf_list, ws);
   CS_LAUNCH_CHECK();
   return CS_OK;
 }

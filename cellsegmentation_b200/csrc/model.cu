@@ -39,6 +39,10 @@ const bool g_snake = !env_is("CELLSEG_SNAKE", "0");          // alternate the ti
 const int g_cluster = env_is("CELLSEG_CLUSTER", "1") ? 1 : 2;
 const bool g_disable_halo = env_is("CELLSEG_HALO", "0");     // diagnostics: generic kernel only
 const bool g_disable_halo_ds = env_is("CELLSEG_HALO_DS", "0");   // layer-2 entry conv2 in the generic kernel
+// 3x3 convs with at most this many output pixels take the dense form (rows = instances, zero taps
+// skipped).  CELLSEG_DENSE_PO=16 also routes the 4x4 stage (layer 2) through it: 17 % fewer MMA
+// cycles than the halo kernel (only in-bounds taps), more weight traffic.  Experiment.
+const int g_dense_max_po = env_is("CELLSEG_DENSE_PO", "16") ? 16 : 4;
 // Residual stream: bf16 by default.  CELLSEG_RESIDUAL=hilo carries a second bf16 tensor
 // lo = value - bf16(value) between blocks (~16 mantissa bits); measured max|dp| moves by < 1.5e-3
 // (ResNet-34 0.0101 -> 0.0098) while the block epilogues move twice the bytes (-11 % throughput).
@@ -137,7 +141,7 @@ int plan_conv(const ConvGeom& g, const float* w_oihw, const float* bias, const C
   int rc;
   const int kk = g.k * g.k;
 
-  if (g.k == 1 || Po >= 16) {
+  if (g.k == 1 || Po > g_dense_max_po) {
     // ---- rows = (instance, oy, ox): shifted boxes (3x3) or pointwise (1x1)
     const bool pointwise = g.k == 1;
     if (!pointwise && (kGemmBM % Po != 0 || g.k != 3 || g.pad != 1)) {

@@ -41,6 +41,12 @@ class BasicBlock(nn.Module):
         self.downsample = downsample
         self.stride = stride
 
+    def forward(self, x):
+        """Autograd path (encoder training, --scratch): the module tree evaluated by torch."""
+        idt = x if self.downsample is None else self.downsample(x)
+        out = self.relu(self.bn1(self.conv1(x)))
+        return self.relu(self.bn2(self.conv2(out)) + idt)
+
 
 class Bottleneck(nn.Module):
     """model/resnet.py:46-78 (groups=1, base_width=64) and model/resnext.py:67-113 (grouped 3x3,
@@ -59,6 +65,13 @@ class Bottleneck(nn.Module):
         self.relu = nn.ReLU(inplace=True)
         self.downsample = downsample
         self.stride = stride
+
+    def forward(self, x):
+        """Autograd path (encoder training, --scratch): the module tree evaluated by torch."""
+        idt = x if self.downsample is None else self.downsample(x)
+        out = self.relu(self.bn1(self.conv1(x)))
+        out = self.relu(self.bn2(self.conv2(out)))
+        return self.relu(self.bn3(self.conv3(out)) + idt)
 
 
 def _fold(conv, bn):
@@ -295,13 +308,24 @@ class MILResNet(nn.Module):
             if self.mode in ("image", "segment"):
                 return self._forward_whole_image(x)
             raise Exception("Something wrong in setmode.")
-        if self.training and not freeze_bn:
-            raise NotImplementedError("tile mode with batch-statistics BN: the hot path always runs the "
-                                      "encoder with running statistics (model.eval() or freeze_bn=True)")
-        if any(p.requires_grad for p in self.conv1.parameters()):
-            raise NotImplementedError("training the encoder in tile mode (--scratch) is out of scope")
+        if self.conv1.weight.requires_grad or (self.training and not freeze_bn):
+            # encoder training (train_tile.py --scratch, :272-273) or batch-statistics BN: gradients /
+            # statistics have to flow through the encoder, which the forward-only sm_100a kernels do
+            # not provide.  Evaluate the module tree with torch autograd instead (functional, not the
+            # accelerated path; the frozen-encoder case below is the hot path).
+            return self._forward_autograd(x, freeze_bn)
         feat = self.encode(x)
         return self.fc_tile(feat)
+
+    def _forward_autograd(self, x, freeze_bn):
+        was_training = self.training
+        if freeze_bn:                                  # model/resnet.py:254-258
+            self.eval()
+        x = self.maxpool(self.relu(self.bn1(self.conv1(x))))
+        x4 = self.layer4(self.layer3(self.layer2(self.layer1(x))))
+        if freeze_bn and was_training:
+            self.train()
+        return self.fc_tile(self.avgpool_tile(x4) + self.maxpool_tile(x4))
 
 
 def MILresnet18(pretrained=False, **kwargs):

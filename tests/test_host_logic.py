@@ -181,3 +181,33 @@ def test_gloo_world2_train_selected_equals_single_process(crit_kind):
         np.testing.assert_allclose(w, w1, rtol=0, atol=2e-6)
         np.testing.assert_allclose(b, b1, rtol=0, atol=2e-6)
     assert np.array_equal(res[0][2], res[1][2])
+
+
+@pytest.mark.parametrize("arch", ["resnet18", "resnet50"])
+def test_scratch_autograd_path_matches_reference_modules(arch):
+    """train_tile.py --scratch (:272-273) trains the encoder: the mirror then evaluates its module
+    tree with torch autograd.  Same logits and gradients as the reference class on CPU (only
+    where /root/reference exists: the build container)."""
+    from oracle import model as omodel, ref_shim
+    if not ref_shim.available():
+        pytest.skip("reference tree not present")
+    from cellsegmentation_b200.model import resnet as mirror
+    sd = omodel.make_state_dict(arch, seed=3)
+    nets = []
+    for mod in (mirror, ref_shim.load_reference_resnet()):
+        m = getattr(mod, "MIL" + arch)()
+        m.load_state_dict(sd, strict=False)
+        m.setmode("tile")
+        m.set_encoder_grads(True)
+        m.train()
+        nets.append(m)
+    x = torch.randn(5, 3, 32, 32, generator=torch.Generator().manual_seed(1))
+    for freeze in (True, False):
+        outs = [m(x, freeze_bn=freeze) for m in nets]
+        assert torch.equal(outs[0], outs[1])
+        assert nets[0].training and nets[1].training
+        for m, o in zip(nets, outs):
+            m.zero_grad()
+            o.square().sum().backward()
+        assert torch.equal(nets[0].layer2[0].conv1.weight.grad, nets[1].layer2[0].conv1.weight.grad)
+        assert torch.equal(nets[0].bn1.running_mean, nets[1].bn1.running_mean)
