@@ -39,10 +39,18 @@ const bool g_snake = !env_is("CELLSEG_SNAKE", "0");          // alternate the ti
 const int g_cluster = env_is("CELLSEG_CLUSTER", "1") ? 1 : 2;
 const bool g_disable_halo = env_is("CELLSEG_HALO", "0");     // diagnostics: generic kernel only
 const bool g_disable_halo_ds = env_is("CELLSEG_HALO_DS", "0");   // layer-2 entry conv2 in the generic kernel
-// 3x3 convs with at most this many output pixels take the dense form (rows = instances, zero taps
-// skipped).  CELLSEG_DENSE_PO=16 also routes the 4x4 stage (layer 2) through it: 17 % fewer MMA
-// cycles than the halo kernel (only in-bounds taps), more weight traffic.  Experiment.
-const int g_dense_max_po = env_is("CELLSEG_DENSE_PO", "16") ? 16 : 4;
+// 3x3 convs with at most this many output pixels take the dense form (rows = instances, N =
+// (output pixel, co), K = (input pixel, ci), all-zero weight blocks skipped): 16 = the 2x2 and
+// the 4x4 stages.  For the 4x4 x 128 stage (layer 2) the dense form issues 17 % fewer MMA cycles
+// than the halo kernel (only in-bounds taps: 1.97 M instead of 2.36 M MACs per instance and conv
+// at N = 256) and streams whole 128-instance M tiles: +5.4 % on the whole step, conv stage
+// 0.574 -> 0.606 of the sustained peak (gpurun r2d).  CELLSEG_DENSE_PO=4 restores the halo
+// kernel for layer 2; =64 also sends the 8x8 stage through the dense form (more MMA work: 3.6 M
+// against 2.36 M MACs per conv -- measured, not the default).
+const int g_dense_max_po = env_is("CELLSEG_DENSE_PO", "4") ? 4 : (env_is("CELLSEG_DENSE_PO", "64") ? 64 : 16);
+// N tile of the dense form: 256 (two 4x4-stage pixels per tile) by default; CELLSEG_DENSE_BN=128
+// gives every output pixel of the 4x4 stage its own tile (exactly the in-bounds taps, smaller MMAs).
+const int g_dense_bn = env_is("CELLSEG_DENSE_BN", "128") ? 128 : 256;
 // Residual stream: bf16 by default.  CELLSEG_RESIDUAL=hilo carries a second bf16 tensor
 // lo = value - bf16(value) between blocks (~16 mantissa bits); measured max|dp| moves by < 1.5e-3
 // (ResNet-34 0.0101 -> 0.0098) while the block epilogues move twice the bytes (-11 % throughput).
@@ -238,7 +246,7 @@ int plan_conv(const ConvGeom& g, const float* w_oihw, const float* bias, const C
     // ---- dense form: rows = instances, N = (out pixel, co), K = (in pixel, ci)
     pc.dense = true;
     const int N_total = Po * g.Cout;
-    pc.BN = (N_total % 256 == 0) ? 256 : (N_total % 128 == 0 ? 128 : 64);
+    pc.BN = (N_total % 256 == 0 && (g_dense_bn == 256 || g.Cout >= 256)) ? 256 : (N_total % 128 == 0 ? 128 : 64);
     pc.p.units_per_mtile = kGemmBM;
     pc.p.n_total = N_total;
     const int64_t K_main = (int64_t)Pi * g.Cin;

@@ -13,14 +13,18 @@
 //      superset of the bag; the up-to-three foreign words at either end are zeroed) -- all
 //      loads of a bag are in flight at once and nothing is staged
 //   1. the raw bit patterns (non-negative floats order like unsigned integers) reduce to thread
-//      maxima, those to 32 column maxima; warp 0 ranks the column maxima with shuffles and
-//      publishes tau = the n-th largest: at least n instances are >= tau
-//   2. one pass over the registers appends the instances >= tau (a few per cent) to a shared
-//      candidate list through a shared atomic; threads whose maximum is below tau skip it
+//      maxima.  tau = the n-th largest of a set of group maxima, so at least n instances are
+//      >= tau: for small n the 32 column maxima, ranked by warp 0 with shuffles; for n >= 20 the
+//      128 thread maxima themselves (every warp sorts its 32 in registers, every thread then
+//      ranks its own maximum by binary searches in the four sorted lists) -- the finer groups
+//      cut the candidates from ~3.3 n to ~1.15 n, and step 3 is quadratic in them
+//   2. one pass over the registers marks the instances >= tau (a few per cent) in a per-thread
+//      bit mask (two instructions per element); the marked ones are re-read (L1 hits) and
+//      appended to a shared candidate list through a shared atomic
 //   3. candidates are ranked by counting, the n best go straight to their output slots in
 //      ascending (prob, index) order (ties keep the larger indices, like the stable lexsort)
 // Declined (handled by the exact kernel through the fallback list): kept set not the plain
-// suffix of the order (wrap-around cases), n > 128, a negative / NaN / -0.0 probability, tau of
+// suffix of the order (wrap-around cases), n > 128 (= THREADS), a negative / NaN / -0.0 probability, tau of
 // +0.0 (padding words would qualify), more than 512 candidates (heavy ties), bags longer than
 // the register budget (select_fast.cu takes those).
 #include "common.cuh"
@@ -31,6 +35,7 @@ namespace {
 
 constexpr int kMaxCand = 512;
 constexpr uint32_t kInf = 0x7f800000u;
+constexpr int kFineN = 20;      // kept counts from here on take tau from the 128 thread maxima
 
 __device__ __forceinline__ uint4 ldg_stream(const uint4* p) {
   uint4 v;
@@ -47,7 +52,8 @@ select_reg_kernel(Segs segs, const float* __restrict__ prob, EmitArgs ea,
   constexpr int kWarps = THREADS / 32;
   __shared__ unsigned long long cand[kMaxCand];
   __shared__ uint32_t tmax[THREADS];
-  __shared__ int s_count;
+  __shared__ uint32_t sorted_max[kWarps][32];
+  __shared__ int s_count, s_bad;
   __shared__ uint32_t s_tau;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int b = blockIdx.x;
@@ -82,6 +88,8 @@ select_reg_kernel(Segs segs, const float* __restrict__ prob, EmitArgs ea,
   }
   if (tid == 0) {                                          // words of the previous bag
     s_count = 0;
+    s_bad = 0;
+    s_tau = 0;
 #pragma unroll
     for (int c = 0; c < 3; ++c)
       if (c < mis) x[0][c] = 0u;
@@ -103,63 +111,90 @@ select_reg_kernel(Segs segs, const float* __restrict__ prob, EmitArgs ea,
 #pragma unroll
   for (int j = 0; j < NV; ++j) m = max(max(m, max(x[j][0], x[j][1])), max(x[j][2], x[j][3]));
   tmax[tid] = m;
-  __syncthreads();
-  if (warp == 0) {
-    uint32_t tau = 0, top = 0;
-    if (n <= 32) {
-      uint32_t cm = tmax[lane];
+  uint32_t top_w = m;                                      // warp-wide maximum: bad inputs surface here
 #pragma unroll
-      for (int w = 1; w < kWarps; ++w) cm = max(cm, tmax[32 * w + lane]);
-      int rank = 0;
+  for (int o = 16; o > 0; o >>= 1) top_w = max(top_w, __shfl_xor_sync(0xffffffffu, top_w, o));
+  if (n >= kFineN) {
+    // every warp sorts its 32 thread maxima (descending, bitonic network in registers) ...
+    uint32_t v = m;
 #pragma unroll
-      for (int j = 0; j < 32; ++j) {
-        const uint32_t mj = __shfl_sync(0xffffffffu, cm, j);
-        rank += (mj > cm || (mj == cm && j < lane)) ? 1 : 0;
-      }
-      const unsigned pick = __ballot_sync(0xffffffffu, rank == n - 1);
-      const unsigned first = __ballot_sync(0xffffffffu, rank == 0);
-      tau = __shfl_sync(0xffffffffu, cm, __ffs(pick) - 1);
-      top = __shfl_sync(0xffffffffu, cm, __ffs(first) - 1);
-    } else {
-      // n-th largest of the THREADS thread maxima: every lane ranks its own share
-      for (int i = lane; i < THREADS; i += 32) {
-        const uint32_t mine = tmax[i];
-        int rank = 0;
-        for (int j = 0; j < THREADS; ++j) {
-          const uint32_t mj = tmax[j];
-          rank += (mj > mine || (mj == mine && j < i)) ? 1 : 0;
-        }
-        if (rank == n - 1) tau = mine;
-        top = max(top, mine);
-      }
+    for (int k = 2; k <= 32; k <<= 1) {
 #pragma unroll
-      for (int o = 16; o > 0; o >>= 1) {
-        tau = max(tau, __shfl_xor_sync(0xffffffffu, tau, o));   // exactly one lane holds it
-        top = max(top, __shfl_xor_sync(0xffffffffu, top, o));
+      for (int j = k >> 1; j > 0; j >>= 1) {
+        const uint32_t other = __shfl_xor_sync(0xffffffffu, v, j);
+        const bool up = ((lane & k) == 0) == ((lane & j) == 0);   // keep the larger of the pair
+        v = up ? max(v, other) : min(v, other);
       }
     }
-    // tau 0 (= +0.0): the zeroed padding words would qualify -> leave the bag to the exact kernel
-    if (lane == 0) s_tau = (top > kInf || tau == 0u) ? 0xffffffffu : tau;
+    sorted_max[warp][lane] = v;                            // sorted_max[w][0] is warp w's largest
+  }
+  __syncthreads();
+  if (n >= kFineN) {
+    // ... and every thread ranks its own maximum among all THREADS maxima: elements greater than
+    // it, plus equal ones held by lower thread ids (a strict total order, exactly one rank n-1)
+    const unsigned same = __match_any_sync(0xffffffffu, m);
+    const int eq_lower_lanes = __popc(same & ((1u << lane) - 1u));   // ties inside the own warp
+    int rank = 0;
+#pragma unroll
+    for (int w = 0; w < kWarps; ++w) {
+      // descending list: count of entries > m (and >= m) by binary search
+      int lo = 0, hi = 32;
+      while (lo < hi) { const int mid = (lo + hi) >> 1; if (sorted_max[w][mid] > m) lo = mid + 1; else hi = mid; }
+      int gt = lo;
+      lo = gt; hi = 32;
+      while (lo < hi) { const int mid = (lo + hi) >> 1; if (sorted_max[w][mid] >= m) lo = mid + 1; else hi = mid; }
+      const int ge = lo;
+      // equal entries of warp w: those with a lower thread id than this one come first
+      const int eq_before = w < warp ? ge - gt : (w == warp ? eq_lower_lanes : 0);
+      rank += gt + eq_before;
+    }
+    if (rank == n - 1) s_tau = m;
+    if (lane == 0 && top_w > kInf) s_bad = 1;
+  } else if (warp == 0) {
+    uint32_t cm = tmax[lane];
+#pragma unroll
+    for (int w = 1; w < kWarps; ++w) cm = max(cm, tmax[32 * w + lane]);
+    int rank = 0;
+#pragma unroll
+    for (int j = 0; j < 32; ++j) {
+      const uint32_t mj = __shfl_sync(0xffffffffu, cm, j);
+      rank += (mj > cm || (mj == cm && j < lane)) ? 1 : 0;
+    }
+    const unsigned pick = __ballot_sync(0xffffffffu, rank == n - 1);
+    const unsigned first = __ballot_sync(0xffffffffu, rank == 0);
+    const uint32_t t32 = __shfl_sync(0xffffffffu, cm, __ffs(pick) - 1);
+    const uint32_t top = __shfl_sync(0xffffffffu, cm, __ffs(first) - 1);
+    if (lane == 0) {
+      s_tau = t32;
+      if (top > kInf) s_bad = 1;
+    }
   }
   __syncthreads();
   const uint32_t tau = s_tau;
-  if (tau == 0xffffffffu) {
+  // bad input (negative / NaN / -0.0), or tau 0 (= +0.0: the zeroed padding words would qualify):
+  // leave the bag to the exact kernel
+  if (s_bad != 0 || tau == 0u) {
     decline();
     return;
   }
 
-  // 2. candidates: (bits << 32 | index in the bag), appended in any order
+  // 2. candidates: (bits << 32 | index in the bag), appended in any order.  Mark first (ISETP +
+  // predicated OR per element), then visit the few marked elements.
   if (m >= tau) {
+    uint32_t mask = 0;
 #pragma unroll
     for (int j = 0; j < NV; ++j) {
 #pragma unroll
-      for (int c = 0; c < 4; ++c) {
-        if (x[j][c] >= tau) {
-          const int pos = atomicAdd(&s_count, 1);
-          const int e = 4 * (tid + THREADS * j) + c - mis;
-          if (pos < kMaxCand) cand[pos] = ((unsigned long long)x[j][c] << 32) | (unsigned)e;
-        }
-      }
+      for (int c = 0; c < 4; ++c)
+        if (x[j][c] >= tau) mask |= 1u << (4 * j + c);
+    }
+    while (mask) {
+      const int q = __ffs(mask) - 1;
+      mask &= mask - 1;
+      const int e = 4 * (tid + THREADS * (q >> 2)) + (q & 3) - mis;
+      const uint32_t bits = __float_as_uint(__ldg(src + e));   // L1 / L2 hit: the bag was just streamed
+      const int pos = atomicAdd(&s_count, 1);
+      if (pos < kMaxCand) cand[pos] = ((unsigned long long)bits << 32) | (unsigned)e;
     }
   }
   __syncthreads();
