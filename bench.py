@@ -50,7 +50,7 @@ def parse():
     ap.add_argument("--workload", default="score_select", choices=["score_select", "mil_epoch"])
     ap.add_argument("--bags-per-step", type=int, default=1024, help="bags scored per step per GPU")
     ap.add_argument("--resident-bags", type=int, default=0, help="bags resident in HBM per GPU (0: auto)")
-    ap.add_argument("--max-batch", type=int, default=37888, help="instances per forward batch")
+    ap.add_argument("--max-batch", type=int, default=75776, help="instances per forward batch")
     ap.add_argument("--ref-bags", type=int, default=8, help="bags per step of the CPU reference arm (configs[0]: 8)")
     ap.add_argument("--mil-bags", type=int, default=18000, help="training bags of the MIL epoch (all ranks together)")
     ap.add_argument("--no-cpu-baseline", action="store_true")

@@ -5,26 +5,26 @@
 // pseudo-label rule dataset/dataset.py:168-169.  Same results as the exact shared-memory sort in
 // select_topk.cu, which stays the fallback for every bag this path declines.
 //
-// The roofline of this stage is the 4 B/instance read (12.1 KB per 3025-instance bag).  The first
-// fast path (select_fast.cu) staged the bag in shared memory and walked it three times with LDS:
-// ~4 800 warp instructions per bag, i.e. issue-bound at 22 % of the HBM roofline (ncu r01_p:
-// 41 % issue-active at 12 CTAs/SM).  Here
+// The roofline of this stage is the 4 B/instance read (12.1 KB per 3025-instance bag), but the
+// kernels are INSTRUCTION-ISSUE bound: the staged fast path of round 1 (select_fast.cu) spent
+// ~4 800 warp instructions per bag (22 % of the HBM roofline), the first register-resident
+// version 2 400 (72 us for 20 000 bags at 64 % issue-active, ncu r2d/r2f).  This version is
+// built to issue as little as possible per element:
 //   0. every thread pulls its NV 16-byte vectors of the bag straight into registers (aligned
-//      superset of the bag; the up-to-three foreign words at either end are zeroed) -- all
-//      loads of a bag are in flight at once and nothing is staged
-//   1. the raw bit patterns (non-negative floats order like unsigned integers) reduce to thread
-//      maxima.  tau = the n-th largest of a set of group maxima, so at least n instances are
-//      >= tau: for small n the 32 column maxima, ranked by warp 0 with shuffles; for n >= 20 the
-//      128 thread maxima themselves (every warp sorts its 32 in registers, every thread then
-//      ranks its own maximum by binary searches in the four sorted lists) -- the finer groups
-//      cut the candidates from ~3.3 n to ~1.15 n, and step 3 is quadratic in them
-//   2. one pass over the registers marks the instances >= tau (a few per cent) in a per-thread
-//      bit mask (two instructions per element); the marked ones are re-read (L1 hits) and
-//      appended to a shared candidate list through a shared atomic
+//      superset of the bag; the up-to-three foreign words at either end are zeroed by the two
+//      threads that hold them) -- all loads of a bag are in flight at once, nothing is staged
+//   1. raw bit patterns (non-negative floats order like unsigned integers) reduce to one maximum
+//      per vector (kept) and one per thread; warp 0 folds the thread maxima into 64 column
+//      maxima, sorts them with a register bitonic network (two per lane) and publishes
+//      tau = the n-th largest: at least n instances are >= tau, and only ~1.1-1.35 n are
+//   2. a thread marks its vectors whose maximum reaches tau (six compares); the few marked
+//      vectors are re-read (L1 hits) and their elements >= tau appended to a shared candidate
+//      list through a shared atomic
 //   3. candidates are ranked by counting, the n best go straight to their output slots in
 //      ascending (prob, index) order (ties keep the larger indices, like the stable lexsort)
+// The bag's kept range (64-bit closed form) is worked out by thread 0 alone while the loads fly.
 // Declined (handled by the exact kernel through the fallback list): kept set not the plain
-// suffix of the order (wrap-around cases), n > 128 (= THREADS), a negative / NaN / -0.0 probability, tau of
+// suffix of the order (wrap-around cases), n > 64, a negative / NaN / -0.0 probability, tau of
 // +0.0 (padding words would qualify), more than 512 candidates (heavy ties), bags longer than
 // the register budget (select_fast.cu takes those).
 #include "common.cuh"
@@ -35,178 +35,165 @@ namespace {
 
 constexpr int kMaxCand = 512;
 constexpr uint32_t kInf = 0x7f800000u;
-constexpr int kFineN = 20;      // kept counts from here on take tau from the 128 thread maxima
+constexpr int kCols = 64;       // column maxima tau is picked from; also the largest n served
 
 __device__ __forceinline__ uint4 ldg_stream(const uint4* p) {
   uint4 v;
-  asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0,%1,%2,%3}, [%4];"
+  asm volatile("ld.global.nc.L1::evict_last.v4.u32 {%0,%1,%2,%3}, [%4];"
                : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w)
                : "l"(p));
   return v;
+}
+
+// One compare-exchange stage of a 64-element bitonic network held two per lane (element i < 32
+// in `a` of lane i, element i >= 32 in `b` of lane i - 32); final order descending.
+template <int K, int J>
+__device__ __forceinline__ void bitonic64_stage(uint32_t& a, uint32_t& b, int lane) {
+  if (J == 32) {                      // partner = the lane's other register (only in the K = 64 merge)
+    const uint32_t hi = max(a, b), lo = min(a, b);
+    a = hi; b = lo;                   // (i & 64) == 0 for all: the lower index keeps the larger
+  } else {
+    const uint32_t oa = __shfl_xor_sync(0xffffffffu, a, J), ob = __shfl_xor_sync(0xffffffffu, b, J);
+    const bool lower = (lane & J) == 0;
+    const bool desc_a = (lane & K) == 0, desc_b = ((lane + 32) & K) == 0;
+    a = (desc_a == lower) ? max(a, oa) : min(a, oa);
+    b = (desc_b == lower) ? max(b, ob) : min(b, ob);
+  }
 }
 
 template <int NV, int THREADS>
 __global__ void __launch_bounds__(THREADS)
 select_reg_kernel(Segs segs, const float* __restrict__ prob, EmitArgs ea,
                   int32_t* __restrict__ fb_count, int32_t* __restrict__ fb_list) {
-  constexpr int kWarps = THREADS / 32;
+  static_assert(THREADS == 128, "two threads per column");
   __shared__ unsigned long long cand[kMaxCand];
   __shared__ uint32_t tmax[THREADS];
-  __shared__ uint32_t sorted_max[kWarps][32];
-  __shared__ int s_count, s_bad;
+  __shared__ int s_count, s_n;        // s_n: kept count, or -1 = this path declines the bag
   __shared__ uint32_t s_tau;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int b = blockIdx.x;
   const int64_t s = segs.start(b);
   const int T = (int)(segs.start(b + 1) - s);
-  if (T <= 0) return;
-  const Kept kr = kept_ranges(segs.gstart(b), T, segs.gtotal(),
-                              bag_k(ea.labels, b, ea.tiles_per_pos, ea.topk_neg));
-  const int n1 = kr.b1 - kr.a1, n2 = kr.b2 - kr.a2, n = n1 + n2;
-  if (n == 0) return;                                     // all conditions block-uniform
-  auto decline = [&]() {
-    if (tid == 0) fb_list[atomicAdd(fb_count, 1)] = b;   // (fb_count was zeroed two stream ops earlier)
-  };
+  if (T <= 0) return;                                     // block-uniform
   const float* src = prob + s;
   const int mis = (int)((reinterpret_cast<uintptr_t>(src) >> 2) & 3);   // words before the bag in its first vector
   const int nvec = (mis + T + 3) >> 2;
-  const bool suffix = (n2 == 0 && kr.b1 == T) || (n1 == 0 && kr.b2 == T);
-  if (!suffix || n > 128 || nvec > NV * THREADS) {
-    decline();
-    return;
-  }
+  const bool fits = nvec <= NV * THREADS;
 
   // 0. the bag, as raw bits: vector v = tid + THREADS*j holds elements 4v - mis .. 4v - mis + 3
   const uint4* vsrc = reinterpret_cast<const uint4*>(src - mis);
-  uint32_t x[NV][4];
+  uint4 x[NV];
 #pragma unroll
   for (int j = 0; j < NV; ++j) {
     const int v = tid + THREADS * j;
-    uint4 q = make_uint4(0u, 0u, 0u, 0u);
-    if (v < nvec) q = ldg_stream(vsrc + v);
-    x[j][0] = q.x; x[j][1] = q.y; x[j][2] = q.z; x[j][3] = q.w;
+    x[j] = make_uint4(0u, 0u, 0u, 0u);
+    if (fits && v < nvec) x[j] = ldg_stream(vsrc + v);
   }
-  if (tid == 0) {                                          // words of the previous bag
+  if (tid == 0) {
+    // the kept range of this bag under the literal predicate, while the loads are in flight
+    const Kept kr = kept_ranges(segs.gstart(b), T, segs.gtotal(),
+                                bag_k(ea.labels, b, ea.tiles_per_pos, ea.topk_neg));
+    const int n1 = kr.b1 - kr.a1, n2 = kr.b2 - kr.a2, n = n1 + n2;
+    const bool suffix = (n2 == 0 && kr.b1 == T) || (n1 == 0 && kr.b2 == T);
+    s_n = (n == 0) ? 0 : ((suffix && n <= kCols && fits) ? n : -1);
     s_count = 0;
-    s_bad = 0;
     s_tau = 0;
-#pragma unroll
-    for (int c = 0; c < 3; ++c)
-      if (c < mis) x[0][c] = 0u;
+    if (mis > 0) x[0].x = 0u;                              // words of the previous bag
+    if (mis > 1) x[0].y = 0u;
+    if (mis > 2) x[0].z = 0u;
   }
   {                                                        // words of the next bag
-    const int last = nvec - 1, end = mis + T - 4 * last;   // valid words in the last vector: 1..4
+    const int last = nvec - 1;
+    if ((last & (THREADS - 1)) == tid) {
+      const int end = mis + T - 4 * last;                  // valid words in the last vector: 1..4
+      const int jl = last / THREADS;
 #pragma unroll
-    for (int j = 0; j < NV; ++j)
-      if (tid + THREADS * j == last) {
-#pragma unroll
-        for (int c = 1; c < 4; ++c)
-          if (c >= end) x[j][c] = 0u;
-      }
+      for (int j = 0; j < NV; ++j)
+        if (j == jl) {
+          if (end < 2) x[j].y = 0u;
+          if (end < 3) x[j].z = 0u;
+          if (end < 4) x[j].w = 0u;
+        }
+    }
   }
 
-  // 1. thread maxima -> column maxima -> tau (negative / NaN inputs have bit patterns above +inf
-  // and surface in every maximum)
+  // 1. vector maxima -> thread maximum -> 64 column maxima -> tau (negative / NaN inputs have bit
+  // patterns above +inf and surface in every maximum)
+  uint32_t vm[NV];
   uint32_t m = 0;
 #pragma unroll
-  for (int j = 0; j < NV; ++j) m = max(max(m, max(x[j][0], x[j][1])), max(x[j][2], x[j][3]));
-  tmax[tid] = m;
-  uint32_t top_w = m;                                      // warp-wide maximum: bad inputs surface here
-#pragma unroll
-  for (int o = 16; o > 0; o >>= 1) top_w = max(top_w, __shfl_xor_sync(0xffffffffu, top_w, o));
-  if (n >= kFineN) {
-    // every warp sorts its 32 thread maxima (descending, bitonic network in registers) ...
-    uint32_t v = m;
-#pragma unroll
-    for (int k = 2; k <= 32; k <<= 1) {
-#pragma unroll
-      for (int j = k >> 1; j > 0; j >>= 1) {
-        const uint32_t other = __shfl_xor_sync(0xffffffffu, v, j);
-        const bool up = ((lane & k) == 0) == ((lane & j) == 0);   // keep the larger of the pair
-        v = up ? max(v, other) : min(v, other);
-      }
-    }
-    sorted_max[warp][lane] = v;                            // sorted_max[w][0] is warp w's largest
+  for (int j = 0; j < NV; ++j) {
+    vm[j] = max(max(x[j].x, x[j].y), max(x[j].z, x[j].w));
+    m = max(m, vm[j]);
   }
+  tmax[tid] = m;
   __syncthreads();
-  if (n >= kFineN) {
-    // ... and every thread ranks its own maximum among all THREADS maxima: elements greater than
-    // it, plus equal ones held by lower thread ids (a strict total order, exactly one rank n-1)
-    const unsigned same = __match_any_sync(0xffffffffu, m);
-    const int eq_lower_lanes = __popc(same & ((1u << lane) - 1u));   // ties inside the own warp
-    int rank = 0;
-#pragma unroll
-    for (int w = 0; w < kWarps; ++w) {
-      // descending list: count of entries > m (and >= m) by binary search
-      int lo = 0, hi = 32;
-      while (lo < hi) { const int mid = (lo + hi) >> 1; if (sorted_max[w][mid] > m) lo = mid + 1; else hi = mid; }
-      int gt = lo;
-      lo = gt; hi = 32;
-      while (lo < hi) { const int mid = (lo + hi) >> 1; if (sorted_max[w][mid] >= m) lo = mid + 1; else hi = mid; }
-      const int ge = lo;
-      // equal entries of warp w: those with a lower thread id than this one come first
-      const int eq_before = w < warp ? ge - gt : (w == warp ? eq_lower_lanes : 0);
-      rank += gt + eq_before;
-    }
-    if (rank == n - 1) s_tau = m;
-    if (lane == 0 && top_w > kInf) s_bad = 1;
-  } else if (warp == 0) {
-    uint32_t cm = tmax[lane];
-#pragma unroll
-    for (int w = 1; w < kWarps; ++w) cm = max(cm, tmax[32 * w + lane]);
-    int rank = 0;
-#pragma unroll
-    for (int j = 0; j < 32; ++j) {
-      const uint32_t mj = __shfl_sync(0xffffffffu, cm, j);
-      rank += (mj > cm || (mj == cm && j < lane)) ? 1 : 0;
-    }
-    const unsigned pick = __ballot_sync(0xffffffffu, rank == n - 1);
-    const unsigned first = __ballot_sync(0xffffffffu, rank == 0);
-    const uint32_t t32 = __shfl_sync(0xffffffffu, cm, __ffs(pick) - 1);
-    const uint32_t top = __shfl_sync(0xffffffffu, cm, __ffs(first) - 1);
-    if (lane == 0) {
-      s_tau = t32;
-      if (top > kInf) s_bad = 1;
-    }
+  const int n = s_n;
+  if (n == 0) return;                                      // nothing kept (block-uniform)
+  if (n < 0) {                                             // wrap-around ranges, n > 64, bag too long
+    if (tid == 0) fb_list[atomicAdd(fb_count, 1)] = b;     // (fb_count was zeroed two stream ops earlier)
+    return;
+  }
+  if (warp == 0) {
+    uint32_t a = max(tmax[lane], tmax[lane + 64]);         // column lane
+    uint32_t c = max(tmax[lane + 32], tmax[lane + 96]);    // column lane + 32
+    bitonic64_stage<2, 1>(a, c, lane);
+    bitonic64_stage<4, 2>(a, c, lane);  bitonic64_stage<4, 1>(a, c, lane);
+    bitonic64_stage<8, 4>(a, c, lane);  bitonic64_stage<8, 2>(a, c, lane);  bitonic64_stage<8, 1>(a, c, lane);
+    bitonic64_stage<16, 8>(a, c, lane); bitonic64_stage<16, 4>(a, c, lane); bitonic64_stage<16, 2>(a, c, lane);
+    bitonic64_stage<16, 1>(a, c, lane);
+    bitonic64_stage<32, 16>(a, c, lane); bitonic64_stage<32, 8>(a, c, lane); bitonic64_stage<32, 4>(a, c, lane);
+    bitonic64_stage<32, 2>(a, c, lane);  bitonic64_stage<32, 1>(a, c, lane);
+    bitonic64_stage<64, 32>(a, c, lane); bitonic64_stage<64, 16>(a, c, lane); bitonic64_stage<64, 8>(a, c, lane);
+    bitonic64_stage<64, 4>(a, c, lane);  bitonic64_stage<64, 2>(a, c, lane);  bitonic64_stage<64, 1>(a, c, lane);
+    // descending: rank r sits in `a` of lane r (r < 32) or in `c` of lane r - 32
+    const uint32_t top = __shfl_sync(0xffffffffu, a, 0);
+    const uint32_t ta = __shfl_sync(0xffffffffu, a, (n - 1) & 31), tc = __shfl_sync(0xffffffffu, c, (n - 1) & 31);
+    const uint32_t t = n <= 32 ? ta : tc;
+    // bad input (negative / NaN / -0.0), or tau 0 (= +0.0: the zeroed padding words would
+    // qualify): 0xffffffff tells everyone to leave the bag to the exact kernel
+    if (lane == 0) s_tau = (top > kInf || t == 0u) ? 0xffffffffu : t;
   }
   __syncthreads();
   const uint32_t tau = s_tau;
-  // bad input (negative / NaN / -0.0), or tau 0 (= +0.0: the zeroed padding words would qualify):
-  // leave the bag to the exact kernel
-  if (s_bad != 0 || tau == 0u) {
-    decline();
+  if (tau == 0xffffffffu) {
+    if (tid == 0) fb_list[atomicAdd(fb_count, 1)] = b;
     return;
   }
 
-  // 2. candidates: (bits << 32 | index in the bag), appended in any order.  Mark first (ISETP +
-  // predicated OR per element), then visit the few marked elements.
+  // 2. candidates: (bits << 32 | index in the bag), appended in any order
   if (m >= tau) {
     uint32_t mask = 0;
 #pragma unroll
-    for (int j = 0; j < NV; ++j) {
-#pragma unroll
-      for (int c = 0; c < 4; ++c)
-        if (x[j][c] >= tau) mask |= 1u << (4 * j + c);
-    }
+    for (int j = 0; j < NV; ++j)
+      if (vm[j] >= tau) mask |= 1u << j;
     while (mask) {
-      const int q = __ffs(mask) - 1;
+      const int j = __ffs(mask) - 1;
       mask &= mask - 1;
-      const int e = 4 * (tid + THREADS * (q >> 2)) + (q & 3) - mis;
-      const uint32_t bits = __float_as_uint(__ldg(src + e));   // L1 / L2 hit: the bag was just streamed
-      const int pos = atomicAdd(&s_count, 1);
-      if (pos < kMaxCand) cand[pos] = ((unsigned long long)bits << 32) | (unsigned)e;
+      const int v = tid + THREADS * j;
+      const uint4 q = __ldg(vsrc + v);                     // L1 / L2 hit: the bag was just streamed
+      const uint32_t w[4] = {q.x, q.y, q.z, q.w};
+#pragma unroll
+      for (int c = 0; c < 4; ++c) {
+        const int e = 4 * v + c - mis;
+        if (w[c] >= tau && e >= 0 && e < T) {
+          const int pos = atomicAdd(&s_count, 1);
+          if (pos < kMaxCand) cand[pos] = ((unsigned long long)w[c] << 32) | (unsigned)e;
+        }
+      }
     }
   }
   __syncthreads();
   const int count = s_count;
   if (count > kMaxCand) {   // heavy ties around the threshold
-    decline();
+    if (tid == 0) fb_list[atomicAdd(fb_count, 1)] = b;
     return;
   }
 
   // 3. rank by counting; the n largest go to slots o0 + (n-1-rank): ascending (prob, index).
   // The offsets come from the scan kernel this one was launched behind (programmatic dependent
   // launch): everything above overlapped with it.
+  if (tid >= count) return;
   asm volatile("griddepcontrol.wait;" ::: "memory");
   const int64_t o0 = ea.out_offsets[b];
   const uint8_t pl = ea.labels[b] == 0 ? 0 : 1;

@@ -132,11 +132,22 @@ select_offsets_kernel(Segs segs, const int32_t* __restrict__ labels, int32_t til
   int64_t carry = 0;
   for (int base = 0; base < n; base += kOffChunk) {
     const int m = min(kOffChunk, n - base);
-    for (int i = tid; i < m; i += 1024) {
-      const int b = base + i;
-      const int64_t s = segs.start(b), e = segs.start(b + 1);
-      cnt[i] = (int32_t)kept_ranges(segs.gstart(b), e - s, segs.gtotal(),
-                                    bag_k(labels, b, tiles_per_pos, topk_neg)).count();
+    // all label loads of the chunk first (independent, coalesced), then the count formula
+    int32_t lab[kOffChunk / 1024];
+#pragma unroll
+    for (int q = 0; q < kOffChunk / 1024; ++q) {
+      const int i = tid + 1024 * q;
+      lab[q] = i < m ? __ldg(labels + base + i) : 0;
+    }
+#pragma unroll
+    for (int q = 0; q < kOffChunk / 1024; ++q) {
+      const int i = tid + 1024 * q;
+      if (i < m) {
+        const int b = base + i;
+        const int64_t s = segs.start(b), e = segs.start(b + 1);
+        const int64_t k = lab[q] == 0 ? (int64_t)topk_neg : (int64_t)lab[q] * (int64_t)tiles_per_pos;
+        cnt[i] = (int32_t)kept_ranges(segs.gstart(b), e - s, segs.gtotal(), k).count();
+      }
     }
     __syncthreads();
     const int per = (m + 1023) / 1024;

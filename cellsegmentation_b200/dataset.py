@@ -245,10 +245,10 @@ class LystoDataset(_TileSetBase):
         idxs = np.asarray(idxs, np.int64)
         T = self.tiles_per_bag
         grid = self._ensure_grid()
-        bag = np.asarray(self._tile_bags, np.int64)[idxs // T] if len(idxs) else np.zeros(0, np.int64)
-        xy = grid[idxs % T] if len(idxs) else np.zeros((0, 2), np.int32)
+        bags_arr = np.asarray(self._tile_bags, np.int64)
         if pseudo_labels is None:
-            lab = (np.asarray(self.labels)[bag] != 0).astype(np.int64) if len(idxs) else np.zeros(0, np.int64)
+            lab = (np.asarray(self.labels)[bags_arr[idxs // T]] != 0).astype(np.int64) if len(idxs) \
+                else np.zeros(0, np.int64)
         else:
             lab = np.asarray(pseudo_labels, np.int64)
         pos = int(lab.sum())
@@ -267,10 +267,15 @@ class LystoDataset(_TileSetBase):
             if flag is not None:
                 rows = np.nonzero(lab[perm] == flag)[0][:n]
                 keep = np.delete(perm, rows)
+        # rows are materialised for the kept selection only (one gather per column)
+        sel = idxs[keep]
+        q, r = np.divmod(sel, max(T, 1))
         td = np.empty(len(keep), dtype=[("bag", np.int32), ("x", np.int32), ("y", np.int32), ("label", np.int64)])
-        td["bag"], td["x"], td["y"], td["label"] = bag[keep], xy[keep, 0], xy[keep, 1], lab[keep]
+        if len(keep):
+            g = grid[r]
+            td["bag"], td["x"], td["y"], td["label"] = bags_arr[q], g[:, 0], g[:, 1], lab[keep]
         self.train_data = td
-        self.train_index = idxs[keep]      # dataset (tile) index of every train_data row
+        self.train_index = sel             # dataset (tile) index of every train_data row
         return pos, neg
 
     def train_tensor(self, begin, count, device=None):

@@ -98,7 +98,7 @@ class MILResNet(nn.Module):
         self.tile_module_prefix = ("fc_tile",)
         self.seg_module_prefix = ("upconv", "seg_out_conv")
         self.precision = "bf16"        # "fp32" selects the CUDA-core parity path
-        self.max_batch = 37888
+        self.max_batch = 75776
 
         self.inplanes = 64
         self.conv1 = nn.Conv2d(3, 64, kernel_size=7, stride=2, padding=3, bias=False)

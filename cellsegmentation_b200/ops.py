@@ -306,7 +306,7 @@ class TileClassifier:
         return self._ws
 
     def forward_tiles(self, img, tile, interval, inst_begin=0, inst_count=None, precision="bf16",
-                      max_batch=37888, want_features=False, prob_out=None):
+                      max_batch=75776, want_features=False, prob_out=None):
         """Fused unfold -> CNN -> softmax[:,1] over instances of the resident u8 bag array."""
         _req_cuda(img, "img", torch.uint8)
         Nb, H, W, _ = img.shape
@@ -324,7 +324,7 @@ class TileClassifier:
               "cs_model_forward_tiles")
         return (prob_out, feat) if want_features else prob_out
 
-    def forward_tensor(self, x, precision="bf16", max_batch=37888, want_features=False, want_logits=True):
+    def forward_tensor(self, x, precision="bf16", max_batch=75776, want_features=False, want_logits=True):
         """Drop-in for model(x): x f32 [n,3,S,S] normalised tiles -> logits f32 [n,2] (and / or the
         pooled features f32 [n,F]; want_logits=False skips the device fc, e.g. when fc_tile runs
         under autograd in torch)."""
