@@ -149,7 +149,9 @@ int plan_conv(const ConvGeom& g, const float* w_oihw, const float* bias, const C
   int rc;
   const int kk = g.k * g.k;
 
-  if (g.k == 1 || Po > g_dense_max_po) {
+  // (grouped 3x3 convs keep the shifted-box form at 4x4: with 64-wide group-aligned N tiles it
+  // visits one K block per tap, the dense form's 256-wide tiles would visit four)
+  if (g.k == 1 || Po > (g.groups > 1 ? 4 : g_dense_max_po)) {
     // ---- rows = (instance, oy, ox): shifted boxes (3x3) or pointwise (1x1)
     const bool pointwise = g.k == 1;
     if (!pointwise && (kGemmBM % Po != 0 || g.k != 3 || g.pad != 1)) {

@@ -23,8 +23,10 @@
 //   3. candidates are ranked by counting, the n best go straight to their output slots in
 //      ascending (prob, index) order (ties keep the larger indices, like the stable lexsort)
 // The bag's kept range (64-bit closed form) is worked out by thread 0 alone while the loads fly.
+// (Kept counts above 64 -- count labels that large are rare -- take tau from the 128 thread
+// maxima by plain counting.)
 // Declined (handled by the exact kernel through the fallback list): kept set not the plain
-// suffix of the order (wrap-around cases), n > 64, a negative / NaN / -0.0 probability, tau of
+// suffix of the order (wrap-around cases), n > 128, a negative / NaN / -0.0 probability, tau of
 // +0.0 (padding words would qualify), more than 512 candidates (heavy ties), bags longer than
 // the register budget (select_fast.cu takes those).
 #include "common.cuh"
@@ -62,7 +64,7 @@ __device__ __forceinline__ void bitonic64_stage(uint32_t& a, uint32_t& b, int la
 }
 
 template <int NV, int THREADS>
-__global__ void __launch_bounds__(THREADS)
+__global__ void __launch_bounds__(THREADS, NV <= 6 ? 10 : 8)
 select_reg_kernel(Segs segs, const float* __restrict__ prob, EmitArgs ea,
                   int32_t* __restrict__ fb_count, int32_t* __restrict__ fb_list) {
   static_assert(THREADS == 128, "two threads per column");
@@ -95,7 +97,7 @@ select_reg_kernel(Segs segs, const float* __restrict__ prob, EmitArgs ea,
                                 bag_k(ea.labels, b, ea.tiles_per_pos, ea.topk_neg));
     const int n1 = kr.b1 - kr.a1, n2 = kr.b2 - kr.a2, n = n1 + n2;
     const bool suffix = (n2 == 0 && kr.b1 == T) || (n1 == 0 && kr.b2 == T);
-    s_n = (n == 0) ? 0 : ((suffix && n <= kCols && fits) ? n : -1);
+    s_n = (n == 0) ? 0 : ((suffix && n <= THREADS && fits) ? n : -1);
     s_count = 0;
     s_tau = 0;
     if (mis > 0) x[0].x = 0u;                              // words of the previous bag
@@ -130,11 +132,22 @@ select_reg_kernel(Segs segs, const float* __restrict__ prob, EmitArgs ea,
   __syncthreads();
   const int n = s_n;
   if (n == 0) return;                                      // nothing kept (block-uniform)
-  if (n < 0) {                                             // wrap-around ranges, n > 64, bag too long
+  if (n < 0) {                                             // wrap-around ranges, n > 128, bag too long
     if (tid == 0) fb_list[atomicAdd(fb_count, 1)] = b;     // (fb_count was zeroed two stream ops earlier)
     return;
   }
-  if (warp == 0) {
+  if (n > kCols) {
+    // rare (count labels above 64): tau = the n-th largest of the 128 thread maxima, every thread
+    // ranks its own by counting (ties: lower thread id first, so exactly one has rank n - 1)
+    int rank = 0;
+    for (int j = 0; j < THREADS; ++j) {
+      const uint32_t mj = tmax[j];
+      rank += (mj > m || (mj == m && j < tid)) ? 1 : 0;
+    }
+    if (m > kInf) s_tau = 0xffffffffu;                     // bad input: decline (wins over the store below)
+    __syncthreads();
+    if (rank == n - 1 && s_tau != 0xffffffffu) s_tau = m == 0u ? 0xffffffffu : m;
+  } else if (warp == 0) {
     uint32_t a = max(tmax[lane], tmax[lane + 64]);         // column lane
     uint32_t c = max(tmax[lane + 32], tmax[lane + 96]);    // column lane + 32
     bitonic64_stage<2, 1>(a, c, lane);

@@ -113,42 +113,42 @@ exclusive_scan_kernel(int64_t* __restrict__ data, int n) {
 }
 
 // Per-bag kept counts AND their exclusive scan in one launch (the counts are closed-form in the
-// count labels): offsets[b] = sum of kept(b') for b' < b, offsets[n] = total.  One CTA walks the
-// bags in chunks of kOffChunk: coalesced label loads -> counts in shared memory -> every thread
-// sums a contiguous slice, one block scan of the 1024 partial sums -> slice prefixes back into
-// shared memory -> coalesced stores.  (The first version gave every thread 20 strided label
-// loads, twice: 21 us for 20 000 bags, and the selection kernel launched behind it waits for the
-// offsets before its stores.)
+// count labels): offsets[b] = sum of kept(b') for b' < b, offsets[n] = total.
+// Every CTA works out the counts of 1024 bags (the 64-bit range formula is ~80 instructions per
+// bag: a single CTA needed 25 us for 20 000 bags, and the selection kernel launched behind this
+// one waits for the offsets before its stores); the CTA that takes the last ticket scans them in
+// place, in chunks staged through shared memory (coalesced loads -> every thread sums a
+// contiguous slice -> block scan of the 1024 partial sums -> coalesced stores).  `ticket` must be
+// zero on entry.
 constexpr int kOffChunk = 8192;
 
 __global__ void __launch_bounds__(1024)
 select_offsets_kernel(Segs segs, const int32_t* __restrict__ labels, int32_t tiles_per_pos,
-                      int32_t topk_neg, int64_t* __restrict__ offsets) {
+                      int32_t topk_neg, int64_t* __restrict__ offsets, int32_t* __restrict__ ticket) {
   asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
   __shared__ int32_t cnt[kOffChunk];
   __shared__ int32_t warp_tot[32];
+  __shared__ int s_last;
   const int n = segs.n_bags;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  {
+    const int b = blockIdx.x * 1024 + tid;
+    if (b < n) {
+      const int64_t s = segs.start(b), e = segs.start(b + 1);
+      offsets[b] = kept_ranges(segs.gstart(b), e - s, segs.gtotal(),
+                               bag_k(labels, b, tiles_per_pos, topk_neg)).count();
+    }
+  }
+  __threadfence();
+  __syncthreads();
+  if (tid == 0) s_last = atomicAdd(ticket, 1) == (int)gridDim.x - 1;
+  __syncthreads();
+  if (!s_last) return;
+  __threadfence();
   int64_t carry = 0;
   for (int base = 0; base < n; base += kOffChunk) {
     const int m = min(kOffChunk, n - base);
-    // all label loads of the chunk first (independent, coalesced), then the count formula
-    int32_t lab[kOffChunk / 1024];
-#pragma unroll
-    for (int q = 0; q < kOffChunk / 1024; ++q) {
-      const int i = tid + 1024 * q;
-      lab[q] = i < m ? __ldg(labels + base + i) : 0;
-    }
-#pragma unroll
-    for (int q = 0; q < kOffChunk / 1024; ++q) {
-      const int i = tid + 1024 * q;
-      if (i < m) {
-        const int b = base + i;
-        const int64_t s = segs.start(b), e = segs.start(b + 1);
-        const int64_t k = lab[q] == 0 ? (int64_t)topk_neg : (int64_t)lab[q] * (int64_t)tiles_per_pos;
-        cnt[i] = (int32_t)kept_ranges(segs.gstart(b), e - s, segs.gtotal(), k).count();
-      }
-    }
+    for (int i = tid; i < m; i += 1024) cnt[i] = (int32_t)__ldcg(offsets + base + i);   // other CTAs' stores: L2
     __syncthreads();
     const int per = (m + 1023) / 1024;
     const int lo = min(tid * per, m), hi = min(lo + per, m);
@@ -181,10 +181,9 @@ select_offsets_kernel(Segs segs, const int32_t* __restrict__ labels, int32_t til
     }
     __syncthreads();
     for (int i = tid; i < m; i += 1024) offsets[base + i] = carry + cnt[i];
-    // chunk total = prefix of the last slice + its sum; every thread reads the same two words
     const int last_t = (m - 1) / per;
     __syncthreads();
-    if (tid == last_t) warp_tot[0] = run;                   // run == chunk total for the last slice owner
+    if (tid == last_t) warp_tot[0] = run;                   // run == chunk total for the owner of the last slice
     __syncthreads();
     carry += warp_tot[0];
     __syncthreads();
@@ -435,8 +434,10 @@ int cs_select_topk_shard(const float* prob, const int64_t* seg_offsets, int64_t 
   Segs segs{seg_offsets, uniform_T, n_bags, global_tile_offset, global_total_tiles};
   int32_t* fb_count = static_cast<int32_t*>(workspace);
   int32_t* fb_list = fb_count + 64;
-  if (!g_disable_fast) CS_CUDA(cudaMemsetAsync(fb_count, 0, sizeof(int32_t), st));
-  select_offsets_kernel<<<1, 1024, 0, st>>>(segs, labels, tiles_per_pos, topk_neg, sel_offsets_out);
+  int32_t* ticket = fb_count + 1;
+  CS_CUDA(cudaMemsetAsync(fb_count, 0, 2 * sizeof(int32_t), st));
+  select_offsets_kernel<<<cs::ceil_div(n_bags, 1024), 1024, 0, st>>>(segs, labels, tiles_per_pos, topk_neg,
+                                                                   sel_offsets_out, ticket);
   CS_LAUNCH_CHECK();
   EmitArgs ea{};
   ea.labels = labels;
