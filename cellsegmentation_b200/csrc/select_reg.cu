@@ -29,6 +29,8 @@
 // suffix of the order (wrap-around cases), n > 128, a negative / NaN / -0.0 probability, tau of
 // +0.0 (padding words would qualify), more than 512 candidates (heavy ties), bags longer than
 // the register budget (select_fast.cu takes those).
+#include <stdlib.h>
+
 #include "common.cuh"
 #include "select_common.cuh"
 
@@ -63,49 +65,70 @@ __device__ __forceinline__ void bitonic64_stage(uint32_t& a, uint32_t& b, int la
   }
 }
 
-template <int NV, int THREADS>
-__global__ void __launch_bounds__(THREADS, NV <= 6 ? 10 : 8)
-select_reg_kernel(Segs segs, const float* __restrict__ prob, EmitArgs ea,
-                  int32_t* __restrict__ fb_count, int32_t* __restrict__ fb_list) {
-  static_assert(THREADS == 128, "two threads per column");
-  __shared__ unsigned long long cand[kMaxCand];
-  __shared__ uint32_t tmax[THREADS];
-  __shared__ int s_count, s_n;        // s_n: kept count, or -1 = this path declines the bag
-  __shared__ uint32_t s_tau;
-  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const int b = blockIdx.x;
-  const int64_t s = segs.start(b);
-  const int T = (int)(segs.start(b + 1) - s);
-  if (T <= 0) return;                                     // block-uniform
-  const float* src = prob + s;
-  const int mis = (int)((reinterpret_cast<uintptr_t>(src) >> 2) & 3);   // words before the bag in its first vector
-  const int nvec = (mis + T + 3) >> 2;
-  const bool fits = nvec <= NV * THREADS;
+// Per-bag shared state; two copies alternate between consecutive bags of a persistent CTA (a
+// thread is never more than one bag ahead of the slowest: every bag has block barriers).
+struct SelState {
+  unsigned long long cand[kMaxCand];
+  uint32_t tmax[128];
+  int count, n;                       // n: kept count, or -1 = this path declines the bag
+  uint32_t tau;
+};
 
-  // 0. the bag, as raw bits: vector v = tid + THREADS*j holds elements 4v - mis .. 4v - mis + 3
-  const uint4* vsrc = reinterpret_cast<const uint4*>(src - mis);
-  uint4 x[NV];
+struct BagView {
+  const float* src;                   // first instance of the bag
+  const uint4* vsrc;                  // 16-byte aligned superset
+  int64_t s;
+  int T, mis, nvec;
+  bool fits;
+};
+
+template <int NV, int THREADS>
+__device__ __forceinline__ BagView bag_view(const Segs& segs, const float* __restrict__ prob, int b) {
+  BagView v;
+  v.s = segs.start(b);
+  v.T = (int)(segs.start(b + 1) - v.s);
+  v.src = prob + v.s;
+  v.mis = (int)((reinterpret_cast<uintptr_t>(v.src) >> 2) & 3);   // words before the bag in its first vector
+  v.nvec = (v.mis + v.T + 3) >> 2;
+  v.fits = v.T > 0 && v.nvec <= NV * THREADS;
+  v.vsrc = reinterpret_cast<const uint4*>(v.src - v.mis);
+  return v;
+}
+
+// 0. the bag, as raw bits: vector v = tid + THREADS*j holds elements 4v - mis .. 4v - mis + 3
+template <int NV, int THREADS>
+__device__ __forceinline__ void bag_load(const BagView& bv, uint4 (&x)[NV], int tid) {
 #pragma unroll
   for (int j = 0; j < NV; ++j) {
     const int v = tid + THREADS * j;
     x[j] = make_uint4(0u, 0u, 0u, 0u);
-    if (fits && v < nvec) x[j] = ldg_stream(vsrc + v);
+    if (bv.fits && v < bv.nvec) x[j] = ldg_stream(bv.vsrc + v);
   }
+}
+
+// Steps 1-3 for the bag whose vectors are in x[].  Block-uniform control flow (every early
+// return is taken by all threads), three block barriers.
+template <int NV, int THREADS>
+__device__ __forceinline__ void bag_process(const Segs& segs, const EmitArgs& ea, int b, const BagView& bv,
+                                            uint4 (&x)[NV], SelState& st, int32_t* __restrict__ fb_count,
+                                            int32_t* __restrict__ fb_list) {
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int T = bv.T, mis = bv.mis;
   if (tid == 0) {
     // the kept range of this bag under the literal predicate, while the loads are in flight
     const Kept kr = kept_ranges(segs.gstart(b), T, segs.gtotal(),
                                 bag_k(ea.labels, b, ea.tiles_per_pos, ea.topk_neg));
     const int n1 = kr.b1 - kr.a1, n2 = kr.b2 - kr.a2, n = n1 + n2;
     const bool suffix = (n2 == 0 && kr.b1 == T) || (n1 == 0 && kr.b2 == T);
-    s_n = (n == 0) ? 0 : ((suffix && n <= THREADS && fits) ? n : -1);
-    s_count = 0;
-    s_tau = 0;
+    st.n = (n == 0) ? 0 : ((suffix && n <= THREADS && bv.fits) ? n : -1);
+    st.count = 0;
+    st.tau = 0;
     if (mis > 0) x[0].x = 0u;                              // words of the previous bag
     if (mis > 1) x[0].y = 0u;
     if (mis > 2) x[0].z = 0u;
   }
   {                                                        // words of the next bag
-    const int last = nvec - 1;
+    const int last = bv.nvec - 1;
     if ((last & (THREADS - 1)) == tid) {
       const int end = mis + T - 4 * last;                  // valid words in the last vector: 1..4
       const int jl = last / THREADS;
@@ -128,9 +151,9 @@ select_reg_kernel(Segs segs, const float* __restrict__ prob, EmitArgs ea,
     vm[j] = max(max(x[j].x, x[j].y), max(x[j].z, x[j].w));
     m = max(m, vm[j]);
   }
-  tmax[tid] = m;
+  st.tmax[tid] = m;
   __syncthreads();
-  const int n = s_n;
+  const int n = st.n;
   if (n == 0) return;                                      // nothing kept (block-uniform)
   if (n < 0) {                                             // wrap-around ranges, n > 128, bag too long
     if (tid == 0) fb_list[atomicAdd(fb_count, 1)] = b;     // (fb_count was zeroed two stream ops earlier)
@@ -141,15 +164,15 @@ select_reg_kernel(Segs segs, const float* __restrict__ prob, EmitArgs ea,
     // ranks its own by counting (ties: lower thread id first, so exactly one has rank n - 1)
     int rank = 0;
     for (int j = 0; j < THREADS; ++j) {
-      const uint32_t mj = tmax[j];
+      const uint32_t mj = st.tmax[j];
       rank += (mj > m || (mj == m && j < tid)) ? 1 : 0;
     }
-    if (m > kInf) s_tau = 0xffffffffu;                     // bad input: decline (wins over the store below)
+    if (m > kInf) st.tau = 0xffffffffu;                    // bad input: decline (wins over the store below)
     __syncthreads();
-    if (rank == n - 1 && s_tau != 0xffffffffu) s_tau = m == 0u ? 0xffffffffu : m;
+    if (rank == n - 1 && st.tau != 0xffffffffu) st.tau = m == 0u ? 0xffffffffu : m;
   } else if (warp == 0) {
-    uint32_t a = max(tmax[lane], tmax[lane + 64]);         // column lane
-    uint32_t c = max(tmax[lane + 32], tmax[lane + 96]);    // column lane + 32
+    uint32_t a = max(st.tmax[lane], st.tmax[lane + 64]);         // column lane
+    uint32_t c = max(st.tmax[lane + 32], st.tmax[lane + 96]);    // column lane + 32
     bitonic64_stage<2, 1>(a, c, lane);
     bitonic64_stage<4, 2>(a, c, lane);  bitonic64_stage<4, 1>(a, c, lane);
     bitonic64_stage<8, 4>(a, c, lane);  bitonic64_stage<8, 2>(a, c, lane);  bitonic64_stage<8, 1>(a, c, lane);
@@ -165,10 +188,10 @@ select_reg_kernel(Segs segs, const float* __restrict__ prob, EmitArgs ea,
     const uint32_t t = n <= 32 ? ta : tc;
     // bad input (negative / NaN / -0.0), or tau 0 (= +0.0: the zeroed padding words would
     // qualify): 0xffffffff tells everyone to leave the bag to the exact kernel
-    if (lane == 0) s_tau = (top > kInf || t == 0u) ? 0xffffffffu : t;
+    if (lane == 0) st.tau = (top > kInf || t == 0u) ? 0xffffffffu : t;
   }
   __syncthreads();
-  const uint32_t tau = s_tau;
+  const uint32_t tau = st.tau;
   if (tau == 0xffffffffu) {
     if (tid == 0) fb_list[atomicAdd(fb_count, 1)] = b;
     return;
@@ -184,20 +207,20 @@ select_reg_kernel(Segs segs, const float* __restrict__ prob, EmitArgs ea,
       const int j = __ffs(mask) - 1;
       mask &= mask - 1;
       const int v = tid + THREADS * j;
-      const uint4 q = __ldg(vsrc + v);                     // L1 / L2 hit: the bag was just streamed
+      const uint4 q = __ldg(bv.vsrc + v);                  // L1 / L2 hit: the bag was just streamed
       const uint32_t w[4] = {q.x, q.y, q.z, q.w};
 #pragma unroll
       for (int c = 0; c < 4; ++c) {
         const int e = 4 * v + c - mis;
         if (w[c] >= tau && e >= 0 && e < T) {
-          const int pos = atomicAdd(&s_count, 1);
-          if (pos < kMaxCand) cand[pos] = ((unsigned long long)w[c] << 32) | (unsigned)e;
+          const int pos = atomicAdd(&st.count, 1);
+          if (pos < kMaxCand) st.cand[pos] = ((unsigned long long)w[c] << 32) | (unsigned)e;
         }
       }
     }
   }
   __syncthreads();
-  const int count = s_count;
+  const int count = st.count;
   if (count > kMaxCand) {   // heavy ties around the threshold
     if (tid == 0) fb_list[atomicAdd(fb_count, 1)] = b;
     return;
@@ -211,23 +234,78 @@ select_reg_kernel(Segs segs, const float* __restrict__ prob, EmitArgs ea,
   const int64_t o0 = ea.out_offsets[b];
   const uint8_t pl = ea.labels[b] == 0 ? 0 : 1;
   for (int j = tid; j < count; j += THREADS) {
-    const unsigned long long me = cand[j];
+    const unsigned long long me = st.cand[j];
     int above = 0;
 #pragma unroll 4
-    for (int i = 0; i < count; ++i) above += cand[i] > me ? 1 : 0;
+    for (int i = 0; i < count; ++i) above += st.cand[i] > me ? 1 : 0;
     if (above < n) {
       const int64_t p = o0 + (n - 1 - above);
       if (p < ea.capacity) {
-        ea.idx_out[p] = (int32_t)(s + (int64_t)(unsigned)(me & 0xffffffffull));
+        ea.idx_out[p] = (int32_t)(bv.s + (int64_t)(unsigned)(me & 0xffffffffull));
         ea.label_out[p] = pl;
       }
     }
   }
 }
 
+// One CTA per bag.
+template <int NV, int THREADS>
+__global__ void __launch_bounds__(THREADS, NV <= 6 ? 10 : 8)
+select_reg_kernel(Segs segs, const float* __restrict__ prob, EmitArgs ea,
+                  int32_t* __restrict__ fb_count, int32_t* __restrict__ fb_list) {
+  static_assert(THREADS == 128, "two threads per column");
+  __shared__ SelState st;
+  const int b = blockIdx.x;
+  const BagView bv = bag_view<NV, THREADS>(segs, prob, b);
+  if (bv.T <= 0) return;                                  // block-uniform
+  uint4 x[NV];
+  bag_load<NV, THREADS>(bv, x, threadIdx.x);
+  bag_process<NV, THREADS>(segs, ea, b, bv, x, st, fb_count, fb_list);
+}
+
+// Persistent CTAs: bag b + k * gridDim.x in turn, with the NEXT bag's vectors requested before the
+// current one is worked on, so the HBM / L2 round trip hides behind a whole bag of instructions
+// instead of behind the other resident CTAs.
+template <int NV, int THREADS>
+__global__ void __launch_bounds__(THREADS, NV <= 6 ? 7 : 5)
+select_reg_persistent_kernel(Segs segs, const float* __restrict__ prob, EmitArgs ea,
+                             int32_t* __restrict__ fb_count, int32_t* __restrict__ fb_list) {
+  static_assert(THREADS == 128, "two threads per column");
+  __shared__ SelState st[2];
+  int b = blockIdx.x;
+  if (b >= segs.n_bags) return;
+  BagView bv = bag_view<NV, THREADS>(segs, prob, b);
+  uint4 x[NV];
+  bag_load<NV, THREADS>(bv, x, threadIdx.x);
+  for (int k = 0; b < segs.n_bags; ++k) {
+    const int bn = b + (int)gridDim.x;
+    BagView bvn = bv;
+    uint4 xn[NV];
+    if (bn < segs.n_bags) {
+      bvn = bag_view<NV, THREADS>(segs, prob, bn);
+      bag_load<NV, THREADS>(bvn, xn, threadIdx.x);
+    }
+    if (bv.T > 0) bag_process<NV, THREADS>(segs, ea, b, bv, x, st[k & 1], fb_count, fb_list);
+    b = bn;
+    bv = bvn;
+#pragma unroll
+    for (int j = 0; j < NV; ++j) x[j] = xn[j];
+  }
+}
+
+// CELLSEG_SELECT_PERSIST=0 keeps one CTA per bag.
+const bool g_persist = []() {
+  const char* e = getenv("CELLSEG_SELECT_PERSIST");
+  return !(e != nullptr && e[0] == '0');
+}();
+
 template <int NV, int THREADS>
 cudaError_t launch_reg(const Segs& segs, const float* prob, const EmitArgs& ea, int32_t* fb_count,
                        int32_t* fb_list, cudaStream_t st) {
+  const int per_sm = NV <= 6 ? 7 : 5;
+  if (g_persist && segs.n_bags > num_sms() * per_sm)
+    return launch_pdl(select_reg_persistent_kernel<NV, THREADS>, dim3((unsigned)(num_sms() * per_sm)), dim3(THREADS),
+                      0, st, 1, segs, prob, ea, fb_count, fb_list);
   return launch_pdl(select_reg_kernel<NV, THREADS>, dim3((unsigned)segs.n_bags), dim3(THREADS), 0, st, 1,
                     segs, prob, ea, fb_count, fb_list);
 }

@@ -120,13 +120,13 @@ exclusive_scan_kernel(int64_t* __restrict__ data, int n) {
 // place, in chunks staged through shared memory (coalesced loads -> every thread sums a
 // contiguous slice -> block scan of the 1024 partial sums -> coalesced stores).  `ticket` must be
 // zero on entry.
-constexpr int kOffChunk = 8192;
+constexpr int kOffChunk = 24576;     // 96 KB of dynamic shared memory: 20 000 bags are one chunk
 
 __global__ void __launch_bounds__(1024)
 select_offsets_kernel(Segs segs, const int32_t* __restrict__ labels, int32_t tiles_per_pos,
                       int32_t topk_neg, int64_t* __restrict__ offsets, int32_t* __restrict__ ticket) {
   asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
-  __shared__ int32_t cnt[kOffChunk];
+  extern __shared__ int32_t cnt[];      // kOffChunk entries (only the scanning CTA touches them)
   __shared__ int32_t warp_tot[32];
   __shared__ int s_last;
   const int n = segs.n_bags;
@@ -148,7 +148,21 @@ select_offsets_kernel(Segs segs, const int32_t* __restrict__ labels, int32_t til
   int64_t carry = 0;
   for (int base = 0; base < n; base += kOffChunk) {
     const int m = min(kOffChunk, n - base);
-    for (int i = tid; i < m; i += 1024) cnt[i] = (int32_t)__ldcg(offsets + base + i);   // other CTAs' stores: L2
+    // other CTAs' stores: read through L2; all of a thread's loads in flight before the first use
+#pragma unroll
+    for (int q0 = 0; q0 < kOffChunk / 1024; q0 += 8) {
+      int64_t v[8];
+#pragma unroll
+      for (int q = 0; q < 8; ++q) {
+        const int i = tid + 1024 * (q0 + q);
+        v[q] = i < m ? __ldcg(offsets + base + i) : 0;
+      }
+#pragma unroll
+      for (int q = 0; q < 8; ++q) {
+        const int i = tid + 1024 * (q0 + q);
+        if (i < m) cnt[i] = (int32_t)v[q];
+      }
+    }
     __syncthreads();
     const int per = (m + 1023) / 1024;
     const int lo = min(tid * per, m), hi = min(lo + per, m);
@@ -436,8 +450,18 @@ int cs_select_topk_shard(const float* prob, const int64_t* seg_offsets, int64_t 
   int32_t* fb_list = fb_count + 64;
   int32_t* ticket = fb_count + 1;
   CS_CUDA(cudaMemsetAsync(fb_count, 0, 2 * sizeof(int32_t), st));
-  select_offsets_kernel<<<cs::ceil_div(n_bags, 1024), 1024, 0, st>>>(segs, labels, tiles_per_pos, topk_neg,
-                                                                   sel_offsets_out, ticket);
+  {
+    static bool attr_done[64] = {false};
+    int dev = 0;
+    CS_CUDA(cudaGetDevice(&dev));
+    if (dev >= 64 || !attr_done[dev]) {
+      CS_CUDA(cudaFuncSetAttribute(select_offsets_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                   kOffChunk * (int)sizeof(int32_t)));
+      if (dev < 64) attr_done[dev] = true;
+    }
+  }
+  select_offsets_kernel<<<cs::ceil_div(n_bags, 1024), 1024, kOffChunk * sizeof(int32_t), st>>>(
+      segs, labels, tiles_per_pos, topk_neg, sel_offsets_out, ticket);
   CS_LAUNCH_CHECK();
   EmitArgs ea{};
   ea.labels = labels;

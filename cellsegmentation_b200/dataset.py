@@ -197,7 +197,9 @@ class LystoDataset(_TileSetBase):
         self.cls_labels = []
         self.transformIDX = []
         self.augment = augment
-        self.train_data = None
+        self.train_index = None
+        self.train_labels = None
+        self._train_data = None
         if _ensemble_init:
             return
         if filepath is None or not os.path.exists(filepath):
@@ -267,16 +269,37 @@ class LystoDataset(_TileSetBase):
             if flag is not None:
                 rows = np.nonzero(lab[perm] == flag)[0][:n]
                 keep = np.delete(perm, rows)
-        # rows are materialised for the kept selection only (one gather per column)
-        sel = idxs[keep]
-        q, r = np.divmod(sel, max(T, 1))
-        td = np.empty(len(keep), dtype=[("bag", np.int32), ("x", np.int32), ("y", np.int32), ("label", np.int64)])
-        if len(keep):
-            g = grid[r]
-            td["bag"], td["x"], td["y"], td["label"] = bags_arr[q], g[:, 0], g[:, 1], lab[keep]
-        self.train_data = td
-        self.train_index = sel             # dataset (tile) index of every train_data row
+        # the (bag, x, y, label) rows are materialised lazily, for the kept selection only: the
+        # feature-cache epoch never looks at them (it trains on train_index / train_labels)
+        self._train_data = None
+        self.train_index = idxs[keep]      # dataset (tile) index of every train_data row
+        self.train_labels = lab[keep]      # pseudo-label of every train_data row (int64)
         return pos, neg
+
+    @property
+    def train_data(self):
+        """Structured (bag, x, y, label) rows in the reference's order; None before make_train_data."""
+        if self._train_data is None and getattr(self, "train_index", None) is not None:
+            self._train_data = self.rows_of(np.arange(len(self.train_index)))
+        return self._train_data
+
+    @train_data.setter
+    def train_data(self, value):
+        self._train_data = value
+        if value is None:
+            self.train_index = None
+            self.train_labels = None
+
+    def rows_of(self, rows):
+        """train_data[rows] without materialising the whole table."""
+        sel = self.train_index[rows]
+        q, r = np.divmod(sel, max(self.tiles_per_bag, 1))
+        td = np.empty(len(sel), dtype=[("bag", np.int32), ("x", np.int32), ("y", np.int32), ("label", np.int64)])
+        if len(sel):
+            g = self._ensure_grid()[r]
+            td["bag"], td["x"], td["y"] = np.asarray(self._tile_bags, np.int64)[q], g[:, 0], g[:, 1]
+            td["label"] = self.train_labels[rows]
+        return td
 
     def train_tensor(self, begin, count, device=None):
         """Normalised tiles of train_data rows begin.. (mode 3), on the device."""
@@ -309,7 +332,7 @@ class LystoDataset(_TileSetBase):
         elif self.mode == 2:
             return len(self.images)
         elif self.mode == 3:
-            return len(self.train_data)
+            return len(self.train_data) if self._train_data is not None else len(self.train_index)
         return len(self.labels)
 
     @classmethod

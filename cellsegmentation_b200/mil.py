@@ -119,8 +119,8 @@ def train_selected(trainset, model, device, criterion, optimizer, batch_size, ga
     from torch.optim.lr_scheduler import CyclicLR, OneCycleLR
     rank, world = _world()
     model.train()
-    td = trainset.train_data
-    n = len(td)
+    n = len(trainset.train_index)
+    labels_all = trainset.train_labels
     order = np.arange(n)
     if shuffle_seed is not None:
         order = np.random.RandomState(shuffle_seed).permutation(n)      # same on every rank
@@ -149,18 +149,18 @@ def train_selected(trainset, model, device, criterion, optimizer, batch_size, ga
         # criterion is class-weighted (what reduction='mean' divides by); known on every rank
         denom = float(len(rows))
         if _is_mean_ce(criterion):
-            lab_rows = td["label"][rows]
+            lab_rows = labels_all[rows]
             valid = lab_rows[lab_rows != criterion.ignore_index]
             denom = float(class_w[valid].sum()) if class_w is not None else float(len(valid))
         denom = max(denom, 1e-30)
         optimizer.zero_grad()
         if len(mine):
-            label = torch.from_numpy(td["label"][mine].copy()).to(dev, non_blocking=True)
+            label = torch.from_numpy(labels_all[mine]).to(dev, non_blocking=True)
             if feature_cache is not None:
                 sel = torch.from_numpy(trainset.train_index[mine] - begin).to(dev, non_blocking=True)
                 out = model.fc_tile(feature_cache["feat"].index_select(0, sel))
             else:
-                sub = td[mine]
+                sub = trainset.rows_of(mine)
                 img = shard.device_images(device)
                 data = ops.gather_normalize(img, trainset.tile_size,
                                             torch.from_numpy((sub["bag"] - first_img).astype(np.int32)).to(dev),
