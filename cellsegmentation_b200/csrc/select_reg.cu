@@ -72,6 +72,7 @@ struct SelState {
   uint32_t tmax[128];
   int count, n;                       // n: kept count, or -1 = this path declines the bag
   uint32_t tau;
+  int pseudo_label;                   // labels[b] != 0
 };
 
 struct BagView {
@@ -123,6 +124,7 @@ __device__ __forceinline__ void bag_process(const Segs& segs, const EmitArgs& ea
     st.n = (n == 0) ? 0 : ((suffix && n <= THREADS && bv.fits) ? n : -1);
     st.count = 0;
     st.tau = 0;
+    st.pseudo_label = ea.labels[b] == 0 ? 0 : 1;
     if (mis > 0) x[0].x = 0u;                              // words of the previous bag
     if (mis > 1) x[0].y = 0u;
     if (mis > 2) x[0].z = 0u;
@@ -197,6 +199,13 @@ __device__ __forceinline__ void bag_process(const Segs& segs, const EmitArgs& ea
     return;
   }
 
+  // The output offsets come from the scan kernel this one was launched behind (programmatic
+  // dependent launch; everything above overlapped with it).  Ask for this bag's offset now, so
+  // the L2 round trip hides behind steps 2 and 3.
+  asm volatile("griddepcontrol.wait;" ::: "memory");
+  const int64_t o0 = ea.out_offsets[b];
+  const uint8_t pl = (uint8_t)st.pseudo_label;
+
   // 2. candidates: (bits << 32 | index in the bag), appended in any order
   if (m >= tau) {
     uint32_t mask = 0;
@@ -226,13 +235,7 @@ __device__ __forceinline__ void bag_process(const Segs& segs, const EmitArgs& ea
     return;
   }
 
-  // 3. rank by counting; the n largest go to slots o0 + (n-1-rank): ascending (prob, index).
-  // The offsets come from the scan kernel this one was launched behind (programmatic dependent
-  // launch): everything above overlapped with it.
-  if (tid >= count) return;
-  asm volatile("griddepcontrol.wait;" ::: "memory");
-  const int64_t o0 = ea.out_offsets[b];
-  const uint8_t pl = ea.labels[b] == 0 ? 0 : 1;
+  // 3. rank by counting; the n largest go to slots o0 + (n-1-rank): ascending (prob, index)
   for (int j = tid; j < count; j += THREADS) {
     const unsigned long long me = st.cand[j];
     int above = 0;
@@ -263,9 +266,8 @@ select_reg_kernel(Segs segs, const float* __restrict__ prob, EmitArgs ea,
   bag_process<NV, THREADS>(segs, ea, b, bv, x, st, fb_count, fb_list);
 }
 
-// Persistent CTAs: bag b + k * gridDim.x in turn, with the NEXT bag's vectors requested before the
-// current one is worked on, so the HBM / L2 round trip hides behind a whole bag of instructions
-// instead of behind the other resident CTAs.
+// Persistent CTAs (experiment, off by default -- see g_persist): bag b + k * gridDim.x in turn, with
+// the NEXT bag's vectors requested before the current one is worked on.
 template <int NV, int THREADS>
 __global__ void __launch_bounds__(THREADS, NV <= 6 ? 7 : 5)
 select_reg_persistent_kernel(Segs segs, const float* __restrict__ prob, EmitArgs ea,
@@ -293,10 +295,13 @@ select_reg_persistent_kernel(Segs segs, const float* __restrict__ prob, EmitArgs
   }
 }
 
-// CELLSEG_SELECT_PERSIST=0 keeps one CTA per bag.
+// CELLSEG_SELECT_PERSIST=1 selects the persistent kernel.  Measured at 20 000 bags x 3025 (ncu r2i):
+// 79.5 us against 54.6 us for one CTA per bag -- a bag's chain of three block barriers, the
+// warp-0 sort and the ranking loop takes ~4 us however early its loads were issued, so what hides
+// it is the NUMBER of resident CTAs (10 of 48 registers against 7 of 72), not the prefetch.
 const bool g_persist = []() {
   const char* e = getenv("CELLSEG_SELECT_PERSIST");
-  return !(e != nullptr && e[0] == '0');
+  return e != nullptr && e[0] == '1';
 }();
 
 template <int NV, int THREADS>
