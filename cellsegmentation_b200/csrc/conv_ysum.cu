@@ -110,7 +110,7 @@ conv_ysum_kernel(const __grid_constant__ YsumParams p) {
   // a cluster walks groups of CL neighbouring M tiles; CTA `rank` owns tile group * CL + rank
   const int m_groups = (p.num_m_tiles + CL - 1) / CL;
   const int first = blockIdx.x / CL, step_g = gridDim.x / CL;
-  auto tile_of = [&](int gi) { return (p.reverse ? m_groups - 1 - gi : gi) * CL + rank; };
+  auto tile_of = [&](int gi) { return p.tile_base + (p.reverse ? m_groups - 1 - gi : gi) * CL + rank; };
 
   if (warp == 0 && lane == 0) {
     for (int s = 0; s < kStages; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }

@@ -131,7 +131,8 @@ struct YsumParams {
   CUtensorMap a_map;  // make_act_map_4d {C, W, H, T}, box {64, 8, 8, 2}
   CUtensorMap b_map;  // [3*192][64] from pack_ysum_weights, box {64, 192 / cluster}
   int cluster;        // 1, or 2: CTA pairs (tcgen05 cta_group::2)
-  int num_m_tiles;    // ceil(instances / 2)
+  int num_m_tiles;    // ceil(instances / 2) of this launch
+  int tile_base;      // first M tile of this launch (sub-batches of a forward batch); multiple of `cluster`
   int reverse;
   int64_t n_inst;
   const float* bias;

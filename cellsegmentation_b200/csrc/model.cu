@@ -51,6 +51,12 @@ const int g_dense_max_po = env_is("CELLSEG_DENSE_PO", "4") ? 4 : (env_is("CELLSE
 // N tile of the dense form: 256 (two 4x4-stage pixels per tile) by default; CELLSEG_DENSE_BN=128
 // gives every output pixel of the 4x4 stage its own tile (exactly the in-bounds taps, smaller MMAs).
 const int g_dense_bn = env_is("CELLSEG_DENSE_BN", "128") ? 128 : 256;
+// Instances per stem + layer-1 sub-batch (0: whole forward batches).  4 736 = 16 y-sum M tiles per
+// CTA (32 stem instances per CTA): x, mid and y of a sub-batch are 3 x 39 MB.
+const int64_t g_l1_sub = []() -> int64_t {
+  const char* e = getenv("CELLSEG_L1_SUB");
+  return e != nullptr ? atoll(e) : 4736;
+}();
 // Residual stream: bf16 by default.  CELLSEG_RESIDUAL=hilo carries a second bf16 tensor
 // lo = value - bf16(value) between blocks (~16 mantissa bits); measured max|dp| moves by < 1.5e-3
 // (ResNet-34 0.0101 -> 0.0098) while the block epilogues move twice the bytes (-11 % throughput).
@@ -400,8 +406,10 @@ int finalize_io_maps(PlannedConv& pc, int64_t b_pad) {
 }
 
 // Launches one planned convolution for `count` instances (pointers / relu taken from pc.p).
+// inst_base (y-sum layers only): the launch covers instances [inst_base, inst_base + count) of
+// the planned buffers -- a sub-batch of the forward batch.
 int launch_planned(const PlannedConv& pc, int64_t count, float* out_f32, cudaStream_t st,
-                   int reverse = 0) {
+                   int reverse = 0, int64_t inst_base = 0) {
   if (pc.ysum) {
     YsumParams yp = pc.yp;
     yp.res_hi = pc.p.res_hi; yp.res_lo = pc.p.res_lo;
@@ -410,8 +418,9 @@ int launch_planned(const PlannedConv& pc, int64_t count, float* out_f32, cudaStr
     yp.out_hi_map = pc.p.out_hi_map; yp.out_lo_map = pc.p.out_lo_map;
     yp.out_f32 = out_f32;
     yp.relu = pc.p.relu;
-    yp.n_inst = count;
+    yp.n_inst = inst_base + count;
     yp.reverse = reverse;
+    yp.tile_base = (int)(inst_base / 2);
     yp.num_m_tiles = (int)ceil_div<int64_t>(count, 2);
     return launch_conv_ysum(yp, st);
   }
@@ -633,17 +642,44 @@ int run_tc_batch(cs_model* m, const StemArgs& stem_in, int64_t count, float* pro
   sa.out_hi = pl.x_hi[0];
   sa.out_lo = nullptr;   // bf16 stream only; the first block's residual add reads x_hi alone
   int rc;
-  if (pl.tile == 32)
-    rc = launch_stem_win(sa, pl.d_stem_w2, pl.d_lut, st);
-  else
-    rc = launch_stem_bf16(sa, st);
-  if (rc != CS_OK) return rc;
-  m->last_launches++;
+  // Layer 1 in sub-batches.  A forward batch of 75 776 instances keeps 621 MB per 8x8x64 tensor:
+  // the stem output and the six layer-1 convs round-trip through HBM (9.6 of the 21.5 GB a batch
+  // moves, the residual convs at 4.9 TB/s = 75 % of the copy peak; ncu r02_full_batch).  The
+  // convs of layer 1 are independent per instance, so stem + layer 1 run for g_l1_sub instances
+  // at a time -- three live tensors of 39 MB stay in the 126 MB L2 -- and only the layer-1 output
+  // goes to HBM; the deeper layers (4 KB ... 1 KB per instance) keep whole batches and their
+  // 128-instance M tiles.
+  size_t n_ysum = 0;
+  while (n_ysum < pl.layers.size() && pl.layers[n_ysum].ysum) ++n_ysum;
+  const bool sub_batched = g_l1_sub > 0 && pl.tile == 32 && n_ysum > 0 && count > g_l1_sub;
+  const int64_t step = sub_batched ? g_l1_sub : count;
+  for (int64_t i0 = 0; i0 < count; i0 += step) {
+    const int64_t cnt = count - i0 < step ? count - i0 : step;
+    StemArgs ss = sa;
+    ss.count = cnt;
+    ss.inst_begin = sa.inst_begin + i0;
+    if (sa.x) ss.x = sa.x + i0 * 3 * pl.tile * pl.tile;
+    ss.out_hi = sa.out_hi + i0 * (int64_t)(pl.tile / 4) * (pl.tile / 4) * 64;
+    if (pl.tile == 32)
+      rc = launch_stem_win(ss, pl.d_stem_w2, pl.d_lut, st);
+    else
+      rc = launch_stem_bf16(ss, st);
+    if (rc != CS_OK) return rc;
+    m->last_launches++;
+    if (!sub_batched) break;
+    for (size_t li = 0; li < n_ysum; ++li) {
+      rc = launch_planned(pl.layers[li], cnt, nullptr, st, g_snake ? (int)((li + 1) & 1) : 0, i0);
+      if (rc != CS_OK) return rc;
+      m->last_launches++;
+    }
+  }
   int li = 0;
   for (PlannedConv& pc : pl.layers) {
     // snake order: odd layers walk their tiles backwards, starting with the rows the previous
     // layer wrote last (still L2 resident when a batch's activations exceed L2)
-    rc = launch_planned(pc, count, nullptr, st, g_snake ? (++li & 1) : 0);
+    ++li;
+    if (sub_batched && (size_t)li <= n_ysum) continue;     // done above, per sub-batch
+    rc = launch_planned(pc, count, nullptr, st, g_snake ? (li & 1) : 0);
     if (rc != CS_OK) return rc;
     m->last_launches++;
   }
