@@ -34,6 +34,7 @@ namespace {
 
 constexpr int kMaxStages = 6;                      // 6 when only bf16 tiles are staged, else 4
 constexpr uint32_t kABytes = 128 * 128;            // one shifted box: 128 rows x 64 ch bf16
+constexpr uint32_t kABoxBytes = 160 * 128;         // one-box form: 2 images x 8 rows x 10 pixels
 constexpr uint32_t kBTileFull = 192 * 128;         // [dy*64 + co][64 ci] of one dx
 constexpr uint32_t kBBytes = 3 * kBTileFull;       // 72 KB resident (36 KB used by a pair member)
 constexpr uint32_t kXchBytes = 2 * 8 * 1024;       // 2 tile parities x 8 warps x 1 KB
@@ -75,10 +76,18 @@ __device__ __forceinline__ void tmem_ld_16x256b<2>(uint32_t taddr, uint32_t (&r)
 // CL = 2: CTA pairs (tcgen05 cta_group::2) as in conv_gemm.cu -- neighbouring M tiles, each CTA
 // holds its own A boxes and 96 of the 192 rows of every weight tile, the leader issues M = 256
 // MMAs for both.
-template <int CL, int EW>
+// OB = true ("one box"): instead of three x-shifted 128-row boxes per M tile (48 KB written into
+// shared memory by TMA), ONE box of 10 pixels per image row {64 ch, x = -1..8, 8 rows, 2 images}
+// = 160 rows = 20 KB; the three horizontal taps are the same tile read through descriptors whose
+// start address moves by one 128-byte row and whose 8-row groups are 10 rows (1280 B) apart.
+// That is legal because tcgen05 (like TMA) applies the 128-byte swizzle XOR on absolute
+// shared-memory address bits (tools/umma_probe.cu, "sw128 start128 sbo1280").
+template <int CL, int EW, bool OB>
 __global__ void __launch_bounds__((EW + 3) * 32, 1)
 conv_ysum_kernel(const __grid_constant__ YsumParams p) {
   constexpr int NI = 32 / EW;                     // 8-channel groups per epilogue thread: 4 | 2
+  constexpr uint32_t kStageBytes = OB ? kABoxBytes : kABytes;
+  constexpr uint32_t kLoadsPerTile = OB ? 1 : 3;
   constexpr int CW = 8 * NI;                      // channels per epilogue warp: 32 | 16
   constexpr uint32_t kBTile = kBTileFull / CL;
   extern __shared__ uint8_t smem_raw[];
@@ -86,10 +95,10 @@ conv_ysum_kernel(const __grid_constant__ YsumParams p) {
   const uint32_t base = (raw + 1023u) & ~1023u;
   uint8_t* base_ptr = smem_raw + (base - raw);
   const bool lo_tiles = p.res_lo != nullptr || p.out_lo != nullptr;
-  const int kStages = lo_tiles ? 4 : kMaxStages;
+  const int kStages = OB ? (lo_tiles ? 3 : 4) : (lo_tiles ? 4 : kMaxStages);
   const uint32_t set_bytes = lo_tiles ? kEpiSetBytes : kEpiTileBytes;
   const uint32_t bres = base + kOffB;
-  const uint32_t staging = base + kStages * kABytes;
+  const uint32_t staging = base + kStages * kStageBytes;
   const uint32_t bar_base = base + kOffBars;
   auto full_bar = [&](int s) { return bar_base + 8u * s; };
   auto empty_bar = [&](int s) { return bar_base + 8u * (kMaxStages + s); };
@@ -121,7 +130,7 @@ conv_ysum_kernel(const __grid_constant__ YsumParams p) {
     mbar_init(bres_bar, 1);
     epi_bars_init(ebars, EW * 32);
     fence_barrier_init();
-    prefetch_tmap(&p.a_map);
+    prefetch_tmap(OB ? &p.a_box_map : &p.a_map);
     prefetch_tmap(&p.b_map);
   }
   if (warp == 1) {
@@ -148,13 +157,14 @@ conv_ysum_kernel(const __grid_constant__ YsumParams p) {
       uint32_t phase = 0;
       for (int gi = first; gi < m_groups; gi += step_g) {
         const int m_tile = tile_of(gi);
-        for (int dx = 0; dx < 3; ++dx) {
+        for (int dx = 0; dx < (int)kLoadsPerTile; ++dx) {
           mbar_wait(empty_bar(stage), phase ^ 1u);
-          if (rank == 0) mbar_expect_tx(full_bar(stage), CL * kABytes);
+          if (rank == 0) mbar_expect_tx(full_bar(stage), CL * kStageBytes);
+          const CUtensorMap* amap = OB ? &p.a_box_map : &p.a_map;
           if (CL == 1)
-            tma_load_4d(base + stage * kABytes, &p.a_map, full_bar(stage), 0, dx - 1, 0, m_tile * 2);
+            tma_load_4d(base + stage * kStageBytes, amap, full_bar(stage), 0, dx - 1, 0, m_tile * 2);
           else
-            tma_load_4d_pair(base + stage * kABytes, &p.a_map, full_bar(stage), 0, dx - 1, 0, m_tile * 2);
+            tma_load_4d_pair(base + stage * kStageBytes, amap, full_bar(stage), 0, dx - 1, 0, m_tile * 2);
           if (++stage == kStages) { stage = 0; phase ^= 1u; }
         }
       }
@@ -170,9 +180,12 @@ conv_ysum_kernel(const __grid_constant__ YsumParams p) {
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + (uint32_t)(acc * kAccCols);
         for (int dx = 0; dx < 3; ++dx) {
-          mbar_wait(full_bar(stage), phase);
-          tc_fence_after();
-          const uint64_t a_desc = umma_desc_sw128(base + stage * kABytes);
+          if (!OB || dx == 0) {
+            mbar_wait(full_bar(stage), phase);
+            tc_fence_after();
+          }
+          const uint64_t a_desc = OB ? umma_desc_sw128_sbo(base + stage * kStageBytes + dx * 128u, 1280u)
+                                     : umma_desc_sw128(base + stage * kStageBytes);
           const uint64_t b_desc = umma_desc_sw128(bres + dx * kBTile);
 #pragma unroll
           for (int k = 0; k < 4; ++k) {
@@ -183,9 +196,11 @@ conv_ysum_kernel(const __grid_constant__ YsumParams p) {
               umma_bf16_pair(d_tmem, a_desc + (uint64_t)(2 * k), b_desc + (uint64_t)(2 * k), idesc,
                              (dx > 0 || k > 0) ? 1u : 0u);
           }
-          if (CL == 1) umma_commit(empty_bar(stage));
-          else umma_commit_pair(empty_bar(stage), kMask);
-          if (++stage == kStages) { stage = 0; phase ^= 1u; }
+          if (!OB || dx == 2) {
+            if (CL == 1) umma_commit(empty_bar(stage));
+            else umma_commit_pair(empty_bar(stage), kMask);
+            if (++stage == kStages) { stage = 0; phase ^= 1u; }
+          }
         }
         if (CL == 1) umma_commit(tfull_bar(acc));
         else umma_commit_pair(tfull_bar(acc), kMask);
@@ -343,20 +358,20 @@ void pack_ysum_weights(const float* w_oihw, uint16_t* out) {
           out[((dx * 192) + dy * 64 + co) * 64 + ci] = rn(w_oihw[((co * 64 + ci) * 3 + dy) * 3 + dx]);
 }
 
-template <int CL, int EW>
+template <int CL, int EW, bool OB>
 int launch_ysum(const YsumParams& p, cudaStream_t st) {
   static bool attr_done[64] = {false};
   int dev = 0;
   CS_CUDA(cudaGetDevice(&dev));
   if (dev >= 64 || !attr_done[dev]) {
-    CS_CUDA(cudaFuncSetAttribute(conv_ysum_kernel<CL, EW>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    CS_CUDA(cudaFuncSetAttribute(conv_ysum_kernel<CL, EW, OB>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                  (int)kSmemBytes));
     if (dev < 64) attr_done[dev] = true;
   }
   const int sms = num_sms();
   const int groups = (p.num_m_tiles + CL - 1) / CL;
   const int clusters = groups < sms / CL ? groups : sms / CL;
-  CS_CUDA(launch_pdl(conv_ysum_kernel<CL, EW>, dim3((unsigned)(clusters * CL)), dim3((EW + 3) * 32), kSmemBytes,
+  CS_CUDA(launch_pdl(conv_ysum_kernel<CL, EW, OB>, dim3((unsigned)(clusters * CL)), dim3((EW + 3) * 32), kSmemBytes,
                      st, CL, p));
   return CS_OK;
 }
@@ -367,10 +382,17 @@ const bool g_epi8 = []() {
   return e != nullptr && strcmp(e, "8") == 0;
 }();
 
+// CELLSEG_YSUM_BOX=1: one 10-pixel-wide box per M tile instead of three shifted boxes (experiment).
+const bool g_one_box = []() {
+  const char* e = getenv("CELLSEG_YSUM_BOX");
+  return e != nullptr && strcmp(e, "1") == 0;
+}();
+
 int launch_conv_ysum(const YsumParams& p, cudaStream_t st) {
   if (p.num_m_tiles <= 0) return CS_OK;
-  if (g_epi8) return p.cluster > 1 ? launch_ysum<2, 8>(p, st) : launch_ysum<1, 8>(p, st);
-  return p.cluster > 1 ? launch_ysum<2, 16>(p, st) : launch_ysum<1, 16>(p, st);
+  if (g_epi8) return p.cluster > 1 ? launch_ysum<2, 8, false>(p, st) : launch_ysum<1, 8, false>(p, st);
+  if (g_one_box) return p.cluster > 1 ? launch_ysum<2, 16, true>(p, st) : launch_ysum<1, 16, true>(p, st);
+  return p.cluster > 1 ? launch_ysum<2, 16, false>(p, st) : launch_ysum<1, 16, false>(p, st);
 }
 
 }  // namespace cs

@@ -129,6 +129,7 @@ int make_act_map_halo(CUtensorMap* map, const void* base, int C, int W, int H, i
 // Layer-1 convs in y-sum form (conv_ysum.cu): 8x8 images, 64 -> 64 channels, stride 1.
 struct YsumParams {
   CUtensorMap a_map;  // make_act_map_4d {C, W, H, T}, box {64, 8, 8, 2}
+  CUtensorMap a_box_map;  // same tensor, box {64, 10, 8, 2} (one-box form: fetched at x = -1)
   CUtensorMap b_map;  // [3*192][64] from pack_ysum_weights, box {64, 192 / cluster}
   int cluster;        // 1, or 2: CTA pairs (tcgen05 cta_group::2)
   int num_m_tiles;    // ceil(instances / 2) of this launch

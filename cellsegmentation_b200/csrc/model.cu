@@ -51,11 +51,14 @@ const int g_dense_max_po = env_is("CELLSEG_DENSE_PO", "4") ? 4 : (env_is("CELLSE
 // N tile of the dense form: 256 (two 4x4-stage pixels per tile) by default; CELLSEG_DENSE_BN=128
 // gives every output pixel of the 4x4 stage its own tile (exactly the in-bounds taps, smaller MMAs).
 const int g_dense_bn = env_is("CELLSEG_DENSE_BN", "128") ? 128 : 256;
-// Instances per stem + layer-1 sub-batch (0: whole forward batches).  4 736 = 16 y-sum M tiles per
-// CTA (32 stem instances per CTA): x, mid and y of a sub-batch are 3 x 39 MB.
+// Instances per stem + layer-1 sub-batch; 0 (default): whole forward batches.  4 736 = 16 y-sum M
+// tiles per CTA: x, mid and y of a sub-batch are 3 x 39 MB and stay in L2.  Measured (gpurun r2j,
+// one box): 0 -> 10.2 M instances/s at 1 390 MHz; 9 472 -> 10.08 M; 4 736 -> 9.93 M at 1 515 MHz;
+// 2 368 -> 9.50 M at 1 612 MHz.  The saved HBM traffic shows as a HIGHER clock under the power cap,
+// but the 7 extra launches per sub-batch cost more than it returns.  Experiment switch.
 const int64_t g_l1_sub = []() -> int64_t {
   const char* e = getenv("CELLSEG_L1_SUB");
-  return e != nullptr ? atoll(e) : 4736;
+  return e != nullptr ? atoll(e) : 0;
 }();
 // Residual stream: bf16 by default.  CELLSEG_RESIDUAL=hilo carries a second bf16 tensor
 // lo = value - bf16(value) between blocks (~16 mantissa bits); measured max|dp| moves by < 1.5e-3
@@ -357,6 +360,9 @@ int plan_conv(const ConvGeom& g, const float* w_oihw, const float* bias, const C
     CS_CUDA(cudaMalloc(&pc.d_B2, B2.size() * sizeof(uint16_t)));
     CS_CUDA(cudaMemcpy(pc.d_B2, B2.data(), B2.size() * sizeof(uint16_t), cudaMemcpyHostToDevice));
     pc.yp.a_map = pc.p.a_map[0];
+    rc = make_act_map_4d(&pc.yp.a_box_map, in_hi, g.Cin, g.Wi, g.Hi, b_pad, g.Cin, (int64_t)g.Wi * g.Cin,
+                         (int64_t)Pi * g.Cin, g.Wi + 2, g.Hi, kGemmBM / Po);
+    if (rc != CS_OK) { free_planned(pc); return rc; }
     pc.yp.cluster = g_ysum_pairs ? g_cluster : 1;
     rc = make_mat_map_2d(&pc.yp.b_map, pc.d_B2, 64, 576, 64, 192 / pc.yp.cluster);
     if (rc != CS_OK) { free_planned(pc); return rc; }
@@ -642,13 +648,12 @@ int run_tc_batch(cs_model* m, const StemArgs& stem_in, int64_t count, float* pro
   sa.out_hi = pl.x_hi[0];
   sa.out_lo = nullptr;   // bf16 stream only; the first block's residual add reads x_hi alone
   int rc;
-  // Layer 1 in sub-batches.  A forward batch of 75 776 instances keeps 621 MB per 8x8x64 tensor:
-  // the stem output and the six layer-1 convs round-trip through HBM (9.6 of the 21.5 GB a batch
-  // moves, the residual convs at 4.9 TB/s = 75 % of the copy peak; ncu r02_full_batch).  The
-  // convs of layer 1 are independent per instance, so stem + layer 1 run for g_l1_sub instances
-  // at a time -- three live tensors of 39 MB stay in the 126 MB L2 -- and only the layer-1 output
-  // goes to HBM; the deeper layers (4 KB ... 1 KB per instance) keep whole batches and their
-  // 128-instance M tiles.
+  // Optional (CELLSEG_L1_SUB, off by default -- see g_l1_sub): layer 1 in sub-batches.  A forward
+  // batch of 75 776 instances keeps 621 MB per 8x8x64 tensor: the stem output and the six layer-1
+  // convs round-trip through HBM (9.6 of the 21.5 GB a batch moves, the residual convs at
+  // 4.9 TB/s = 75 % of the copy peak; ncu r02_full_batch).  The convs of layer 1 are independent
+  // per instance, so stem + layer 1 can run for g_l1_sub instances at a time -- three live tensors
+  // of 39 MB stay in the 126 MB L2 -- with only the layer-1 output going to HBM.
   size_t n_ysum = 0;
   while (n_ysum < pl.layers.size() && pl.layers[n_ysum].ysum) ++n_ysum;
   const bool sub_batched = g_l1_sub > 0 && pl.tile == 32 && n_ysum > 0 && count > g_l1_sub;

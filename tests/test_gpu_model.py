@@ -229,7 +229,7 @@ def test_hilo_residual_mode_subprocess(cuda):
 @pytest.mark.parametrize("env", [{"CELLSEG_YSUM": "0"}, {"CELLSEG_YSUM_PAIRS": "0"}, {"CELLSEG_CLUSTER": "1"},
                                  {"CELLSEG_YSUM_EPI": "8"}, {"CELLSEG_DENSE_PO": "4"},
                                  {"CELLSEG_DENSE_PO": "4", "CELLSEG_HALO_DS": "0"}, {"CELLSEG_DENSE_BN": "128"},
-                                 {"CELLSEG_DENSE_PO": "64"},
+                                 {"CELLSEG_DENSE_PO": "64"}, {"CELLSEG_L1_SUB": "4736"},
                                  {"CELLSEG_RESIDUAL": "hilo", "CELLSEG_YSUM": "0"},
                                  {"CELLSEG_RESIDUAL": "hilo"}],
                          ids=lambda e: ",".join("%s=%s" % kv for kv in e.items()))
@@ -237,7 +237,7 @@ def test_alternative_kernel_paths_subprocess(cuda, env):
     """The switches are read when the library loads: run the conv-form and ResNet-34 parity tests in a
     child process for every alternative kernel path (halo layer 1, y-sum CTA pairs, single-CTA MMAs,
     8-warp y-sum epilogue, halo kernel for layer 2 with and without the fused shortcut, 128-wide dense
-    tiles, dense 8x8 stage, hi/lo residual stream)."""
+    tiles, dense 8x8 stage, L2-resident layer-1 sub-batches, hi/lo residual stream)."""
     import os
     import subprocess
     import sys

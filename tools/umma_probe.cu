@@ -76,6 +76,8 @@ int main() {
       {"none lbo16 sbo128 start48", 48, 128, 16, 0, 0},
       {"sw64 start0 sbo512", 0, 512, 16, 4, 0},  {"sw64 start32 sbo512", 32, 512, 16, 4, 0},
       {"sw128 start0 sbo1024", 0, 1024, 16, 2, 0}, {"sw128 start64 sbo1200", 64, 1200, 16, 2, 0},
+      {"sw128 start128 sbo1280", 128, 1280, 16, 2, 0}, {"sw128 start256 sbo1280", 256, 1280, 16, 2, 0},
+      {"sw128 start288 sbo1280", 288, 1280, 16, 2, 0}, {"sw128 start128 sbo1280 boff1", 128, 1280, 16, 2, 1},
   };
   float* d_out;
   cudaMalloc(&d_out, 128 * 16 * 4);
