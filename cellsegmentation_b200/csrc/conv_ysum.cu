@@ -382,10 +382,13 @@ const bool g_epi8 = []() {
   return e != nullptr && strcmp(e, "8") == 0;
 }();
 
-// CELLSEG_YSUM_BOX=1: one 10-pixel-wide box per M tile instead of three shifted boxes (experiment).
+// One 10-pixel-wide box per M tile (default) instead of three shifted boxes: 20 instead of 48 KB
+// written into shared memory per tile and 58 % less L2 -> SM traffic for the activations;
+// 10.25 -> 10.38 M instances/s on one box (gpurun r2k, two runs each).  CELLSEG_YSUM_BOX=0
+// restores the three-box form.
 const bool g_one_box = []() {
   const char* e = getenv("CELLSEG_YSUM_BOX");
-  return e != nullptr && strcmp(e, "1") == 0;
+  return !(e != nullptr && strcmp(e, "0") == 0);
 }();
 
 int launch_conv_ysum(const YsumParams& p, cudaStream_t st) {

@@ -160,57 +160,63 @@ head_bf16_kernel(const __nv_bfloat16* __restrict__ x_hi, const __nv_bfloat16* __
                  float* __restrict__ logits_out, float* __restrict__ feat_out) {
   pdl_launch_dependents();
   pdl_wait();
-  int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-  int lane = threadIdx.x & 31;
-  if (warp >= n) return;
-  const __nv_bfloat16* xh = x_hi + warp * (int64_t)P * C;
-  const __nv_bfloat16* xl = x_lo ? x_lo + warp * (int64_t)P * C : nullptr;
+  const int lane = threadIdx.x & 31;
+  const int64_t warp0 = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int64_t n_warps = ((int64_t)gridDim.x * blockDim.x) >> 5;
   const float fp = (float)P;
-  float z0 = 0.f, z1 = 0.f;
+  const float b0 = fc_b[0], b1 = fc_b[1];
+  // a warp walks instances warp0, warp0 + n_warps, ...: the grid is a few CTAs per SM, so the
+  // loads of the next instance are issued while this one reduces (round 1 launched one
+  // short-lived warp per instance: 0.8 TB/s)
+  for (int64_t inst = warp0; inst < n; inst += n_warps) {
+    const __nv_bfloat16* xh = x_hi + inst * (int64_t)P * C;
+    const __nv_bfloat16* xl = x_lo ? x_lo + inst * (int64_t)P * C : nullptr;
+    float z0 = 0.f, z1 = 0.f;
 #pragma unroll 2
-  for (int c = lane * 8; c < C; c += 256) {
-    float s[8], mx[8];
+    for (int c = lane * 8; c < C; c += 256) {
+      float s[8], mx[8];
 #pragma unroll
-    for (int e = 0; e < 8; ++e) { s[e] = 0.f; mx[e] = -INFINITY; }
-    for (int q = 0; q < P; ++q) {
-      float v[8];
-      unpack8(__ldg(reinterpret_cast<const uint4*>(xh + (int64_t)q * C + c)), v);
-      if (xl) {
-        float w[8];
-        unpack8(__ldg(reinterpret_cast<const uint4*>(xl + (int64_t)q * C + c)), w);
+      for (int e = 0; e < 8; ++e) { s[e] = 0.f; mx[e] = -INFINITY; }
+      for (int q = 0; q < P; ++q) {
+        float v[8];
+        unpack8(__ldg(reinterpret_cast<const uint4*>(xh + (int64_t)q * C + c)), v);
+        if (xl) {
+          float w[8];
+          unpack8(__ldg(reinterpret_cast<const uint4*>(xl + (int64_t)q * C + c)), w);
 #pragma unroll
-        for (int e = 0; e < 8; ++e) v[e] += w[e];
+          for (int e = 0; e < 8; ++e) v[e] += w[e];
+        }
+#pragma unroll
+        for (int e = 0; e < 8; ++e) { s[e] += v[e]; mx[e] = fmaxf(mx[e], v[e]); }
       }
+      float f[8];
 #pragma unroll
-      for (int e = 0; e < 8; ++e) { s[e] += v[e]; mx[e] = fmaxf(mx[e], v[e]); }
+      for (int e = 0; e < 8; ++e) f[e] = s[e] / fp + mx[e];
+      if (feat_out) {
+        float4* fo = reinterpret_cast<float4*>(feat_out + inst * C + c);
+        fo[0] = make_float4(f[0], f[1], f[2], f[3]);
+        fo[1] = make_float4(f[4], f[5], f[6], f[7]);
+      }
+      const float4 a0 = __ldg(reinterpret_cast<const float4*>(fc_w + c)), a1 = __ldg(reinterpret_cast<const float4*>(fc_w + c + 4));
+      const float4 c0 = __ldg(reinterpret_cast<const float4*>(fc_w + C + c)), c1 = __ldg(reinterpret_cast<const float4*>(fc_w + C + c + 4));
+      z0 = fmaf(f[0], a0.x, z0); z0 = fmaf(f[1], a0.y, z0); z0 = fmaf(f[2], a0.z, z0); z0 = fmaf(f[3], a0.w, z0);
+      z0 = fmaf(f[4], a1.x, z0); z0 = fmaf(f[5], a1.y, z0); z0 = fmaf(f[6], a1.z, z0); z0 = fmaf(f[7], a1.w, z0);
+      z1 = fmaf(f[0], c0.x, z1); z1 = fmaf(f[1], c0.y, z1); z1 = fmaf(f[2], c0.z, z1); z1 = fmaf(f[3], c0.w, z1);
+      z1 = fmaf(f[4], c1.x, z1); z1 = fmaf(f[5], c1.y, z1); z1 = fmaf(f[6], c1.z, z1); z1 = fmaf(f[7], c1.w, z1);
     }
-    float f[8];
-#pragma unroll
-    for (int e = 0; e < 8; ++e) f[e] = s[e] / fp + mx[e];
-    if (feat_out) {
-      float4* fo = reinterpret_cast<float4*>(feat_out + warp * C + c);
-      fo[0] = make_float4(f[0], f[1], f[2], f[3]);
-      fo[1] = make_float4(f[4], f[5], f[6], f[7]);
+    for (int o = 16; o > 0; o >>= 1) {
+      z0 += __shfl_xor_sync(0xffffffffu, z0, o);
+      z1 += __shfl_xor_sync(0xffffffffu, z1, o);
     }
-    const float4 a0 = __ldg(reinterpret_cast<const float4*>(fc_w + c)), a1 = __ldg(reinterpret_cast<const float4*>(fc_w + c + 4));
-    const float4 b0 = __ldg(reinterpret_cast<const float4*>(fc_w + C + c)), b1 = __ldg(reinterpret_cast<const float4*>(fc_w + C + c + 4));
-    z0 = fmaf(f[0], a0.x, z0); z0 = fmaf(f[1], a0.y, z0); z0 = fmaf(f[2], a0.z, z0); z0 = fmaf(f[3], a0.w, z0);
-    z0 = fmaf(f[4], a1.x, z0); z0 = fmaf(f[5], a1.y, z0); z0 = fmaf(f[6], a1.z, z0); z0 = fmaf(f[7], a1.w, z0);
-    z1 = fmaf(f[0], b0.x, z1); z1 = fmaf(f[1], b0.y, z1); z1 = fmaf(f[2], b0.z, z1); z1 = fmaf(f[3], b0.w, z1);
-    z1 = fmaf(f[4], b1.x, z1); z1 = fmaf(f[5], b1.y, z1); z1 = fmaf(f[6], b1.z, z1); z1 = fmaf(f[7], b1.w, z1);
-  }
-  for (int o = 16; o > 0; o >>= 1) {
-    z0 += __shfl_xor_sync(0xffffffffu, z0, o);
-    z1 += __shfl_xor_sync(0xffffffffu, z1, o);
-  }
-  if (lane == 0) {
-    z0 += fc_b[0];
-    z1 += fc_b[1];
-    if (logits_out) { logits_out[warp * 2] = z0; logits_out[warp * 2 + 1] = z1; }
-    if (prob_out) {
-      float mx = fmaxf(z0, z1);
-      float e0 = expf(z0 - mx), e1 = expf(z1 - mx);
-      prob_out[warp] = e1 / (e0 + e1);
+    if (lane == 0) {
+      z0 += b0;
+      z1 += b1;
+      if (logits_out) { logits_out[inst * 2] = z0; logits_out[inst * 2 + 1] = z1; }
+      if (prob_out) {
+        float mx = fmaxf(z0, z1);
+        float e0 = expf(z0 - mx), e1 = expf(z1 - mx);
+        prob_out[inst] = e1 / (e0 + e1);
+      }
     }
   }
 }
@@ -314,6 +320,8 @@ int launch_head_bf16(const __nv_bfloat16* x_hi, const __nv_bfloat16* x_lo, int64
   if (n <= 0) return CS_OK;
   CS_REQUIRE(C % 256 == 0, "launch_head_bf16: feature width %d must be a multiple of 256", C);
   int64_t blocks = ceil_div<int64_t>(n * 32, 256);
+  const int64_t cap = (int64_t)num_sms() * 8;                 // 64 warps per SM, each walking instances
+  if (blocks > cap) blocks = cap;
   CS_CUDA(launch_pdl(head_bf16_kernel, dim3((unsigned)blocks), dim3(256), 0, st, 1, x_hi, x_lo, n, P, C,
                      fc_w, fc_b, prob_out, logits_out, feat_out));
   return CS_OK;

@@ -205,45 +205,42 @@ def test_forward_tile16(cuda, arch):
     clf.close()
 
 
-def test_hilo_residual_mode_subprocess(cuda):
-    """CELLSEG_RESIDUAL=hilo (read when the library loads) keeps the hi/lo residual stream: same gate."""
-    import os
-    import subprocess
-    import sys
-    code = (
-        "import sys, numpy as np, torch; sys.path.insert(0, %r); sys.path.insert(0, %r)\n"
-        "from test_gpu_model import _setup, _ops, BF16_TOL\n"
-        "from oracle import model as omodel\n"
-        "ops = _ops(); bags, x, sd = _setup('resnet34')\n"
-        "want = omodel.forward_probs(sd, x, 'resnet34')\n"
-        "clf = ops.TileClassifier('resnet34', omodel.fold_bn(sd, 'resnet34'), sd['fc_tile.1.weight'], sd['fc_tile.1.bias'])\n"
-        "got = clf.forward_tiles(torch.from_numpy(bags).cuda(), 32, 20, precision='bf16', max_batch=256).cpu().numpy()\n"
-        "d = float(np.abs(got - want).max()); print('hilo max|dp|', d); assert d < BF16_TOL\n"
-    ) % (os.path.dirname(os.path.dirname(os.path.abspath(__file__))), os.path.dirname(os.path.abspath(__file__)))
-    env = dict(os.environ, CELLSEG_RESIDUAL="hilo")
-    r = subprocess.run([sys.executable, "-c", code], env=env, capture_output=True, text=True, timeout=600)
-    assert r.returncode == 0, r.stdout + r.stderr
-    assert "hilo max|dp|" in r.stdout
+ALT_PATHS = [
+    # (environment, also run the many-iteration and at-scale cases)
+    ({"CELLSEG_YSUM": "0"}, False), ({"CELLSEG_YSUM_PAIRS": "0"}, True), ({"CELLSEG_CLUSTER": "1"}, True),
+    ({"CELLSEG_YSUM_EPI": "8"}, False), ({"CELLSEG_YSUM_BOX": "0"}, True), ({"CELLSEG_DENSE_PO": "4"}, True),
+    ({"CELLSEG_DENSE_PO": "4", "CELLSEG_HALO_DS": "0"}, False), ({"CELLSEG_DENSE_BN": "128"}, False),
+    ({"CELLSEG_DENSE_PO": "64"}, False), ({"CELLSEG_L1_SUB": "4736"}, True),
+    ({"CELLSEG_RESIDUAL": "hilo", "CELLSEG_YSUM": "0"}, False), ({"CELLSEG_RESIDUAL": "hilo"}, False),
+]
 
 
-@pytest.mark.parametrize("env", [{"CELLSEG_YSUM": "0"}, {"CELLSEG_YSUM_PAIRS": "0"}, {"CELLSEG_CLUSTER": "1"},
-                                 {"CELLSEG_YSUM_EPI": "8"}, {"CELLSEG_DENSE_PO": "4"},
-                                 {"CELLSEG_DENSE_PO": "4", "CELLSEG_HALO_DS": "0"}, {"CELLSEG_DENSE_BN": "128"},
-                                 {"CELLSEG_DENSE_PO": "64"}, {"CELLSEG_L1_SUB": "4736"},
-                                 {"CELLSEG_RESIDUAL": "hilo", "CELLSEG_YSUM": "0"},
-                                 {"CELLSEG_RESIDUAL": "hilo"}],
-                         ids=lambda e: ",".join("%s=%s" % kv for kv in e.items()))
-def test_alternative_kernel_paths_subprocess(cuda, env):
-    """The switches are read when the library loads: run the conv-form and ResNet-34 parity tests in a
-    child process for every alternative kernel path (halo layer 1, y-sum CTA pairs, single-CTA MMAs,
-    8-warp y-sum epilogue, halo kernel for layer 2 with and without the fused shortcut, 128-wide dense
-    tiles, dense 8x8 stage, L2-resident layer-1 sub-batches, hi/lo residual stream)."""
+def test_alternative_kernel_paths_subprocess(cuda):
+    """The switches are read when the library loads: run the conv-form and ResNet-34 parity tests in
+    child processes for every alternative kernel path (halo layer 1, single-CTA y-sum MMAs, single-CTA
+    MMAs everywhere, 8-warp y-sum epilogue, three-box y-sum, halo kernel for layer 2 with and without
+    the fused shortcut, 128-wide dense tiles, dense 8x8 stage, L2-resident layer-1 sub-batches, hi/lo
+    residual stream); the paths that change how a forward batch is walked also run the
+    many-iteration and at-scale cases.  The children run concurrently (they share the GPU)."""
     import os
     import subprocess
     import sys
     here = os.path.abspath(__file__)
-    r = subprocess.run([sys.executable, "-m", "pytest", here, "-x", "-q", "-p", "no:cacheprovider", "-k",
-                        "conv_matches or (within_2e2 and resnet34) or tile16 or many_iterations or "
-                        "(bench_scale and resnet34)"],
-                       env=dict(os.environ, **env), capture_output=True, text=True, timeout=900)
-    assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-2000:]
+    light = "conv_matches or (within_2e2 and resnet34) or tile16"
+    heavy = light + " or many_iterations or (bench_scale and resnet34)"
+    procs = []
+    for env, is_heavy in ALT_PATHS:
+        procs.append((env, subprocess.Popen(
+            [sys.executable, "-m", "pytest", here, "-x", "-q", "-p", "no:cacheprovider", "-k", heavy if is_heavy else light],
+            env=dict(os.environ, OMP_NUM_THREADS="4", **env), stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)))
+    failed = []
+    for env, pr in procs:
+        try:
+            out, _ = pr.communicate(timeout=1500)
+        except subprocess.TimeoutExpired:
+            pr.kill()
+            out, _ = pr.communicate()
+            out += "\n[timed out]"
+        if pr.returncode != 0:
+            failed.append("%s:\n%s" % (env, out[-2500:]))
+    assert not failed, "\n\n".join(failed)
