@@ -153,6 +153,12 @@ __device__ __forceinline__ void unpack8(const uint4& u, float (&v)[8]) {
   v[4] = bf16_lo_f(u.z); v[5] = bf16_hi_f(u.z); v[6] = bf16_lo_f(u.w); v[7] = bf16_hi_f(u.w);
 }
 
+// P1 = true: the 1x1 final map of tile sizes 16 and 32 (avgpool = maxpool = the value itself, so the
+// pooled feature is v + v exactly) with the lane's fc_tile columns held in registers across the
+// instances it walks.  The generic form below it (any P, C) spent ~1 050 warp instructions per
+// instance on IEEE divisions and 64-bit index arithmetic and was issue-bound at 0.8 TB/s
+// (ncu r02: 73 % issue-active, 101 us per 75 776 instances).
+template <bool P1>
 __global__ void __launch_bounds__(256)
 head_bf16_kernel(const __nv_bfloat16* __restrict__ x_hi, const __nv_bfloat16* __restrict__ x_lo,
                  int64_t n, int P, int C, const float* __restrict__ fc_w,
@@ -163,11 +169,72 @@ head_bf16_kernel(const __nv_bfloat16* __restrict__ x_hi, const __nv_bfloat16* __
   const int lane = threadIdx.x & 31;
   const int64_t warp0 = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int64_t n_warps = ((int64_t)gridDim.x * blockDim.x) >> 5;
-  const float fp = (float)P;
   const float b0 = fc_b[0], b1 = fc_b[1];
-  // a warp walks instances warp0, warp0 + n_warps, ...: the grid is a few CTAs per SM, so the
-  // loads of the next instance are issued while this one reduces (round 1 launched one
-  // short-lived warp per instance: 0.8 TB/s)
+  if (P1) {
+    // C == 512: two groups of 8 channels per lane
+    float w0[2][8], w1[2][8];
+#pragma unroll
+    for (int g = 0; g < 2; ++g) {
+      const int c = lane * 8 + 256 * g;
+#pragma unroll
+      for (int e = 0; e < 8; ++e) { w0[g][e] = fc_w[c + e]; w1[g][e] = fc_w[C + c + e]; }
+    }
+    for (int64_t inst = warp0; inst < n; inst += n_warps) {
+      const uint4* xh = reinterpret_cast<const uint4*>(x_hi + inst * 512) + lane;
+      uint4 q[2] = {__ldg(xh), __ldg(xh + 32)};
+      float f[2][8];
+#pragma unroll
+      for (int g = 0; g < 2; ++g) {
+        float v[8];
+        unpack8(q[g], v);
+#pragma unroll
+        for (int e = 0; e < 8; ++e) f[g][e] = v[e];
+      }
+      if (x_lo) {
+        const uint4* xl = reinterpret_cast<const uint4*>(x_lo + inst * 512) + lane;
+        const uint4 l[2] = {__ldg(xl), __ldg(xl + 32)};
+#pragma unroll
+        for (int g = 0; g < 2; ++g) {
+          float v[8];
+          unpack8(l[g], v);
+#pragma unroll
+          for (int e = 0; e < 8; ++e) f[g][e] += v[e];
+        }
+      }
+      float z0 = 0.f, z1 = 0.f;
+#pragma unroll
+      for (int g = 0; g < 2; ++g) {
+#pragma unroll
+        for (int e = 0; e < 8; ++e) {
+          f[g][e] = f[g][e] / 1.0f + f[g][e];          // s / P + max with P = 1 (the division is exact)
+          z0 = fmaf(f[g][e], w0[g][e], z0);
+          z1 = fmaf(f[g][e], w1[g][e], z1);
+        }
+        if (feat_out) {
+          float4* fo = reinterpret_cast<float4*>(feat_out + inst * 512 + lane * 8 + 256 * g);
+          fo[0] = make_float4(f[g][0], f[g][1], f[g][2], f[g][3]);
+          fo[1] = make_float4(f[g][4], f[g][5], f[g][6], f[g][7]);
+        }
+      }
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) {
+        z0 += __shfl_xor_sync(0xffffffffu, z0, o);
+        z1 += __shfl_xor_sync(0xffffffffu, z1, o);
+      }
+      if (lane == 0) {
+        z0 += b0;
+        z1 += b1;
+        if (logits_out) { logits_out[inst * 2] = z0; logits_out[inst * 2 + 1] = z1; }
+        if (prob_out) {
+          const float mx = fmaxf(z0, z1);
+          const float e0 = expf(z0 - mx), e1 = expf(z1 - mx);
+          prob_out[inst] = e1 / (e0 + e1);
+        }
+      }
+    }
+    return;
+  }
+  const float fp = (float)P;
   for (int64_t inst = warp0; inst < n; inst += n_warps) {
     const __nv_bfloat16* xh = x_hi + inst * (int64_t)P * C;
     const __nv_bfloat16* xl = x_lo ? x_lo + inst * (int64_t)P * C : nullptr;
@@ -322,8 +389,12 @@ int launch_head_bf16(const __nv_bfloat16* x_hi, const __nv_bfloat16* x_lo, int64
   int64_t blocks = ceil_div<int64_t>(n * 32, 256);
   const int64_t cap = (int64_t)num_sms() * 8;                 // 64 warps per SM, each walking instances
   if (blocks > cap) blocks = cap;
-  CS_CUDA(launch_pdl(head_bf16_kernel, dim3((unsigned)blocks), dim3(256), 0, st, 1, x_hi, x_lo, n, P, C,
-                     fc_w, fc_b, prob_out, logits_out, feat_out));
+  if (P == 1 && C == 512)
+    CS_CUDA(launch_pdl(head_bf16_kernel<true>, dim3((unsigned)blocks), dim3(256), 0, st, 1, x_hi, x_lo, n, P, C,
+                       fc_w, fc_b, prob_out, logits_out, feat_out));
+  else
+    CS_CUDA(launch_pdl(head_bf16_kernel<false>, dim3((unsigned)blocks), dim3(256), 0, st, 1, x_hi, x_lo, n, P, C,
+                       fc_w, fc_b, prob_out, logits_out, feat_out));
   return CS_OK;
 }
 
