@@ -74,6 +74,7 @@ const bool g_disable_ysum = env_is("CELLSEG_YSUM", "0");
 // epilogue the kernel is no longer epilogue-bound and the halved B-operand reads pay, +1.5..2 %
 // on the whole step.  CELLSEG_YSUM_PAIRS=0 keeps single-CTA MMAs.
 const bool g_ysum_pairs = !env_is("CELLSEG_YSUM_PAIRS", "0");
+const bool g_no_group_ysum = env_is("CELLSEG_GROUP_YSUM", "0");   // grouped 8x8 convs back in the generic kernel
 
 struct ConvW {
   int cin = 0, cout = 0, k = 0, stride = 1, pad = 0, groups = 1;
@@ -102,6 +103,7 @@ struct PlannedConv {
   HaloParams hp;
   int halo_W = 0, halo_Cin = 0;
   bool ysum = false;   // layer-1 y-sum kernel (conv_ysum.cu)
+  bool io_final = false;  // residual / output maps were built by the planner (plan_ysum_block)
   YsumParams yp;
   uint16_t* d_B2 = nullptr;
   __nv_bfloat16* d_B = nullptr;
@@ -391,9 +393,54 @@ int plan_conv(const ConvGeom& g, const float* w_oihw, const float* bias, const C
   return CS_OK;
 }
 
+// One 64-channel block of a grouped stride-1 3x3 conv on 8x8 maps, through the y-sum kernel.
+// A grouped conv whose groups do not straddle 64-channel blocks (ResNeXt layer 1: 32 groups of 4
+// or 8 channels) is C/64 independent 64 -> 64 convolutions on channel slices of the same tensors:
+// exactly the layer-1 shape of the BasicBlock nets, so each slice runs in conv_ysum_kernel on
+// strided views (channel extent 64, pixel pitch C) instead of the generic shifted-box kernel
+// (nine boxes per M tile; 774 us per 37 888 instances at 21 % tensor pipe, L2 -> SM bound, ncu
+// r02_resnext50_batch).  w_oihw is the DENSE [C][C][3][3] weight, blk the block index; in / out are
+// the full [b_pad][64][C] tensors.  The output maps are final (no finalize_io_maps).
+int plan_ysum_block(int C, int blk, const float* w_oihw, const float* bias, const __nv_bfloat16* in_hi,
+                    __nv_bfloat16* out_hi, int relu, int64_t b_pad, PlannedConv* out) {
+  PlannedConv pc;
+  memset(&pc.p, 0, sizeof(pc.p));
+  memset(&pc.yp, 0, sizeof(pc.yp));
+  pc.Po = 64;
+  pc.BN = 64;
+  pc.ysum = true;
+  pc.io_final = true;
+  std::vector<float> wb((size_t)64 * 64 * 9);
+  for (int co = 0; co < 64; ++co)
+    for (int ci = 0; ci < 64; ++ci)
+      memcpy(&wb[((size_t)co * 64 + ci) * 9], &w_oihw[((size_t)(blk * 64 + co) * C + blk * 64 + ci) * 9], 9 * sizeof(float));
+  std::vector<uint16_t> B2(576 * 64);
+  pack_ysum_weights(wb.data(), B2.data());
+  CS_CUDA(cudaMalloc(&pc.d_B2, B2.size() * sizeof(uint16_t)));
+  CS_CUDA(cudaMemcpy(pc.d_B2, B2.data(), B2.size() * sizeof(uint16_t), cudaMemcpyHostToDevice));
+  CS_CUDA(cudaMalloc(&pc.d_bias, 64 * sizeof(float)));
+  CS_CUDA(cudaMemcpy(pc.d_bias, bias + blk * 64, 64 * sizeof(float), cudaMemcpyHostToDevice));
+  const __nv_bfloat16* in = in_hi + blk * 64;
+  __nv_bfloat16* o = out_hi + blk * 64;
+  int rc = make_act_map_4d(&pc.yp.a_map, in, 64, 8, 8, b_pad, C, (int64_t)8 * C, (int64_t)64 * C, 8, 8, 2);
+  if (rc == CS_OK)
+    rc = make_act_map_4d(&pc.yp.a_box_map, in, 64, 8, 8, b_pad, C, (int64_t)8 * C, (int64_t)64 * C, 10, 8, 2);
+  pc.yp.cluster = g_ysum_pairs ? g_cluster : 1;
+  if (rc == CS_OK) rc = make_mat_map_2d(&pc.yp.b_map, pc.d_B2, 64, 576, 64, 192 / pc.yp.cluster);
+  if (rc == CS_OK) rc = make_mat_map_2d(&pc.p.out_hi_map, o, 64, b_pad * 64, C, kGemmBM);
+  if (rc != CS_OK) { free_planned(pc); return rc; }
+  pc.yp.bias = pc.d_bias;
+  pc.p.bias = pc.d_bias;
+  pc.p.out_hi = o;
+  pc.p.relu = relu;
+  *out = pc;
+  return CS_OK;
+}
+
 // Builds the TMA views of the residual / output tensors once their pointers are known.
 int finalize_io_maps(PlannedConv& pc, int64_t b_pad) {
   int rc = CS_OK;
+  if (pc.io_final) return CS_OK;
   if (pc.halo) {
     const int W = pc.halo_W, C = pc.p.n_total;
     if (pc.p.res_hi && (rc = make_act_map_halo(&pc.hp.res_hi_map, pc.p.res_hi, C, W, W, b_pad, 0))) return rc;
@@ -594,9 +641,20 @@ int build_tc_plan(cs_model* m, int tile, int64_t max_batch, void* ws, int64_t ws
       rc = plan_conv(g1, c1.w.data(), c1.b.data(), nullptr, nullptr, nullptr, plan->x_hi[xi], nullptr, bp, &p);
       if (rc != CS_OK) return rc;
       if ((rc = push(p, nullptr, nullptr, plan->mid[0], nullptr, 1)) != CS_OK) return rc;
-      rc = plan_conv(g2, c2.w.data(), c2.b.data(), nullptr, nullptr, nullptr, plan->mid[0], nullptr, bp, &p);
-      if (rc != CS_OK) return rc;
-      if ((rc = push(p, nullptr, nullptr, plan->mid[1], nullptr, 1)) != CS_OK) return rc;
+      const int cin_g = b.width / c2.groups;
+      if (c2.groups > 1 && H == 8 && W == 8 && b.stride == 1 && b.width % 64 == 0 && 64 % cin_g == 0 &&
+          !g_disable_ysum && !g_no_group_ysum) {
+        // grouped 3x3 of ResNeXt layer 1: one y-sum conv per 64-channel block
+        for (int blk = 0; blk < b.width / 64; ++blk) {
+          rc = plan_ysum_block(b.width, blk, c2.w.data(), c2.b.data(), plan->mid[0], plan->mid[1], 1, bp, &p);
+          if (rc != CS_OK) return rc;
+          plan->layers.push_back(p);
+        }
+      } else {
+        rc = plan_conv(g2, c2.w.data(), c2.b.data(), nullptr, nullptr, nullptr, plan->mid[0], nullptr, bp, &p);
+        if (rc != CS_OK) return rc;
+        if ((rc = push(p, nullptr, nullptr, plan->mid[1], nullptr, 1)) != CS_OK) return rc;
+      }
       if (b.ds >= 0) {   // downsample as its own launch into y, then conv3 adds y in place
         const ConvW& cd = m->convs[b.ds];
         ConvGeom gd{H, W, C, Ho, Wo, b.cout, 1, b.stride, 0, 1};
