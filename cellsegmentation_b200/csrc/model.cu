@@ -51,6 +51,12 @@ const int g_dense_max_po = env_is("CELLSEG_DENSE_PO", "4") ? 4 : (env_is("CELLSE
 // N tile of the dense form: 256 (two 4x4-stage pixels per tile) by default; CELLSEG_DENSE_BN=128
 // gives every output pixel of the 4x4 stage its own tile (exactly the in-bounds taps, smaller MMAs).
 const int g_dense_bn = env_is("CELLSEG_DENSE_BN", "128") ? 128 : 256;
+// Grouped 3x3 convs on 4x4 maps (ResNeXt layer 2) also take the dense form, with one (pixel,
+// 64-channel block) per 64-wide N tile: only the in-bounds taps of the tile's own channel block
+// are visited (1.64 M instead of 2.36 M MACs per instance and conv) on 128-instance M tiles;
+// ResNeXt-50 2.95 -> 3.06 M instances/s (gpurun r2n).  CELLSEG_DENSE_GROUP_PO=4 restores the
+// shifted-box form.
+const int g_dense_group_po = env_is("CELLSEG_DENSE_GROUP_PO", "4") ? 4 : 16;
 // Instances per stem + layer-1 sub-batch; 0 (default): whole forward batches.  4 736 = 16 y-sum M
 // tiles per CTA: x, mid and y of a sub-batch are 3 x 39 MB and stay in L2.  Measured (gpurun r2j,
 // one box): 0 -> 10.2 M instances/s at 1 390 MHz; 9 472 -> 10.08 M; 4 736 -> 9.93 M at 1 515 MHz;
@@ -160,9 +166,8 @@ int plan_conv(const ConvGeom& g, const float* w_oihw, const float* bias, const C
   int rc;
   const int kk = g.k * g.k;
 
-  // (grouped 3x3 convs keep the shifted-box form at 4x4: with 64-wide group-aligned N tiles it
-  // visits one K block per tap, the dense form's 256-wide tiles would visit four)
-  if (g.k == 1 || Po > (g.groups > 1 ? 4 : g_dense_max_po)) {
+  // (grouped 3x3 convs: dense form up to g_dense_group_po output pixels, 64-wide N tiles)
+  if (g.k == 1 || Po > (g.groups > 1 ? g_dense_group_po : g_dense_max_po)) {
     // ---- rows = (instance, oy, ox): shifted boxes (3x3) or pointwise (1x1)
     const bool pointwise = g.k == 1;
     if (!pointwise && (kGemmBM % Po != 0 || g.k != 3 || g.pad != 1)) {
@@ -260,6 +265,7 @@ int plan_conv(const ConvGeom& g, const float* w_oihw, const float* bias, const C
     pc.dense = true;
     const int N_total = Po * g.Cout;
     pc.BN = (N_total % 256 == 0 && (g_dense_bn == 256 || g.Cout >= 256)) ? 256 : (N_total % 128 == 0 ? 128 : 64);
+    if (g.groups > 1 && Po > 4) pc.BN = 64;     // one (pixel, 64-channel block) per N tile
     pc.p.units_per_mtile = kGemmBM;
     pc.p.n_total = N_total;
     const int64_t K_main = (int64_t)Pi * g.Cin;

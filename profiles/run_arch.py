@@ -20,4 +20,12 @@ clf = ops.TileClassifier(arch, c, fw, fb, device=dev)
 for _ in range(2):
     p = clf.forward_tiles(bags, 32, interval, inst_count=max_batch, precision="bf16", max_batch=max_batch)
 torch.cuda.synchronize()
-print(arch, "interval", interval, "instances", max_batch, "launches per batch", clf.last_launch_count)
+a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+a.record()
+for _ in range(5):
+    p = clf.forward_tiles(bags, 32, interval, inst_count=max_batch, precision="bf16", max_batch=max_batch)
+b.record()
+torch.cuda.synchronize()
+ms = a.elapsed_time(b) / 5
+print(arch, "interval", interval, "instances", max_batch, "launches per batch", clf.last_launch_count,
+      "| %.3f ms per batch, %.4g instances/s" % (ms, max_batch / ms * 1e3))

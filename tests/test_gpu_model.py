@@ -213,6 +213,8 @@ ALT_PATHS = [
     ({"CELLSEG_DENSE_PO": "64"}, False), ({"CELLSEG_L1_SUB": "4736"}, True),
     ({"CELLSEG_RESIDUAL": "hilo", "CELLSEG_YSUM": "0"}, False), ({"CELLSEG_RESIDUAL": "hilo"}, False),
 ]
+# Bottleneck / ResNeXt switches: grouped convs back in the generic shifted-box kernel
+ALT_PATHS_RX = [{"CELLSEG_GROUP_YSUM": "0"}, {"CELLSEG_DENSE_GROUP_PO": "4"}]
 
 
 def test_alternative_kernel_paths_subprocess(cuda):
@@ -229,6 +231,11 @@ def test_alternative_kernel_paths_subprocess(cuda):
     light = "conv_matches or (within_2e2 and resnet34) or tile16"
     heavy = light + " or many_iterations or (bench_scale and resnet34)"
     procs = []
+    for env in ALT_PATHS_RX:
+        procs.append((env, subprocess.Popen(
+            [sys.executable, "-m", "pytest", here, "-x", "-q", "-p", "no:cacheprovider", "-k",
+             "conv_matches or (within_2e2 and resnext)"],
+            env=dict(os.environ, OMP_NUM_THREADS="4", **env), stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)))
     for env, is_heavy in ALT_PATHS:
         procs.append((env, subprocess.Popen(
             [sys.executable, "-m", "pytest", here, "-x", "-q", "-p", "no:cacheprovider", "-k", heavy if is_heavy else light],
