@@ -26,6 +26,8 @@
 #include <stdlib.h>
 #include <string.h>
 
+#include <type_traits>
+
 #include "fwd.cuh"
 #include "gemm_epilogue.cuh"
 
@@ -224,6 +226,23 @@ conv_ysum_kernel(const __grid_constant__ YsumParams p) {
     }
     const bool rh = p.res_hi != nullptr, rl = p.res_lo != nullptr;
     const bool oh = p.out_hi != nullptr, ol = p.out_lo != nullptr;
+    // Everything that does not depend on the tile is worked out once: the epilogue issues ~440
+    // instructions per tile and warp, 16 warps deep -- more issue slots than the tile's 1 152
+    // cycles of MMA offer (ncu r02: 49-58 % tensor pipe), and 160 of them were address arithmetic.
+    uint32_t off[4][NI];                       // byte offset of (row yy, channel group i) in a staging tile
+#pragma unroll
+    for (int yy = 0; yy < 4; ++yy)
+#pragma unroll
+      for (int i = 0; i < NI; ++i)
+        off[yy][i] = (uint32_t)(quad * 32 + yy * 8 + g) * 128u + 4u * t + ((((uint32_t)(cg * NI + i)) ^ (uint32_t)g) << 4);
+    constexpr int kXw = 64 * NI;               // floats per warp slot (kXchBytes covers 2 x EW slots)
+    float* const xch = reinterpret_cast<float*>(base_ptr + kOffXch);
+    float* const xw0 = xch + (warp - 2) * kXw + lane * 2 * NI;
+    const float* const xr0 = xch + partner * kXw + lane * 2 * NI;
+    float2 bias2[NI];
+#pragma unroll
+    for (int i = 0; i < NI; ++i) bias2[i] = make_float2(bias_r[i][0], bias_r[i][1]);
+    const bool fast_cfg = !rl && !ol && oh && p.relu != 0 && p.out_f32 == nullptr;
     int acc = 0;
     uint32_t acc_phase = 0;
     int64_t q = 0;
@@ -250,63 +269,75 @@ conv_ysum_kernel(const __grid_constant__ YsumParams p) {
       }
       acc ^= 1;
       if (acc == 0) acc_phase ^= 1u;
-      auto D = [&](int dy, int yy, int i, int e) -> float {
-        return __uint_as_float(R[dy][yy >> 1][4 * i + 2 * (yy & 1) + e]);
+      // the channel pair (e = 0, 1) of one (tap row, image row, channel group): packed fp32 adds
+      auto D2 = [&](int dy, int yy, int i) -> float2 {
+        return make_float2(__uint_as_float(R[dy][yy >> 1][4 * i + 2 * (yy & 1)]),
+                           __uint_as_float(R[dy][yy >> 1][4 * i + 2 * (yy & 1) + 1]));
       };
       // rows 3 | 4 of an image live in different lane quarters: exchange them (fp32, 2*NI per thread)
-      constexpr int kXw = 64 * NI;               // floats per warp slot (kXchBytes covers 2 x EW slots)
-      float* xw = reinterpret_cast<float*>(base_ptr + kOffXch) + ((q & 1) * EW + (warp - 2)) * kXw + lane * 2 * NI;
-      const float* xr = reinterpret_cast<const float*>(base_ptr + kOffXch) + ((q & 1) * EW + partner) * kXw + lane * 2 * NI;
+      const int par = (int)(q & 1);
+      float* xw = xw0 + par * EW * kXw;
+      const float* xr = xr0 + par * EW * kXw;
 #pragma unroll
       for (int i = 0; i < NI; i += 2) {
         // D_0 of row 3 feeds row 4 of the lower quarter; D_2 of row 4 feeds row 3 of the upper one
-        reinterpret_cast<float4*>(xw)[i >> 1] =
-            upper ? make_float4(D(0, 3, i, 0), D(0, 3, i, 1), D(0, 3, i + 1, 0), D(0, 3, i + 1, 1))
-                  : make_float4(D(2, 0, i, 0), D(2, 0, i, 1), D(2, 0, i + 1, 0), D(2, 0, i + 1, 1));
+        const float2 a = upper ? D2(0, 3, i) : D2(2, 0, i), b = upper ? D2(0, 3, i + 1) : D2(2, 0, i + 1);
+        reinterpret_cast<float4*>(xw)[i >> 1] = make_float4(a.x, a.y, b.x, b.y);
       }
       named_bar(pair_bar, 64);
-      float imp[2 * NI];
+      float2 imp[NI];
 #pragma unroll
       for (int i = 0; i < NI; i += 2) {
         const float4 v4 = reinterpret_cast<const float4*>(xr)[i >> 1];
-        imp[2 * i] = v4.x; imp[2 * i + 1] = v4.y; imp[2 * i + 2] = v4.z; imp[2 * i + 3] = v4.w;
+        imp[i] = make_float2(v4.x, v4.y);
+        imp[i + 1] = make_float2(v4.z, v4.w);
       }
 
-      const int s = (int)(q & 1);
-      mbar_wait(ebars.res_full[s], (uint32_t)((q >> 1) & 1));
-      const uint32_t stg = staging + s * set_bytes;
+      mbar_wait(ebars.res_full[par], (uint32_t)((q >> 1) & 1));
+      const uint32_t stg = staging + par * set_bytes;
+      const float2 zero2 = make_float2(0.f, 0.f);
+      // kFast: the two configurations the forward runs (bf16 stream, ReLU, with or without a
+      // residual) with the flags as compile-time constants -- tested per element, the five
+      // runtime flags cost ~10 instructions each time they were re-materialised
+      auto emit = [&](auto rh_c, auto fast_c) {
+        constexpr bool kRH = decltype(rh_c)::value, kFast = decltype(fast_c)::value;
 #pragma unroll
-      for (int yy = 0; yy < 4; ++yy) {
-        const int row = quad * 32 + yy * 8 + g;          // row of the 128-row tile; row & 7 == g
-        const uint32_t row_addr = stg + (uint32_t)row * 128u + 4u * t;
+        for (int yy = 0; yy < 4; ++yy) {
 #pragma unroll
-        for (int i = 0; i < NI; ++i) {
-          float v[2];
-#pragma unroll
-          for (int e = 0; e < 2; ++e) {
-            float above, below;                           // D_0 of row y-1, D_2 of row y+1
-            if (yy > 0) above = D(0, yy - 1, i, e);
-            else above = upper ? 0.f : imp[2 * i + e];
-            if (yy < 3) below = D(2, yy + 1, i, e);
-            else below = upper ? imp[2 * i + e] : 0.f;
-            v[e] = above + D(1, yy, i, e) + below + bias_r[i][e];
+          for (int i = 0; i < NI; ++i) {
+            // D_0 of row y-1 + D_1 of row y + D_2 of row y+1 + bias, in that order
+            const float2 above = yy > 0 ? D2(0, yy - 1, i) : (upper ? zero2 : imp[i]);
+            const float2 below = yy < 3 ? D2(2, yy + 1, i) : (upper ? imp[i] : zero2);
+            float2 v = __fadd2_rn(__fadd2_rn(__fadd2_rn(above, D2(1, yy, i)), below), bias2[i]);
+            const uint32_t addr = stg + off[yy][i];
+            if (kFast) {
+              if (kRH) { const uint32_t r2 = lds32(addr); v = __fadd2_rn(v, make_float2(bf16_lo_f(r2), bf16_hi_f(r2))); }
+              sts32(addr, pack_bf16x2(fmaxf(v.x, 0.f), fmaxf(v.y, 0.f)));
+            } else {
+              if (rh) { const uint32_t r2 = lds32(addr); v = __fadd2_rn(v, make_float2(bf16_lo_f(r2), bf16_hi_f(r2))); }
+              if (rl) { const uint32_t r2 = lds32(addr + kEpiTileBytes); v = __fadd2_rn(v, make_float2(bf16_lo_f(r2), bf16_hi_f(r2))); }
+              if (p.relu) { v.x = fmaxf(v.x, 0.f); v.y = fmaxf(v.y, 0.f); }
+              if (p.out_f32 != nullptr) {
+                const int row = quad * 32 + yy * 8 + g;      // row of the 128-row tile
+                const int64_t grow = (int64_t)m_tile * 128 + row;
+                if (grow < p.n_inst * 64)
+                  *reinterpret_cast<float2*>(p.out_f32 + grow * 64 + cg * CW + 8 * i + 2 * t) = v;
+              }
+              const uint32_t hi = pack_bf16x2(v.x, v.y);
+              if (oh) sts32(addr, hi);
+              if (ol) sts32(addr + kEpiTileBytes, pack_bf16x2(v.x - bf16_lo_f(hi), v.y - bf16_hi_f(hi)));
+            }
           }
-          const uint32_t addr = row_addr + ((((uint32_t)(cg * NI + i)) ^ (uint32_t)g) << 4);
-          if (rh) { const uint32_t r2 = lds32(addr); v[0] += bf16_lo_f(r2); v[1] += bf16_hi_f(r2); }
-          if (rl) { const uint32_t r2 = lds32(addr + kEpiTileBytes); v[0] += bf16_lo_f(r2); v[1] += bf16_hi_f(r2); }
-          if (p.relu) { v[0] = fmaxf(v[0], 0.f); v[1] = fmaxf(v[1], 0.f); }
-          if (p.out_f32 != nullptr) {
-            const int64_t grow = (int64_t)m_tile * 128 + row;
-            if (grow < p.n_inst * 64)
-              *reinterpret_cast<float2*>(p.out_f32 + grow * 64 + cg * CW + 8 * i + 2 * t) = make_float2(v[0], v[1]);
-          }
-          const uint32_t hi = pack_bf16x2(v[0], v[1]);
-          if (oh) sts32(addr, hi);
-          if (ol) sts32(addr + kEpiTileBytes, pack_bf16x2(v[0] - bf16_lo_f(hi), v[1] - bf16_hi_f(hi)));
         }
+      };
+      if (fast_cfg) {
+        if (rh) emit(std::true_type{}, std::true_type{});
+        else emit(std::false_type{}, std::true_type{});
+      } else {
+        emit(std::false_type{}, std::false_type{});
       }
       fence_async_shared();
-      mbar_arrive(ebars.out_ready[s]);
+      mbar_arrive(ebars.out_ready[par]);
     }
   } else if (lane == 0) {
     pdl_wait();
