@@ -27,6 +27,7 @@ SOURCES = [
     "fwd_tc.cu",
     "conv_gemm.cu",
     "stem_win.cu",
+    "stem_ts.cu",
     "conv_halo.cu", "conv_ysum.cu",
     "model.cu",
 ]

@@ -31,7 +31,7 @@ int launch_head_fp32(const float* x4, int64_t n, int P, int C, const float* fc_w
                      cudaStream_t st);
 
 // ---------------------------------------------------------------------------
-// bf16 tcgen05 path (stem_win.cu, conv_ysum.cu, conv_halo.cu, conv_gemm.cu, fwd_tc.cu)
+// bf16 tcgen05 path (stem_ts.cu, stem_win.cu, conv_ysum.cu, conv_halo.cu, conv_gemm.cu, fwd_tc.cu)
 // ---------------------------------------------------------------------------
 constexpr int kGemmBM = 128;       // UMMA M (rows per CTA tile)
 constexpr int kGemmBK = 64;        // bf16 elements per K step = one 128-byte swizzle row
@@ -171,6 +171,11 @@ int stem_win_weight_bytes();
 void pack_stem_weights_win(const float* w_oihw, uint16_t* out);
 int launch_stem_win(const StemArgs& a, const void* w_packed_dev, const uint16_t* lut_bf16_dev,
                     cudaStream_t st);
+// Weights-stationary stem (stem_ts.cu), tile 32 only, the default: the filters live in tensor
+// memory as the A operand, the staged image is the B operand (half the shared-memory operand reads).
+int stem_ts_weight_bytes();
+void pack_stem_weights_ts(const float* w_oihw, uint16_t* out);
+int launch_stem_ts(const StemArgs& a, const void* w_packed_dev, cudaStream_t st);
 
 int launch_head_bf16(const __nv_bfloat16* x_hi, const __nv_bfloat16* x_lo, int64_t n, int P,
                      int C, const float* fc_w, const float* fc_b, float* prob_out,

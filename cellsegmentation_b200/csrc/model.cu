@@ -66,6 +66,10 @@ const int64_t g_l1_sub = []() -> int64_t {
   const char* e = getenv("CELLSEG_L1_SUB");
   return e != nullptr ? atoll(e) : 0;
 }();
+// Stem form for tile 32.  Default: weights-stationary (stem_ts.cu: filters in tensor memory, the
+// staged image as the shared-memory operand).  CELLSEG_STEM=win restores the window form with
+// both operands in shared memory (stem_win.cu).
+const bool g_stem_win = env_is("CELLSEG_STEM", "win");
 // Residual stream: bf16 by default.  CELLSEG_RESIDUAL=hilo carries a second bf16 tensor
 // lo = value - bf16(value) between blocks (~16 mantissa bits); measured max|dp| moves by < 1.5e-3
 // (ResNet-34 0.0101 -> 0.0098) while the block epilogues move twice the bytes (-11 % throughput).
@@ -515,10 +519,12 @@ struct TcPlan {
   const __nv_bfloat16* x4_lo = nullptr;
   int P4 = 1, C4 = 512;
   uint16_t* d_stem_w2 = nullptr; // window-form stem weights (stem_win.cu)
+  uint16_t* d_stem_w3 = nullptr; // weights-stationary stem weights (stem_ts.cu)
   uint16_t* d_lut = nullptr;     // [3][256] bf16 normalisation LUT
   ~TcPlan() {
     for (auto& l : layers) free_planned(l);
     if (d_stem_w2) cudaFree(d_stem_w2);
+    if (d_stem_w3) cudaFree(d_stem_w3);
     if (d_lut) cudaFree(d_lut);
   }
 };
@@ -695,6 +701,10 @@ int build_tc_plan(cs_model* m, int tile, int64_t max_batch, void* ws, int64_t ws
     pack_stem_weights_win(m->convs[0].w.data(), sw2.data());
     CS_CUDA(cudaMalloc(&plan->d_stem_w2, sw2.size() * 2));
     CS_CUDA(cudaMemcpy(plan->d_stem_w2, sw2.data(), sw2.size() * 2, cudaMemcpyHostToDevice));
+    std::vector<uint16_t> sw3(stem_ts_weight_bytes() / 2);
+    pack_stem_weights_ts(m->convs[0].w.data(), sw3.data());
+    CS_CUDA(cudaMalloc(&plan->d_stem_w3, sw3.size() * 2));
+    CS_CUDA(cudaMemcpy(plan->d_stem_w3, sw3.data(), sw3.size() * 2, cudaMemcpyHostToDevice));
     CS_CUDA(cudaMalloc(&plan->d_lut, lut.size() * 2));
     CS_CUDA(cudaMemcpy(plan->d_lut, lut.data(), lut.size() * 2, cudaMemcpyHostToDevice));
   }
@@ -730,7 +740,7 @@ int run_tc_batch(cs_model* m, const StemArgs& stem_in, int64_t count, float* pro
     if (sa.x) ss.x = sa.x + i0 * 3 * pl.tile * pl.tile;
     ss.out_hi = sa.out_hi + i0 * (int64_t)(pl.tile / 4) * (pl.tile / 4) * 64;
     if (pl.tile == 32)
-      rc = launch_stem_win(ss, pl.d_stem_w2, pl.d_lut, st);
+      rc = g_stem_win ? launch_stem_win(ss, pl.d_stem_w2, pl.d_lut, st) : launch_stem_ts(ss, pl.d_stem_w3, st);
     else
       rc = launch_stem_bf16(ss, st);
     if (rc != CS_OK) return rc;
@@ -1209,6 +1219,48 @@ int cs_debug_conv_bf16(const void* in_hi, int64_t n, int Hi, int Wi, int Cin, in
   rc = launch_planned(pc, n, out_f32, as_stream(stream), reverse != 0);
   cudaError_t e = cudaStreamSynchronize(as_stream(stream));
   free_planned(pc);
+  if (rc != CS_OK) return rc;
+  CS_CUDA(e);
+  return CS_OK;
+}
+
+// The tile-32 tensor-core stem in isolation (default form, or stem_win.cu with CELLSEG_STEM=win):
+// img u8 [n_bags][H][W][3] (device), folded conv1 weights [64][3][7][7] / bias [64] fp32 (host)
+// -> out_bf16 [inst_count][8*8][64] (device) = maxpool3x3/2(relu(conv7x7/2(normalise(tile)) + bias)).
+int cs_debug_stem_bf16(const uint8_t* img, int n_bags, int H, int W, int interval, int64_t inst_begin,
+                       int64_t inst_count, const float* w_host, const float* bias_host, void* out_bf16,
+                       void* stream) {
+  CS_REQUIRE(img && w_host && bias_host && out_bf16, "cs_debug_stem_bf16: NULL pointer");
+  CS_REQUIRE(n_bags > 0 && H >= 32 && W >= 32 && interval > 0 && inst_count > 0 && inst_begin >= 0,
+             "cs_debug_stem_bf16: bad geometry");
+  int rc = cs_check_device();
+  if (rc != CS_OK) return rc;
+  const int gh = cs_grid_count(H, 32, interval), gw = cs_grid_count(W, 32, interval);
+  CS_REQUIRE(inst_begin + inst_count <= (int64_t)n_bags * gh * gw, "cs_debug_stem_bf16: instance range");
+  const int nw = g_stem_win ? stem_win_weight_bytes() : stem_ts_weight_bytes();
+  std::vector<uint16_t> packed(nw / 2);
+  if (g_stem_win) pack_stem_weights_win(w_host, packed.data());
+  else pack_stem_weights_ts(w_host, packed.data());
+  uint16_t* d_w = nullptr;
+  float* d_b = nullptr;
+  CS_CUDA(cudaMalloc(&d_w, nw));
+  CS_CUDA(cudaMalloc(&d_b, 64 * sizeof(float)));
+  CS_CUDA(cudaMemcpy(d_w, packed.data(), nw, cudaMemcpyHostToDevice));
+  CS_CUDA(cudaMemcpy(d_b, bias_host, 64 * sizeof(float), cudaMemcpyHostToDevice));
+  StemArgs sa{};
+  sa.img = img; sa.H = H; sa.W = W; sa.tile = 32; sa.interval = interval; sa.grid_w = gw;
+  sa.tiles_per_bag = (int64_t)gh * gw;
+  sa.inst_begin = inst_begin;
+  sa.x = nullptr;
+  sa.count = inst_count;
+  sa.w = nullptr;
+  sa.bias = d_b;
+  sa.out_hi = reinterpret_cast<__nv_bfloat16*>(out_bf16);
+  sa.out_lo = nullptr;
+  rc = g_stem_win ? launch_stem_win(sa, d_w, nullptr, as_stream(stream)) : launch_stem_ts(sa, d_w, as_stream(stream));
+  cudaError_t e = cudaStreamSynchronize(as_stream(stream));
+  cudaFree(d_w);
+  cudaFree(d_b);
   if (rc != CS_OK) return rc;
   CS_CUDA(e);
   return CS_OK;

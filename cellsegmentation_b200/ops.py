@@ -417,6 +417,22 @@ def debug_gemm_bf16(a, b, bias, bn):
     return out
 
 
+def debug_stem_bf16(images, w, bias, interval, inst_begin=0, inst_count=None):
+    """images u8 [B,H,W,3] (cuda), folded conv1 w f32 [64,3,7,7] / bias f32 [64] (cpu) -> bf16
+    [count,8,8,64]: the tile-32 tensor-core stem (normalise, conv 7x7/2, bias, ReLU, maxpool 3x3/2)."""
+    _req_cuda(images, "images", torch.uint8)
+    B, H, W, _ = images.shape
+    T = grid_count(H, 32, interval) * grid_count(W, 32, interval)
+    if inst_count is None:
+        inst_count = B * T - inst_begin
+    wn = np.ascontiguousarray(w.detach().cpu().numpy(), dtype=np.float32)
+    bn_ = np.ascontiguousarray(bias.detach().cpu().numpy(), dtype=np.float32)
+    out = torch.zeros((inst_count, 8, 8, 64), dtype=torch.bfloat16, device=images.device)
+    check(lib().cs_debug_stem_bf16(ptr(images), B, H, W, interval, inst_begin, inst_count, wn.ctypes.data,
+                                   bn_.ctypes.data, ptr(out), cur_stream()), "cs_debug_stem_bf16")
+    return out
+
+
 def debug_conv_bf16(x_hi, w, bias, stride, groups=1, reverse=False):
     """x_hi bf16 [n,H,W,Cin] (cuda), w f32 [Cout,Cin/groups,k,k] (cpu), bias f32 [Cout] (cpu)
     -> f32 [n,Ho,Wo,Cout] through the production planner + tcgen05 kernels (k = 1 or 3)."""

@@ -321,6 +321,14 @@ int cs_debug_conv_bf16(const void* in_hi, int64_t n, int Hi, int Wi, int Cin, in
                        int stride, int groups, const float* w_host, const float* bias_host,
                        int reverse, float* out_f32, void* stream);
 
+/* The tile-32 tensor-core stem in isolation: img u8 [n_bags][H][W][3] (device), folded conv1
+ * weights [64][3][7][7] and bias [64] fp32 (host) -> out_bf16 [inst_count][64 px][64 ch] (device)
+ * = maxpool3x3/2(relu(conv7x7/2(normalise(tile)) + bias)) of instances inst_begin.. of the
+ * uniform grid (model/resnet.py:236-239 on dataset/dataset.py:409-416 tiles).  Synchronises. */
+int cs_debug_stem_bf16(const uint8_t* img, int n_bags, int H, int W, int interval, int64_t inst_begin,
+                       int64_t inst_count, const float* w_host, const float* bias_host, void* out_bf16,
+                       void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -100,6 +100,27 @@ def test_tcgen05_conv_many_iterations_per_cta(cuda, H, Cin, Cout, k, stride, gro
     assert (got[n - 64:].cpu().double() - want).abs().max().item() < 2e-3
 
 
+@pytest.mark.parametrize("interval,n_bags,begin", [(20, 2, 0), (10, 3, 0), (7, 2, 37)])
+def test_tcgen05_stem_matches_conv_pool(cuda, interval, n_bags, begin):
+    """The tile-32 stem kernel alone (normalise, conv 7x7/2 + bias, ReLU, maxpool 3x3/2) against
+    fp64 conv2d on the same bf16-rounded inputs and weights (model/resnet.py:236-239)."""
+    ops = _ops()
+    bags = synth.make_bags(n_bags + 1, seed=5)[1:]
+    x = torch.from_numpy(otiles.unfold(list(bags), interval, 32))[begin:]
+    g = torch.Generator().manual_seed(interval)
+    w = _bf16_round(torch.randn(64, 3, 7, 7, generator=g) / 147 ** 0.5)
+    b = torch.randn(64, generator=g) * 0.5
+    images = torch.from_numpy(np.stack(bags)).to(cuda)
+    got = ops.debug_stem_bf16(images, w, b, interval, inst_begin=begin).float().cpu()      # [n, 8, 8, 64]
+    assert got.shape[0] == x.shape[0]
+    conv = F.conv2d(_bf16_round(x).double(), w.double(), b.double(), stride=2, padding=3)
+    want = F.max_pool2d(F.relu(_bf16_round(conv.float())), 3, 2, 1).permute(0, 2, 3, 1)
+    diff = (got - want).abs()
+    # fp32 accumulation order can move a sum across a bf16 rounding boundary: one ulp at most
+    assert (diff <= 2.0 ** -7 * want.abs() + 1e-6).all(), diff.max().item()
+    assert (diff == 0).float().mean().item() > 0.99
+
+
 def _setup(arch, n_bags=2, interval=20, tile=32, seed=3):
     bags = synth.make_bags(n_bags + 1, seed=11)[1:]
     x = torch.from_numpy(otiles.unfold(list(bags), interval, tile))
@@ -207,7 +228,7 @@ def test_forward_tile16(cuda, arch):
 
 ALT_PATHS = [
     # (environment, also run the many-iteration and at-scale cases)
-    ({"CELLSEG_YSUM": "0"}, False), ({"CELLSEG_YSUM_PAIRS": "0"}, True), ({"CELLSEG_CLUSTER": "1"}, True),
+    ({"CELLSEG_STEM": "win"}, True), ({"CELLSEG_YSUM": "0"}, False), ({"CELLSEG_YSUM_PAIRS": "0"}, True), ({"CELLSEG_CLUSTER": "1"}, True),
     ({"CELLSEG_YSUM_EPI": "8"}, False), ({"CELLSEG_YSUM_BOX": "0"}, True), ({"CELLSEG_DENSE_PO": "4"}, True),
     ({"CELLSEG_DENSE_PO": "4", "CELLSEG_HALO_DS": "0"}, False), ({"CELLSEG_DENSE_BN": "128"}, False),
     ({"CELLSEG_DENSE_PO": "64"}, False), ({"CELLSEG_L1_SUB": "4736"}, True),
@@ -219,7 +240,7 @@ ALT_PATHS_RX = [{"CELLSEG_GROUP_YSUM": "0"}, {"CELLSEG_DENSE_GROUP_PO": "4"}]
 
 def test_alternative_kernel_paths_subprocess(cuda):
     """The switches are read when the library loads: run the conv-form and ResNet-34 parity tests in
-    child processes for every alternative kernel path (halo layer 1, single-CTA y-sum MMAs, single-CTA
+    child processes for every alternative kernel path (window-form stem, halo layer 1, single-CTA y-sum MMAs, single-CTA
     MMAs everywhere, 8-warp y-sum epilogue, three-box y-sum, halo kernel for layer 2 with and without
     the fused shortcut, 128-wide dense tiles, dense 8x8 stage, L2-resident layer-1 sub-batches, hi/lo
     residual stream); the paths that change how a forward batch is walked also run the
@@ -228,7 +249,7 @@ def test_alternative_kernel_paths_subprocess(cuda):
     import subprocess
     import sys
     here = os.path.abspath(__file__)
-    light = "conv_matches or (within_2e2 and resnet34) or tile16"
+    light = "conv_matches or stem_matches or (within_2e2 and resnet34) or tile16"
     heavy = light + " or many_iterations or (bench_scale and resnet34)"
     procs = []
     for env in ALT_PATHS_RX:
