@@ -79,6 +79,8 @@ _PROTOS = {
                                    c_void_p, c_void_p]),
     "cs_debug_stem_bf16": (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_int64, c_int64, c_void_p, c_void_p,
                                    c_void_p, c_void_p]),
+    "cs_debug_basic_block_bf16": (c_int, [c_void_p, c_int64, c_void_p, c_void_p, c_void_p, c_void_p, c_int,
+                                          c_void_p, POINTER(c_int), c_void_p]),
     "cs_debug_conv_bf16": (c_int, [c_void_p, c_int64, c_int, c_int, c_int, c_int, c_int, c_int, c_int,
                                    c_void_p, c_void_p, c_int, c_void_p, c_void_p]),
 }

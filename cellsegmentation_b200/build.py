@@ -28,7 +28,7 @@ SOURCES = [
     "conv_gemm.cu",
     "stem_win.cu",
     "stem_ts.cu",
-    "conv_halo.cu", "conv_ysum.cu",
+    "conv_halo.cu", "conv_ysum.cu", "conv_block.cu",
     "model.cu",
 ]
 

@@ -145,6 +145,19 @@ struct YsumParams {
   int relu;
   CUtensorMap res_hi_map, res_lo_map, out_hi_map, out_lo_map;   // [rows][64], box {64, 128}
 };
+// A whole layer-1 BasicBlock in one kernel (conv_block.cu): both convs in y-sum form, the
+// intermediate tensor in shared memory, the residual taken from conv1's operand box.  CTA pairs.
+struct YsumBlockParams {
+  CUtensorMap x_box_map;        // block input {C, W, H, T}, box {64, 10, 8, 2} (fetched at x = -1)
+  CUtensorMap b1_map, b2_map;   // [3*192][64] from pack_ysum_weights, box {64, 96}
+  CUtensorMap out_map;          // [rows][64], box {64, 128}
+  int num_m_tiles;              // ceil(instances / 2) of this launch
+  int tile_base;                // first M tile of this launch; even
+  int reverse;
+  const float* bias1;
+  const float* bias2;
+};
+int launch_ysum_block(const YsumBlockParams& p, cudaStream_t st);
 bool ysum_supported(int W, int Cin, int Cout);
 void pack_ysum_weights(const float* w_oihw, uint16_t* out /* [576 * 64] */);
 int launch_conv_ysum(const YsumParams& p, cudaStream_t st);

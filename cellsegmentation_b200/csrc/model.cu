@@ -84,6 +84,10 @@ const bool g_disable_ysum = env_is("CELLSEG_YSUM", "0");
 // epilogue the kernel is no longer epilogue-bound and the halved B-operand reads pay, +1.5..2 %
 // on the whole step.  CELLSEG_YSUM_PAIRS=0 keeps single-CTA MMAs.
 const bool g_ysum_pairs = !env_is("CELLSEG_YSUM_PAIRS", "0");
+// Layer-1 BasicBlocks as ONE kernel (conv_block.cu): conv1 -> ReLU -> conv2 -> + x -> ReLU with the
+// intermediate tensor in shared memory (16 instead of 40 KB of HBM traffic per instance and block).
+// Needs CTA pairs and the bf16 residual stream.  CELLSEG_BLOCK_FUSE=0 restores two y-sum launches.
+const bool g_block_fuse = !env_is("CELLSEG_BLOCK_FUSE", "0");
 const bool g_no_group_ysum = env_is("CELLSEG_GROUP_YSUM", "0");   // grouped 8x8 convs back in the generic kernel
 
 struct ConvW {
@@ -115,6 +119,9 @@ struct PlannedConv {
   bool ysum = false;   // layer-1 y-sum kernel (conv_ysum.cu)
   bool io_final = false;  // residual / output maps were built by the planner (plan_ysum_block)
   YsumParams yp;
+  bool block = false;  // this conv1 and the next entry (conv2) run as one fused BasicBlock (conv_block.cu)
+  bool skip = false;   // conv2 of a fused block: launched by the entry before it
+  YsumBlockParams bp;
   uint16_t* d_B2 = nullptr;
   __nv_bfloat16* d_B = nullptr;
   float* d_bias = nullptr;
@@ -471,8 +478,36 @@ int finalize_io_maps(PlannedConv& pc, int64_t b_pad) {
 // Launches one planned convolution for `count` instances (pointers / relu taken from pc.p).
 // inst_base (y-sum layers only): the launch covers instances [inst_base, inst_base + count) of
 // the planned buffers -- a sub-batch of the forward batch.
+// conv1 / conv2 of a BasicBlock without downsample were just pushed: if both run in the y-sum
+// kernel on CTA pairs with the bf16 stream only, the pair becomes one fused launch.
+void fuse_basic_block(std::vector<PlannedConv>& layers, const __nv_bfloat16* x_in) {
+  if (!g_block_fuse || g_l1_sub > 0 || layers.size() < 2) return;
+  PlannedConv& c1 = layers[layers.size() - 2];
+  PlannedConv& c2 = layers[layers.size() - 1];
+  if (!c1.ysum || !c2.ysum || c1.io_final || c2.io_final) return;
+  if (c2.p.res_hi != x_in) return;       // the residual must be the block input
+  if (c1.yp.cluster != 2 || c2.yp.cluster != 2) return;
+  if (c1.p.res_hi || c1.p.res_lo || c1.p.out_lo || !c1.p.relu) return;
+  if (!c2.p.res_hi || c2.p.res_lo || c2.p.out_lo || !c2.p.out_hi || !c2.p.relu) return;
+  c1.bp.x_box_map = c1.yp.a_box_map;     // the block input is conv1's operand and conv2's residual
+  c1.bp.b1_map = c1.yp.b_map;
+  c1.bp.b2_map = c2.yp.b_map;
+  c1.bp.out_map = c2.p.out_hi_map;
+  c1.bp.bias1 = c1.yp.bias;
+  c1.bp.bias2 = c2.yp.bias;
+  c1.block = true;
+  c2.skip = true;
+}
+
 int launch_planned(const PlannedConv& pc, int64_t count, float* out_f32, cudaStream_t st,
                    int reverse = 0, int64_t inst_base = 0) {
+  if (pc.block) {
+    YsumBlockParams bp = pc.bp;
+    bp.reverse = reverse;
+    bp.tile_base = (int)(inst_base / 2);
+    bp.num_m_tiles = (int)ceil_div<int64_t>(count, 2);
+    return launch_ysum_block(bp, st);
+  }
   if (pc.ysum) {
     YsumParams yp = pc.yp;
     yp.res_hi = pc.p.res_hi; yp.res_lo = pc.p.res_lo;
@@ -643,6 +678,7 @@ int build_tc_plan(cs_model* m, int tile, int64_t max_batch, void* ws, int64_t ws
         if (rc != CS_OK) return rc;
         rc = push(p, plan->x_hi[xi], x_has_lo ? plan->x_lo[xi] : nullptr, plan->x_hi[1 - xi],
                   plan->x_lo[1 - xi], 1);
+        if (rc == CS_OK) fuse_basic_block(plan->layers, plan->x_hi[xi]);
       }
       if (rc != CS_OK) return rc;
     } else {
@@ -752,13 +788,15 @@ int run_tc_batch(cs_model* m, const StemArgs& stem_in, int64_t count, float* pro
       m->last_launches++;
     }
   }
-  int li = 0;
+  int li = 0, launches = 0;
   for (PlannedConv& pc : pl.layers) {
-    // snake order: odd layers walk their tiles backwards, starting with the rows the previous
-    // layer wrote last (still L2 resident when a batch's activations exceed L2)
+    // snake order: odd launches walk their tiles backwards, starting with the rows the previous
+    // launch wrote last (still L2 resident when a batch's activations exceed L2)
     ++li;
     if (sub_batched && (size_t)li <= n_ysum) continue;     // done above, per sub-batch
-    rc = launch_planned(pc, count, nullptr, st, g_snake ? (li & 1) : 0);
+    if (pc.skip) continue;                                  // conv2 of a fused BasicBlock
+    ++launches;
+    rc = launch_planned(pc, count, nullptr, st, g_snake ? (launches & 1) : 0);
     if (rc != CS_OK) return rc;
     m->last_launches++;
   }
@@ -1261,6 +1299,55 @@ int cs_debug_stem_bf16(const uint8_t* img, int n_bags, int H, int W, int interva
   cudaError_t e = cudaStreamSynchronize(as_stream(stream));
   cudaFree(d_w);
   cudaFree(d_b);
+  if (rc != CS_OK) return rc;
+  CS_CUDA(e);
+  return CS_OK;
+}
+
+// One layer-1 BasicBlock (8x8 x 64 channels, no downsample) through the production planner:
+// y = relu(conv2(relu(conv1(x) + b1)) + b2 + x), one fused launch (conv_block.cu) or, with
+// CELLSEG_BLOCK_FUSE=0, two y-sum launches (*launches_out says which).  in_hi / out_bf16 bf16
+// [n][64][64] (device), weights [64][64][3][3] / biases [64] fp32 (host).  n % 128 == 0.  Synchronises.
+int cs_debug_basic_block_bf16(const void* in_hi, int64_t n, const float* w1_host, const float* b1_host,
+                              const float* w2_host, const float* b2_host, int reverse, void* out_bf16,
+                              int* launches_out, void* stream) {
+  CS_REQUIRE(in_hi && w1_host && b1_host && w2_host && b2_host && out_bf16, "cs_debug_basic_block_bf16: NULL pointer");
+  CS_REQUIRE(n > 0 && n % kGemmBM == 0, "cs_debug_basic_block_bf16: n must be a positive multiple of 128");
+  int rc = cs_check_device();
+  if (rc != CS_OK) return rc;
+  const __nv_bfloat16* x = reinterpret_cast<const __nv_bfloat16*>(in_hi);
+  __nv_bfloat16* mid = nullptr;
+  CS_CUDA(cudaMalloc(&mid, (size_t)n * 64 * 64 * sizeof(__nv_bfloat16)));
+  ConvGeom g{8, 8, 64, 8, 8, 64, 3, 1, 1, 1};
+  std::vector<PlannedConv> layers(2);
+  rc = plan_conv(g, w1_host, b1_host, nullptr, nullptr, nullptr, x, nullptr, n, &layers[0]);
+  if (rc == CS_OK) {
+    layers[0].p.res_hi = nullptr; layers[0].p.res_lo = nullptr; layers[0].p.out_hi = mid;
+    layers[0].p.out_lo = nullptr; layers[0].p.relu = 1;
+    rc = finalize_io_maps(layers[0], n);
+  }
+  if (rc == CS_OK) rc = plan_conv(g, w2_host, b2_host, nullptr, nullptr, nullptr, mid, nullptr, n, &layers[1]);
+  if (rc == CS_OK) {
+    layers[1].p.res_hi = x; layers[1].p.res_lo = nullptr;
+    layers[1].p.out_hi = reinterpret_cast<__nv_bfloat16*>(out_bf16);
+    layers[1].p.out_lo = nullptr; layers[1].p.relu = 1;
+    rc = finalize_io_maps(layers[1], n);
+  }
+  if (rc == CS_OK) {
+    fuse_basic_block(layers, x);
+    int launches = 0;
+    for (PlannedConv& pc : layers) {
+      if (pc.skip) continue;
+      rc = launch_planned(pc, n, nullptr, as_stream(stream), (reverse != 0) ^ (launches & 1));
+      ++launches;
+      if (rc != CS_OK) break;
+    }
+    if (launches_out) *launches_out = launches;
+  }
+  cudaError_t e = cudaStreamSynchronize(as_stream(stream));
+  free_planned(layers[0]);
+  free_planned(layers[1]);
+  cudaFree(mid);
   if (rc != CS_OK) return rc;
   CS_CUDA(e);
   return CS_OK;

@@ -433,6 +433,21 @@ def debug_stem_bf16(images, w, bias, interval, inst_begin=0, inst_count=None):
     return out
 
 
+def debug_basic_block_bf16(x_hi, w1, b1, w2, b2, reverse=False):
+    """x_hi bf16 [n,8,8,64] (cuda), w1/w2 f32 [64,64,3,3], b1/b2 f32 [64] (cpu) -> (bf16 [n,8,8,64],
+    launches): relu(conv2(relu(conv1(x)+b1))+b2+x) through the production planner (layer-1 BasicBlock)."""
+    import ctypes
+    _req_cuda(x_hi, "x_hi", torch.bfloat16)
+    n = x_hi.shape[0]
+    arrs = [np.ascontiguousarray(t.detach().cpu().numpy(), dtype=np.float32) for t in (w1, b1, w2, b2)]
+    out = torch.zeros_like(x_hi)
+    launches = ctypes.c_int(0)
+    check(lib().cs_debug_basic_block_bf16(ptr(x_hi), n, arrs[0].ctypes.data, arrs[1].ctypes.data,
+                                          arrs[2].ctypes.data, arrs[3].ctypes.data, int(bool(reverse)), ptr(out),
+                                          ctypes.byref(launches), cur_stream()), "cs_debug_basic_block_bf16")
+    return out, launches.value
+
+
 def debug_conv_bf16(x_hi, w, bias, stride, groups=1, reverse=False):
     """x_hi bf16 [n,H,W,Cin] (cuda), w f32 [Cout,Cin/groups,k,k] (cpu), bias f32 [Cout] (cpu)
     -> f32 [n,Ho,Wo,Cout] through the production planner + tcgen05 kernels (k = 1 or 3)."""

@@ -329,6 +329,15 @@ int cs_debug_stem_bf16(const uint8_t* img, int n_bags, int H, int W, int interva
                        int64_t inst_count, const float* w_host, const float* bias_host, void* out_bf16,
                        void* stream);
 
+/* One layer-1 BasicBlock (8x8 maps, 64 channels, no downsample) through the production planner:
+ * y = relu(conv2(relu(conv1(x) + b1)) + b2 + x) (model/resnet.py:28-43, eval-mode BN folded).
+ * in_hi / out_bf16: bf16 [n][8*8][64] (device); w*_host [64][64][3][3], b*_host [64] fp32 (host);
+ * n % 128 == 0.  *launches_out (nullable) receives the number of kernel launches used: 1 = the
+ * fused block kernel, 2 = two y-sum convolutions.  Synchronises. */
+int cs_debug_basic_block_bf16(const void* in_hi, int64_t n, const float* w1_host, const float* b1_host,
+                              const float* w2_host, const float* b2_host, int reverse, void* out_bf16,
+                              int* launches_out, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -100,6 +100,32 @@ def test_tcgen05_conv_many_iterations_per_cta(cuda, H, Cin, Cout, k, stride, gro
     assert (got[n - 64:].cpu().double() - want).abs().max().item() < 2e-3
 
 
+@pytest.mark.parametrize("n,reverse", [(128, False), (384, True), (16384 + 128, False), (16384 + 128, True)])
+def test_tcgen05_basic_block_matches_two_convs(cuda, n, reverse):
+    """A layer-1 BasicBlock through the planner (one fused launch by default: conv_block.cu) against
+    the two convolutions run separately through the y-sum kernel with the glue in torch -- the same
+    arithmetic in the same order, so bit-exact -- and a sample against fp64 (model/resnet.py:28-43)."""
+    import os
+    ops = _ops()
+    g = torch.Generator().manual_seed(n + 17 * reverse)
+    x = torch.randn(n, 8, 8, 64, generator=g).to(torch.bfloat16).to(cuda)
+    w1 = _bf16_round(torch.randn(64, 64, 3, 3, generator=g) / 24.0)
+    w2 = _bf16_round(torch.randn(64, 64, 3, 3, generator=g) / 24.0)
+    b1, b2 = torch.randn(64, generator=g) * 0.3, torch.randn(64, generator=g) * 0.3
+    got, launches = ops.debug_basic_block_bf16(x, w1, b1, w2, b2, reverse=reverse)
+    assert launches == (2 if os.environ.get("CELLSEG_BLOCK_FUSE") == "0" or
+                        os.environ.get("CELLSEG_YSUM_PAIRS") == "0" or os.environ.get("CELLSEG_YSUM") == "0" or
+                        os.environ.get("CELLSEG_L1_SUB") else 1)
+    mid = F.relu(ops.debug_conv_bf16(x, w1, b1, 1)).to(torch.bfloat16)
+    want = F.relu(ops.debug_conv_bf16(mid, w2, b2, 1) + x.float()).to(torch.bfloat16)
+    assert torch.equal(got, want), (got.float() - want.float()).abs().max().item()
+    xs = x[n - 32:].float().cpu().permute(0, 3, 1, 2).double()
+    m64 = _bf16_round(F.relu(F.conv2d(xs, w1.double(), b1.double(), padding=1)).float()).double()
+    y64 = F.relu(F.conv2d(m64, w2.double(), b2.double(), padding=1) + xs).permute(0, 2, 3, 1)
+    err = (got[n - 32:].float().cpu().double() - y64).abs()
+    assert (err <= 2.0 ** -7 * y64.abs() + 2e-3).all(), err.max().item()
+
+
 @pytest.mark.parametrize("interval,n_bags,begin", [(20, 2, 0), (10, 3, 0), (7, 2, 37)])
 def test_tcgen05_stem_matches_conv_pool(cuda, interval, n_bags, begin):
     """The tile-32 stem kernel alone (normalise, conv 7x7/2 + bias, ReLU, maxpool 3x3/2) against
@@ -228,7 +254,7 @@ def test_forward_tile16(cuda, arch):
 
 ALT_PATHS = [
     # (environment, also run the many-iteration and at-scale cases)
-    ({"CELLSEG_STEM": "win"}, True), ({"CELLSEG_YSUM": "0"}, False), ({"CELLSEG_YSUM_PAIRS": "0"}, True), ({"CELLSEG_CLUSTER": "1"}, True),
+    ({"CELLSEG_STEM": "win"}, True), ({"CELLSEG_BLOCK_FUSE": "0"}, True), ({"CELLSEG_YSUM": "0"}, False), ({"CELLSEG_YSUM_PAIRS": "0"}, True), ({"CELLSEG_CLUSTER": "1"}, True),
     ({"CELLSEG_YSUM_EPI": "8"}, False), ({"CELLSEG_YSUM_BOX": "0"}, True), ({"CELLSEG_DENSE_PO": "4"}, True),
     ({"CELLSEG_DENSE_PO": "4", "CELLSEG_HALO_DS": "0"}, False), ({"CELLSEG_DENSE_BN": "128"}, False),
     ({"CELLSEG_DENSE_PO": "64"}, False), ({"CELLSEG_L1_SUB": "4736"}, True),
@@ -240,7 +266,7 @@ ALT_PATHS_RX = [{"CELLSEG_GROUP_YSUM": "0"}, {"CELLSEG_DENSE_GROUP_PO": "4"}]
 
 def test_alternative_kernel_paths_subprocess(cuda):
     """The switches are read when the library loads: run the conv-form and ResNet-34 parity tests in
-    child processes for every alternative kernel path (window-form stem, halo layer 1, single-CTA y-sum MMAs, single-CTA
+    child processes for every alternative kernel path (window-form stem, unfused layer-1 blocks, halo layer 1, single-CTA y-sum MMAs, single-CTA
     MMAs everywhere, 8-warp y-sum epilogue, three-box y-sum, halo kernel for layer 2 with and without
     the fused shortcut, 128-wide dense tiles, dense 8x8 stage, L2-resident layer-1 sub-batches, hi/lo
     residual stream); the paths that change how a forward batch is walked also run the
@@ -249,7 +275,7 @@ def test_alternative_kernel_paths_subprocess(cuda):
     import subprocess
     import sys
     here = os.path.abspath(__file__)
-    light = "conv_matches or stem_matches or (within_2e2 and resnet34) or tile16"
+    light = "conv_matches or stem_matches or basic_block or (within_2e2 and resnet34) or tile16"
     heavy = light + " or many_iterations or (bench_scale and resnet34)"
     procs = []
     for env in ALT_PATHS_RX:
