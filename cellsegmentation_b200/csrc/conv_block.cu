@@ -170,7 +170,9 @@ ysum_block_kernel(const __grid_constant__ YsumBlockParams p) {
       }
     }
   } else if (warp == 1) {
-    if (lane == 0 && rank == 0) {
+    // The whole warp walks the loop and waits; one elected lane issues a job's twelve MMAs
+    // (tc_ptx.cuh: elect_one_sync keeps the issue sequence on the uniform datapath).
+    if (rank == 0) {
       constexpr uint32_t idesc = umma_idesc_bf16(256, 192);
       mbar_wait(w_bar, 0);
       int acc = 0;
@@ -178,16 +180,20 @@ ysum_block_kernel(const __grid_constant__ YsumBlockParams p) {
       auto job = [&](uint32_t box, int conv) {
         mbar_wait(tempty_bar(acc), acc_phase ^ 1u);
         tc_fence_after();
-        const uint32_t d_tmem = tmem_base + (uint32_t)(acc * kAccCols);
-        for (int dx = 0; dx < 3; ++dx) {
-          const uint64_t a_desc = umma_desc_sw128_sbo(box + dx * 128u, 1280u);
-          const uint64_t b_desc = umma_desc_sw128(wres + (conv * 3 + dx) * kBTile);
+        if (elect_one_sync()) {
+          const uint32_t d_tmem = tmem_base + (uint32_t)(acc * kAccCols);
+          const uint64_t a0 = umma_desc_sw128_sbo(box, 1280u);
+          const uint64_t b0 = umma_desc_sw128(wres + conv * 3 * kBTile);
 #pragma unroll
-          for (int k = 0; k < 4; ++k)
-            umma_bf16_pair(d_tmem, a_desc + (uint64_t)(2 * k), b_desc + (uint64_t)(2 * k), idesc,
-                           (dx > 0 || k > 0) ? 1u : 0u);
+          for (int dx = 0; dx < 3; ++dx) {
+#pragma unroll
+            for (int k = 0; k < 4; ++k)
+              umma_bf16_pair(d_tmem, a0 + (uint64_t)(dx * 8 + 2 * k), b0 + (uint64_t)(dx * (kBTile >> 4) + 2 * k),
+                             idesc, (dx > 0 || k > 0) ? 1u : 0u);
+          }
+          umma_commit_pair(tfull_bar(acc), kMask);
         }
-        umma_commit_pair(tfull_bar(acc), kMask);
+        __syncwarp();
         acc ^= 1;
         if (acc == 0) acc_phase ^= 1u;
       };

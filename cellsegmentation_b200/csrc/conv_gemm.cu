@@ -160,7 +160,9 @@ conv_gemm_kernel(const __grid_constant__ GemmParams p) {
       }
     }
   } else if (warp == 1) {
-    if (lane == 0 && rank == 0) {
+    // The whole warp walks the loop and waits; one elected lane issues the MMAs and commits of a
+    // K step (tc_ptx.cuh: elect_one_sync keeps the issue sequence on the uniform datapath).
+    if (rank == 0) {
       constexpr uint32_t idesc = umma_idesc_bf16(kGemmBM * CL, BN);
       int stage = 0;
       uint32_t phase = 0;
@@ -177,27 +179,31 @@ conv_gemm_kernel(const __grid_constant__ GemmParams p) {
         for (int s = 0; s < ns; ++s) {
           mbar_wait(full_bar(stage), phase);
           tc_fence_after();
-          const uint32_t a_src = base + stage * Cfg::kStageBytes;
-          const uint64_t a_desc = umma_desc_sw128(a_src);
-          const uint64_t b_desc = umma_desc_sw128(a_src + Cfg::kABytes);
+          if (elect_one_sync()) {
+            const uint32_t a_src = base + stage * Cfg::kStageBytes;
+            const uint64_t a_desc = umma_desc_sw128(a_src);
+            const uint64_t b_desc = umma_desc_sw128(a_src + Cfg::kABytes);
 #pragma unroll
-          for (int k = 0; k < kGemmBK / 16; ++k) {
-            // +32 B per K=16 slice inside the 128-byte swizzle row: +2 in (addr >> 4)
-            if (CL == 1)
-              umma_bf16(d_tmem, a_desc + (uint64_t)(2 * k), b_desc + (uint64_t)(2 * k), idesc,
-                        (s > 0 || k > 0) ? 1u : 0u);
-            else
-              umma_bf16_pair(d_tmem, a_desc + (uint64_t)(2 * k), b_desc + (uint64_t)(2 * k), idesc,
-                             (s > 0 || k > 0) ? 1u : 0u);
+            for (int k = 0; k < kGemmBK / 16; ++k) {
+              // +32 B per K=16 slice inside the 128-byte swizzle row: +2 in (addr >> 4)
+              if (CL == 1)
+                umma_bf16(d_tmem, a_desc + (uint64_t)(2 * k), b_desc + (uint64_t)(2 * k), idesc,
+                          (s > 0 || k > 0) ? 1u : 0u);
+              else
+                umma_bf16_pair(d_tmem, a_desc + (uint64_t)(2 * k), b_desc + (uint64_t)(2 * k), idesc,
+                               (s > 0 || k > 0) ? 1u : 0u);
+            }
+            // frees the stage when these MMAs retire -- in both CTAs of a pair
+            if (CL == 1) umma_commit(empty_bar(stage));
+            else umma_commit_pair(empty_bar(stage), kMask);
+            if (s == ns - 1) {   // accumulator complete -> epilogue(s)
+              if (CL == 1) umma_commit(tfull_bar(acc));
+              else umma_commit_pair(tfull_bar(acc), kMask);
+            }
           }
-          // frees the stage when these MMAs retire -- in both CTAs of a pair
-          if (CL == 1) umma_commit(empty_bar(stage));
-          else umma_commit_pair(empty_bar(stage), kMask);
+          __syncwarp();
           if (++stage == n_stages) { stage = 0; phase ^= 1u; }
         }
-        // accumulator complete -> epilogue(s)
-        if (CL == 1) umma_commit(tfull_bar(acc));
-        else umma_commit_pair(tfull_bar(acc), kMask);
         acc ^= 1;
         if (acc == 0) acc_phase ^= 1u;
       }

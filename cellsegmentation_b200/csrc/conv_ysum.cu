@@ -172,7 +172,9 @@ conv_ysum_kernel(const __grid_constant__ YsumParams p) {
       }
     }
   } else if (warp == 1) {
-    if (lane == 0 && rank == 0) {
+    // The whole warp walks the loop and waits; one elected lane issues (tc_ptx.cuh: elect_one_sync
+    // keeps the issue sequence on the uniform datapath).
+    if (rank == 0) {
       constexpr uint32_t idesc = umma_idesc_bf16(128 * CL, 192);
       mbar_wait(bres_bar, 0);
       int stage = 0, acc = 0;
@@ -181,31 +183,39 @@ conv_ysum_kernel(const __grid_constant__ YsumParams p) {
         mbar_wait(tempty_bar(acc), acc_phase ^ 1u);
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + (uint32_t)(acc * kAccCols);
+#pragma unroll
         for (int dx = 0; dx < 3; ++dx) {
           if (!OB || dx == 0) {
             mbar_wait(full_bar(stage), phase);
             tc_fence_after();
           }
-          const uint64_t a_desc = OB ? umma_desc_sw128_sbo(base + stage * kStageBytes + dx * 128u, 1280u)
-                                     : umma_desc_sw128(base + stage * kStageBytes);
-          const uint64_t b_desc = umma_desc_sw128(bres + dx * kBTile);
+          if (elect_one_sync()) {
+            const uint64_t a_desc = OB ? umma_desc_sw128_sbo(base + stage * kStageBytes + dx * 128u, 1280u)
+                                       : umma_desc_sw128(base + stage * kStageBytes);
+            const uint64_t b_desc = umma_desc_sw128(bres + dx * kBTile);
 #pragma unroll
-          for (int k = 0; k < 4; ++k) {
-            if (CL == 1)
-              umma_bf16(d_tmem, a_desc + (uint64_t)(2 * k), b_desc + (uint64_t)(2 * k), idesc,
-                        (dx > 0 || k > 0) ? 1u : 0u);
-            else
-              umma_bf16_pair(d_tmem, a_desc + (uint64_t)(2 * k), b_desc + (uint64_t)(2 * k), idesc,
-                             (dx > 0 || k > 0) ? 1u : 0u);
+            for (int k = 0; k < 4; ++k) {
+              if (CL == 1)
+                umma_bf16(d_tmem, a_desc + (uint64_t)(2 * k), b_desc + (uint64_t)(2 * k), idesc,
+                          (dx > 0 || k > 0) ? 1u : 0u);
+              else
+                umma_bf16_pair(d_tmem, a_desc + (uint64_t)(2 * k), b_desc + (uint64_t)(2 * k), idesc,
+                               (dx > 0 || k > 0) ? 1u : 0u);
+            }
+            if (!OB || dx == 2) {
+              if (CL == 1) umma_commit(empty_bar(stage));
+              else umma_commit_pair(empty_bar(stage), kMask);
+            }
+            if (dx == 2) {
+              if (CL == 1) umma_commit(tfull_bar(acc));
+              else umma_commit_pair(tfull_bar(acc), kMask);
+            }
           }
+          __syncwarp();
           if (!OB || dx == 2) {
-            if (CL == 1) umma_commit(empty_bar(stage));
-            else umma_commit_pair(empty_bar(stage), kMask);
             if (++stage == kStages) { stage = 0; phase ^= 1u; }
           }
         }
-        if (CL == 1) umma_commit(tfull_bar(acc));
-        else umma_commit_pair(tfull_bar(acc), kMask);
         acc ^= 1;
         if (acc == 0) acc_phase ^= 1u;
       }

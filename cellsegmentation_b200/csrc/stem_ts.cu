@@ -249,30 +249,31 @@ stem_ts_kernel(const __grid_constant__ StemTsParams p) {
     }
   } else if (warp == kMmaWarp) {
     // ================= MMA issue =================
-    if (lane == 0) {
-      constexpr uint32_t idesc = umma_idesc_bf16(128, 128);
-      int stage = 0, acc = 0;
-      uint32_t phase = 0, acc_phase = 0;
-      for (int64_t t = blockIdx.x; t < n_inst; t += gridDim.x) {
-        mbar_wait(tempty_bar(acc), acc_phase ^ 1u);
-        mbar_wait(full_bar(stage), phase);
-        tc_fence_after();
-        const uint32_t img = base + Smem::img + stage * kImgBytes;
+    // The whole warp walks the loop and waits; one elected lane issues.  All 21 descriptors of an
+    // instance are the first one plus a constant (the start address field counts 16-byte units).
+    constexpr uint32_t idesc = umma_idesc_bf16(128, 128);
+    int stage = 0, acc = 0;
+    uint32_t phase = 0, acc_phase = 0;
+    for (int64_t t = blockIdx.x; t < n_inst; t += gridDim.x) {
+      mbar_wait(tempty_bar(acc), acc_phase ^ 1u);
+      mbar_wait(full_bar(stage), phase);
+      tc_fence_after();
+      if (elect_one_sync()) {
+        const uint64_t bd0 = desc_sw32(base + Smem::img + stage * kImgBytes, 2 * kPitch);
         const uint32_t d_tmem = tmem_base + (uint32_t)(kAccCol0 + acc * 128);
 #pragma unroll
         for (int ky = 0; ky < 7; ++ky) {
 #pragma unroll
-          for (int s = 0; s < 3; ++s) {
-            const uint64_t bd = desc_sw32(img + ky * kPitch + s * 32, 2 * kPitch);
-            umma_bf16_ts(d_tmem, tmem_base + (uint32_t)((ky * 3 + s) * 8), bd, idesc,
-                         (ky > 0 || s > 0) ? 1u : 0u);
-          }
+          for (int s = 0; s < 3; ++s)
+            umma_bf16_ts(d_tmem, tmem_base + (uint32_t)((ky * 3 + s) * 8),
+                         bd0 + (uint64_t)((ky * kPitch + s * 32) >> 4), idesc, (ky > 0 || s > 0) ? 1u : 0u);
         }
         umma_commit(empty_bar(stage));
         umma_commit(tfull_bar(acc));
-        if (++stage == kStages) { stage = 0; phase ^= 1u; }
-        if (++acc == kAccs) { acc = 0; acc_phase ^= 1u; }
       }
+      __syncwarp();
+      if (++stage == kStages) { stage = 0; phase ^= 1u; }
+      if (++acc == kAccs) { acc = 0; acc_phase ^= 1u; }
     }
   } else {
     // ================= epilogue: bias, bf16 pack, pool in registers, ReLU, TMA store ========
