@@ -27,6 +27,8 @@
 //   warp 0 : TMA producer (one lane)          warp 1 : TMEM alloc + MMA issuer (one lane)
 //   warps 2-9 : epilogue; warp % 4 = TMEM lane quadrant, (warp-2)/4 = column half.
 //   warp 10 : epilogue DMA (residual tiles in, result tiles out by TMA; gemm_epilogue.cuh)
+#include <stdlib.h>
+
 #include "fwd.cuh"
 #include "gemm_epilogue.cuh"
 
@@ -42,12 +44,12 @@ struct GemmCfg {
   static constexpr uint32_t kSmemLimit = 227 * 1024;
   // Shared memory: [stages x (A|B)] [staging: 2 sets of hi(+lo) tiles] [barriers]; the stage
   // count is whatever fits once the epilogue staging (16 or 32 KB per set) is reserved.
-  static constexpr int stages_for(uint32_t set_bytes) {
-    int s = (int)((kSmemLimit - 1024 - 256 - 2 * set_bytes) / kStageBytes);
+  static constexpr int stages_for(uint32_t staging_bytes) {
+    int s = (int)((kSmemLimit - 1024 - 256 - staging_bytes) / kStageBytes);
     return s > kMaxStages ? kMaxStages : s;
   }
-  static constexpr uint32_t smem_bytes(int stages, uint32_t set_bytes) {
-    return stages * kStageBytes + 2 * set_bytes + 256 + 1024;
+  static constexpr uint32_t smem_bytes(int stages, uint32_t staging_bytes) {
+    return stages * kStageBytes + staging_bytes + 256 + 1024;
   }
   static constexpr int kChunks = BN / 64;                          // 64-column epilogue chunks
   static constexpr uint32_t kTmemCols = 2 * BN;                    // two accumulator stages
@@ -66,19 +68,20 @@ conv_gemm_kernel(const __grid_constant__ GemmParams p) {
   const int n_stages = p.stages;
   const uint32_t set_bytes = p.epi_set_bytes;                 // 16 KB (hi only) or 32 KB (hi + lo)
   const uint32_t staging = base + n_stages * Cfg::kStageBytes;
-  const uint32_t bar_off = n_stages * Cfg::kStageBytes + 2 * set_bytes;
+  const int n_sets = (int)p.epi_sets;                         // 2, or a ring of 4 (gemm_epilogue.cuh)
+  const uint32_t bar_off = n_stages * Cfg::kStageBytes + n_sets * set_bytes;
   const uint32_t bar_base = base + bar_off;
   auto full_bar = [&](int s) { return bar_base + 8u * s; };
   auto empty_bar = [&](int s) { return bar_base + 8u * (Cfg::kMaxStages + s); };
   auto tfull_bar = [&](int a) { return bar_base + 8u * (2 * Cfg::kMaxStages + a); };
   auto tempty_bar = [&](int a) { return bar_base + 8u * (2 * Cfg::kMaxStages + 2 + a); };
   EpiBars ebars;
-  for (int s = 0; s < 2; ++s) {
+  for (int s = 0; s < kEpiMaxSets; ++s) {
     ebars.res_full[s] = bar_base + 8u * (2 * Cfg::kMaxStages + 4 + s);
-    ebars.out_ready[s] = bar_base + 8u * (2 * Cfg::kMaxStages + 6 + s);
+    ebars.out_ready[s] = bar_base + 8u * (2 * Cfg::kMaxStages + 4 + kEpiMaxSets + s);
   }
-  volatile uint32_t* tmem_slot =
-      reinterpret_cast<volatile uint32_t*>(base_ptr + bar_off + 8 * (2 * Cfg::kMaxStages + 8));
+  volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(
+      base_ptr + bar_off + 8 * (2 * Cfg::kMaxStages + 4 + 2 * kEpiMaxSets));
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -96,7 +99,7 @@ conv_gemm_kernel(const __grid_constant__ GemmParams p) {
       // both CTAs arrives on the leader's barrier
       mbar_init(tempty_bar(a), CL == 1 ? kEpiThreads : CL * kEpiWarps);
     }
-    epi_bars_init(ebars);
+    epi_bars_init(ebars, kEpiThreads, n_sets);
     fence_barrier_init();
     prefetch_tmap(&p.b_map);
     prefetch_tmap(&p.a_map[0]);
@@ -227,8 +230,8 @@ conv_gemm_kernel(const __grid_constant__ GemmParams p) {
       tc_fence_after();
 #pragma unroll 1
       for (int c = 0; c < Cfg::kChunks; ++c, ++q) {
-        const int s = (int)(q & 1);
-        mbar_wait(ebars.res_full[s], (uint32_t)((q >> 1) & 1));
+        const int s = (int)(q & (n_sets - 1));
+        mbar_wait(ebars.res_full[s], (uint32_t)((q >> (n_sets >> 1)) & 1));   // q / n_sets for 2 | 4
         const int col = n_tile * BN + c * 64 + half * 32;
         epi_chunk(ea, staging + s * set_bytes, r, half,
                   tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(acc * BN + c * 64 + half * 32),
@@ -274,7 +277,8 @@ conv_gemm_kernel(const __grid_constant__ GemmParams p) {
           coords(q, &col, &row);
           if (oh) tma_store_2d(&p.out_hi_map, set, col, row);
           if (ol) tma_store_2d(&p.out_lo_map, set + kEpiTileBytes, col, row);
-        });
+        },
+        n_sets);
   }
 
   tc_fence_before();
@@ -286,6 +290,14 @@ conv_gemm_kernel(const __grid_constant__ GemmParams p) {
     else tmem_dealloc_pair(tmem_base, Cfg::kTmemCols);
   }
 }
+
+// CELLSEG_EPI_RING=1: a ring of four staging sets for the residual GEMMs (gemm_epilogue.cuh).  Off by
+// default: it removes the res_full stalls of those launches under ncu, but the step is power-bound
+// and the same-box A/B is a tie (12.08-12.12 vs 12.12 M instances/s at 1 237 MHz, gpurun r2y).
+const bool g_epi_ring = []() {
+  const char* e = getenv("CELLSEG_EPI_RING");
+  return e != nullptr && e[0] == '1' && e[1] == 0;
+}();
 
 template <int BN, int CL>
 int launch_gemm_bn(const GemmParams& p, cudaStream_t st) {
@@ -300,8 +312,10 @@ int launch_gemm_bn(const GemmParams& p, cudaStream_t st) {
   }
   GemmParams q = p;
   q.epi_set_bytes = (p.out_lo || p.res_lo) ? kEpiSetBytes : kEpiTileBytes;
-  q.stages = Cfg::stages_for(q.epi_set_bytes);
-  const uint32_t smem = Cfg::smem_bytes(q.stages, q.epi_set_bytes);
+  // optionally a ring of four 16 KB sets when a residual is loaded (one operand stage less)
+  q.epi_sets = (g_epi_ring && p.res_hi && q.epi_set_bytes == kEpiTileBytes) ? 4u : 2u;
+  q.stages = Cfg::stages_for(q.epi_sets * q.epi_set_bytes);
+  const uint32_t smem = Cfg::smem_bytes(q.stages, q.epi_sets * q.epi_set_bytes);
   const int m_groups = (p.num_m_tiles + CL - 1) / CL;
   const int work = m_groups * p.num_n_tiles;
   int clusters = work < num_sms() / CL ? work : num_sms() / CL;

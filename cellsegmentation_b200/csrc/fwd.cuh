@@ -73,6 +73,7 @@ struct GemmParams {
   int reverse;        // walk work items from the last to the first (L2 snake order between layers)
   int stages;         // set by the launcher: TMA/MMA ring depth that fits shared memory
   uint32_t epi_set_bytes;  // set by the launcher: epilogue staging set, 16 KB (hi) or 32 KB (hi+lo)
+  uint32_t epi_sets;       // set by the launcher: 2 staging sets, or a ring of 4 (residual GEMMs)
   int cluster;        // 1, or 2: CTA pairs share the B tile by TMA multicast (b_map box = BN/2 rows)
   int n_total;        // output row pitch, elements
   int64_t m_valid;    // rows that exist

@@ -113,14 +113,17 @@ __device__ __forceinline__ void epi_chunk(const EpiArgs& e, uint32_t stg, int r,
   }
 }
 
-// Barrier addresses of the staging protocol (two sets).
+// Barrier addresses of the staging protocol (two sets; four in the generic GEMM kernel when a
+// residual is loaded and the bf16-only stream leaves room, see epi_dma_loop).
+constexpr int kEpiMaxSets = 4;
 struct EpiBars {
-  uint32_t res_full[2];
-  uint32_t out_ready[2];
+  uint32_t res_full[kEpiMaxSets];
+  uint32_t out_ready[kEpiMaxSets];
 };
 
-__device__ __forceinline__ void epi_bars_init(const EpiBars& b, uint32_t epi_threads = kEpiThreads) {
-  for (int s = 0; s < 2; ++s) {
+__device__ __forceinline__ void epi_bars_init(const EpiBars& b, uint32_t epi_threads = kEpiThreads,
+                                              int nsets = 2) {
+  for (int s = 0; s < nsets; ++s) {
     mbar_init(b.res_full[s], 1);
     mbar_init(b.out_ready[s], epi_threads);
   }
@@ -129,11 +132,44 @@ __device__ __forceinline__ void epi_bars_init(const EpiBars& b, uint32_t epi_thr
 // DMA-thread loop over Q chunks.  load(q, set_addr, bar) issues the residual TMA loads of
 // chunk q (or nothing), store(q, set_addr) the TMA stores.  res_bytes = bytes the loads of one
 // chunk deliver (0: no residual, the set is handed over with a plain arrive).
+//
+// nsets = 4 (a ring): with two sets the residual of chunk q+2 can only be requested once the
+// store of chunk q has read its set, so every chunk waits for a full TMA round trip (ncu r02w:
+// the epilogue warps of the residual GEMMs spend 25 % of their samples on res_full, 78-80 %
+// tensor pipe against 88-91 % without a residual).  With four sets the DMA thread lets the
+// latest store stay in flight and hands over the set of the chunk before it: three residual
+// tiles are on their way while one chunk is being worked on.
 template <class LoadFn, class StoreFn>
 __device__ __forceinline__ void epi_dma_loop(int64_t Q, uint32_t staging, uint32_t set_bytes,
                                              const EpiBars& bars,
                                              uint32_t res_bytes, bool any_store, LoadFn load,
-                                             StoreFn store) {
+                                             StoreFn store, int nsets = 2) {
+  if (nsets == 4) {
+    auto hand_over = [&](int64_t q) {
+      const int s = (int)(q & 3);
+      if (res_bytes) {
+        mbar_expect_tx(bars.res_full[s], res_bytes);
+        load(q, staging + s * set_bytes, bars.res_full[s]);
+      } else {
+        mbar_arrive(bars.res_full[s]);
+      }
+    };
+    for (int64_t q = 0; q < 4 && q < Q; ++q) hand_over(q);
+    for (int64_t q = 0; q < Q; ++q) {
+      const int s = (int)(q & 3);
+      mbar_wait(bars.out_ready[s], (uint32_t)((q >> 2) & 1));
+      if (any_store) {
+        store(q, staging + s * set_bytes);
+        bulk_commit_group();
+        bulk_wait_read_1();            // every store but the latest has read its set
+        if (q >= 1 && q + 3 < Q) hand_over(q + 3);
+      } else if (q + 4 < Q) {
+        hand_over(q + 4);
+      }
+    }
+    if (any_store) bulk_wait_all();
+    return;
+  }
   auto hand_over = [&](int64_t q) {
     const int s = (int)(q & 1);
     if (res_bytes) {

@@ -254,7 +254,7 @@ def test_forward_tile16(cuda, arch):
 
 ALT_PATHS = [
     # (environment, also run the many-iteration and at-scale cases)
-    ({"CELLSEG_STEM": "win"}, True), ({"CELLSEG_BLOCK_FUSE": "0"}, True), ({"CELLSEG_YSUM": "0"}, False), ({"CELLSEG_YSUM_PAIRS": "0"}, True), ({"CELLSEG_CLUSTER": "1"}, True),
+    ({"CELLSEG_STEM": "win"}, True), ({"CELLSEG_BLOCK_FUSE": "0"}, True), ({"CELLSEG_EPI_RING": "1"}, True), ({"CELLSEG_YSUM": "0"}, False), ({"CELLSEG_YSUM_PAIRS": "0"}, True), ({"CELLSEG_CLUSTER": "1"}, True),
     ({"CELLSEG_YSUM_EPI": "8"}, False), ({"CELLSEG_YSUM_BOX": "0"}, True), ({"CELLSEG_DENSE_PO": "4"}, True),
     ({"CELLSEG_DENSE_PO": "4", "CELLSEG_HALO_DS": "0"}, False), ({"CELLSEG_DENSE_BN": "128"}, False),
     ({"CELLSEG_DENSE_PO": "64"}, False), ({"CELLSEG_L1_SUB": "4736"}, True),
@@ -266,7 +266,7 @@ ALT_PATHS_RX = [{"CELLSEG_GROUP_YSUM": "0"}, {"CELLSEG_DENSE_GROUP_PO": "4"}]
 
 def test_alternative_kernel_paths_subprocess(cuda):
     """The switches are read when the library loads: run the conv-form and ResNet-34 parity tests in
-    child processes for every alternative kernel path (window-form stem, unfused layer-1 blocks, halo layer 1, single-CTA y-sum MMAs, single-CTA
+    child processes for every alternative kernel path (window-form stem, unfused layer-1 blocks, four-set epilogue ring, halo layer 1, single-CTA y-sum MMAs, single-CTA
     MMAs everywhere, 8-warp y-sum epilogue, three-box y-sum, halo kernel for layer 2 with and without
     the fused shortcut, 128-wide dense tiles, dense 8x8 stage, L2-resident layer-1 sub-batches, hi/lo
     residual stream); the paths that change how a forward batch is walked also run the
