@@ -21,6 +21,7 @@ SOURCES = [
     "select_topk.cu",
     "select_fast.cu",
     "select_reg.cu",
+    "select_warp.cu",
     "paint.cu",
     "cc.cu",
     "fwd_fp32.cu",

@@ -79,6 +79,8 @@ struct EmitArgs {
 
 int launch_select_fast(const Segs& segs, const float* prob, const EmitArgs& ea, int64_t max_T,
                        int32_t* fb_count, int32_t* fb_list, cudaStream_t st, bool* handled);
+int launch_select_warp(const Segs& segs, const float* prob, const EmitArgs& ea, int64_t max_T,
+                       int32_t* fb_count, int32_t* fb_list, cudaStream_t st, bool* handled);
 int launch_select_reg(const Segs& segs, const float* prob, const EmitArgs& ea, int64_t max_T,
                       int32_t* fb_count, int32_t* fb_list, cudaStream_t st, bool* handled);
 

@@ -205,6 +205,66 @@ select_offsets_kernel(Segs segs, const int32_t* __restrict__ labels, int32_t til
   if (tid == 0) offsets[n] = carry;
 }
 
+// The same for up to 31 x 1024 bags without the last-block pass: every CTA scans the counts of its
+// 1024 bags, publishes the block total (bit 63 = ready) and adds the totals of the CTAs before it as
+// soon as they show up (at most 30 words, read by one warp).  The whole grid is co-resident (<= 31
+// CTAs) and a CTA only waits for lower-numbered ones, so the wait cannot deadlock.  One L2 round
+// trip instead of ticket -> reload of all counts -> second scan: the selection kernel launched
+// behind this one waits that much less for its offsets.  `flags` (gridDim.x words) must be zero on entry.
+constexpr int kLookbackMaxBlocks = 31;
+
+__global__ void __launch_bounds__(1024)
+select_offsets_lookback_kernel(Segs segs, const int32_t* __restrict__ labels, int32_t tiles_per_pos,
+                               int32_t topk_neg, int64_t* __restrict__ offsets,
+                               unsigned long long* __restrict__ flags) {
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+  __shared__ int32_t warp_tot[32];
+  __shared__ long long s_base;
+  const int n = segs.n_bags;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int b = blockIdx.x * 1024 + tid;
+  int32_t cnt = 0;
+  if (b < n) {
+    const int64_t s = segs.start(b), e = segs.start(b + 1);
+    cnt = kept_ranges(segs.gstart(b), e - s, segs.gtotal(), bag_k(labels, b, tiles_per_pos, topk_neg)).count();
+  }
+  int32_t x = cnt;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    const int32_t y = __shfl_up_sync(0xffffffffu, x, o);
+    if (lane >= o) x += y;
+  }
+  if (lane == 31) warp_tot[warp] = x;
+  __syncthreads();
+  if (warp == 0) {
+    const int32_t w = warp_tot[lane];
+    int32_t xs = w;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const int32_t y = __shfl_up_sync(0xffffffffu, xs, o);
+      if (lane >= o) xs += y;
+    }
+    warp_tot[lane] = xs - w;                                // exclusive prefix of the warp totals
+    const long long block_total = __shfl_sync(0xffffffffu, xs, 31);
+    volatile unsigned long long* vf = flags;
+    if (lane == 0) vf[blockIdx.x] = (1ull << 63) | (unsigned long long)block_total;
+    long long before = 0;
+    if (lane < (int)blockIdx.x) {
+      unsigned long long f;
+      do { f = vf[lane]; } while ((f >> 63) == 0ull);
+      before = (long long)(f & ~(1ull << 63));
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) before += __shfl_xor_sync(0xffffffffu, before, o);
+    if (lane == 0) {
+      s_base = before;
+      if (blockIdx.x == gridDim.x - 1) offsets[n] = before + block_total;
+    }
+  }
+  __syncthreads();
+  if (b < n) offsets[b] = s_base + (int64_t)(warp_tot[warp] + x - cnt);
+}
+
 // ---- per-bag sort + emit ----------------------------------------------------
 enum Mode { kLexsort = 0, kSelect = 1, kRank = 2 };
 
@@ -353,6 +413,13 @@ const bool g_staged_fast = []() {
   return e != nullptr && e[0] == 's';
 }();
 
+// CELLSEG_SELECT_OFFSETS=ticket keeps the last-block scan for every bag count (the default for more
+// than 31 744 bags); otherwise the offsets come from the look-back kernel.
+const bool g_offsets_ticket = []() {
+  const char* e = getenv("CELLSEG_SELECT_OFFSETS");
+  return e != nullptr && e[0] == 't';
+}();
+
 struct SegHostInfo {
   int max_pow2;
 };
@@ -449,8 +516,17 @@ int cs_select_topk_shard(const float* prob, const int64_t* seg_offsets, int64_t 
   int32_t* fb_count = static_cast<int32_t*>(workspace);
   int32_t* fb_list = fb_count + 64;
   int32_t* ticket = fb_count + 1;
-  CS_CUDA(cudaMemsetAsync(fb_count, 0, 2 * sizeof(int32_t), st));
-  {
+  // workspace: [0] declined-bag count, [1] ticket, bytes 8..255 look-back words, 256.. declined list
+  const int off_blocks = cs::ceil_div(n_bags, 1024);
+  const bool lookback = !g_offsets_ticket && off_blocks <= kLookbackMaxBlocks && off_blocks <= cs::num_sms() &&
+                        (reinterpret_cast<uintptr_t>(workspace) & 7) == 0;
+  CS_CUDA(cudaMemsetAsync(fb_count, 0, lookback ? 256 : 2 * sizeof(int32_t), st));
+  if (lookback) {
+    select_offsets_lookback_kernel<<<off_blocks, 1024, 0, st>>>(
+        segs, labels, tiles_per_pos, topk_neg, sel_offsets_out,
+        reinterpret_cast<unsigned long long*>(fb_count + 2));
+    CS_LAUNCH_CHECK();
+  } else {
     static bool attr_done[64] = {false};
     int dev = 0;
     CS_CUDA(cudaGetDevice(&dev));
@@ -459,10 +535,10 @@ int cs_select_topk_shard(const float* prob, const int64_t* seg_offsets, int64_t 
                                    kOffChunk * (int)sizeof(int32_t)));
       if (dev < 64) attr_done[dev] = true;
     }
+    select_offsets_kernel<<<off_blocks, 1024, kOffChunk * sizeof(int32_t), st>>>(
+        segs, labels, tiles_per_pos, topk_neg, sel_offsets_out, ticket);
+    CS_LAUNCH_CHECK();
   }
-  select_offsets_kernel<<<cs::ceil_div(n_bags, 1024), 1024, kOffChunk * sizeof(int32_t), st>>>(
-      segs, labels, tiles_per_pos, topk_neg, sel_offsets_out, ticket);
-  CS_LAUNCH_CHECK();
   EmitArgs ea{};
   ea.labels = labels;
   ea.tiles_per_pos = tiles_per_pos;
@@ -471,13 +547,15 @@ int cs_select_topk_shard(const float* prob, const int64_t* seg_offsets, int64_t 
   ea.label_out = sel_label_out;
   ea.out_offsets = sel_offsets_out;
   ea.capacity = capacity;
-  // CTA-per-bag fast paths first: register-resident (select_reg.cu) for bags of up to 4093
-  // instances, shared-memory staged (select_fast.cu) beyond; bags they decline are listed and
-  // ordered exactly
+  // Fast paths first: a warp per bag (select_warp.cu) for bags of up to 3069 instances, a
+  // register-resident CTA per bag (select_reg.cu) up to 4093, shared-memory staged
+  // (select_fast.cu) beyond; bags they decline are listed and ordered exactly
   bool handled = false;
   if (!g_disable_fast) {
     if (!g_staged_fast) {
-      rc = launch_select_reg(segs, prob, ea, uniform_T, fb_count, fb_list, st, &handled);
+      rc = launch_select_warp(segs, prob, ea, uniform_T, fb_count, fb_list, st, &handled);
+      if (rc != CS_OK) return rc;
+      if (!handled) rc = launch_select_reg(segs, prob, ea, uniform_T, fb_count, fb_list, st, &handled);
       if (rc != CS_OK) return rc;
     }
     if (!handled) {
