@@ -547,9 +547,9 @@ int cs_select_topk_shard(const float* prob, const int64_t* seg_offsets, int64_t 
   ea.label_out = sel_label_out;
   ea.out_offsets = sel_offsets_out;
   ea.capacity = capacity;
-  // Fast paths first: a warp per bag (select_warp.cu) for bags of up to 3069 instances, a
-  // register-resident CTA per bag (select_reg.cu) up to 4093, shared-memory staged
-  // (select_fast.cu) beyond; bags they decline are listed and ordered exactly
+  // Fast paths first: a register-resident CTA per bag (select_reg.cu) for bags of up to 4093
+  // instances (with CELLSEG_SELECT_WARP=1 a warp per bag, select_warp.cu, up to 3069),
+  // shared-memory staged (select_fast.cu) beyond; bags they decline are listed and ordered exactly
   bool handled = false;
   if (!g_disable_fast) {
     if (!g_staged_fast) {

@@ -1,4 +1,5 @@
-// K3 fast path, warp-per-bag form: adaptive top-k of one bag by ONE WARP, no block barrier.
+// K3 fast path, warp-per-bag form (experiment, off by default -- see g_enable_warp for the
+// measurement): adaptive top-k of one bag by ONE WARP, no block barrier.
 //
 // Reference: sample() inference.py:31-42 (np.lexsort + per-position predicate) and the
 // pseudo-label rule dataset/dataset.py:168-169.  Same results as the exact shared-memory sort in
@@ -10,7 +11,8 @@
 // 3025, 1 450 warp instructions per bag at 55 % issue-active).  Here a warp owns a bag:
 //   0. a lane pulls NV 16-byte vectors (vector v = lane + 32 j of the aligned superset of the bag)
 //      straight into registers -- 24 vectors = 96 registers for a 3025-instance bag, sixteen bags
-//      in flight per SM; the up-to-three foreign words at either end are zeroed in registers
+//      in flight per SM; the previous bag's words in vector 0 are zeroed in registers, the next
+//      bag's words in the last vector have their marks masked off in step 2
 //   1. vector maxima fold into four group maxima per lane; tau = a value with at least n of the
 //      64 (n <= 64) or 128 (n <= 128) group maxima >= tau, found by a 23-step binary search on the
 //      bit pattern (one REDUX per step; the low 8 mantissa bits are left open: tau is then at most
@@ -223,21 +225,28 @@ select_warp_kernel(Segs segs, const float* __restrict__ prob, EmitArgs ea,
   asm volatile("griddepcontrol.wait;" ::: "memory");
 }
 
-// CELLSEG_SELECT_WARP=0 keeps the CTA-per-bag kernel of select_reg.cu for every bag size.
-const bool g_disable_warp = []() {
+// CELLSEG_SELECT_WARP=1 selects this kernel; the default stays the CTA-per-bag kernel of select_reg.cu.
+// Measured at 20 000 bags x 3025 (gpurun r2aa, same box, outputs identical): 75.8 us against 54.6 us
+// under ncu (27.8 M warp instructions at 45 % issue-active, 13 resident warps per SM), whole call
+// 0.124 against 0.070 ms.  A bag takes ~7.4 us in one warp against ~4 us in a four-warp CTA: with
+// 127 registers per thread only 3-4 warps share a scheduler, too few to cover the dependent chains
+// of the threshold search (23 REDUX round trips), the mark words and the ranking loop.  Second
+// cost: the ~0.2 % of bags whose next-bag words beat their own threshold (count < n, small n) are
+// declined, and a single declined 3025-instance bag costs the exact kernel ~40 us of latency.
+const bool g_enable_warp = []() {
   const char* e = getenv("CELLSEG_SELECT_WARP");
-  return e != nullptr && e[0] == '0';
+  return e != nullptr && e[0] == '1';
 }();
 
 }  // namespace
 
 // Warp-per-bag fast path for bags of up to 3069 instances; *handled = false for longer bags (or
-// when switched off): the caller goes on to launch_select_reg / launch_select_fast.  fb_count must
+// when not switched on): the caller goes on to launch_select_reg / launch_select_fast.  fb_count must
 // be zero on entry; declined bags are appended to fb_list[0 .. *fb_count).
 int launch_select_warp(const Segs& segs, const float* prob, const EmitArgs& ea, int64_t max_T,
                        int32_t* fb_count, int32_t* fb_list, cudaStream_t st, bool* handled) {
   *handled = false;
-  if (g_disable_warp) return CS_OK;
+  if (!g_enable_warp) return CS_OK;
   const int64_t words = max_T + 3;                      // worst-case misalignment
   const dim3 grid((unsigned)ceil_div(segs.n_bags, kWarpsPerCta)), block(32 * kWarpsPerCta);
   cudaError_t e;

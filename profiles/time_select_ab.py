@@ -1,7 +1,7 @@
 """K3 at the full config size (20 000 bags x 3025), timed like bench.py's select_20k leg (whole
 cs_select_topk call, pre-allocated outputs, no host sync, L2 flushed between repetitions, CUDA
 events) under each kernel variant.  The switches are read when the library loads, so every variant
-runs in its own process.  Also checks the default variant's output against the CTA-per-bag one.
+runs in its own process.  Also checks that every variant produces the same selection.
 
     python profiles/time_select_ab.py            # all variants, one JSON line each
     python profiles/time_select_ab.py --one      # the variant of the current environment
@@ -12,10 +12,10 @@ import subprocess
 import sys
 
 VARIANTS = {
-    "warp+lookback (default)": {},
-    "cta+lookback": {"CELLSEG_SELECT_WARP": "0"},
-    "warp+ticket": {"CELLSEG_SELECT_OFFSETS": "ticket"},
-    "cta+ticket (round-2 r2i build)": {"CELLSEG_SELECT_WARP": "0", "CELLSEG_SELECT_OFFSETS": "ticket"},
+    "cta+lookback (default)": {},
+    "warp+lookback": {"CELLSEG_SELECT_WARP": "1"},
+    "warp+ticket": {"CELLSEG_SELECT_WARP": "1", "CELLSEG_SELECT_OFFSETS": "ticket"},
+    "cta+ticket (round-2 r2i build)": {"CELLSEG_SELECT_OFFSETS": "ticket"},
 }
 
 

@@ -204,21 +204,21 @@ def test_select_topk_shards_equal_global(cuda, T, sizes):
         assert np.array_equal(np.concatenate(got_pl), oselect.pseudo_labels(tid, lab, want))
 
 
-@pytest.mark.parametrize("mode", ["staged", "0", "persist", "cta", "ticket"])
+@pytest.mark.parametrize("mode", ["staged", "0", "persist", "warp", "ticket"])
 def test_select_topk_other_paths_subprocess(cuda, mode):
     """CELLSEG_SELECT_FAST is read when the library loads: =staged routes every bag through the
     shared-memory fast path of round 1 (still used for bags longer than 4093 instances), =0 through
-    the exact bitonic kernel alone; CELLSEG_SELECT_WARP=0 keeps the CTA-per-bag register kernel for
-    the bag sizes the warp-per-bag kernel takes by default, with CELLSEG_SELECT_PERSIST=1 its
-    persistent form; CELLSEG_SELECT_OFFSETS=ticket the last-block offsets scan."""
+    the exact bitonic kernel alone; CELLSEG_SELECT_PERSIST=1 takes the persistent form of the
+    CTA-per-bag register kernel, CELLSEG_SELECT_WARP=1 the warp-per-bag kernel,
+    CELLSEG_SELECT_OFFSETS=ticket the last-block offsets scan instead of the look-back one."""
     import os
     import subprocess
     import sys
     here = os.path.abspath(__file__)
     r = subprocess.run([sys.executable, "-m", "pytest", here, "-x", "-q", "-p", "no:cacheprovider", "-k",
                         "select_topk and not subprocess"],
-                       env=dict(os.environ, **({"persist": {"CELLSEG_SELECT_PERSIST": "1", "CELLSEG_SELECT_WARP": "0"},
-                                                "cta": {"CELLSEG_SELECT_WARP": "0"},
+                       env=dict(os.environ, **({"persist": {"CELLSEG_SELECT_PERSIST": "1"},
+                                                "warp": {"CELLSEG_SELECT_WARP": "1"},
                                                 "ticket": {"CELLSEG_SELECT_OFFSETS": "ticket"}}.get(
                                                     mode, {"CELLSEG_SELECT_FAST": mode}))),
                        capture_output=True, text=True, timeout=900)

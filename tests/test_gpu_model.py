@@ -113,9 +113,11 @@ def test_tcgen05_basic_block_matches_two_convs(cuda, n, reverse):
     w2 = _bf16_round(torch.randn(64, 64, 3, 3, generator=g) / 24.0)
     b1, b2 = torch.randn(64, generator=g) * 0.3, torch.randn(64, generator=g) * 0.3
     got, launches = ops.debug_basic_block_bf16(x, w1, b1, w2, b2, reverse=reverse)
-    assert launches == (2 if os.environ.get("CELLSEG_BLOCK_FUSE") == "0" or
-                        os.environ.get("CELLSEG_YSUM_PAIRS") == "0" or os.environ.get("CELLSEG_YSUM") == "0" or
-                        os.environ.get("CELLSEG_L1_SUB") else 1)
+    # the fused kernel needs CTA pairs and the y-sum form of layer 1
+    unfused = (os.environ.get("CELLSEG_BLOCK_FUSE") == "0" or os.environ.get("CELLSEG_YSUM_PAIRS") == "0" or
+               os.environ.get("CELLSEG_YSUM") == "0" or os.environ.get("CELLSEG_CLUSTER") == "1" or
+               os.environ.get("CELLSEG_DENSE_PO") == "64" or os.environ.get("CELLSEG_L1_SUB"))
+    assert launches == (2 if unfused else 1)
     mid = F.relu(ops.debug_conv_bf16(x, w1, b1, 1)).to(torch.bfloat16)
     want = F.relu(ops.debug_conv_bf16(mid, w2, b2, 1) + x.float()).to(torch.bfloat16)
     assert torch.equal(got, want), (got.float() - want.float()).abs().max().item()
