@@ -251,9 +251,10 @@ __device__ __forceinline__ void bag_process(const Segs& segs, const EmitArgs& ea
   }
 }
 
-// One CTA per bag.
-template <int NV, int THREADS>
-__global__ void __launch_bounds__(THREADS, NV <= 6 ? 10 : 8)
+// One CTA per bag.  OCC = resident CTAs per SM the register allocation is held to (NV <= 6: 10 ->
+// 48 registers, 12 -> 40 registers with four spilled words, 16 -> 32 registers with ~30).
+template <int NV, int THREADS, int OCC>
+__global__ void __launch_bounds__(THREADS, NV <= 6 ? OCC : 8)
 select_reg_kernel(Segs segs, const float* __restrict__ prob, EmitArgs ea,
                   int32_t* __restrict__ fb_count, int32_t* __restrict__ fb_list) {
   static_assert(THREADS == 128, "two threads per column");
@@ -304,6 +305,14 @@ const bool g_persist = []() {
   return e != nullptr && e[0] == '1';
 }();
 
+// CELLSEG_SELECT_OCC=12 | 16: more bags in flight per SM at the price of a tighter register budget
+// (see select_reg_kernel).  Default 10.
+const int g_occ = []() {
+  const char* e = getenv("CELLSEG_SELECT_OCC");
+  const int v = e != nullptr ? atoi(e) : 10;
+  return v == 12 || v == 16 ? v : 10;
+}();
+
 template <int NV, int THREADS>
 cudaError_t launch_reg(const Segs& segs, const float* prob, const EmitArgs& ea, int32_t* fb_count,
                        int32_t* fb_list, cudaStream_t st) {
@@ -311,8 +320,10 @@ cudaError_t launch_reg(const Segs& segs, const float* prob, const EmitArgs& ea, 
   if (g_persist && segs.n_bags > num_sms() * per_sm)
     return launch_pdl(select_reg_persistent_kernel<NV, THREADS>, dim3((unsigned)(num_sms() * per_sm)), dim3(THREADS),
                       0, st, 1, segs, prob, ea, fb_count, fb_list);
-  return launch_pdl(select_reg_kernel<NV, THREADS>, dim3((unsigned)segs.n_bags), dim3(THREADS), 0, st, 1,
-                    segs, prob, ea, fb_count, fb_list);
+  const dim3 grid((unsigned)segs.n_bags), block(THREADS);
+  if (g_occ == 12) return launch_pdl(select_reg_kernel<NV, THREADS, 12>, grid, block, 0, st, 1, segs, prob, ea, fb_count, fb_list);
+  if (g_occ == 16) return launch_pdl(select_reg_kernel<NV, THREADS, 16>, grid, block, 0, st, 1, segs, prob, ea, fb_count, fb_list);
+  return launch_pdl(select_reg_kernel<NV, THREADS, 10>, grid, block, 0, st, 1, segs, prob, ea, fb_count, fb_list);
 }
 
 }  // namespace

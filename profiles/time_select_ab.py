@@ -13,8 +13,9 @@ import sys
 
 VARIANTS = {
     "cta+lookback (default)": {},
+    "cta, 12 CTAs/SM (40 registers)": {"CELLSEG_SELECT_OCC": "12"},
+    "cta, 16 CTAs/SM (32 registers)": {"CELLSEG_SELECT_OCC": "16"},
     "warp+lookback": {"CELLSEG_SELECT_WARP": "1"},
-    "warp+ticket": {"CELLSEG_SELECT_WARP": "1", "CELLSEG_SELECT_OFFSETS": "ticket"},
     "cta+ticket (round-2 r2i build)": {"CELLSEG_SELECT_OFFSETS": "ticket"},
 }
 

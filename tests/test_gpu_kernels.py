@@ -204,13 +204,14 @@ def test_select_topk_shards_equal_global(cuda, T, sizes):
         assert np.array_equal(np.concatenate(got_pl), oselect.pseudo_labels(tid, lab, want))
 
 
-@pytest.mark.parametrize("mode", ["staged", "0", "persist", "warp", "ticket"])
+@pytest.mark.parametrize("mode", ["staged", "0", "persist", "warp", "ticket", "occ12", "occ16"])
 def test_select_topk_other_paths_subprocess(cuda, mode):
     """CELLSEG_SELECT_FAST is read when the library loads: =staged routes every bag through the
     shared-memory fast path of round 1 (still used for bags longer than 4093 instances), =0 through
     the exact bitonic kernel alone; CELLSEG_SELECT_PERSIST=1 takes the persistent form of the
     CTA-per-bag register kernel, CELLSEG_SELECT_WARP=1 the warp-per-bag kernel,
-    CELLSEG_SELECT_OFFSETS=ticket the last-block offsets scan instead of the look-back one."""
+    CELLSEG_SELECT_OFFSETS=ticket the last-block offsets scan instead of the look-back one,
+    CELLSEG_SELECT_OCC=12 | 16 the register kernel held to 40 / 32 registers."""
     import os
     import subprocess
     import sys
@@ -219,6 +220,8 @@ def test_select_topk_other_paths_subprocess(cuda, mode):
                         "select_topk and not subprocess"],
                        env=dict(os.environ, **({"persist": {"CELLSEG_SELECT_PERSIST": "1"},
                                                 "warp": {"CELLSEG_SELECT_WARP": "1"},
+                                                "occ12": {"CELLSEG_SELECT_OCC": "12"},
+                                                "occ16": {"CELLSEG_SELECT_OCC": "16"},
                                                 "ticket": {"CELLSEG_SELECT_OFFSETS": "ticket"}}.get(
                                                     mode, {"CELLSEG_SELECT_FAST": mode}))),
                        capture_output=True, text=True, timeout=900)

@@ -17,6 +17,7 @@ timeout 900 ncu --set full --clock-control none --import-source on -k "$K" -s 62
 echo "full capture rc=$?"; ls -la gpurun_out/prof_r02.ncu-rep
 timeout 300 python bench.py --no-side-legs --no-cpu-baseline --max-batch 151552 > gpurun_out/r2z_bench_mb151552.json 2> gpurun_out/r2z_bench_mb151552.err; echo "mb151552 rc=$?"
 timeout 300 python bench.py --no-side-legs --no-cpu-baseline > gpurun_out/r2z_bench_mb75776.json 2> gpurun_out/r2z_bench_mb75776.err; echo "mb75776 rc=$?"
+timeout 400 python profiles/time_select_ab.py > gpurun_out/r2z_select_ab.log 2>&1; echo "select ab rc=$?"; cat gpurun_out/r2z_select_ab.log
 timeout 400 python bench.py --impl reference --steps 2 --warmup 1 > gpurun_out/r2z_bench_ref.json 2>&1; echo "ref rc=$?"
 python - <<'PY'
 import json
