@@ -489,13 +489,25 @@ def main():
         p_all = torch.rand(nb_sel * T_PER_BAG, device=dev, generator=g)
         lab_all = torch.from_numpy(synthetic.make_labels(nb_sel, seed=3)).to(dev)
         buf20 = ops.select_buffers(nb_sel, nb_sel * 330, dev)
-        ms = time_alone(lambda: ops.select_topk(p_all, lab_all, nb_sel, T_PER_BAG, 1, 30, sync=False, out=buf20))
+        sel20 = lambda: ops.select_topk(p_all, lab_all, nb_sel, T_PER_BAG, 1, 30, sync=False, out=buf20)  # noqa: E731
+        # The selection is latency / issue bound, so its time follows the SM clock, and the step loop
+        # that just ended leaves the GPU power capped (~1.35 of 1.965 GHz).  It is timed twice: right
+        # away, and after a short idle -- the state in which the copy peak it is compared with was
+        # measured (MEASURED_PEAKS.json: best of 10 on an idle GPU).  `ms` / `frac` are the kernel
+        # timed alone (the faster of the two), `ms_after_step` the power-capped figure.
+        ms_hot = time_alone(sel20)
+        time.sleep(2.0)
+        ms = min(ms_hot, time_alone(sel20, reps=7))
         m_kept = int(buf20[2][-1].item())
         sel_bytes = 4.0 * p_all.numel() + 5.0 * m_kept + 4.0 * nb_sel
         side["select_20k"] = {"bound": "hbm", "bags": nb_sel, "instances": int(p_all.numel()), "kept": m_kept,
                               "ms": ms, "instances_per_s": p_all.numel() / (ms * 1e-3),
                               "achieved": sel_bytes / (ms * 1e-3) / 1e9, "unit": "GB/s",
-                              "note": "whole cs_select_topk call (all its launches), pre-allocated outputs, no host sync"}
+                              "ms_after_step": ms_hot,
+                              "frac_after_step": sel_bytes / (ms_hot * 1e-3) / 1e9 / pk["hbm_gbs"],
+                              "note": "whole cs_select_topk call (all its launches), pre-allocated outputs, no host sync; "
+                                      "ms = timed alone after 2 s of idle (boost clocks, like the copy peak), "
+                                      "ms_after_step = immediately after the power-capped step loop"}
         del p_all, buf20
         # K4b at the config-5 size class: 8000 bags (3.6 GB of traffic per launch, >> L2)
         nb_m = max(resident, 8000)
