@@ -146,13 +146,9 @@ __device__ __forceinline__ void bag_process(const Segs& segs, const EmitArgs& ea
 
   // 1. vector maxima -> thread maximum -> 64 column maxima -> tau (negative / NaN inputs have bit
   // patterns above +inf and surface in every maximum)
-  uint32_t vm[NV];
   uint32_t m = 0;
 #pragma unroll
-  for (int j = 0; j < NV; ++j) {
-    vm[j] = max(max(x[j].x, x[j].y), max(x[j].z, x[j].w));
-    m = max(m, vm[j]);
-  }
+  for (int j = 0; j < NV; ++j) m = max(m, max(max(x[j].x, x[j].y), max(x[j].z, x[j].w)));
   st.tmax[tid] = m;
   __syncthreads();
   const int n = st.n;
@@ -173,8 +169,14 @@ __device__ __forceinline__ void bag_process(const Segs& segs, const EmitArgs& ea
     __syncthreads();
     if (rank == n - 1 && st.tau != 0xffffffffu) st.tau = m == 0u ? 0xffffffffu : m;
   } else if (warp == 0) {
-    uint32_t a = max(st.tmax[lane], st.tmax[lane + 64]);         // column lane
-    uint32_t c = max(st.tmax[lane + 32], st.tmax[lane + 96]);    // column lane + 32
+    uint32_t a, c;
+    if (THREADS == 128) {
+      a = max(st.tmax[lane], st.tmax[lane + 64]);                // column lane
+      c = max(st.tmax[lane + 32], st.tmax[lane + 96]);           // column lane + 32
+    } else {                                                     // 64 threads: a thread is a column
+      a = st.tmax[lane];
+      c = st.tmax[lane + 32];
+    }
     bitonic64_stage<2, 1>(a, c, lane);
     bitonic64_stage<4, 2>(a, c, lane);  bitonic64_stage<4, 1>(a, c, lane);
     bitonic64_stage<8, 4>(a, c, lane);  bitonic64_stage<8, 2>(a, c, lane);  bitonic64_stage<8, 1>(a, c, lane);
@@ -210,8 +212,8 @@ __device__ __forceinline__ void bag_process(const Segs& segs, const EmitArgs& ea
   if (m >= tau) {
     uint32_t mask = 0;
 #pragma unroll
-    for (int j = 0; j < NV; ++j)
-      if (vm[j] >= tau) mask |= 1u << j;
+    for (int j = 0; j < NV; ++j)           // (the vector maxima are recomputed: two instructions each)
+      if (max(max(x[j].x, x[j].y), max(x[j].z, x[j].w)) >= tau) mask |= 1u << j;
     while (mask) {
       const int j = __ffs(mask) - 1;
       mask &= mask - 1;
@@ -254,17 +256,25 @@ __device__ __forceinline__ void bag_process(const Segs& segs, const EmitArgs& ea
 // One CTA per bag.  OCC = resident CTAs per SM the register allocation is held to (NV <= 6: 10 ->
 // 48 registers, 12 -> 40 registers with four spilled words, 16 -> 32 registers with ~30).
 template <int NV, int THREADS, int OCC>
-__global__ void __launch_bounds__(THREADS, NV <= 6 ? OCC : 8)
+__global__ void __launch_bounds__(THREADS, OCC)
 select_reg_kernel(Segs segs, const float* __restrict__ prob, EmitArgs ea,
                   int32_t* __restrict__ fb_count, int32_t* __restrict__ fb_list) {
-  static_assert(THREADS == 128, "two threads per column");
+  static_assert(THREADS == 128 || THREADS == 64, "two threads, or one, per column");
+  // The exact clean-up pass is launched behind this grid as a programmatic dependent: it may become
+  // resident once every CTA of this grid has started, i.e. in the slots the last wave leaves free,
+  // and waits there for this grid to complete.
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
   __shared__ SelState st;
   const int b = blockIdx.x;
   const BagView bv = bag_view<NV, THREADS>(segs, prob, b);
-  if (bv.T <= 0) return;                                  // block-uniform
-  uint4 x[NV];
-  bag_load<NV, THREADS>(bv, x, threadIdx.x);
-  bag_process<NV, THREADS>(segs, ea, b, bv, x, st, fb_count, fb_list);
+  if (bv.T > 0) {                                         // block-uniform
+    uint4 x[NV];
+    bag_load<NV, THREADS>(bv, x, threadIdx.x);
+    bag_process<NV, THREADS>(segs, ea, b, bv, x, st, fb_count, fb_list);
+  }
+  // every thread orders itself behind the offsets kernel before it exits, whichever way its bag
+  // went: this grid must not complete (and release the clean-up pass) ahead of the offsets
+  asm volatile("griddepcontrol.wait;" ::: "memory");
 }
 
 // Persistent CTAs (experiment, off by default -- see g_persist): bag b + k * gridDim.x in turn, with
@@ -313,17 +323,38 @@ const int g_occ = []() {
   return v == 12 || v == 16 ? v : 10;
 }();
 
-template <int NV, int THREADS>
+// CELLSEG_SELECT_CTA=64: two warps per bag (a thread holds twice the vectors and is a column of
+// its own), more bags in flight per SM and ~30 % fewer warp instructions per bag.  Bags keeping
+// 65..128 instances go to the exact kernel in this form.  CELLSEG_SELECT_OCC64 = 12 | 14 | 16
+// resident CTAs per SM for the 12-vector form (85 / 73 / 64 registers).
+const int g_cta = []() {
+  const char* e = getenv("CELLSEG_SELECT_CTA");
+  return e != nullptr && atoi(e) == 64 ? 64 : 128;
+}();
+const int g_occ64 = []() {
+  const char* e = getenv("CELLSEG_SELECT_OCC64");
+  const int v = e != nullptr ? atoi(e) : 12;
+  return v == 14 || v == 16 ? v : 12;
+}();
+
+template <int NV, int THREADS, int OCC>
+cudaError_t launch_one(const Segs& segs, const float* prob, const EmitArgs& ea, int32_t* fb_count,
+                       int32_t* fb_list, cudaStream_t st) {
+  return launch_pdl(select_reg_kernel<NV, THREADS, OCC>, dim3((unsigned)segs.n_bags), dim3(THREADS), 0, st, 1,
+                    segs, prob, ea, fb_count, fb_list);
+}
+
+template <int NV>
 cudaError_t launch_reg(const Segs& segs, const float* prob, const EmitArgs& ea, int32_t* fb_count,
                        int32_t* fb_list, cudaStream_t st) {
   const int per_sm = NV <= 6 ? 7 : 5;
   if (g_persist && segs.n_bags > num_sms() * per_sm)
-    return launch_pdl(select_reg_persistent_kernel<NV, THREADS>, dim3((unsigned)(num_sms() * per_sm)), dim3(THREADS),
+    return launch_pdl(select_reg_persistent_kernel<NV, 128>, dim3((unsigned)(num_sms() * per_sm)), dim3(128),
                       0, st, 1, segs, prob, ea, fb_count, fb_list);
-  const dim3 grid((unsigned)segs.n_bags), block(THREADS);
-  if (g_occ == 12) return launch_pdl(select_reg_kernel<NV, THREADS, 12>, grid, block, 0, st, 1, segs, prob, ea, fb_count, fb_list);
-  if (g_occ == 16) return launch_pdl(select_reg_kernel<NV, THREADS, 16>, grid, block, 0, st, 1, segs, prob, ea, fb_count, fb_list);
-  return launch_pdl(select_reg_kernel<NV, THREADS, 10>, grid, block, 0, st, 1, segs, prob, ea, fb_count, fb_list);
+  if (NV > 6) return launch_one<NV, 128, 8>(segs, prob, ea, fb_count, fb_list, st);
+  if (g_occ == 12) return launch_one<NV, 128, 12>(segs, prob, ea, fb_count, fb_list, st);
+  if (g_occ == 16) return launch_one<NV, 128, 16>(segs, prob, ea, fb_count, fb_list, st);
+  return launch_one<NV, 128, 10>(segs, prob, ea, fb_count, fb_list, st);
 }
 
 }  // namespace
@@ -336,9 +367,18 @@ int launch_select_reg(const Segs& segs, const float* prob, const EmitArgs& ea, i
   *handled = false;
   const int64_t words = max_T + 3;                      // worst-case misalignment
   cudaError_t e;
-  if (words <= 2 * 128 * 4) e = launch_reg<2, 128>(segs, prob, ea, fb_count, fb_list, st);
-  else if (words <= 6 * 128 * 4) e = launch_reg<6, 128>(segs, prob, ea, fb_count, fb_list, st);
-  else if (words <= 8 * 128 * 4) e = launch_reg<8, 128>(segs, prob, ea, fb_count, fb_list, st);
+  if (g_cta == 64 && !g_persist) {
+    if (words <= 2 * 64 * 4) e = launch_one<2, 64, 16>(segs, prob, ea, fb_count, fb_list, st);
+    else if (words <= 4 * 64 * 4) e = launch_one<4, 64, 16>(segs, prob, ea, fb_count, fb_list, st);
+    else if (words <= 12 * 64 * 4) {
+      if (g_occ64 == 16) e = launch_one<12, 64, 16>(segs, prob, ea, fb_count, fb_list, st);
+      else if (g_occ64 == 14) e = launch_one<12, 64, 14>(segs, prob, ea, fb_count, fb_list, st);
+      else e = launch_one<12, 64, 12>(segs, prob, ea, fb_count, fb_list, st);
+    } else if (words <= 16 * 64 * 4) e = launch_one<16, 64, 9>(segs, prob, ea, fb_count, fb_list, st);
+    else return CS_OK;
+  } else if (words <= 2 * 128 * 4) e = launch_reg<2>(segs, prob, ea, fb_count, fb_list, st);
+  else if (words <= 6 * 128 * 4) e = launch_reg<6>(segs, prob, ea, fb_count, fb_list, st);
+  else if (words <= 8 * 128 * 4) e = launch_reg<8>(segs, prob, ea, fb_count, fb_list, st);
   else return CS_OK;
   CS_CUDA(e);
   *handled = true;

@@ -265,6 +265,77 @@ select_offsets_lookback_kernel(Segs segs, const int32_t* __restrict__ labels, in
   if (b < n) offsets[b] = s_base + (int64_t)(warp_tot[warp] + x - cnt);
 }
 
+// Offsets without any inter-CTA traffic (experiment, CELLSEG_SELECT_OFFSETS=recount): the kept counts are
+// closed-form and cheap (~20 instructions for a bag no wrap-around reaches), so CTA i simply
+// recomputes the counts of the i x 1024 bags before its own (i per thread) instead of waiting for
+// the CTAs that own them.  No flags, hence no zero-fill launch in front: CTA 0 clears the
+// declined-bag counter itself BEFORE it releases the dependent selection kernel (a dependent grid
+// starts only once every CTA of this one has triggered).  Measured: no gain over memset + look-back.
+__global__ void __launch_bounds__(1024)
+select_offsets_recount_kernel(Segs segs, const int32_t* __restrict__ labels, int32_t tiles_per_pos,
+                              int32_t topk_neg, int64_t* __restrict__ offsets, int32_t* __restrict__ fb_count) {
+  if (blockIdx.x == 0) {                                    // block-uniform
+    if (threadIdx.x == 0) {
+      fb_count[0] = 0;
+      __threadfence();
+    }
+    __syncthreads();                                         // no thread of CTA 0 triggers before the store is out
+  }
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+  __shared__ int32_t warp_tot[32];
+  __shared__ long long warp_before[32];
+  __shared__ long long s_base;
+  const int n = segs.n_bags;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  // uniform bags only (the host checks): a count needs nothing but the bag's label, and all the
+  // labels a thread needs are requested before the first one is used
+  const int64_t T = segs.uniform_T, N = segs.gtotal();
+  auto count_of = [&](int b, int32_t label) -> int32_t {
+    const int64_t k = label == 0 ? (int64_t)topk_neg : (int64_t)label * (int64_t)tiles_per_pos;
+    return kept_ranges((int64_t)b * T + segs.g_off, T, N, k).count();
+  };
+  const int b = blockIdx.x * 1024 + tid;
+  const int32_t my_label = b < n ? labels[b] : 0;
+  int32_t lab[kLookbackMaxBlocks - 1];
+#pragma unroll
+  for (int q = 0; q < kLookbackMaxBlocks - 1; ++q) lab[q] = q < (int)blockIdx.x ? labels[q * 1024 + tid] : 0;
+  const int32_t cnt = b < n ? count_of(b, my_label) : 0;
+  long long before = 0;                                      // bags tid, tid + 1024, ... of the earlier blocks
+#pragma unroll
+  for (int q = 0; q < kLookbackMaxBlocks - 1; ++q)
+    if (q < (int)blockIdx.x) before += count_of(q * 1024 + tid, lab[q]);
+  int32_t x = cnt;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    const int32_t y = __shfl_up_sync(0xffffffffu, x, o);
+    if (lane >= o) x += y;
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) before += __shfl_xor_sync(0xffffffffu, before, o);
+  if (lane == 31) warp_tot[warp] = x;
+  if (lane == 0) warp_before[warp] = before;
+  __syncthreads();
+  if (warp == 0) {
+    const int32_t w = warp_tot[lane];
+    int32_t xs = w;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const int32_t y = __shfl_up_sync(0xffffffffu, xs, o);
+      if (lane >= o) xs += y;
+    }
+    warp_tot[lane] = xs - w;                                // exclusive prefix of the warp totals
+    long long base = warp_before[lane];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) base += __shfl_xor_sync(0xffffffffu, base, o);
+    if (lane == 31) {
+      s_base = base;
+      if (blockIdx.x == gridDim.x - 1) offsets[n] = base + xs;
+    }
+  }
+  __syncthreads();
+  if (b < n) offsets[b] = s_base + (int64_t)(warp_tot[warp] + x - cnt);
+}
+
 // ---- per-bag sort + emit ----------------------------------------------------
 enum Mode { kLexsort = 0, kSelect = 1, kRank = 2 };
 
@@ -272,6 +343,10 @@ template <int kMode>
 __global__ void __launch_bounds__(kThreads)
 seg_sort_kernel(Segs segs, const float* __restrict__ prob, EmitArgs ea) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
+  // Behind a fast-path kernel this grid is launched with the programmatic-dependent-launch
+  // attribute: its CTAs become resident while the fast path's last wave drains and wait here for
+  // that grid to complete (a no-op for a plain launch).
+  asm volatile("griddepcontrol.wait;" ::: "memory");
   // Either every bag (one CTA each) or, after the fast path, only the bags it declined.
   const int n_items = ea.fb_list != nullptr ? *ea.fb_count : segs.n_bags;
   for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
@@ -413,11 +488,18 @@ const bool g_staged_fast = []() {
   return e != nullptr && e[0] == 's';
 }();
 
-// CELLSEG_SELECT_OFFSETS=ticket keeps the last-block scan for every bag count (the default for more
-// than 31 744 bags); otherwise the offsets come from the look-back kernel.
-const bool g_offsets_ticket = []() {
+// Offsets kernel: 1 = look-back scan (default), 0 = CELLSEG_SELECT_OFFSETS=recount (uniform bags
+// only; a tie with the look-back scan: 0.0685 vs 0.0675 ms per 20 000 bags, gpurun r2af), 2 = =ticket
+// (the last-block scan; also what runs for more than 31 744 bags).
+const int g_offsets_mode = []() {
   const char* e = getenv("CELLSEG_SELECT_OFFSETS");
-  return e != nullptr && e[0] == 't';
+  return e == nullptr ? 1 : (e[0] == 'r' ? 0 : (e[0] == 't' ? 2 : 1));
+}();
+
+// CELLSEG_SELECT_SORT_PDL=0: plain stream-ordered launch of the exact clean-up pass.
+const bool g_sort_plain_launch = []() {
+  const char* e = getenv("CELLSEG_SELECT_SORT_PDL");
+  return e != nullptr && e[0] == '0';
 }();
 
 struct SegHostInfo {
@@ -452,6 +534,11 @@ int launch_sort(const Segs& segs, const float* prob, const EmitArgs& ea, int64_t
     if (dev < 64) attr_set[dev][kMode] = true;
   }
   const int grid = ea.fb_list != nullptr ? (segs.n_bags < cs::num_sms() * 4 ? segs.n_bags : cs::num_sms() * 4) : segs.n_bags;
+  if (ea.fb_list != nullptr && !g_sort_plain_launch) {
+    // clean-up pass behind a fast-path kernel: launch + CTA start-up overlap that kernel's tail
+    CS_CUDA(cs::launch_pdl(seg_sort_kernel<kMode>, dim3((unsigned)grid), dim3(kThreads), smem, st, 1, segs, prob, ea));
+    return CS_OK;
+  }
   seg_sort_kernel<kMode><<<grid, kThreads, smem, st>>>(segs, prob, ea);
   CS_LAUNCH_CHECK();
   return CS_OK;
@@ -518,10 +605,15 @@ int cs_select_topk_shard(const float* prob, const int64_t* seg_offsets, int64_t 
   int32_t* ticket = fb_count + 1;
   // workspace: [0] declined-bag count, [1] ticket, bytes 8..255 look-back words, 256.. declined list
   const int off_blocks = cs::ceil_div(n_bags, 1024);
-  const bool lookback = !g_offsets_ticket && off_blocks <= kLookbackMaxBlocks && off_blocks <= cs::num_sms() &&
-                        (reinterpret_cast<uintptr_t>(workspace) & 7) == 0;
-  CS_CUDA(cudaMemsetAsync(fb_count, 0, lookback ? 256 : 2 * sizeof(int32_t), st));
-  if (lookback) {
+  const bool small_grid = off_blocks <= kLookbackMaxBlocks && off_blocks <= cs::num_sms();
+  const bool recount = g_offsets_mode == 0 && small_grid && seg_offsets == nullptr;
+  const bool lookback = !recount && g_offsets_mode <= 1 && small_grid && (reinterpret_cast<uintptr_t>(workspace) & 7) == 0;
+  if (!recount) CS_CUDA(cudaMemsetAsync(fb_count, 0, lookback ? 256 : 2 * sizeof(int32_t), st));
+  if (recount) {
+    select_offsets_recount_kernel<<<off_blocks, 1024, 0, st>>>(segs, labels, tiles_per_pos, topk_neg,
+                                                              sel_offsets_out, fb_count);
+    CS_LAUNCH_CHECK();
+  } else if (lookback) {
     select_offsets_lookback_kernel<<<off_blocks, 1024, 0, st>>>(
         segs, labels, tiles_per_pos, topk_neg, sel_offsets_out,
         reinterpret_cast<unsigned long long*>(fb_count + 2));

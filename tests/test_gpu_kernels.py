@@ -204,14 +204,17 @@ def test_select_topk_shards_equal_global(cuda, T, sizes):
         assert np.array_equal(np.concatenate(got_pl), oselect.pseudo_labels(tid, lab, want))
 
 
-@pytest.mark.parametrize("mode", ["staged", "0", "persist", "warp", "ticket", "occ12", "occ16"])
+@pytest.mark.parametrize("mode", ["staged", "0", "persist", "warp", "ticket", "occ12", "occ16", "cta64", "cta64occ16", "sortplain", "recount"])
 def test_select_topk_other_paths_subprocess(cuda, mode):
     """CELLSEG_SELECT_FAST is read when the library loads: =staged routes every bag through the
     shared-memory fast path of round 1 (still used for bags longer than 4093 instances), =0 through
     the exact bitonic kernel alone; CELLSEG_SELECT_PERSIST=1 takes the persistent form of the
     CTA-per-bag register kernel, CELLSEG_SELECT_WARP=1 the warp-per-bag kernel,
-    CELLSEG_SELECT_OFFSETS=ticket the last-block offsets scan instead of the look-back one,
-    CELLSEG_SELECT_OCC=12 | 16 the register kernel held to 40 / 32 registers."""
+    CELLSEG_SELECT_OFFSETS=ticket | recount the last-block scan / the recount kernel instead of the
+    look-back offsets scan,
+    CELLSEG_SELECT_OCC=12 | 16 the register kernel held to 40 / 32 registers, CELLSEG_SELECT_CTA=64
+    its two-warp form (CELLSEG_SELECT_OCC64: resident CTAs per SM), CELLSEG_SELECT_SORT_PDL=0 a plain
+    launch of the exact clean-up pass."""
     import os
     import subprocess
     import sys
@@ -222,7 +225,11 @@ def test_select_topk_other_paths_subprocess(cuda, mode):
                                                 "warp": {"CELLSEG_SELECT_WARP": "1"},
                                                 "occ12": {"CELLSEG_SELECT_OCC": "12"},
                                                 "occ16": {"CELLSEG_SELECT_OCC": "16"},
-                                                "ticket": {"CELLSEG_SELECT_OFFSETS": "ticket"}}.get(
+                                                "sortplain": {"CELLSEG_SELECT_SORT_PDL": "0"},
+                                                "cta64": {"CELLSEG_SELECT_CTA": "64"},
+                                                "cta64occ16": {"CELLSEG_SELECT_CTA": "64", "CELLSEG_SELECT_OCC64": "16"},
+                                                "ticket": {"CELLSEG_SELECT_OFFSETS": "ticket"},
+                                                "recount": {"CELLSEG_SELECT_OFFSETS": "recount"}}.get(
                                                     mode, {"CELLSEG_SELECT_FAST": mode}))),
                        capture_output=True, text=True, timeout=900)
     assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-2000:]
