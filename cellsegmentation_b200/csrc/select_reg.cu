@@ -65,6 +65,14 @@ __device__ __forceinline__ void bitonic64_stage(uint32_t& a, uint32_t& b, int la
   }
 }
 
+// The same for 32 elements, one per lane; final order descending (rank r in lane r).
+template <int K, int J>
+__device__ __forceinline__ void bitonic32_stage(uint32_t& a, int lane) {
+  const uint32_t o = __shfl_xor_sync(0xffffffffu, a, J);
+  const bool lower = (lane & J) == 0, desc = (lane & K) == 0;
+  a = (desc == lower) ? max(a, o) : min(a, o);
+}
+
 // Per-bag shared state; two copies alternate between consecutive bags of a persistent CTA (a
 // thread is never more than one bag ahead of the slowest: every bag has block barriers).
 struct SelState {
@@ -168,6 +176,23 @@ __device__ __forceinline__ void bag_process(const Segs& segs, const EmitArgs& ea
     if (m > kInf) st.tau = 0xffffffffu;                    // bad input: decline (wins over the store below)
     __syncthreads();
     if (rank == n - 1 && st.tau != 0xffffffffu) st.tau = m == 0u ? 0xffffffffu : m;
+  } else if (warp == 0 && n <= 16 && ea.small_n_cols32) {
+    // small kept counts (most positive bags): the n-th largest of 32 column maxima (a column = the
+    // four / two threads lane, lane + 32, ...) is as sharp a threshold for n <= 16 as 64 columns are
+    // for n <= 32 (~1.15-1.4 n candidates) and its network has 15 single-register stages, not 21
+    // double ones
+    uint32_t a = max(st.tmax[lane], st.tmax[lane + 32]);
+    if (THREADS == 128) a = max(a, max(st.tmax[lane + 64], st.tmax[lane + 96]));
+    bitonic32_stage<2, 1>(a, lane);
+    bitonic32_stage<4, 2>(a, lane);   bitonic32_stage<4, 1>(a, lane);
+    bitonic32_stage<8, 4>(a, lane);   bitonic32_stage<8, 2>(a, lane);   bitonic32_stage<8, 1>(a, lane);
+    bitonic32_stage<16, 8>(a, lane);  bitonic32_stage<16, 4>(a, lane);  bitonic32_stage<16, 2>(a, lane);
+    bitonic32_stage<16, 1>(a, lane);
+    bitonic32_stage<32, 16>(a, lane); bitonic32_stage<32, 8>(a, lane);  bitonic32_stage<32, 4>(a, lane);
+    bitonic32_stage<32, 2>(a, lane);  bitonic32_stage<32, 1>(a, lane);
+    const uint32_t top = __shfl_sync(0xffffffffu, a, 0);
+    const uint32_t t = __shfl_sync(0xffffffffu, a, n - 1);
+    if (lane == 0) st.tau = (top > kInf || t == 0u) ? 0xffffffffu : t;
   } else if (warp == 0) {
     uint32_t a, c;
     if (THREADS == 128) {

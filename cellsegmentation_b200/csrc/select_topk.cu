@@ -502,6 +502,12 @@ const bool g_sort_plain_launch = []() {
   return e != nullptr && e[0] == '0';
 }();
 
+// CELLSEG_SELECT_COL32=0: always take the threshold from 64 column maxima (select_reg.cu).
+const bool g_cols32 = []() {
+  const char* e = getenv("CELLSEG_SELECT_COL32");
+  return !(e != nullptr && e[0] == '0');
+}();
+
 struct SegHostInfo {
   int max_pow2;
 };
@@ -639,6 +645,7 @@ int cs_select_topk_shard(const float* prob, const int64_t* seg_offsets, int64_t 
   ea.label_out = sel_label_out;
   ea.out_offsets = sel_offsets_out;
   ea.capacity = capacity;
+  ea.small_n_cols32 = g_cols32 ? 1 : 0;
   // Fast paths first: a register-resident CTA per bag (select_reg.cu) for bags of up to 4093
   // instances (with CELLSEG_SELECT_WARP=1 a warp per bag, select_warp.cu, up to 3069),
   // shared-memory staged (select_fast.cu) beyond; bags they decline are listed and ordered exactly

@@ -13,6 +13,7 @@ import sys
 
 VARIANTS = {
     "cta+lookback offsets (default)": {},
+    "cta+lookback, threshold always from 64 columns": {"CELLSEG_SELECT_COL32": "0"},
     "cta+recount offsets": {"CELLSEG_SELECT_OFFSETS": "recount"},
     "cta+lookback, plain launch of the clean-up pass": {"CELLSEG_SELECT_SORT_PDL": "0"},
     "cta, 12 CTAs/SM (40 registers)": {"CELLSEG_SELECT_OCC": "12"},

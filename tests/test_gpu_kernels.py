@@ -174,6 +174,25 @@ def test_select_topk_many_bags_ring_wraps(cuda, T, n_bags, misalign):
     assert np.array_equal(pl.cpu().numpy(), oselect.pseudo_labels(tid, lab, want))
 
 
+def test_select_topk_more_bags_than_the_lookback_scan_takes(cuda):
+    """40 000 small bags: 40 offset blocks > the 31 the look-back scan takes, so the last-block
+    ("ticket") scan runs, in two shared-memory chunks (24 576 counts each), in front of the two-vector
+    register kernel; checked against the oracle incl. the offsets themselves."""
+    ops = _ops()
+    T, n_bags = 21, 40000
+    rng = np.random.default_rng(5)
+    p = rng.uniform(0, 1, T * n_bags).astype(np.float32)
+    lab = np.minimum(rng.geometric(1.0 / 3.0, n_bags), 40).astype(np.int32)
+    lab[rng.uniform(size=n_bags) < 0.3] = 0
+    tid = np.repeat(np.arange(n_bags), T)
+    want = oselect.sample_indices(tid, lab, p, 1, 4)
+    idx, pl, off = ops.select_topk(torch.from_numpy(p).to(cuda), torch.from_numpy(lab).to(cuda), n_bags, T, 1, 4)
+    assert np.array_equal(idx.cpu().numpy().astype(np.int64), want)
+    assert np.array_equal(pl.cpu().numpy(), oselect.pseudo_labels(tid, lab, want))
+    kept = np.bincount(tid[want], minlength=n_bags)
+    assert np.array_equal(np.diff(off.cpu().numpy()), kept)
+
+
 @pytest.mark.parametrize("T,sizes", [(225, [2, 1, 1, 3, 1]), (64, [1, 1, 1, 1]), (300, [3, 0, 2, 1])])
 def test_select_topk_shards_equal_global(cuda, T, sizes):
     """Bags partitioned over ranks: every shard evaluates the wrap-around predicate at its GLOBAL
@@ -204,7 +223,7 @@ def test_select_topk_shards_equal_global(cuda, T, sizes):
         assert np.array_equal(np.concatenate(got_pl), oselect.pseudo_labels(tid, lab, want))
 
 
-@pytest.mark.parametrize("mode", ["staged", "0", "persist", "warp", "ticket", "occ12", "occ16", "cta64", "cta64occ16", "sortplain", "recount"])
+@pytest.mark.parametrize("mode", ["staged", "0", "persist", "warp", "ticket", "occ12", "occ16", "cta64", "cta64occ16", "sortplain", "recount", "col64"])
 def test_select_topk_other_paths_subprocess(cuda, mode):
     """CELLSEG_SELECT_FAST is read when the library loads: =staged routes every bag through the
     shared-memory fast path of round 1 (still used for bags longer than 4093 instances), =0 through
@@ -214,7 +233,7 @@ def test_select_topk_other_paths_subprocess(cuda, mode):
     look-back offsets scan,
     CELLSEG_SELECT_OCC=12 | 16 the register kernel held to 40 / 32 registers, CELLSEG_SELECT_CTA=64
     its two-warp form (CELLSEG_SELECT_OCC64: resident CTAs per SM), CELLSEG_SELECT_SORT_PDL=0 a plain
-    launch of the exact clean-up pass."""
+    launch of the exact clean-up pass, CELLSEG_SELECT_COL32=0 the 64-column threshold for every kept count."""
     import os
     import subprocess
     import sys
@@ -229,7 +248,8 @@ def test_select_topk_other_paths_subprocess(cuda, mode):
                                                 "cta64": {"CELLSEG_SELECT_CTA": "64"},
                                                 "cta64occ16": {"CELLSEG_SELECT_CTA": "64", "CELLSEG_SELECT_OCC64": "16"},
                                                 "ticket": {"CELLSEG_SELECT_OFFSETS": "ticket"},
-                                                "recount": {"CELLSEG_SELECT_OFFSETS": "recount"}}.get(
+                                                "recount": {"CELLSEG_SELECT_OFFSETS": "recount"},
+                                                "col64": {"CELLSEG_SELECT_COL32": "0"}}.get(
                                                     mode, {"CELLSEG_SELECT_FAST": mode}))),
                        capture_output=True, text=True, timeout=900)
     assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-2000:]
