@@ -72,6 +72,7 @@ struct EmitArgs {
   int64_t capacity;
   const int32_t* fb_count;      // exact kernel after the fast path: number of declined bags ...
   const int32_t* fb_list;       // ... and their indices (nullptr: process every bag)
+  int sort_pdl;                 // host side: the clean-up pass may be launched as a programmatic dependent
   int small_n_cols32;           // select_reg.cu: threshold from 32 column maxima when a bag keeps <= 16
   int rank_fast_cap;            // kRank: bags with <= this many kept entries were emitted by the
                                 // fast kernel and are skipped by the exact one (0: none)

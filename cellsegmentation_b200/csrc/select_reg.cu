@@ -311,24 +311,27 @@ select_reg_persistent_kernel(Segs segs, const float* __restrict__ prob, EmitArgs
   static_assert(THREADS == 128, "two threads per column");
   __shared__ SelState st[2];
   int b = blockIdx.x;
-  if (b >= segs.n_bags) return;
-  BagView bv = bag_view<NV, THREADS>(segs, prob, b);
-  uint4 x[NV];
-  bag_load<NV, THREADS>(bv, x, threadIdx.x);
-  for (int k = 0; b < segs.n_bags; ++k) {
-    const int bn = b + (int)gridDim.x;
-    BagView bvn = bv;
-    uint4 xn[NV];
-    if (bn < segs.n_bags) {
-      bvn = bag_view<NV, THREADS>(segs, prob, bn);
-      bag_load<NV, THREADS>(bvn, xn, threadIdx.x);
-    }
-    if (bv.T > 0) bag_process<NV, THREADS>(segs, ea, b, bv, x, st[k & 1], fb_count, fb_list);
-    b = bn;
-    bv = bvn;
+  if (b < segs.n_bags) {
+    BagView bv = bag_view<NV, THREADS>(segs, prob, b);
+    uint4 x[NV];
+    bag_load<NV, THREADS>(bv, x, threadIdx.x);
+    for (int k = 0; b < segs.n_bags; ++k) {
+      const int bn = b + (int)gridDim.x;
+      BagView bvn = bv;
+      uint4 xn[NV];
+      if (bn < segs.n_bags) {
+        bvn = bag_view<NV, THREADS>(segs, prob, bn);
+        bag_load<NV, THREADS>(bvn, xn, threadIdx.x);
+      }
+      if (bv.T > 0) bag_process<NV, THREADS>(segs, ea, b, bv, x, st[k & 1], fb_count, fb_list);
+      b = bn;
+      bv = bvn;
 #pragma unroll
-    for (int j = 0; j < NV; ++j) x[j] = xn[j];
+      for (int j = 0; j < NV; ++j) x[j] = xn[j];
+    }
   }
+  // like select_reg_kernel: no thread leaves before the offsets kernel has completed
+  asm volatile("griddepcontrol.wait;" ::: "memory");
 }
 
 // CELLSEG_SELECT_PERSIST=1 selects the persistent kernel.  Measured at 20 000 bags x 3025 (ncu r2i):

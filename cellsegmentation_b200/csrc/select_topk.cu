@@ -540,7 +540,7 @@ int launch_sort(const Segs& segs, const float* prob, const EmitArgs& ea, int64_t
     if (dev < 64) attr_set[dev][kMode] = true;
   }
   const int grid = ea.fb_list != nullptr ? (segs.n_bags < cs::num_sms() * 4 ? segs.n_bags : cs::num_sms() * 4) : segs.n_bags;
-  if (ea.fb_list != nullptr && !g_sort_plain_launch) {
+  if (ea.fb_list != nullptr && ea.sort_pdl && !g_sort_plain_launch) {
     // clean-up pass behind a fast-path kernel: launch + CTA start-up overlap that kernel's tail
     CS_CUDA(cs::launch_pdl(seg_sort_kernel<kMode>, dim3((unsigned)grid), dim3(kThreads), smem, st, 1, segs, prob, ea));
     return CS_OK;
@@ -649,13 +649,16 @@ int cs_select_topk_shard(const float* prob, const int64_t* seg_offsets, int64_t 
   // Fast paths first: a register-resident CTA per bag (select_reg.cu) for bags of up to 4093
   // instances (with CELLSEG_SELECT_WARP=1 a warp per bag, select_warp.cu, up to 3069),
   // shared-memory staged (select_fast.cu) beyond; bags they decline are listed and ordered exactly
-  bool handled = false;
+  bool handled = false, ordered = false;
   if (!g_disable_fast) {
     if (!g_staged_fast) {
       rc = launch_select_warp(segs, prob, ea, uniform_T, fb_count, fb_list, st, &handled);
       if (rc != CS_OK) return rc;
       if (!handled) rc = launch_select_reg(segs, prob, ea, uniform_T, fb_count, fb_list, st, &handled);
       if (rc != CS_OK) return rc;
+      // every thread of these kernels waits for the offsets kernel before it exits, so a clean-up
+      // pass that is their programmatic dependent is ordered behind the offsets too
+      ordered = handled;
     }
     if (!handled) {
       rc = launch_select_fast(segs, prob, ea, uniform_T, fb_count, fb_list, st, &handled);
@@ -665,6 +668,7 @@ int cs_select_topk_shard(const float* prob, const int64_t* seg_offsets, int64_t 
   if (handled) {
     ea.fb_count = fb_count;
     ea.fb_list = fb_list;
+    ea.sort_pdl = ordered ? 1 : 0;
   }
   return launch_sort<kSelect>(segs, prob, ea, uniform_T, st);
 }
