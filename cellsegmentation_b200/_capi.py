@@ -66,6 +66,9 @@ _PROTOS = {
                                  c_int, c_void_p, c_void_p]),
     "cs_paint_mask_xy": (c_int, [c_void_p, c_void_p, c_void_p, c_int64, c_int, c_int, c_int, c_int,
                                  c_void_p, c_void_p]),
+    "cs_paint_heatmap_gather_workspace_bytes": (c_int64, [c_int, c_int, c_int, c_int, c_int]),
+    "cs_paint_heatmap_gather": (c_int, [c_void_p, c_void_p, c_int64, c_int, c_int, c_int, c_int, c_int,
+                                        c_int, c_void_p, c_void_p, c_int64, c_void_p]),
     "cs_paint_heatmap_xy": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_int, c_int,
                                     c_int, c_int, c_void_p, c_void_p]),
     "cs_heatmap_blend": (c_int, [c_void_p, c_void_p, c_void_p, c_int64, c_void_p, c_void_p]),

@@ -7,8 +7,10 @@
 //                   largest kept covering probability: per-pixel max.
 //   heatmap         :165   255 - np.uint8(255 * map)   (float64 product, truncation)
 //
-// One warp paints one tile row-by-row; masks are idempotent byte stores, heatmaps
-// use atomicMax on the int view of non-negative floats.
+// Scatter form: one warp paints one tile row-by-row; masks are idempotent byte stores, heatmaps
+// use atomicMax on the int view of non-negative floats (the caller zero-fills the maps).
+// Gather form (heatmaps of tiles on the regular grid, cs_paint_heatmap_gather): every pixel is
+// written once as the maximum over the kept tiles covering it.
 #include "common.cuh"
 
 namespace {
@@ -142,6 +144,103 @@ heat_blend_kernel(const float* __restrict__ heat, const uint8_t* __restrict__ im
   }
 }
 
+// ---- heatmap, gather form -------------------------------------------------------------------
+// The kept tiles of the regular grid are first written into a dense per-bag table of
+// probabilities (T floats per bag, 3 % of a map); a CTA then builds one bag's map by a
+// separable maximum -- over the covering grid columns for every (grid row, x), then over the
+// covering grid rows for every pixel -- and writes every pixel exactly once: no zero-fill of the
+// maps, no atomics on them, no read of them.  The covering ranges of every x and y are tabulated
+// once per CTA, so the per-pixel work has no division.  Grid positions covering coordinate c along an axis
+// are a contiguous range, because the position coordinates min(g * I, dim - S) are monotonic.
+__device__ __forceinline__ void cover_range(int c, int dim, int S, int I, int gcnt, int* lo, int* hi) {
+  const int last = dim - S;
+  int h = c / I;
+  if (h > gcnt - 1 || c >= last) h = gcnt - 1;
+  int l = c - S + 1 <= 0 ? 0 : (c - S + I) / I;            // ceil((c - S + 1) / I)
+  if (l > gcnt - 1) l = gcnt - 1;
+  *lo = l;
+  *hi = h;
+}
+
+__global__ void __launch_bounds__(256)
+heat_table_kernel(Grid g, const int32_t* __restrict__ sel, const float* __restrict__ prob, int64_t n_sel,
+                  int* __restrict__ table) {
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; j < n_sel; j += stride) {
+    const int32_t inst = sel[j];
+    if (inst < 0) continue;
+    const int64_t b = inst / g.tiles_per_bag;
+    if (g.bag_base + b >= g.n_bags) continue;
+    const float p = prob[j];
+    if (!(p >= 0.0f)) continue;                            // negative or NaN never passes `prob > thr >= 0`
+    // a tile listed twice keeps its larger probability, like the last write of the reference loop
+    atomicMax(table + (g.bag_base + b) * g.tiles_per_bag + (inst - b * g.tiles_per_bag), __float_as_int(p));
+  }
+}
+
+constexpr int kGatherThreads = 640;
+
+// Shared memory: colmax [grid_h][W] | bag table [grid_h][grid_w] | xlo, xhi [W] | ylo, yhi [H]
+__host__ __device__ inline size_t gather_smem_bytes(int grid_h, int grid_w, int H, int W) {
+  return ((size_t)grid_h * W + (size_t)grid_h * grid_w + 2 * (size_t)W + 2 * (size_t)H) * 4;
+}
+
+__global__ void __launch_bounds__(kGatherThreads, 2)
+heat_gather_kernel(Grid g, int grid_h, const float* __restrict__ table, float* __restrict__ out) {
+  extern __shared__ float gsm[];
+  const int W = g.W, H = g.H, S = g.tile, I = g.interval, gw = g.grid_w;
+  const int T = grid_h * gw;
+  float* colmax = gsm;                                     // maximum over the covering grid columns
+  float* tab = colmax + grid_h * W;                        // this bag's table
+  int* xlo = reinterpret_cast<int*>(tab + T);
+  int* xhi = xlo + W;
+  int* ylo = xhi + W;
+  int* yhi = ylo + H;
+  // the covering ranges depend on the geometry only: once per CTA
+  for (int i = threadIdx.x; i < W; i += kGatherThreads) cover_range(i, W, S, I, gw, xlo + i, xhi + i);
+  for (int i = threadIdx.x; i < H; i += kGatherThreads) cover_range(i, H, S, I, grid_h, ylo + i, yhi + i);
+  const int step_gy = kGatherThreads / W, step_x = kGatherThreads - step_gy * W;
+  const int segs = max(1, kGatherThreads / W);
+  for (int bag = blockIdx.x; bag < g.n_bags; bag += gridDim.x) {
+    const float* tb = table + (int64_t)bag * g.tiles_per_bag;
+    for (int i = threadIdx.x; i < T; i += kGatherThreads) tab[i] = __ldg(tb + i);
+    __syncthreads();                                       // (also orders the range tables on the first bag)
+    // phase A: colmax[gy][x]; consecutive threads take consecutive x of a grid row
+    {
+      int gy = threadIdx.x / W, x = threadIdx.x - gy * W;
+      while (gy < grid_h) {
+        float m = 0.0f;
+        const float* row = tab + gy * gw;
+        for (int gx = xlo[x]; gx <= xhi[x]; ++gx) m = fmaxf(m, row[gx]);
+        colmax[gy * W + x] = m;
+        gy += step_gy;
+        x += step_x;
+        if (x >= W) { x -= W; ++gy; }
+      }
+    }
+    __syncthreads();
+    // phase B: thread (segment, x) walks its rows of column x; consecutive threads write consecutive
+    // x; the maximum over the covering grid rows is recomputed only when that range moves
+    for (int col = threadIdx.x; col < segs * W; col += kGatherThreads) {
+      const int seg = col / W, x = col - seg * W;
+      const int y0 = (int)((int64_t)H * seg / segs), y1 = (int)((int64_t)H * (seg + 1) / segs);
+      float* o = out + ((int64_t)bag * H + y0) * W + x;
+      int clo = -1, chi = -2;
+      float m = 0.0f;
+      for (int y = y0; y < y1; ++y, o += W) {
+        const int lo = ylo[y], hi = yhi[y];
+        if (lo != clo || hi != chi) {
+          m = 0.0f;
+          for (int gy = lo; gy <= hi; ++gy) m = fmaxf(m, colmax[gy * W + x]);
+          clo = lo; chi = hi;
+        }
+        __stcs(o, m);
+      }
+    }
+    __syncthreads();                                       // colmax / tab are rewritten for the next bag
+  }
+}
+
 int make_grid(const char* fn, int H, int W, int tile, int interval, int bag_base, int n_bags,
               Grid* g) {
   int gh = cs::grid_count(H, tile, interval), gw = cs::grid_count(W, tile, interval);
@@ -187,6 +286,54 @@ int cs_paint_heatmap(const int32_t* sel_idx, const float* sel_prob, int64_t n_se
   if (n_sel == 0) return CS_OK;
   paint_heat_kernel<<<warp_grid(n_sel), 256, 0, cs::as_stream(stream)>>>(g, sel_idx, XY{}, sel_prob,
                                                                         n_sel, heat_out);
+  CS_LAUNCH_CHECK();
+  return CS_OK;
+}
+
+int64_t cs_paint_heatmap_gather_workspace_bytes(int H, int W, int tile, int interval, int n_bags) {
+  const int gh = cs::grid_count(H, tile, interval), gw = cs::grid_count(W, tile, interval);
+  if (gh <= 0 || gw <= 0 || n_bags <= 0) return 0;
+  return (int64_t)n_bags * gh * gw * (int64_t)sizeof(float);
+}
+
+int cs_paint_heatmap_gather(const int32_t* sel_idx, const float* sel_prob, int64_t n_sel, int H, int W,
+                            int tile, int interval, int bag_base, int n_bags, float* heat_out,
+                            void* workspace, int64_t workspace_bytes, void* stream) {
+  CS_REQUIRE(heat_out != nullptr && ((sel_idx != nullptr && sel_prob != nullptr) || n_sel == 0),
+             "cs_paint_heatmap_gather: NULL pointer");
+  CS_REQUIRE(n_sel >= 0, "cs_paint_heatmap_gather: n_sel < 0");
+  Grid g;
+  int rc = make_grid("cs_paint_heatmap_gather", H, W, tile, interval, bag_base, n_bags, &g);
+  if (rc != CS_OK) return rc;
+  const int gh = cs::grid_count(H, tile, interval);
+  const int64_t need = cs_paint_heatmap_gather_workspace_bytes(H, W, tile, interval, n_bags);
+  CS_REQUIRE(workspace != nullptr && workspace_bytes >= need,
+             "cs_paint_heatmap_gather: workspace too small (need %lld bytes)", (long long)need);
+  const size_t smem = gather_smem_bytes(gh, g.grid_w, H, W);
+  if (smem > 200 * 1024) {
+    cs::set_error("cs_paint_heatmap_gather: %d grid rows x %d pixels do not fit shared memory; use cs_paint_heatmap",
+                  gh, W);
+    return CS_ERR_UNSUPPORTED;
+  }
+  cudaStream_t st = cs::as_stream(stream);
+  static bool attr_done[64] = {false};
+  int dev = 0;
+  CS_CUDA(cudaGetDevice(&dev));
+  if (dev >= 64 || !attr_done[dev]) {
+    CS_CUDA(cudaFuncSetAttribute(heat_gather_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    if (dev < 64) attr_done[dev] = true;
+  }
+  CS_CUDA(cudaMemsetAsync(workspace, 0, (size_t)need, st));
+  if (n_sel > 0) {
+    int64_t want = cs::ceil_div<int64_t>(n_sel, 256);
+    int grid = (int)(want < (int64_t)cs::num_sms() * 8 ? want : (int64_t)cs::num_sms() * 8);
+    heat_table_kernel<<<grid, 256, 0, st>>>(g, sel_idx, sel_prob, n_sel, static_cast<int*>(workspace));
+    CS_LAUNCH_CHECK();
+  }
+  const int per_sm = (int)((size_t)(220 * 1024) / (smem + 1024));
+  const int resident = cs::num_sms() * (per_sm < 1 ? 1 : (per_sm > 2 ? 2 : per_sm));
+  heat_gather_kernel<<<n_bags < resident ? n_bags : resident, kGatherThreads, smem, st>>>(
+      g, gh, static_cast<const float*>(workspace), heat_out);
   CS_LAUNCH_CHECK();
   return CS_OK;
 }

@@ -165,6 +165,22 @@ def paint_heatmap(sel_idx, sel_prob, n_bags, H, W, tile, interval, bag_base=0, o
     return out
 
 
+def paint_heatmap_gather(sel_idx, sel_prob, n_bags, H, W, tile, interval, bag_base=0, out=None):
+    """paint_heatmap as a gather: every pixel written once as the max over the kept covering tiles
+    (no zero-fill, no atomics on the maps).  Raises CellSegError (unsupported) when the geometry
+    does not fit shared memory -- callers fall back to paint_heatmap."""
+    _req_cuda(sel_idx, "sel_idx", torch.int32)
+    _req_cuda(sel_prob, "sel_prob", torch.float32)
+    if out is None:
+        out = torch.empty((n_bags, H, W), dtype=torch.float32, device=sel_idx.device)
+    nbytes = int(lib().cs_paint_heatmap_gather_workspace_bytes(H, W, tile, interval, n_bags))
+    ws = torch.empty(max(nbytes, 4), dtype=torch.uint8, device=sel_idx.device)
+    check(lib().cs_paint_heatmap_gather(ptr(sel_idx), ptr(sel_prob), sel_idx.numel(), H, W, tile, interval,
+                                        bag_base, n_bags, ptr(out), ptr(ws), nbytes, cur_stream()),
+          "cs_paint_heatmap_gather")
+    return out
+
+
 def paint_mask_xy(bag, x, y, n_bags, H, W, tile, out=None):
     """paint_mask for explicit (bag, row, col) int32 arrays."""
     for t, nm in ((bag, "bag"), (x, "x"), (y, "y")):

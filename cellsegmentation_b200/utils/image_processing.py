@@ -12,7 +12,7 @@ import os
 import numpy as np
 import torch
 
-from .. import ops
+from .. import _capi, ops
 
 
 def _cuda_dev():
@@ -36,6 +36,36 @@ def _xy_tensors(tiles, groups, dev):
     x = torch.from_numpy(np.ascontiguousarray(tiles[:, 0])).to(dev)
     y = torch.from_numpy(np.ascontiguousarray(tiles[:, 1])).to(dev)
     return g, x, y
+
+
+def _grid_instances(dataset, tiles, groups):
+    """Instance indices (bag * T + grid position) of an explicit tile list when every tile lies on
+    the dataset's regular grid (what rank() / sample() hand out), else None."""
+    if not getattr(dataset, "has_tiles", False):
+        return None
+    grid = dataset._ensure_grid()
+    tiles = np.asarray(tiles).reshape(-1, 2).astype(np.int64)
+    groups = np.asarray(groups).astype(np.int64)
+    n, T = len(dataset.images), len(grid)
+    if len(tiles) == 0 or T == 0 or n * T >= 2 ** 31:
+        return None
+    H, W = int(dataset.image_size[0]), int(dataset.image_size[1])
+    S, I = int(dataset.tile_size), int(dataset.interval)
+
+    def inv(c, dim):
+        last = dim - S
+        ok = (c >= 0) & (c <= last) & ((c == last) | (c % I == 0))
+        cnt = (last // I) + 1 + (1 if last % I else 0)
+        return np.where(c == last, cnt - 1, c // I), ok, cnt
+
+    gy, ok_y, _ = inv(tiles[:, 0], H)
+    gx, ok_x, gw = inv(tiles[:, 1], W)
+    if not (ok_y.all() and ok_x.all() and (groups >= 0).all() and (groups < n).all()):
+        return None
+    t = gy * gw + gx
+    if not np.array_equal(np.asarray(grid)[t].astype(np.int64), tiles):
+        return None
+    return (groups * T + t).astype(np.int32)
 
 
 def hsv_refine_batch(images_dev, masks_dev, v_thresh=170):
@@ -93,9 +123,20 @@ def heatmap_arrays(testset, tiles, probs, groups, chunk=2048):
     dev = _cuda_dev()
     n = len(testset.images)
     H, W = int(testset.image_size[0]), int(testset.image_size[1])
-    g, x, y = _xy_tensors(tiles, groups, dev)
     p = torch.from_numpy(np.ascontiguousarray(np.asarray(probs, dtype=np.float32))).to(dev)
-    heat = ops.paint_heatmap_xy(g, x, y, p, n, H, W, testset.tile_size)
+    heat = None
+    inst = _grid_instances(testset, tiles, groups)
+    if inst is not None:
+        # tiles of the regular grid (rank() output): gather form, every pixel written once
+        try:
+            heat = ops.paint_heatmap_gather(torch.from_numpy(inst).to(dev), p, n, H, W, testset.tile_size,
+                                            testset.interval)
+        except _capi.CellSegError as e:
+            if "shared memory" not in str(e):
+                raise
+    if heat is None:
+        g, x, y = _xy_tensors(tiles, groups, dev)
+        heat = ops.paint_heatmap_xy(g, x, y, p, n, H, W, testset.tile_size)
     lut = _jet_lut(dev)
     out = np.empty((n, H, W, 3), np.uint8)
     for b0 in range(0, n, chunk):

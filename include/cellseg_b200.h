@@ -230,6 +230,18 @@ int cs_paint_heatmap(const int32_t* sel_idx, const float* sel_prob, int64_t n_se
                      int W, int tile, int interval, int bag_base, int n_bags,
                      float* heat_out, void* stream);
 
+/* The same map by a gather (no zero-fill of heat_out, no atomics on it, every pixel written
+ * once): the kept tiles go into a dense table of T floats per bag in `workspace`
+ * (cs_paint_heatmap_gather_workspace_bytes), then heat_out[b][y][x] = the maximum over the
+ * kept tiles covering (y, x).  heat_out f32 [n_bags][H][W] is OVERWRITTEN for all n_bags maps
+ * (0 where no kept tile covers a pixel).  CS_ERR_UNSUPPORTED when grid_rows x W floats exceed
+ * 200 KB of shared memory (interval 1 on 299 x 299): use cs_paint_heatmap. */
+int64_t cs_paint_heatmap_gather_workspace_bytes(int H, int W, int tile, int interval, int n_bags);
+int cs_paint_heatmap_gather(const int32_t* sel_idx, const float* sel_prob, int64_t n_sel, int H,
+                            int W, int tile, int interval, int bag_base, int n_bags,
+                            float* heat_out, void* workspace, int64_t workspace_bytes,
+                            void* stream);
+
 /* Same two painting loops for explicit tile lists, the form the reference API passes
  * around (`tiles` [n][2] = (row, col) and `groups` [n] = bag): tiles outside the image
  * or bag range are ignored. */

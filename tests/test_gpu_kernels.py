@@ -323,6 +323,33 @@ def test_paint_mask_and_heatmap_golden(cuda):
         assert np.array_equal(np.uint8(img), g["heat_imgs"][i])
 
 
+@pytest.mark.parametrize("H,W,S,I,n_bags,bag_base", [(96, 96, 16, 5, 3, 0), (299, 299, 32, 5, 5, 0), (100, 131, 32, 7, 4, 1),
+                                                       (64, 64, 16, 8, 2, 0), (299, 299, 32, 20, 6, 2), (40, 33, 32, 3, 2, 0)])
+def test_paint_heatmap_gather_equals_scatter(cuda, H, W, S, I, n_bags, bag_base):
+    """cs_paint_heatmap_gather (every pixel written once: max over the kept covering tiles) against
+    the scatter form cs_paint_heatmap (atomicMax on zeroed maps), bit-exact: stride not dividing the
+    span, S a multiple of I, single-position axes, a bag offset, duplicates, NaN / negative
+    probabilities, bags without kept tiles, and an output buffer full of garbage."""
+    ops = _ops()
+    rng = np.random.default_rng(H * 7 + W + I)
+    T = len(otiles.get_tiles((H, W, 3), I, S))
+    own = n_bags - bag_base                                   # bags the instance indices can address
+    n_sel = max(1, (own * T) // 3)
+    sel = rng.integers(0, own * T, n_sel).astype(np.int32)
+    if own > 1:
+        sel = sel[sel // T != own - 1]                        # one bag keeps nothing
+    sel = np.concatenate([sel, sel[:5]])                      # duplicates with other probabilities
+    p = rng.uniform(0, 1, sel.size).astype(np.float32)
+    p[::17] = np.float32(-0.25)
+    p[5::23] = np.float32("nan")
+    d_sel, d_p = torch.from_numpy(sel).to(cuda), torch.from_numpy(p).to(cuda)
+    want = ops.paint_heatmap(d_sel, d_p, n_bags, H, W, S, I, bag_base=bag_base)
+    out = torch.full((n_bags, H, W), 7.5, dtype=torch.float32, device=cuda)
+    got = ops.paint_heatmap_gather(d_sel, d_p, n_bags, H, W, S, I, bag_base=bag_base, out=out)
+    assert torch.equal(got, want)
+    assert float(want.max()) > 0
+
+
 def test_heatmap_to_gray_all_thresholded_probs(cuda):
     """uint8(255*p) in float64 for every float32 p in [0.9, 1] plus a sweep of [0,1]."""
     ops = _ops()

@@ -211,3 +211,36 @@ def test_scratch_autograd_path_matches_reference_modules(arch):
             o.square().sum().backward()
         assert torch.equal(nets[0].layer2[0].conv1.weight.grad, nets[1].layer2[0].conv1.weight.grad)
         assert torch.equal(nets[0].bn1.running_mean, nets[1].bn1.running_mean)
+
+
+def test_grid_instances_inverts_the_tile_grid():
+    """utils.image_processing._grid_instances: (row, col, bag) of grid tiles -> bag * T + position,
+    None for a tile off the grid (heatmap() then keeps the explicit-coordinate painter)."""
+    from cellsegmentation_b200.utils import image_processing as ip
+
+    class DS:
+        has_tiles = True
+        image_size = (100, 131)
+        tile_size, interval = 32, 7
+
+        def __init__(self):
+            self.images = [None] * 4
+            self._g = np.array(otiles.get_tiles((100, 131, 3), 7, 32), np.int32)
+
+        def _ensure_grid(self):
+            return self._g
+
+    ds = DS()
+    T = len(ds._g)
+    rng = np.random.default_rng(0)
+    t = rng.integers(0, T, 200)
+    g = rng.integers(0, 4, 200)
+    inst = ip._grid_instances(ds, ds._g[t], g)
+    assert inst is not None and np.array_equal(inst, g * T + t)
+    # the final (clamped) position of either axis and position 0
+    edge = np.array([0, T - 1, len(set(ds._g[:, 1])) - 1])
+    assert np.array_equal(ip._grid_instances(ds, ds._g[edge], np.zeros(3, int)), edge)
+    off = ds._g[t].copy()
+    off[3, 1] += 1
+    assert ip._grid_instances(ds, off, g) is None
+    assert ip._grid_instances(ds, ds._g[t], np.where(np.arange(200) == 7, 4, g)) is None
