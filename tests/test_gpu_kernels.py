@@ -223,7 +223,7 @@ def test_select_topk_shards_equal_global(cuda, T, sizes):
         assert np.array_equal(np.concatenate(got_pl), oselect.pseudo_labels(tid, lab, want))
 
 
-@pytest.mark.parametrize("mode", ["staged", "0", "persist", "warp", "ticket", "occ12", "occ16", "cta64", "cta64occ16", "sortplain", "recount", "col64"])
+@pytest.mark.parametrize("mode", ["staged", "0", "persist", "warp", "ticket", "occ16", "cta64", "sortplain", "recount", "col64"])
 def test_select_topk_other_paths_subprocess(cuda, mode):
     """CELLSEG_SELECT_FAST is read when the library loads: =staged routes every bag through the
     shared-memory fast path of round 1 (still used for bags longer than 4093 instances), =0 through
@@ -242,11 +242,10 @@ def test_select_topk_other_paths_subprocess(cuda, mode):
                         "select_topk and not subprocess"],
                        env=dict(os.environ, **({"persist": {"CELLSEG_SELECT_PERSIST": "1"},
                                                 "warp": {"CELLSEG_SELECT_WARP": "1"},
-                                                "occ12": {"CELLSEG_SELECT_OCC": "12"},
                                                 "occ16": {"CELLSEG_SELECT_OCC": "16"},
                                                 "sortplain": {"CELLSEG_SELECT_SORT_PDL": "0"},
                                                 "cta64": {"CELLSEG_SELECT_CTA": "64"},
-                                                "cta64occ16": {"CELLSEG_SELECT_CTA": "64", "CELLSEG_SELECT_OCC64": "16"},
+
                                                 "ticket": {"CELLSEG_SELECT_OFFSETS": "ticket"},
                                                 "recount": {"CELLSEG_SELECT_OFFSETS": "recount"},
                                                 "col64": {"CELLSEG_SELECT_COL32": "0"}}.get(
