@@ -417,7 +417,7 @@ def main():
         ops.select_topk(prob, labels[b0:b0 + B], B, T_PER_BAG, 1, 30, sync=False, out=sel_buf)
         if ev:
             ev[2].record()
-        launches[0] += clf.last_launch_count + 3   # + offsets (count + scan), fast select, exact fallback
+        launches[0] += clf.last_launch_count + 3   # + look-back offsets scan, register select, exact clean-up pass
         return b0
 
     for i in range(args.warmup):
