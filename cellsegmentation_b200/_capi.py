@@ -29,6 +29,7 @@ _PROTOS = {
     "cs_check_device": (c_int, []),
     "cs_grid_count": (c_int, [c_int, c_int, c_int]),
     "cs_grid_coords_host": (c_int, [c_int, c_int, c_int, c_int, POINTER(c_int32), c_int64]),
+    "cs_grid_cover_host": (c_int, [c_int, c_int, c_int, c_int, POINTER(c_int32), POINTER(c_int32)]),
     "cs_unfold_normalize": (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_int, c_int64, c_int64,
                                     c_void_p, c_void_p]),
     "cs_gather_normalize": (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_void_p,

@@ -52,6 +52,18 @@ int cs_check_device(void) {
 int cs_grid_count(int dim, int tile, int interval) { return cs::grid_count(dim, tile, interval); }
 
 // dataset/dataset.py:718-742 (row-major over (x = row, y = col))
+int cs_grid_cover_host(int c, int dim, int tile, int interval, int32_t* lo, int32_t* hi) {
+  CS_REQUIRE(lo != nullptr && hi != nullptr, "cs_grid_cover_host: NULL pointer");
+  const int cnt = cs::grid_count(dim, tile, interval);
+  CS_REQUIRE(cnt > 0 && c >= 0 && c < dim, "cs_grid_cover_host: bad geometry dim=%d tile=%d interval=%d c=%d", dim,
+             tile, interval, c);
+  int l, h;
+  cs::grid_cover(c, dim, tile, interval, cnt, &l, &h);
+  *lo = l;
+  *hi = h;
+  return CS_OK;
+}
+
 int cs_grid_coords_host(int H, int W, int tile, int interval, int32_t* xy_host,
                         int64_t capacity_tiles) {
   CS_REQUIRE(xy_host != nullptr, "cs_grid_coords_host: xy_host is NULL");

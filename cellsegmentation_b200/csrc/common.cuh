@@ -34,6 +34,19 @@ __host__ __device__ inline int grid_coord(int g, int dim, int tile, int interval
   return c < last ? c : last;
 }
 
+// Grid positions whose tile covers coordinate c along one axis: the contiguous range [*lo, *hi]
+// (position coordinates are monotonic); empty (*lo > *hi) for a pixel in the gap between tiles
+// when the stride exceeds the tile.  gcnt = grid_count(dim, S, I) > 0, 0 <= c < dim.
+__host__ __device__ inline void grid_cover(int c, int dim, int S, int I, int gcnt, int* lo, int* hi) {
+  const int last = dim - S;
+  int h = c / I;
+  if (h > gcnt - 1 || c >= last) h = gcnt - 1;
+  int l = c - S + 1 <= 0 ? 0 : (c - S + I) / I;            // ceil((c - S + 1) / I)
+  if (l > gcnt - 1) l = gcnt - 1;
+  *lo = l;
+  *hi = h;
+}
+
 // float -> uint32 key whose unsigned order is numpy's sort order for float32:
 // ascending value, -0.0 == +0.0, every NaN equal and last.
 __host__ __device__ inline uint32_t float_sort_key(float f) {

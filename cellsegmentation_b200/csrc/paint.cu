@@ -151,17 +151,8 @@ heat_blend_kernel(const float* __restrict__ heat, const uint8_t* __restrict__ im
 // covering grid rows for every pixel -- and writes every pixel exactly once: no zero-fill of the
 // maps, no atomics on them, no read of them.  The covering ranges of every x and y are tabulated
 // once per CTA, so the per-pixel work has no division.  Grid positions covering coordinate c along an axis
-// are a contiguous range, because the position coordinates min(g * I, dim - S) are monotonic.
-__device__ __forceinline__ void cover_range(int c, int dim, int S, int I, int gcnt, int* lo, int* hi) {
-  const int last = dim - S;
-  int h = c / I;
-  if (h > gcnt - 1 || c >= last) h = gcnt - 1;
-  int l = c - S + 1 <= 0 ? 0 : (c - S + I) / I;            // ceil((c - S + 1) / I)
-  if (l > gcnt - 1) l = gcnt - 1;
-  *lo = l;
-  *hi = h;
-}
-
+// are a contiguous range, because the position coordinates min(g * I, dim - S) are monotonic
+// (cs::grid_cover, common.cuh).
 __global__ void __launch_bounds__(256)
 heat_table_kernel(Grid g, const int32_t* __restrict__ sel, const float* __restrict__ prob, int64_t n_sel,
                   int* __restrict__ table) {
@@ -197,8 +188,8 @@ heat_gather_kernel(Grid g, int grid_h, const float* __restrict__ table, float* _
   int* ylo = xhi + W;
   int* yhi = ylo + H;
   // the covering ranges depend on the geometry only: once per CTA
-  for (int i = threadIdx.x; i < W; i += kGatherThreads) cover_range(i, W, S, I, gw, xlo + i, xhi + i);
-  for (int i = threadIdx.x; i < H; i += kGatherThreads) cover_range(i, H, S, I, grid_h, ylo + i, yhi + i);
+  for (int i = threadIdx.x; i < W; i += kGatherThreads) cs::grid_cover(i, W, S, I, gw, xlo + i, xhi + i);
+  for (int i = threadIdx.x; i < H; i += kGatherThreads) cs::grid_cover(i, H, S, I, grid_h, ylo + i, yhi + i);
   const int step_gy = kGatherThreads / W, step_x = kGatherThreads - step_gy * W;
   const int segs = max(1, kGatherThreads / W);
   for (int bag = blockIdx.x; bag < g.n_bags; bag += gridDim.x) {

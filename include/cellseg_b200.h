@@ -71,6 +71,10 @@ int cs_grid_count(int dim, int tile, int interval);
 /* Fills xy_host[2*t] = row, xy_host[2*t+1] = col for all tiles of one HxW bag. */
 int cs_grid_coords_host(int H, int W, int tile, int interval, int32_t* xy_host,
                         int64_t capacity_tiles);
+/* Grid positions along one axis whose tile covers coordinate c (0 <= c < dim): the contiguous
+ * range [*lo, *hi], empty (*lo > *hi) in the gap between tiles when interval > tile.  The
+ * inverse of get_tiles used by cs_paint_heatmap_gather; host function, for tests. */
+int cs_grid_cover_host(int c, int dim, int tile, int interval, int32_t* lo, int32_t* hi);
 
 /* ---------------------------------------------------------------------------
  * K1  unfold + ToTensor + Normalize.
